@@ -1,0 +1,116 @@
+// Embedding gather (a2.1), RMSNorm (a2.2) and the synthetic-weight generator.
+// All three are HBM-bound: 16-byte accesses, one row per CTA, no re-reads.
+#include "../../include/llmlb_b200.h"
+#include "common.cuh"
+
+namespace llmlb {
+
+// x[t, :] = float(E[ids[t], :]).  One CTA per token; 8 bf16 per thread per trip.
+__global__ void __launch_bounds__(256) embed_kernel(const __nv_bfloat16* __restrict__ table,
+                                                    const int32_t* __restrict__ ids,
+                                                    float* __restrict__ x, uint32_t hidden,
+                                                    uint32_t vocab) {
+  const uint32_t t = blockIdx.x;
+  int32_t id = ids[t];
+  if (id < 0 || uint32_t(id) >= vocab) id = 0;  // out-of-range ids read row 0 (host validates)
+  const uint4* src = reinterpret_cast<const uint4*>(table + size_t(id) * hidden);
+  float4* dst = reinterpret_cast<float4*>(x + size_t(t) * hidden);
+  for (uint32_t i = threadIdx.x; i < hidden / 8; i += blockDim.x) {
+    uint4 v = __ldg(src + i);
+    dst[2 * i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+    dst[2 * i + 1] = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+  }
+}
+
+// y = x * rsqrt(mean(x^2) + eps) * g.  fp32 residual in, bf16 out; one CTA (256 thr) per token.
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x,
+                                                      const __nv_bfloat16* __restrict__ gain,
+                                                      __nv_bfloat16* __restrict__ y,
+                                                      uint32_t hidden, float eps) {
+  __shared__ float red[8];
+  const uint32_t t = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(x + size_t(t) * hidden);
+  float ss = 0.f;
+  for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
+    float4 v = src[i];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float r = rsqrtf(tot / float(hidden) + eps);
+  uint2* dst = reinterpret_cast<uint2*>(y + size_t(t) * hidden);
+  const uint2* g2 = reinterpret_cast<const uint2*>(gain);
+  for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
+    float4 v = src[i];
+    uint2 g = __ldg(g2 + i);
+    uint2 o;
+    o.x = pack_bf16(v.x * r * bf16_lo(g.x), v.y * r * bf16_hi(g.x));
+    o.y = pack_bf16(v.z * r * bf16_lo(g.y), v.w * r * bf16_hi(g.y));
+    dst[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(__nv_bfloat16* __restrict__ out,
+                                                    uint64_t rows, uint64_t cols, uint64_t row0,
+                                                    uint64_t col0, uint64_t ld, uint64_t seed,
+                                                    uint32_t tensor_id, float scale) {
+  const uint64_t n = rows * cols;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += uint64_t(gridDim.x) * blockDim.x) {
+    uint64_t r = i / cols, c = i - r * cols;
+    uint64_t gidx = (row0 + r) * ld + (col0 + c);
+    out[i] = __float2bfloat16_rn(synth_value(seed, tensor_id, gidx, scale));
+  }
+}
+
+}  // namespace llmlb
+
+using namespace llmlb;
+
+extern "C" int llmlb_op_embed(const void* table, const int32_t* ids, float* x, uint32_t n_tokens,
+                              uint32_t hidden, uint32_t vocab, void* stream) {
+  if (!table || !ids || !x || hidden % 8) {
+    set_error("llmlb_op_embed: bad argument");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (n_tokens == 0) return LLMLB_OK;
+  embed_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)table, ids, x, hidden, vocab);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_op_rmsnorm(const float* x, const void* gain, void* y, uint32_t n_tokens,
+                                uint32_t hidden, float eps, void* stream) {
+  if (!x || !gain || !y || hidden % 4) {
+    set_error("llmlb_op_rmsnorm: bad argument");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (n_tokens == 0) return LLMLB_OK;
+  rmsnorm_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>(
+      x, (const __nv_bfloat16*)gain, (__nv_bfloat16*)y, hidden, eps);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_op_synth_bf16(void* out, uint64_t rows, uint64_t cols, uint64_t row0,
+                                   uint64_t col0, uint64_t ld, uint64_t seed, uint32_t tensor_id,
+                                   float std, void* stream) {
+  if (!out) {
+    set_error("llmlb_op_synth_bf16: null output");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (rows * cols == 0) return LLMLB_OK;
+  uint64_t n = rows * cols;
+  uint32_t grid = (uint32_t)((n + 255) / 256 < uint64_t(kNumSMs) * 16 ? (n + 255) / 256
+                                                                        : uint64_t(kNumSMs) * 16);
+  synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, rows, cols, row0,
+                                                       col0, ld, seed, tensor_id,
+                                                       std / kSynthSumStd);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}

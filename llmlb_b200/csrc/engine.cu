@@ -1,0 +1,1259 @@
+// llmlb_engine: the in-process replacement for the gateway's HTTP hop to an inference endpoint
+// (reference boundary: llmlb/src/api/openai.rs:995-1005, llmlb/src/api/proxy.rs:372-401).
+//
+// One engine per GPU rank.  Host side (this file): weights + paged-KV pool + sequence slots, an
+// iteration-level continuous-batching scheduler on its own thread, per-request
+// token-event queues for non-blocking submit/poll/cancel.  Device side: the kernels in the
+// sibling .cu files, chained on one stream; decode steps are captured into CUDA graphs per batch
+// width and all per-sequence decode state (length, last token, sampler counters) lives in HBM so
+// the GPU never waits for the host between tokens — the host reads tokens `lookahead` steps late.
+#include <cuda.h>
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/llmlb_b200.h"
+#include "common.cuh"
+
+namespace llmlb {
+
+// ---- pieces defined in the other translation units ----
+int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
+                   uint32_t box_rows);
+uint32_t tc_pick_bn(uint32_t n_tokens);
+int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
+                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,
+                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+
+constexpr int kArMaxRanks = 8;
+struct ArPeers {
+  uint8_t* base[kArMaxRanks];
+  uint32_t rank, size;
+  uint64_t slot_bytes;
+};
+size_t ar_signal_bytes();
+int ar_allreduce_add(const ArPeers& P, uint32_t slot, float* x, uint64_t n, cudaStream_t st);
+int ar_allgather_cols(const ArPeers& P, uint32_t slot, float* out, uint32_t rows,
+                      uint32_t cols_local, cudaStream_t st);
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+std::atomic<uint64_t> g_kernel_launches{0};
+
+#define RC(expr)                 \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != LLMLB_OK) return _rc; \
+  } while (0)
+
+// ------------------------------------------------------------------ small device kernels ----
+__global__ void fill_bf16_kernel(__nv_bfloat16* p, uint64_t n, float v) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += uint64_t(gridDim.x) * blockDim.x)
+    p[i] = __float2bfloat16_rn(v);
+}
+__global__ void synth_strided_kernel(__nv_bfloat16* __restrict__ out, uint64_t rows, uint64_t cols,
+                                     uint64_t out_ld, uint64_t row0, uint64_t col0, uint64_t ld,
+                                     uint64_t seed, uint32_t tensor_id, float scale) {
+  const uint64_t n = rows * cols;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += uint64_t(gridDim.x) * blockDim.x) {
+    uint64_t r = i / cols, c = i - r * cols;
+    out[r * out_ld + c] =
+        __float2bfloat16_rn(synth_value(seed, tensor_id, (row0 + r) * ld + (col0 + c), scale));
+  }
+}
+
+struct SlotState {  // per-sequence decode state, device resident
+  int32_t* seq_len;     // tokens whose K/V are in the cache
+  int32_t* last_token;  // next input token
+  float* temperature;
+  float* top_p;
+  int32_t* top_k;
+  uint64_t* seed;
+  uint64_t* step;
+};
+struct BatchView {  // compact per-step arrays
+  int32_t* slots;     // batch position -> slot
+  int32_t* ids;
+  int32_t* seq_lens;  // including the new token
+  float* temperature;
+  float* top_p;
+  int32_t* top_k;
+  uint64_t* seed;
+  uint64_t* step;
+  int32_t* out_ids;
+};
+
+// decode: pull the per-slot state into the compact batch arrays and advance the lengths
+__global__ void decode_prepare_kernel(SlotState S, BatchView B, uint32_t n) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  int32_t slot = B.slots[b];
+  B.ids[b] = S.last_token[slot];
+  int32_t L = S.seq_len[slot] + 1;
+  S.seq_len[slot] = L;
+  B.seq_lens[b] = L;
+  B.temperature[b] = S.temperature[slot];
+  B.top_p[b] = S.top_p[slot];
+  B.top_k[b] = S.top_k[slot];
+  B.seed[b] = S.seed[slot];
+  B.step[b] = S.step[slot];
+}
+// first token after prefill: only the sampler state is gathered
+__global__ void sample_prepare_kernel(SlotState S, BatchView B, uint32_t n) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  int32_t slot = B.slots[b];
+  B.temperature[b] = S.temperature[slot];
+  B.top_p[b] = S.top_p[slot];
+  B.top_k[b] = S.top_k[slot];
+  B.seed[b] = S.seed[slot];
+  B.step[b] = S.step[slot];
+}
+__global__ void step_finish_kernel(SlotState S, BatchView B, uint32_t n) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  int32_t slot = B.slots[b];
+  S.last_token[slot] = B.out_ids[b];
+  S.step[slot] += 1;
+}
+// y_last[r, :] = x[rows[r], :]  (fp32 -> fp32 gather of the rows that need logits)
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ rows,
+                                   float* __restrict__ out, uint32_t hidden) {
+  const float4* src = reinterpret_cast<const float4*>(x + size_t(rows[blockIdx.x]) * hidden);
+  float4* dst = reinterpret_cast<float4*>(out + size_t(blockIdx.x) * hidden);
+  for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ host structures ---------
+struct Request {
+  uint64_t id = 0;
+  std::vector<int32_t> prompt;
+  llmlb_sampling s{};
+  std::vector<int32_t> stop_ids;
+  int slot = -1;
+  std::vector<int32_t> pages;
+  uint32_t prefilled = 0;   // prompt tokens whose KV is (being) written
+  uint32_t launched = 0;    // generated tokens whose computation has been launched
+  uint32_t harvested = 0;   // generated tokens seen by the host
+  bool finished = false;
+  bool cancel = false;
+  bool client_released = false;
+  uint32_t finish_reason = LLMLB_FINISH_NONE;
+  std::deque<llmlb_token_event> events;
+  std::chrono::steady_clock::time_point t_submit;
+};
+using ReqPtr = std::shared_ptr<Request>;
+
+struct InflightStep {
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+  int32_t* host_ids = nullptr;        // pinned
+  std::vector<ReqPtr> reqs;           // batch position -> request
+  bool is_prefill = false;
+  uint32_t n_tokens = 0;
+};
+
+struct LayerW {
+  __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
+  CUtensorMap m_wqkv, m_wo, m_wgu, m_wdown;
+};
+
+}  // namespace llmlb
+
+using namespace llmlb;
+
+struct llmlb_engine {
+  llmlb_engine_config cfg{};
+  llmlb_model_config M{};
+  // derived geometry (per rank)
+  uint32_t tp = 1, rank = 0;
+  uint32_t nq_l = 0, nkv_l = 0, ffn_l = 0, vocab_l = 0, qkv_w = 0;
+  uint32_t t_cap = 0;             // activation rows
+  uint32_t pages_per_seq = 0, n_pages = 0;
+  uint32_t lookahead = 2;
+  cudaStream_t st = nullptr;
+
+  // weights
+  __nv_bfloat16* embed = nullptr;
+  __nv_bfloat16* final_norm = nullptr;
+  __nv_bfloat16* lm_head = nullptr;
+  CUtensorMap m_lm_head{};
+  std::vector<LayerW> layers;
+  uint64_t param_bytes = 0;
+
+  // KV pool [layer][page][kv_head][64][128]
+  __nv_bfloat16 *k_pool = nullptr, *v_pool = nullptr;
+  size_t layer_pool_elems = 0;
+  float* rope = nullptr;
+  int32_t* d_block_tables = nullptr;  // [max_seqs][pages_per_seq]
+  std::vector<int32_t> free_pages;
+  std::vector<int32_t> free_slots;
+
+  // activations
+  float* x = nullptr;
+  __nv_bfloat16 *y = nullptr, *qkv = nullptr, *attn = nullptr, *h = nullptr;
+  float* logits = nullptr;       // [max_seqs][vocab]
+  float* logits_l = nullptr;     // [max_seqs][vocab_l] local slice when tp > 1
+  float* x_last = nullptr;       // [max_seqs][hidden]
+  void* attn_ws = nullptr;
+  CUtensorMap m_y[5]{}, m_attn[5]{}, m_h[5]{};  // box rows 16,32,64,128,256
+
+  // per-step metadata (device) + pinned staging ring
+  int32_t *d_ids = nullptr, *d_pos = nullptr, *d_page_of_tok = nullptr, *d_tiles = nullptr,
+          *d_last_rows = nullptr;
+  SlotState S{};
+  BatchView B{};
+  static constexpr int kRing = 8;
+  uint8_t* h_stage[kRing] = {};
+  size_t stage_bytes = 0;
+  uint64_t stage_seq = 0;
+  int32_t* h_out[kRing] = {};
+  uint64_t out_seq = 0;
+  std::vector<cudaEvent_t> ev_pool;
+
+  // TP exchange
+  uint8_t* xchg = nullptr;
+  size_t xchg_bytes = 0;
+  ArPeers peers{};
+  bool tp_ready = false;
+
+  // decode graphs by batch width
+  std::unordered_map<uint32_t, cudaGraphExec_t> graphs;
+  std::unordered_map<uint32_t, uint64_t> graph_nodes;  // kernels per captured step
+  bool paused = false;
+  std::string fatal_error;
+  int warmup();
+  std::vector<int32_t> cur_batch_slots;  // what d B.slots currently holds
+
+  // scheduler
+  std::mutex mu;               // requests / queues / events
+  std::condition_variable cv_sched, cv_events;
+  std::mutex step_mu;          // held while a step (or a debug call) uses the GPU state
+  std::thread worker;
+  bool stop = false;
+  uint64_t next_id = 1;
+  std::map<uint64_t, ReqPtr> requests;
+  std::deque<ReqPtr> waiting;
+  std::vector<ReqPtr> running;   // have a slot; prefilling or decoding
+  std::deque<InflightStep> inflight;
+  // stats
+  std::atomic<uint64_t> steps_prefill{0}, steps_decode{0}, tokens_prefill{0}, tokens_decode{0};
+  double gpu_ms_prefill = 0, gpu_ms_decode = 0;  // under mu
+  int debug_slot = -1;
+  std::vector<int32_t> debug_pages;
+  uint32_t debug_len = 0;
+
+  // ---- helpers ----
+  __nv_bfloat16* kpool(uint32_t l) { return k_pool + size_t(l) * layer_pool_elems; }
+  __nv_bfloat16* vpool(uint32_t l) { return v_pool + size_t(l) * layer_pool_elems; }
+  static int bn_index(uint32_t bn) { return bn == 16 ? 0 : bn == 32 ? 1 : bn == 64 ? 2 : bn == 128 ? 3 : 4; }
+
+  int init();
+  int alloc_all();
+  int gen_weights();
+  int proj(const LayerW* L, int which, const void* w, const CUtensorMap& mw, const void* xin,
+           const CUtensorMap* mx, const __nv_bfloat16* gain, void* out, uint32_t T, uint32_t n_out,
+           uint32_t k, uint32_t epi, uint32_t out_stride);
+  int layer_stack_decode(uint32_t nb);
+  int launch_decode_step(uint32_t nb);
+  int forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles);
+  int logits_for_rows(uint32_t R, bool from_x_rows);
+  int run_prefill(const std::vector<ReqPtr>& reqs, const std::vector<uint32_t>& take);
+  int run_decode(const std::vector<ReqPtr>& batch);
+  void harvest_one();
+  void loop();
+  void finish_request(const ReqPtr& r, uint32_t reason);
+  void release_resources(const ReqPtr& r);
+  cudaEvent_t get_event();
+  uint8_t* next_stage() { return h_stage[(stage_seq++) % kRing]; }
+  uint32_t decode_splits(uint32_t nb) const {
+    uint32_t ctas = nb * (nq_l / 4);
+    uint32_t sp = (2 * kNumSMs + ctas - 1) / ctas;
+    if (sp > 16) sp = 16;
+    if (sp < 1) sp = 1;
+    return sp;
+  }
+  int resolve_tensor(const std::string& name, __nv_bfloat16** base, uint64_t* rows, uint64_t* cols,
+                     uint64_t* ld, uint64_t* full_rows, uint64_t* full_cols, uint64_t* row0,
+                     uint64_t* col0);
+};
+
+extern "C" int llmlb_op_rope_table(float* table, uint32_t max_pos, float theta, void* stream);
+extern "C" int llmlb_op_rope_append(void* qkv, const int32_t* positions,
+                                    const int32_t* page_of_token, const float* rope_table,
+                                    void* k_pages, void* v_pages, uint32_t n_tokens,
+                                    uint32_t n_heads, uint32_t n_kv, void* stream);
+extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v_pages,
+                                         const int32_t* block_tables, uint32_t bt_stride,
+                                         const int32_t* bt_rows, const int32_t* seq_lens,
+                                         uint32_t n_seqs, void* out, uint32_t n_heads,
+                                         uint32_t n_kv, const float* rope_table, uint32_t n_splits,
+                                         uint32_t ws_seqs, void* workspace, void* stream);
+
+static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ creation ----------------
+int llmlb_engine::init() {
+  M = cfg.model;
+  tp = cfg.tp_size ? cfg.tp_size : 1;
+  rank = cfg.tp_rank;
+  if (cfg.abi_version != LLMLB_ABI_VERSION) { set_error("abi_version mismatch"); return LLMLB_E_INVALID_ARG; }
+  if (M.head_dim != (uint32_t)kHeadDim) { set_error("head_dim must be 128"); return LLMLB_E_INVALID_ARG; }
+  if (cfg.kv_block_tokens != 0 && cfg.kv_block_tokens != (uint32_t)kPageTokens) {
+    set_error("kv_block_tokens must be 64"); return LLMLB_E_INVALID_ARG;
+  }
+  if (!(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank >= tp) { set_error("bad tp_size/tp_rank"); return LLMLB_E_INVALID_ARG; }
+  if (M.n_kv_heads == 0 || M.n_heads % M.n_kv_heads || M.n_kv_heads % tp || M.ffn % tp || M.vocab % tp ||
+      ((M.n_heads / M.n_kv_heads) % 4) || M.hidden % 8 || (M.ffn / tp) % 8 || (M.vocab / tp) % 4 ||
+      M.n_layers == 0 || M.vocab == 0) {
+    set_error("unsupported model geometry (GQA group must be a multiple of 4; dims divisible by tp)");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (cfg.max_seqs == 0 || cfg.max_ctx == 0) { set_error("max_seqs/max_ctx must be > 0"); return LLMLB_E_INVALID_ARG; }
+  nq_l = M.n_heads / tp; nkv_l = M.n_kv_heads / tp; ffn_l = M.ffn / tp; vocab_l = M.vocab / tp;
+  qkv_w = (nq_l + 2 * nkv_l) * kHeadDim;
+  uint32_t mst = cfg.max_step_tokens ? cfg.max_step_tokens : 2048;
+  t_cap = std::max(mst, cfg.max_seqs);
+  t_cap = ceil_div(t_cap, 64) * 64;
+  cfg.max_step_tokens = mst;
+  pages_per_seq = ceil_div(cfg.max_ctx, kPageTokens);
+  n_pages = cfg.kv_pages ? cfg.kv_pages : cfg.max_seqs * pages_per_seq;
+  lookahead = cfg.lookahead ? cfg.lookahead : 2;
+  if (lookahead > 4) lookahead = 4;
+  LLMLB_CUDA_CHECK(cudaSetDevice(cfg.device));
+  LLMLB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  RC(alloc_all());
+  RC(gen_weights());
+  LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (tp == 1) RC(warmup());
+  for (int32_t p = int32_t(n_pages) - 1; p >= 0; --p) free_pages.push_back(p);
+  for (int32_t s = int32_t(cfg.max_seqs) - 1; s >= 0; --s) free_slots.push_back(s);
+  worker = std::thread([this] { this->loop(); });
+  return LLMLB_OK;
+}
+
+template <class T>
+static int dmalloc(T** p, size_t n_elems, bool zero = true) {
+  size_t bytes = n_elems * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  cudaError_t e = cudaMalloc((void**)p, bytes);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    return LLMLB_E_DEVICE;
+  }
+  if (zero) cudaMemset(*p, 0, bytes);
+  return LLMLB_OK;
+}
+
+int llmlb_engine::alloc_all() {
+  const size_t H = M.hidden;
+  RC(dmalloc(&embed, size_t(M.vocab) * H, false));
+  RC(dmalloc(&final_norm, H, false));
+  RC(dmalloc(&lm_head, size_t(vocab_l) * H, false));
+  param_bytes = size_t(vocab_l) * H * 2;
+  layers.resize(M.n_layers);
+  for (auto& L : layers) {
+    RC(dmalloc(&L.wqkv, size_t(qkv_w) * H, false));
+    RC(dmalloc(&L.wo, H * size_t(nq_l) * kHeadDim, false));
+    RC(dmalloc(&L.wgu, size_t(2) * ffn_l * H, false));
+    RC(dmalloc(&L.wdown, H * size_t(ffn_l), false));
+    RC(dmalloc(&L.attn_norm, H, false));
+    RC(dmalloc(&L.ffn_norm, H, false));
+    param_bytes += (size_t(qkv_w) * H + H * size_t(nq_l) * kHeadDim + size_t(2) * ffn_l * H + H * size_t(ffn_l)) * 2;
+    if (cfg.gemm_impl == 0) {
+      RC(make_tmap_bf16(&L.m_wqkv, L.wqkv, qkv_w, H, 128));
+      RC(make_tmap_bf16(&L.m_wo, L.wo, H, size_t(nq_l) * kHeadDim, 128));
+      RC(make_tmap_bf16(&L.m_wgu, L.wgu, 2 * ffn_l, H, 128));
+      RC(make_tmap_bf16(&L.m_wdown, L.wdown, H, ffn_l, 128));
+    }
+  }
+  if (cfg.gemm_impl == 0) RC(make_tmap_bf16(&m_lm_head, lm_head, vocab_l, H, 128));
+
+  layer_pool_elems = size_t(n_pages) * nkv_l * kPageTokens * kHeadDim;
+  RC(dmalloc(&k_pool, layer_pool_elems * M.n_layers));
+  RC(dmalloc(&v_pool, layer_pool_elems * M.n_layers));
+  RC(dmalloc(&rope, size_t(cfg.max_ctx) * 64 * 2));
+  RC(llmlb_op_rope_table(rope, cfg.max_ctx, M.rope_theta, st));
+  RC(dmalloc(&d_block_tables, size_t(cfg.max_seqs) * pages_per_seq));
+
+  RC(dmalloc(&x, size_t(t_cap) * H));
+  RC(dmalloc(&y, size_t(t_cap) * H));
+  RC(dmalloc(&qkv, size_t(t_cap) * qkv_w));
+  RC(dmalloc(&attn, size_t(t_cap) * nq_l * kHeadDim));
+  RC(dmalloc(&h, size_t(t_cap) * ffn_l));
+  RC(dmalloc(&logits, size_t(cfg.max_seqs) * M.vocab));
+  if (tp > 1) RC(dmalloc(&logits_l, size_t(cfg.max_seqs) * vocab_l));
+  RC(dmalloc(&x_last, size_t(cfg.max_seqs) * H));
+  size_t ws = llmlb_op_decode_attention_ws(cfg.max_seqs, nq_l, 16);
+  RC(dmalloc((uint8_t**)&attn_ws, ws));
+  if (cfg.gemm_impl == 0) {
+    const uint32_t boxes[5] = {16, 32, 64, 128, 256};
+    for (int i = 0; i < 5; ++i) {
+      RC(make_tmap_bf16(&m_y[i], y, t_cap, H, boxes[i]));
+      RC(make_tmap_bf16(&m_attn[i], attn, t_cap, size_t(nq_l) * kHeadDim, boxes[i]));
+      RC(make_tmap_bf16(&m_h[i], h, t_cap, ffn_l, boxes[i]));
+    }
+  }
+  RC(dmalloc(&d_ids, t_cap));
+  RC(dmalloc(&d_pos, t_cap));
+  RC(dmalloc(&d_page_of_tok, t_cap));
+  RC(dmalloc(&d_tiles, size_t(t_cap / 64 + cfg.max_seqs + 1) * 4));
+  RC(dmalloc(&d_last_rows, cfg.max_seqs));
+  const size_t ms = cfg.max_seqs;
+  RC(dmalloc(&S.seq_len, ms)); RC(dmalloc(&S.last_token, ms)); RC(dmalloc(&S.temperature, ms));
+  RC(dmalloc(&S.top_p, ms)); RC(dmalloc(&S.top_k, ms)); RC(dmalloc(&S.seed, ms)); RC(dmalloc(&S.step, ms));
+  RC(dmalloc(&B.slots, ms)); RC(dmalloc(&B.ids, ms)); RC(dmalloc(&B.seq_lens, ms));
+  RC(dmalloc(&B.temperature, ms)); RC(dmalloc(&B.top_p, ms)); RC(dmalloc(&B.top_k, ms));
+  RC(dmalloc(&B.seed, ms)); RC(dmalloc(&B.step, ms)); RC(dmalloc(&B.out_ids, ms));
+  stage_bytes = size_t(t_cap) * 4 * 3 + size_t(t_cap / 64 + ms + 1) * 16 + ms * 4 * 2 + 256;
+  for (int i = 0; i < kRing; ++i) {
+    LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_stage[i], stage_bytes, cudaHostAllocDefault));
+    LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_out[i], ms * 4, cudaHostAllocDefault));
+  }
+  if (tp > 1) {
+    size_t slot = std::max(size_t(t_cap) * H * 4, size_t(cfg.max_seqs) * vocab_l * 4);
+    slot = (slot + 255) & ~size_t(255);
+    xchg_bytes = ar_signal_bytes() + 3 * slot;
+    RC(dmalloc(&xchg, xchg_bytes));
+    peers.rank = rank; peers.size = tp; peers.slot_bytes = slot;
+    // signal struct offset must match ar_signal_bytes(): slots start right after sizeof(ArSignals)
+  }
+  return LLMLB_OK;
+}
+
+static int synth(__nv_bfloat16* out, uint64_t rows, uint64_t cols, uint64_t out_ld, uint64_t row0,
+                 uint64_t col0, uint64_t ld, uint64_t seed, uint32_t id, float std, cudaStream_t st) {
+  uint64_t n = rows * cols;
+  if (n == 0) return LLMLB_OK;
+  uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, uint64_t(kNumSMs) * 16);
+  synth_strided_kernel<<<grid, 256, 0, st>>>(out, rows, cols, out_ld, row0, col0, ld, seed, id,
+                                             std / kSynthSumStd);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+static int fill(__nv_bfloat16* p, uint64_t n, float v, cudaStream_t st) {
+  fill_bf16_kernel<<<(uint32_t)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, st>>>(p, n, v);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
+// tensor ids: layer*16 + kind (0 q,1 k,2 v,3 o,4 gate,5 up,6 down); globals 0xFFFF0000+{0 embed,2 lm_head}
+int llmlb_engine::gen_weights() {
+  const uint64_t H = M.hidden, seed = cfg.synthetic_seed;
+  const float sd = 0.02f;
+  RC(synth(embed, M.vocab, H, H, 0, 0, H, seed, 0xFFFF0000u, sd, st));
+  RC(fill(final_norm, H, 1.0f, st));
+  RC(synth(lm_head, vocab_l, H, H, uint64_t(rank) * vocab_l, 0, H, seed, 0xFFFF0002u, sd, st));
+  for (uint32_t l = 0; l < M.n_layers; ++l) {
+    LayerW& L = layers[l];
+    const uint32_t id = l * 16;
+    const uint64_t qr = uint64_t(nq_l) * kHeadDim, kr = uint64_t(nkv_l) * kHeadDim;
+    RC(synth(L.wqkv, qr, H, H, rank * qr, 0, H, seed, id + 0, sd, st));
+    RC(synth(L.wqkv + qr * H, kr, H, H, rank * kr, 0, H, seed, id + 1, sd, st));
+    RC(synth(L.wqkv + (qr + kr) * H, kr, H, H, rank * kr, 0, H, seed, id + 2, sd, st));
+    RC(synth(L.wo, H, qr, qr, 0, rank * qr, uint64_t(M.n_heads) * kHeadDim, seed, id + 3, sd, st));
+    RC(synth(L.wgu, ffn_l, H, 2 * H, uint64_t(rank) * ffn_l, 0, H, seed, id + 4, sd, st));      // even rows
+    RC(synth(L.wgu + H, ffn_l, H, 2 * H, uint64_t(rank) * ffn_l, 0, H, seed, id + 5, sd, st));  // odd rows
+    RC(synth(L.wdown, H, ffn_l, ffn_l, 0, uint64_t(rank) * ffn_l, M.ffn, seed, id + 6, sd, st));
+    RC(fill(L.attn_norm, H, 1.0f, st));
+    RC(fill(L.ffn_norm, H, 1.0f, st));
+  }
+  return LLMLB_OK;
+}
+
+// ------------------------------------------------------------------ forward passes ----------
+// One projection: GEMV (<= 4 tokens, optional fused RMSNorm) or tensor-core GEMM.
+int llmlb_engine::proj(const LayerW*, int, const void* w, const CUtensorMap& mw, const void* xin,
+                       const CUtensorMap* mx, const __nv_bfloat16* gain, void* out, uint32_t T,
+                       uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride) {
+  if (T <= 4) return llmlb_op_gemv(w, xin, gain, M.rms_eps, out, T, n_out, k, epi, out_stride, st);
+  // callers pass bf16 activations (already normalised) on this path
+  if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, out, T, n_out, k, epi, out_stride, st);
+  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st);
+}
+
+// Runs the layer stack over T rows already embedded in x.  decode: rows are one new token per
+// sequence (nb of them); else rows are prefill tokens described by d_pos/d_page_of_tok/d_tiles.
+int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles) {
+  const uint32_t H = M.hidden;
+  const bool small = T <= 4;
+  uint32_t coll = 0;
+  for (uint32_t l = 0; l < M.n_layers; ++l) {
+    LayerW& L = layers[l];
+    // --- attention block ---
+    if (small) {
+      RC(llmlb_op_gemv(L.wqkv, x, L.attn_norm, M.rms_eps, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st));
+    } else {
+      RC(llmlb_op_rmsnorm(x, L.attn_norm, y, T, H, M.rms_eps, st));
+      RC(proj(&L, 0, L.wqkv, L.m_wqkv, y, m_y, nullptr, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
+    }
+    if (decode) {
+      RC(llmlb_op_decode_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots,
+                                   B.seq_lens, nb, attn, nq_l, nkv_l, rope, decode_splits(nb),
+                                   cfg.max_seqs, attn_ws, st));
+    } else {
+      RC(llmlb_op_rope_append(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, st));
+      RC(llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles,
+                                    n_tiles, attn, nq_l, nkv_l, st));
+    }
+    const uint32_t ko = nq_l * kHeadDim;
+    if (tp == 1) {
+      RC(proj(&L, 1, L.wo, L.m_wo, attn, m_attn, nullptr, x, T, H, ko, LLMLB_EPI_RESID_F32, H));
+    } else {
+      float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
+      RC(proj(&L, 1, L.wo, L.m_wo, attn, m_attn, nullptr, part, T, H, ko, LLMLB_EPI_STORE_F32, H));
+      RC(ar_allreduce_add(peers, coll & 1, x, uint64_t(T) * H, st));
+      ++coll;
+    }
+    // --- feed-forward block ---
+    if (small) {
+      RC(llmlb_op_gemv(L.wgu, x, L.ffn_norm, M.rms_eps, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, st));
+    } else {
+      RC(llmlb_op_rmsnorm(x, L.ffn_norm, y, T, H, M.rms_eps, st));
+      RC(proj(&L, 2, L.wgu, L.m_wgu, y, m_y, nullptr, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
+    }
+    if (tp == 1) {
+      RC(proj(&L, 3, L.wdown, L.m_wdown, h, m_h, nullptr, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H));
+    } else {
+      float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
+      RC(proj(&L, 3, L.wdown, L.m_wdown, h, m_h, nullptr, part, T, H, ffn_l, LLMLB_EPI_STORE_F32, H));
+      RC(ar_allreduce_add(peers, coll & 1, x, uint64_t(T) * H, st));
+      ++coll;
+    }
+  }
+  return LLMLB_OK;
+}
+
+// logits[r, :] for R rows.  from_x_rows: rows are x[0..R) (decode); else x_last[0..R) (gathered).
+int llmlb_engine::logits_for_rows(uint32_t R, bool from_x_rows) {
+  const uint32_t H = M.hidden;
+  const float* src = from_x_rows ? x : x_last;
+  float* dst = (tp == 1) ? logits
+                         : reinterpret_cast<float*>(xchg + ar_signal_bytes() + 2 * peers.slot_bytes);
+  if (R <= 4) {
+    RC(llmlb_op_gemv(lm_head, src, final_norm, M.rms_eps, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
+  } else {
+    RC(llmlb_op_rmsnorm(src, final_norm, y, R, H, M.rms_eps, st));
+    if (cfg.gemm_impl == 1)
+      RC(gemm_mma_launch(lm_head, y, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
+    else
+      RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
+  }
+  if (tp > 1) RC(ar_allgather_cols(peers, 2, logits, R, vocab_l, st));
+  return LLMLB_OK;
+}
+
+int llmlb_engine::layer_stack_decode(uint32_t nb) {
+  decode_prepare_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(S, B, nb);
+  LLMLB_LAUNCH_CHECK();
+  RC(llmlb_op_embed(embed, B.ids, x, nb, M.hidden, M.vocab, st));
+  RC(forward_tokens(nb, true, nb, 0));
+  RC(logits_for_rows(nb, true));
+  RC(llmlb_op_sample(logits, nb, M.vocab, B.temperature, B.top_p, B.top_k, B.seed, B.step, B.out_ids, st));
+  step_finish_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(S, B, nb);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
+int llmlb_engine::launch_decode_step(uint32_t nb) {
+  if (!cfg.use_cuda_graphs) return layer_stack_decode(nb);
+  auto it = graphs.find(nb);
+  if (it == graphs.end()) {
+    // kernel attributes (max dynamic smem) were set by the eager warm-up in init()
+    cudaGraph_t g = nullptr;
+    uint64_t launches_before = g_kernel_launches.load();
+    LLMLB_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = layer_stack_decode(nb);
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc != LLMLB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return LLMLB_E_DEVICE; }
+    cudaGraphExec_t ge = nullptr;
+    LLMLB_CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    graphs[nb] = ge;
+    graph_nodes[nb] = g_kernel_launches.load() - launches_before;
+    g_kernel_launches.store(launches_before);  // capture did not execute anything
+    it = graphs.find(nb);
+  }
+  LLMLB_CUDA_CHECK(cudaGraphLaunch(it->second, st));
+  g_kernel_launches.fetch_add(graph_nodes[nb]);
+  return LLMLB_OK;
+}
+
+// ------------------------------------------------------------------ steps -------------------
+__global__ void slot_init_kernel(SlotState S, int32_t slot, float temperature, float top_p,
+                                 int32_t top_k, uint64_t seed) {
+  S.seq_len[slot] = 0;
+  S.last_token[slot] = 0;
+  S.temperature[slot] = temperature;
+  S.top_p[slot] = top_p;
+  S.top_k[slot] = top_k;
+  S.seed[slot] = seed;
+  S.step[slot] = 0;
+}
+__global__ void prefill_finish_kernel(SlotState S, BatchView B, uint32_t n) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  S.seq_len[B.slots[b]] = B.seq_lens[b];  // tokens now in the cache
+}
+
+cudaEvent_t llmlb_engine::get_event() {
+  if (!ev_pool.empty()) {
+    cudaEvent_t e = ev_pool.back();
+    ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// reqs[i] contributes take[i] prompt tokens starting at reqs[i]->prefilled
+int llmlb_engine::run_prefill(const std::vector<ReqPtr>& reqs, const std::vector<uint32_t>& take) {
+  uint32_t T = 0;
+  for (uint32_t t : take) T += t;
+  uint8_t* stg = next_stage();
+  int32_t* s_ids = reinterpret_cast<int32_t*>(stg);
+  int32_t* s_pos = s_ids + t_cap;
+  int32_t* s_page = s_pos + t_cap;
+  int32_t* s_tiles = s_page + t_cap;
+  const uint32_t tiles_cap = t_cap / 64 + cfg.max_seqs + 1;
+  int32_t* s_rows = s_tiles + size_t(tiles_cap) * 4;
+  int32_t* s_slots = s_rows + cfg.max_seqs;
+  int32_t* s_lens = s_slots + cfg.max_seqs;
+
+  InflightStep step;
+  step.is_prefill = true;
+  step.n_tokens = T;
+  uint32_t row = 0, n_tiles = 0, R = 0;
+  for (size_t i = 0; i < reqs.size(); ++i) {
+    Request& r = *reqs[i];
+    if (r.prefilled == 0) {  // first chunk: publish block table + sampler state
+      LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_block_tables + size_t(r.slot) * pages_per_seq, r.pages.data(),
+                                       r.pages.size() * 4, cudaMemcpyHostToDevice, st));
+      slot_init_kernel<<<1, 1, 0, st>>>(S, r.slot, r.s.temperature, r.s.top_p, (int32_t)r.s.top_k, r.s.seed);
+      LLMLB_LAUNCH_CHECK();
+    }
+    const uint32_t p0 = r.prefilled;
+    for (uint32_t j = 0; j < take[i]; ++j) {
+      uint32_t pos = p0 + j;
+      s_ids[row + j] = r.prompt[pos];
+      s_pos[row + j] = int32_t(pos);
+      s_page[row + j] = r.pages[pos / kPageTokens];
+    }
+    for (uint32_t j = 0; j < take[i]; j += 64) {
+      s_tiles[n_tiles * 4 + 0] = int32_t(row + j);
+      s_tiles[n_tiles * 4 + 1] = int32_t(std::min<uint32_t>(64, take[i] - j));
+      s_tiles[n_tiles * 4 + 2] = int32_t(p0 + j);
+      s_tiles[n_tiles * 4 + 3] = r.slot;
+      ++n_tiles;
+    }
+    if (p0 + take[i] == r.prompt.size()) {
+      s_rows[R] = int32_t(row + take[i] - 1);
+      s_slots[R] = r.slot;
+      s_lens[R] = int32_t(r.prompt.size());
+      step.reqs.push_back(reqs[i]);
+      ++R;
+    }
+    row += take[i];
+  }
+  // note: r.pages.data() above is pageable host memory: the async copy is staged by the driver
+  LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_ids, s_ids, T * 4, cudaMemcpyHostToDevice, st));
+  LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_pos, s_pos, T * 4, cudaMemcpyHostToDevice, st));
+  LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_page_of_tok, s_page, T * 4, cudaMemcpyHostToDevice, st));
+  LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_tiles, s_tiles, n_tiles * 16, cudaMemcpyHostToDevice, st));
+  if (R) {
+    LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_last_rows, s_rows, R * 4, cudaMemcpyHostToDevice, st));
+    LLMLB_CUDA_CHECK(cudaMemcpyAsync(B.slots, s_slots, R * 4, cudaMemcpyHostToDevice, st));
+    LLMLB_CUDA_CHECK(cudaMemcpyAsync(B.seq_lens, s_lens, R * 4, cudaMemcpyHostToDevice, st));
+    cur_batch_slots.clear();  // B.slots no longer holds a decode batch
+  }
+  step.ev_start = get_event();
+  step.ev_end = get_event();
+  LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_start, st));
+  RC(llmlb_op_embed(embed, d_ids, x, T, M.hidden, M.vocab, st));
+  RC(forward_tokens(T, false, 0, n_tiles));
+  if (R) {
+    gather_rows_kernel<<<R, 256, 0, st>>>(x, d_last_rows, x_last, M.hidden);
+    LLMLB_LAUNCH_CHECK();
+    RC(logits_for_rows(R, false));
+    sample_prepare_kernel<<<ceil_div(R, 128), 128, 0, st>>>(S, B, R);
+    LLMLB_LAUNCH_CHECK();
+    RC(llmlb_op_sample(logits, R, M.vocab, B.temperature, B.top_p, B.top_k, B.seed, B.step, B.out_ids, st));
+    step_finish_kernel<<<ceil_div(R, 128), 128, 0, st>>>(S, B, R);
+    LLMLB_LAUNCH_CHECK();
+    prefill_finish_kernel<<<ceil_div(R, 128), 128, 0, st>>>(S, B, R);
+    LLMLB_LAUNCH_CHECK();
+    step.host_ids = h_out[(out_seq++) % kRing];
+    LLMLB_CUDA_CHECK(cudaMemcpyAsync(step.host_ids, B.out_ids, R * 4, cudaMemcpyDeviceToHost, st));
+  }
+  LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_end, st));
+  for (size_t i = 0; i < reqs.size(); ++i) {
+    reqs[i]->prefilled += take[i];
+    if (reqs[i]->prefilled == reqs[i]->prompt.size()) reqs[i]->launched = 1;
+  }
+  steps_prefill++;
+  tokens_prefill += T;
+  inflight.push_back(std::move(step));
+  return LLMLB_OK;
+}
+
+int llmlb_engine::run_decode(const std::vector<ReqPtr>& batch) {
+  const uint32_t nb = (uint32_t)batch.size();
+  std::vector<int32_t> slots(nb);
+  for (uint32_t b = 0; b < nb; ++b) slots[b] = batch[b]->slot;
+  if (slots != cur_batch_slots) {
+    int32_t* stg = reinterpret_cast<int32_t*>(next_stage());
+    memcpy(stg, slots.data(), nb * 4);
+    LLMLB_CUDA_CHECK(cudaMemcpyAsync(B.slots, stg, nb * 4, cudaMemcpyHostToDevice, st));
+    cur_batch_slots = slots;
+  }
+  InflightStep step;
+  step.n_tokens = nb;
+  step.reqs = batch;
+  step.ev_start = get_event();
+  step.ev_end = get_event();
+  LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_start, st));
+  RC(launch_decode_step(nb));
+  step.host_ids = h_out[(out_seq++) % kRing];
+  LLMLB_CUDA_CHECK(cudaMemcpyAsync(step.host_ids, B.out_ids, nb * 4, cudaMemcpyDeviceToHost, st));
+  LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_end, st));
+  for (auto& r : batch) r->launched++;
+  steps_decode++;
+  tokens_decode += nb;
+  inflight.push_back(std::move(step));
+  return LLMLB_OK;
+}
+
+void llmlb_engine::release_resources(const ReqPtr& r) {  // mu held
+  if (r->slot >= 0) {
+    free_slots.push_back(r->slot);
+    r->slot = -1;
+  }
+  for (int32_t p : r->pages) free_pages.push_back(p);
+  r->pages.clear();
+  running.erase(std::remove(running.begin(), running.end(), r), running.end());
+}
+
+void llmlb_engine::finish_request(const ReqPtr& r, uint32_t reason) {  // mu held
+  if (r->finished) return;
+  r->finished = true;
+  r->finish_reason = reason;
+  if (r->events.empty() || r->events.back().finish_reason == LLMLB_FINISH_NONE) {
+    if (!r->events.empty() && reason != LLMLB_FINISH_CANCELLED && reason != LLMLB_FINISH_ERROR) {
+      r->events.back().finish_reason = reason;
+    } else {
+      llmlb_token_event ev{};
+      ev.token_id = -1;
+      ev.index = r->harvested;
+      ev.finish_reason = reason;
+      ev.prompt_tokens = (uint32_t)r->prompt.size();
+      ev.completion_tokens = r->harvested;
+      ev.t_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - r->t_submit).count();
+      r->events.push_back(ev);
+    }
+  }
+  release_resources(r);
+  if (r->client_released) requests.erase(r->id);
+  cv_events.notify_all();
+}
+
+void llmlb_engine::harvest_one() {
+  InflightStep step = std::move(inflight.front());
+  inflight.pop_front();
+  cudaError_t ce = cudaEventSynchronize(step.ev_end);
+  float ms = 0.f;
+  if (ce == cudaSuccess) cudaEventElapsedTime(&ms, step.ev_start, step.ev_end);
+  std::lock_guard<std::mutex> lk(mu);
+  if (step.is_prefill) gpu_ms_prefill += ms; else gpu_ms_decode += ms;
+  ev_pool.push_back(step.ev_start);
+  ev_pool.push_back(step.ev_end);
+  auto now = std::chrono::steady_clock::now();
+  for (size_t b = 0; b < step.reqs.size(); ++b) {
+    const ReqPtr& r = step.reqs[b];
+    if (r->finished) continue;  // tokens computed past a stop are dropped
+    if (ce != cudaSuccess) { finish_request(r, LLMLB_FINISH_ERROR); continue; }
+    const int32_t tok = step.host_ids[b];
+    llmlb_token_event ev{};
+    ev.token_id = tok;
+    ev.index = r->harvested++;
+    ev.prompt_tokens = (uint32_t)r->prompt.size();
+    ev.completion_tokens = r->harvested;
+    ev.t_ms = std::chrono::duration<double, std::milli>(now - r->t_submit).count();
+    r->events.push_back(ev);
+    bool stop_hit = false;
+    if (!r->s.ignore_eos)
+      for (int32_t sid : r->stop_ids) stop_hit |= (sid == tok);
+    if (stop_hit) finish_request(r, LLMLB_FINISH_STOP);
+    else if (r->harvested >= r->s.max_tokens) finish_request(r, LLMLB_FINISH_LENGTH);
+  }
+  cv_events.notify_all();
+}
+
+void llmlb_engine::loop() {
+  cudaSetDevice(cfg.device);
+  for (;;) {
+    std::vector<ReqPtr> pf_reqs;
+    std::vector<uint32_t> pf_take;
+    std::vector<ReqPtr> dec;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_sched.wait(lk, [&] {
+        return stop || !inflight.empty() || (!paused && (!waiting.empty() || !running.empty()));
+      });
+      if (stop) break;
+      // cancellations
+      for (auto it = waiting.begin(); it != waiting.end();) {
+        if ((*it)->cancel) { ReqPtr r = *it; it = waiting.erase(it); finish_request(r, LLMLB_FINISH_CANCELLED); }
+        else ++it;
+      }
+      for (size_t i = 0; i < running.size();) {
+        if (running[i]->cancel && !running[i]->finished) finish_request(running[i], LLMLB_FINISH_CANCELLED);
+        else ++i;
+      }
+      if (!paused) {
+        uint32_t budget = cfg.max_step_tokens;
+        // continue chunked prefills first
+        for (auto& r : running) {
+          if (budget == 0) break;
+          if (r->prefilled < r->prompt.size()) {
+            uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size() - r->prefilled);
+            pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
+          }
+        }
+        // admit in FIFO order while a slot, the pages for prompt+max_tokens and token budget exist
+        while (!waiting.empty() && budget > 0 && !free_slots.empty()) {
+          ReqPtr r = waiting.front();
+          uint32_t need = ceil_div((uint32_t)r->prompt.size() + r->s.max_tokens, kPageTokens);
+          if (need > free_pages.size()) break;
+          waiting.pop_front();
+          r->slot = free_slots.back(); free_slots.pop_back();
+          for (uint32_t i = 0; i < need; ++i) { r->pages.push_back(free_pages.back()); free_pages.pop_back(); }
+          running.push_back(r);
+          uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size());
+          pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
+        }
+        if (pf_reqs.empty()) {
+          for (auto& r : running)
+            if (!r->finished && r->prefilled == r->prompt.size() && r->launched < r->s.max_tokens)
+              dec.push_back(r);
+        }
+      }
+    }
+    bool launched = false;
+    if (!pf_reqs.empty() || !dec.empty()) {
+      std::lock_guard<std::mutex> sl(step_mu);
+      int rc = !pf_reqs.empty() ? run_prefill(pf_reqs, pf_take) : run_decode(dec);
+      launched = true;
+      if (rc != LLMLB_OK) {
+        std::string msg = g_err;
+        cudaStreamSynchronize(st);
+        std::lock_guard<std::mutex> lk(mu);
+        fatal_error = msg;
+        for (auto& r : std::vector<ReqPtr>(running)) finish_request(r, LLMLB_FINISH_ERROR);
+      }
+    }
+    while (inflight.size() > lookahead || (!launched && !inflight.empty())) {
+      harvest_one();
+      launched = true;  // harvest at most until the window is back to `lookahead`
+      if (inflight.size() <= lookahead) break;
+    }
+  }
+  while (!inflight.empty()) harvest_one();
+}
+
+// ------------------------------------------------------------------ C ABI -------------------
+extern "C" uint32_t llmlb_abi_version(void) { return LLMLB_ABI_VERSION; }
+extern "C" const char* llmlb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int llmlb_engine_create(const llmlb_engine_config* cfg, llmlb_engine** out) {
+  if (!cfg || !out) { set_error("llmlb_engine_create: null argument"); return LLMLB_E_INVALID_ARG; }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    set_error("llmlb_engine_create: no CUDA device (this library has no CPU path)");
+    return LLMLB_E_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) { set_error("llmlb_engine_create: bad device ordinal"); return LLMLB_E_INVALID_ARG; }
+  llmlb_engine* e = new llmlb_engine();
+  e->cfg = *cfg;
+  int rc = e->init();
+  if (rc != LLMLB_OK) {
+    std::string msg = g_err;
+    llmlb_engine_destroy(e);
+    set_error(msg);
+    return rc;
+  }
+  *out = e;
+  return LLMLB_OK;
+}
+
+extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
+  if (!e) return;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->stop = true;
+  }
+  e->cv_sched.notify_all();
+  if (e->worker.joinable()) e->worker.join();
+  cudaSetDevice(e->cfg.device);
+  if (e->st) cudaStreamSynchronize(e->st);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(e->embed); F(e->final_norm); F(e->lm_head);
+  for (auto& L : e->layers) { F(L.wqkv); F(L.wo); F(L.wgu); F(L.wdown); F(L.attn_norm); F(L.ffn_norm); }
+  F(e->k_pool); F(e->v_pool); F(e->rope); F(e->d_block_tables);
+  F(e->x); F(e->y); F(e->qkv); F(e->attn); F(e->h); F(e->logits); F(e->logits_l); F(e->x_last); F(e->attn_ws);
+  F(e->d_ids); F(e->d_pos); F(e->d_page_of_tok); F(e->d_tiles); F(e->d_last_rows);
+  F(e->S.seq_len); F(e->S.last_token); F(e->S.temperature); F(e->S.top_p); F(e->S.top_k); F(e->S.seed); F(e->S.step);
+  F(e->B.slots); F(e->B.ids); F(e->B.seq_lens); F(e->B.temperature); F(e->B.top_p); F(e->B.top_k);
+  F(e->B.seed); F(e->B.step); F(e->B.out_ids);
+  for (int i = 0; i < llmlb_engine::kRing; ++i) {
+    if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+    if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
+  }
+  if (e->tp_ready)
+    for (uint32_t r = 0; r < e->tp; ++r)
+      if (r != e->rank && e->peers.base[r]) cudaIpcCloseMemHandle(e->peers.base[r]);
+  F(e->xchg);
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->st) cudaStreamDestroy(e->st);
+  delete e;
+}
+
+extern "C" int llmlb_engine_model_info(const llmlb_engine* e, llmlb_model_info* out) {
+  if (!e || !out) { set_error("null argument"); return LLMLB_E_INVALID_ARG; }
+  memset(out, 0, sizeof(*out));
+  strncpy(out->id, e->cfg.model_id, sizeof(out->id) - 1);
+  out->context_length = e->cfg.max_ctx;
+  out->vocab = e->M.vocab;
+  out->n_layers = e->M.n_layers;
+  out->hidden = e->M.hidden;
+  out->param_bytes = e->param_bytes;
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_engine_health(const llmlb_engine* ce, llmlb_health* out) {
+  llmlb_engine* e = const_cast<llmlb_engine*>(ce);
+  if (!e || !out) { set_error("null argument"); return LLMLB_E_INVALID_ARG; }
+  memset(out, 0, sizeof(*out));
+  size_t fr = 0, tot = 0;
+  cudaSetDevice(e->cfg.device);
+  cudaMemGetInfo(&fr, &tot);
+  out->device_count = e->tp;
+  out->total_memory_bytes = tot;
+  out->used_memory_bytes = tot - fr;
+  std::lock_guard<std::mutex> lk(e->mu);
+  out->active_requests = (uint32_t)e->running.size();
+  out->queued_requests = (uint32_t)e->waiting.size();
+  out->free_kv_pages = (uint32_t)e->free_pages.size();
+  out->total_kv_pages = e->n_pages;
+  out->steps_prefill = e->steps_prefill; out->steps_decode = e->steps_decode;
+  out->tokens_prefill = e->tokens_prefill; out->tokens_decode = e->tokens_decode;
+  out->gpu_ms_prefill = e->gpu_ms_prefill; out->gpu_ms_decode = e->gpu_ms_decode;
+  out->kernel_launches = g_kernel_launches.load();
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_request_submit(llmlb_engine* e, const int32_t* prompt_ids, uint32_t n_prompt,
+                                    const llmlb_sampling* s, uint64_t* req_id) {
+  if (!e || !prompt_ids || !s || !req_id || n_prompt == 0) { set_error("llmlb_request_submit: bad argument"); return LLMLB_E_INVALID_ARG; }
+  if (s->max_tokens == 0) { set_error("max_tokens must be > 0"); return LLMLB_E_INVALID_ARG; }
+  if (uint64_t(n_prompt) + s->max_tokens > e->cfg.max_ctx) {
+    set_error("prompt + max_tokens exceeds the context length");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (ceil_div(n_prompt + s->max_tokens, kPageTokens) > e->n_pages) { set_error("request can never fit the KV pool"); return LLMLB_E_INVALID_ARG; }
+  for (uint32_t i = 0; i < n_prompt; ++i)
+    if (prompt_ids[i] < 0 || uint32_t(prompt_ids[i]) >= e->M.vocab) { set_error("token id out of range"); return LLMLB_E_INVALID_ARG; }
+  if (s->temperature < 0.f || s->top_p < 0.f) { set_error("negative temperature/top_p"); return LLMLB_E_INVALID_ARG; }
+  auto r = std::make_shared<Request>();
+  r->prompt.assign(prompt_ids, prompt_ids + n_prompt);
+  r->s = *s;
+  if (s->stop_ids && s->n_stop_ids) r->stop_ids.assign(s->stop_ids, s->stop_ids + s->n_stop_ids);
+  r->s.stop_ids = nullptr;
+  r->t_submit = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->fatal_error.empty()) { set_error("engine failed: " + e->fatal_error); return LLMLB_E_DEVICE; }
+    if (e->waiting.size() >= 4096) { set_error("queue full"); return LLMLB_E_QUEUE_FULL; }
+    r->id = e->next_id++;
+    e->requests[r->id] = r;
+    e->waiting.push_back(r);
+    *req_id = r->id;
+  }
+  e->cv_sched.notify_all();
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_request_poll(llmlb_engine* e, uint64_t req_id, llmlb_token_event* out,
+                                  uint32_t cap, uint32_t* n_out, int timeout_ms) {
+  if (!e || !out || !n_out || cap == 0) { set_error("llmlb_request_poll: bad argument"); return LLMLB_E_INVALID_ARG; }
+  *n_out = 0;
+  std::unique_lock<std::mutex> lk(e->mu);
+  auto it = e->requests.find(req_id);
+  if (it == e->requests.end()) { set_error("unknown request id"); return LLMLB_E_NOT_FOUND; }
+  ReqPtr r = it->second;
+  auto ready = [&] { return !r->events.empty() || r->finished; };
+  if (!ready() && timeout_ms != 0) {
+    if (timeout_ms < 0) e->cv_events.wait(lk, ready);
+    else if (!e->cv_events.wait_for(lk, std::chrono::milliseconds(timeout_ms), ready)) return LLMLB_E_TIMEOUT;
+  }
+  while (*n_out < cap && !r->events.empty()) {
+    out[(*n_out)++] = r->events.front();
+    r->events.pop_front();
+  }
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_request_cancel(llmlb_engine* e, uint64_t req_id) {
+  if (!e) { set_error("null engine"); return LLMLB_E_INVALID_ARG; }
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->requests.find(req_id);
+    if (it == e->requests.end()) { set_error("unknown request id"); return LLMLB_E_NOT_FOUND; }
+    it->second->cancel = true;
+  }
+  e->cv_sched.notify_all();
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_request_release(llmlb_engine* e, uint64_t req_id) {
+  if (!e) { set_error("null engine"); return LLMLB_E_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto it = e->requests.find(req_id);
+  if (it == e->requests.end()) { set_error("unknown request id"); return LLMLB_E_NOT_FOUND; }
+  if (it->second->finished) e->requests.erase(it);
+  else { it->second->client_released = true; it->second->cancel = true; e->cv_sched.notify_all(); }
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_engine_pause(llmlb_engine* e, uint32_t paused) {
+  if (!e) { set_error("null engine"); return LLMLB_E_INVALID_ARG; }
+  { std::lock_guard<std::mutex> lk(e->mu); e->paused = paused != 0; }
+  e->cv_sched.notify_all();
+  return LLMLB_OK;
+}
+
+// Run every decode-kernel instantiation once eagerly (sets max-dynamic-smem attributes outside of
+// graph capture and surfaces launch errors at create time), then clear the state it touched.
+int llmlb_engine::warmup() {
+  const uint32_t widths[9] = {1, 2, 3, 4, 5, 17, 33, 65, 129};
+  for (uint32_t w : widths) {
+    if (w > cfg.max_seqs) break;
+    RC(layer_stack_decode(w));
+  }
+  const size_t ms = cfg.max_seqs;
+  LLMLB_CUDA_CHECK(cudaMemsetAsync(S.seq_len, 0, ms * 4, st));
+  LLMLB_CUDA_CHECK(cudaMemsetAsync(S.last_token, 0, ms * 4, st));
+  LLMLB_CUDA_CHECK(cudaMemsetAsync(S.step, 0, ms * 8, st));
+  LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LLMLB_OK;
+}
+
+// ------------------------------------------------------------------ TP wiring ---------------
+extern "C" int llmlb_engine_tp_export(llmlb_engine* e, uint8_t handle[LLMLB_IPC_HANDLE_BYTES]) {
+  if (!e || !handle) { set_error("null argument"); return LLMLB_E_INVALID_ARG; }
+  if (e->tp == 1 || !e->xchg) { set_error("engine is not tensor-parallel"); return LLMLB_E_UNSUPPORTED; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == LLMLB_IPC_HANDLE_BYTES, "ipc handle size");
+  cudaSetDevice(e->cfg.device);
+  cudaIpcMemHandle_t hnd;
+  LLMLB_CUDA_CHECK(cudaIpcGetMemHandle(&hnd, e->xchg));
+  memcpy(handle, &hnd, sizeof(hnd));
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_engine_tp_import(llmlb_engine* e, const uint8_t* handles, uint32_t n) {
+  if (!e || !handles || n != e->tp) { set_error("llmlb_engine_tp_import: need tp_size handles"); return LLMLB_E_INVALID_ARG; }
+  if (e->tp == 1) { set_error("engine is not tensor-parallel"); return LLMLB_E_UNSUPPORTED; }
+  cudaSetDevice(e->cfg.device);
+  std::lock_guard<std::mutex> sl(e->step_mu);
+  for (uint32_t r = 0; r < n; ++r) {
+    if (r == e->rank) { e->peers.base[r] = e->xchg; continue; }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handles + size_t(r) * LLMLB_IPC_HANDLE_BYTES, sizeof(hnd));
+    void* p = nullptr;
+    LLMLB_CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    e->peers.base[r] = (uint8_t*)p;
+  }
+  e->tp_ready = true;
+  return e->warmup();
+}
+
+extern "C" int llmlb_engine_tp_plan_channel(llmlb_engine*, const char*) {
+  set_error("plan channel: not implemented yet; submit identical requests on every rank while "
+            "paused (llmlb_engine_pause) and resume after a barrier");
+  return LLMLB_E_UNSUPPORTED;
+}
+
+extern "C" int llmlb_op_allreduce(llmlb_engine* e, float* buf, uint64_t n, void* stream) {
+  if (!e || !buf || n % 4) { set_error("llmlb_op_allreduce: bad argument"); return LLMLB_E_INVALID_ARG; }
+  if (e->tp == 1) return LLMLB_OK;
+  if (!e->tp_ready) { set_error("tp handles not imported"); return LLMLB_E_UNSUPPORTED; }
+  if (n * 4 > e->peers.slot_bytes) { set_error("llmlb_op_allreduce: larger than the exchange slot"); return LLMLB_E_INVALID_ARG; }
+  // sum = buf_0 + ... ; implemented as: copy buf into slot, zero buf, then allreduce-add
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(e->xchg + ar_signal_bytes());
+  LLMLB_CUDA_CHECK(cudaMemcpyAsync(part, buf, n * 4, cudaMemcpyDeviceToDevice, st));
+  LLMLB_CUDA_CHECK(cudaMemsetAsync(buf, 0, n * 4, st));
+  RC(ar_allreduce_add(e->peers, 0, buf, n, st));
+  // keep slot parity even for the engine: a second (empty) collective on slot 1
+  return ar_allreduce_add(e->peers, 1, buf, 0, st);
+}
+
+// ------------------------------------------------------------------ tensors by HF name ------
+int llmlb_engine::resolve_tensor(const std::string& name, __nv_bfloat16** base, uint64_t* rows,
+                                 uint64_t* cols, uint64_t* ld, uint64_t* full_rows,
+                                 uint64_t* full_cols, uint64_t* row0, uint64_t* col0) {
+  const uint64_t H = M.hidden, qr = uint64_t(nq_l) * kHeadDim, kr = uint64_t(nkv_l) * kHeadDim;
+  *row0 = 0; *col0 = 0;
+  if (name == "model.embed_tokens.weight") { *base = embed; *rows = M.vocab; *cols = H; *ld = H; *full_rows = M.vocab; *full_cols = H; return LLMLB_OK; }
+  if (name == "model.norm.weight") { *base = final_norm; *rows = 1; *cols = H; *ld = H; *full_rows = 1; *full_cols = H; return LLMLB_OK; }
+  if (name == "lm_head.weight") { *base = lm_head; *rows = vocab_l; *cols = H; *ld = H; *full_rows = M.vocab; *full_cols = H; *row0 = uint64_t(rank) * vocab_l; return LLMLB_OK; }
+  unsigned l = 0; char rest[96] = {0};
+  if (sscanf(name.c_str(), "model.layers.%u.%95s", &l, rest) == 2 && l < M.n_layers) {
+    LayerW& L = layers[l];
+    std::string r(rest);
+    if (r == "self_attn.q_proj.weight") { *base = L.wqkv; *rows = qr; *cols = H; *ld = H; *full_rows = uint64_t(M.n_heads) * kHeadDim; *full_cols = H; *row0 = rank * qr; return LLMLB_OK; }
+    if (r == "self_attn.k_proj.weight") { *base = L.wqkv + qr * H; *rows = kr; *cols = H; *ld = H; *full_rows = uint64_t(M.n_kv_heads) * kHeadDim; *full_cols = H; *row0 = rank * kr; return LLMLB_OK; }
+    if (r == "self_attn.v_proj.weight") { *base = L.wqkv + (qr + kr) * H; *rows = kr; *cols = H; *ld = H; *full_rows = uint64_t(M.n_kv_heads) * kHeadDim; *full_cols = H; *row0 = rank * kr; return LLMLB_OK; }
+    if (r == "self_attn.o_proj.weight") { *base = L.wo; *rows = H; *cols = qr; *ld = qr; *full_rows = H; *full_cols = uint64_t(M.n_heads) * kHeadDim; *col0 = rank * qr; return LLMLB_OK; }
+    if (r == "mlp.gate_proj.weight") { *base = L.wgu; *rows = ffn_l; *cols = H; *ld = 2 * H; *full_rows = M.ffn; *full_cols = H; *row0 = uint64_t(rank) * ffn_l; return LLMLB_OK; }
+    if (r == "mlp.up_proj.weight") { *base = L.wgu + H; *rows = ffn_l; *cols = H; *ld = 2 * H; *full_rows = M.ffn; *full_cols = H; *row0 = uint64_t(rank) * ffn_l; return LLMLB_OK; }
+    if (r == "mlp.down_proj.weight") { *base = L.wdown; *rows = H; *cols = ffn_l; *ld = ffn_l; *full_rows = H; *full_cols = M.ffn; *col0 = uint64_t(rank) * ffn_l; return LLMLB_OK; }
+    if (r == "input_layernorm.weight") { *base = L.attn_norm; *rows = 1; *cols = H; *ld = H; *full_rows = 1; *full_cols = H; return LLMLB_OK; }
+    if (r == "post_attention_layernorm.weight") { *base = L.ffn_norm; *rows = 1; *cols = H; *ld = H; *full_rows = 1; *full_cols = H; return LLMLB_OK; }
+  }
+  set_error("unknown tensor name: " + name);
+  return LLMLB_E_NOT_FOUND;
+}
+
+extern "C" int llmlb_engine_load_tensor(llmlb_engine* e, const char* name, const void* host,
+                                        uint64_t rows, uint64_t cols) {
+  if (!e || !name || !host) { set_error("null argument"); return LLMLB_E_INVALID_ARG; }
+  __nv_bfloat16* base; uint64_t r, c, ld, fr, fc, r0, c0;
+  RC(e->resolve_tensor(name, &base, &r, &c, &ld, &fr, &fc, &r0, &c0));
+  if (rows * cols != fr * fc || (fr > 1 && (rows != fr || cols != fc))) {
+    set_error(std::string("shape mismatch for ") + name);
+    return LLMLB_E_INVALID_ARG;
+  }
+  cudaSetDevice(e->cfg.device);
+  std::lock_guard<std::mutex> sl(e->step_mu);
+  LLMLB_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  const __nv_bfloat16* src = (const __nv_bfloat16*)host + r0 * fc + c0;
+  LLMLB_CUDA_CHECK(cudaMemcpy2D(base, ld * 2, src, fc * 2, c * 2, r, cudaMemcpyHostToDevice));
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_engine_read_tensor(llmlb_engine* e, const char* name, void* host,
+                                        uint64_t cap_bytes, uint64_t* rows, uint64_t* cols) {
+  if (!e || !name || !host || !rows || !cols) { set_error("null argument"); return LLMLB_E_INVALID_ARG; }
+  __nv_bfloat16* base; uint64_t r, c, ld, fr, fc, r0, c0;
+  RC(e->resolve_tensor(name, &base, &r, &c, &ld, &fr, &fc, &r0, &c0));
+  if (r * c * 2 > cap_bytes) { set_error("buffer too small"); return LLMLB_E_INVALID_ARG; }
+  cudaSetDevice(e->cfg.device);
+  std::lock_guard<std::mutex> sl(e->step_mu);
+  LLMLB_CUDA_CHECK(cudaStreamSynchronize(e->st));
+  LLMLB_CUDA_CHECK(cudaMemcpy2D(host, c * 2, base, ld * 2, c * 2, r, cudaMemcpyDeviceToHost));
+  *rows = r; *cols = c;
+  return LLMLB_OK;
+}
+
+// ------------------------------------------------------------------ parity hooks ------------
+static int debug_acquire(llmlb_engine* e) {  // step_mu held
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->running.empty() || !e->waiting.empty() || !e->inflight.empty()) {
+    set_error("debug hooks need an idle engine");
+    return LLMLB_E_QUEUE_FULL;
+  }
+  if (e->debug_slot < 0) {
+    if (e->free_slots.empty() || e->free_pages.size() < e->pages_per_seq) { set_error("no free slot/pages"); return LLMLB_E_QUEUE_FULL; }
+    e->debug_slot = e->free_slots.back(); e->free_slots.pop_back();
+    for (uint32_t i = 0; i < e->pages_per_seq; ++i) { e->debug_pages.push_back(e->free_pages.back()); e->free_pages.pop_back(); }
+  }
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_debug_reset(llmlb_engine* e) {
+  if (!e) { set_error("null engine"); return LLMLB_E_INVALID_ARG; }
+  std::lock_guard<std::mutex> sl(e->step_mu);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->debug_slot >= 0) {
+    e->free_slots.push_back(e->debug_slot);
+    for (int32_t p : e->debug_pages) e->free_pages.push_back(p);
+    e->debug_pages.clear();
+    e->debug_slot = -1;
+  }
+  e->debug_len = 0;
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_debug_prefill_logits(llmlb_engine* e, const int32_t* prompt, uint32_t n,
+                                          float* logits_last, float* logits_all) {
+  if (!e || !prompt || n == 0 || !logits_last) { set_error("bad argument"); return LLMLB_E_INVALID_ARG; }
+  if (n > e->cfg.max_step_tokens || n > e->cfg.max_ctx) { set_error("prompt longer than max_step_tokens/max_ctx"); return LLMLB_E_INVALID_ARG; }
+  cudaSetDevice(e->cfg.device);
+  std::lock_guard<std::mutex> sl(e->step_mu);
+  RC(debug_acquire(e));
+  cudaStream_t st = e->st;
+  const int slot = e->debug_slot;
+  std::vector<int32_t> pos(n), page(n), tiles;
+  for (uint32_t i = 0; i < n; ++i) { pos[i] = int32_t(i); page[i] = e->debug_pages[i / kPageTokens]; }
+  for (uint32_t j = 0; j < n; j += 64) { tiles.push_back(int32_t(j)); tiles.push_back(int32_t(std::min<uint32_t>(64, n - j))); tiles.push_back(int32_t(j)); tiles.push_back(slot); }
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->d_block_tables + size_t(slot) * e->pages_per_seq, e->debug_pages.data(), e->debug_pages.size() * 4, cudaMemcpyHostToDevice));
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->d_ids, prompt, n * 4, cudaMemcpyHostToDevice));
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->d_pos, pos.data(), n * 4, cudaMemcpyHostToDevice));
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->d_page_of_tok, page.data(), n * 4, cudaMemcpyHostToDevice));
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->d_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice));
+  slot_init_kernel<<<1, 1, 0, st>>>(e->S, slot, 0.f, 1.f, 0, 0);
+  LLMLB_LAUNCH_CHECK();
+  RC(llmlb_op_embed(e->embed, e->d_ids, e->x, n, e->M.hidden, e->M.vocab, st));
+  RC(e->forward_tokens(n, false, 0, (uint32_t)tiles.size() / 4));
+  const uint32_t chunk = e->cfg.max_seqs;
+  const size_t H = e->M.hidden, V = e->M.vocab;
+  for (uint32_t c0 = logits_all ? 0 : n - 1; c0 < n; c0 += chunk) {
+    uint32_t R = std::min(chunk, n - c0);
+    LLMLB_CUDA_CHECK(cudaMemcpyAsync(e->x_last, e->x + size_t(c0) * H, size_t(R) * H * 4, cudaMemcpyDeviceToDevice, st));
+    RC(e->logits_for_rows(R, false));
+    LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (logits_all) LLMLB_CUDA_CHECK(cudaMemcpy(logits_all + size_t(c0) * V, e->logits, size_t(R) * V * 4, cudaMemcpyDeviceToHost));
+    if (c0 + R == n) LLMLB_CUDA_CHECK(cudaMemcpy(logits_last, e->logits + size_t(R - 1) * V, V * 4, cudaMemcpyDeviceToHost));
+  }
+  int32_t len = int32_t(n);
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->S.seq_len + slot, &len, 4, cudaMemcpyHostToDevice));
+  e->debug_len = n;
+  e->cur_batch_slots.clear();
+  return LLMLB_OK;
+}
+
+extern "C" int llmlb_debug_decode_logits(llmlb_engine* e, int32_t token, float* logits_out) {
+  if (!e || !logits_out || token < 0 || uint32_t(token) >= e->M.vocab) { set_error("bad argument"); return LLMLB_E_INVALID_ARG; }
+  cudaSetDevice(e->cfg.device);
+  std::lock_guard<std::mutex> sl(e->step_mu);
+  if (e->debug_slot < 0 || e->debug_len == 0) { set_error("call llmlb_debug_prefill_logits first"); return LLMLB_E_INVALID_ARG; }
+  if (e->debug_len + 1 > e->cfg.max_ctx) { set_error("context full"); return LLMLB_E_INVALID_ARG; }
+  cudaStream_t st = e->st;
+  int32_t slot = e->debug_slot;
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->S.last_token + slot, &token, 4, cudaMemcpyHostToDevice));
+  LLMLB_CUDA_CHECK(cudaMemcpy(e->B.slots, &slot, 4, cudaMemcpyHostToDevice));
+  e->cur_batch_slots.clear();
+  decode_prepare_kernel<<<1, 128, 0, st>>>(e->S, e->B, 1);
+  LLMLB_LAUNCH_CHECK();
+  RC(llmlb_op_embed(e->embed, e->B.ids, e->x, 1, e->M.hidden, e->M.vocab, st));
+  RC(e->forward_tokens(1, true, 1, 0));
+  RC(e->logits_for_rows(1, true));
+  LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  LLMLB_CUDA_CHECK(cudaMemcpy(logits_out, e->logits, size_t(e->M.vocab) * 4, cudaMemcpyDeviceToHost));
+  e->debug_len += 1;
+  return LLMLB_OK;
+}

@@ -1,0 +1,404 @@
+// Prefill / batched-decode projections on the 5th-gen tensor cores.
+//
+//   out[t, n] = sum_k X[t, k] * W[n, k]        X bf16 [T, K], W bf16 [N, K] (both K-major)
+//
+// "Weights-as-M" tiling: a CTA owns a 128-row slab of W as the MMA's M operand and BN tokens
+// as the N operand (BN = 16..256 picked from T), so one kernel serves 16-token batched decode
+// (HBM-bound: W streamed once through a deep TMA ring) and 512-token prefill (tensor-bound).
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer   — cp.async.bulk.tensor 2D, 128B-swizzled 64-wide K slabs
+//   warp 1 lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, fp32 accum in TMEM
+//   warp 2        : TMEM allocator — 2 accumulator stages (epilogue of tile i overlaps MMA of i+1)
+//   warps 4..7    : epilogue       — tcgen05.ld 32x32b, fused residual-add / SiLU*up / store
+// Split-K (residual epilogue only) uses fp32 red.global.add.
+#include <cuda.h>
+
+#include "../../include/llmlb_b200.h"
+#include "common.cuh"
+
+namespace llmlb {
+
+constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
+constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row
+constexpr int kTcThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B), LBO unused (=1).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in set
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // bf16 x bf16 -> f32, A and B K-major, M=128, N=BN
+  static constexpr uint32_t kIdesc =
+      (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+               void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K,
+               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t k_blocks_total = (K + kBK - 1) / kBK;
+  const uint32_t k_per_split = (k_blocks_total + split_k - 1) / split_k;
+  const uint32_t n_tiles = m_tiles * t_tiles * split_k;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + i, 1);
+      mbar_init(tempty_bar + i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(uint32_t(Cfg::kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (m_tile, t_tile, split): t fastest so consecutive CTAs share the W slab in L2
+  auto decode_tile = [&](uint32_t tile, uint32_t& mt, uint32_t& tt, uint32_t& ks) {
+    tt = tile % t_tiles;
+    uint32_t r = tile / t_tiles;
+    ks = r % split_k;
+    mt = r / split_k;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t mt, tt, ks;
+        decode_tile(tile, mt, tt, ks);
+        const uint32_t kb0 = ks * k_per_split;
+        const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kBM * kBK * 2;
+          mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_w, full_bar + stage, int32_t(kb * kBK), int32_t(mt * kBM));
+          tma_load_2d(sb, &tmap_x, full_bar + stage, int32_t(kb * kBK), int32_t(tt * BN));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t mt, tt, ks;
+        decode_tile(tile, mt, tt, ks);
+        const uint32_t kb0 = ks * k_per_split;
+        const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kBM * kBK * 2;
+          const uint64_t adesc = make_sw128_desc(sa);
+          const uint64_t bdesc = make_sw128_desc(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the 16-byte address field
+            tc_mma(tmem_d, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), Cfg::kIdesc,
+                   (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar + acc);      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      uint32_t mt, tt, ks;
+      decode_tile(tile, mt, tt, ks);
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t n = mt * kBM + q * 32 + lane;      // output feature of this thread
+      const uint32_t t0 = tt * BN;
+#pragma unroll 1
+      for (uint32_t c = 0; c < BN; c += 16) {
+        if (t0 + c >= n_tokens) break;                  // warp-uniform
+        uint32_t r[16];
+        tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
+        tc_wait_ld();
+        if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(r[j]);
+            float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 1) == 0 && n + 1 < n_out && t0 + c + j < n_tokens) {
+              float s = v / (1.f + __expf(-v));
+              o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(s * other);
+            }
+          }
+        } else {
+          if (n < n_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t t = t0 + c + j;
+              if (t < n_tokens) {
+                const float v = __uint_as_float(r[j]);
+                const size_t idx = size_t(t) * out_stride + n;
+                if constexpr (EPI == LLMLB_EPI_STORE_BF16)
+                  reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+                else if constexpr (EPI == LLMLB_EPI_STORE_F32)
+                  reinterpret_cast<float*>(out)[idx] = v;
+                else {
+                  if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
+                  else reinterpret_cast<float*>(out)[idx] += v;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(uint32_t(Cfg::kTmemCols))
+                 : "memory");
+  }
+}
+
+// ----------------------------------------------------------------- host side ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols]; box = {64 cols, box_rows}; 128B swizzle
+int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
+                   uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return LLMLB_E_DEVICE;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return LLMLB_E_DEVICE;
+  }
+  return LLMLB_OK;
+}
+
+template <int BN, int EPI>
+static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
+                     uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t split_k,
+                     cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    LLMLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    configured = true;
+  }
+  uint32_t m_tiles = (n_out + kBM - 1) / kBM;
+  uint32_t t_tiles = (n_tokens + BN - 1) / BN;
+  uint32_t tiles = m_tiles * t_tiles * split_k;
+  uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tw, tx, out, n_tokens, n_out, k, out_stride,
+                                                  m_tiles, t_tiles, split_k);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
+template <int BN>
+static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMap& tx, void* out,
+                           uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t out_stride,
+                           uint32_t split_k, cudaStream_t st) {
+  switch (epi) {
+    case LLMLB_EPI_STORE_BF16:
+      return launch_tc<BN, LLMLB_EPI_STORE_BF16>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+    case LLMLB_EPI_RESID_F32:
+      return launch_tc<BN, LLMLB_EPI_RESID_F32>(tw, tx, out, n_tokens, n_out, k, out_stride,
+                                                split_k, st);
+    case LLMLB_EPI_SILU_MUL:
+      return launch_tc<BN, LLMLB_EPI_SILU_MUL>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+    case LLMLB_EPI_STORE_F32:
+      return launch_tc<BN, LLMLB_EPI_STORE_F32>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+  }
+  set_error("gemm_tc: unknown epilogue");
+  return LLMLB_E_INVALID_ARG;
+}
+
+uint32_t tc_pick_bn(uint32_t n_tokens) {
+  if (n_tokens <= 16) return 16;
+  if (n_tokens <= 32) return 32;
+  if (n_tokens <= 64) return 64;
+  if (n_tokens <= 128) return 128;
+  return 256;
+}
+
+// Launch with prebuilt tensor maps (the engine caches them: weights never move, activation
+// buffers are fixed).  The X map's box rows must equal tc_pick_bn(n_tokens).
+int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
+                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
+                   cudaStream_t st) {
+  const uint32_t bn = tc_pick_bn(n_tokens);
+  // split K for the residual epilogue when the tile count cannot fill the GPU
+  uint32_t split_k = 1;
+  if (epi == LLMLB_EPI_RESID_F32) {
+    uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
+    uint32_t kblocks = (k + kBK - 1) / kBK;
+    while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8) split_k *= 2;
+  }
+  switch (bn) {
+    case 16: return dispatch_tc_epi<16>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case 32: return dispatch_tc_epi<32>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case 64: return dispatch_tc_epi<64>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case 128: return dispatch_tc_epi<128>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+    default: return dispatch_tc_epi<256>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+  }
+}
+
+}  // namespace llmlb
