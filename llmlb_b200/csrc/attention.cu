@@ -105,6 +105,28 @@ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
   return row * 128 + ((chunk ^ (row & 7)) << 3);  // element offset
 }
 
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// read a float / float4 at shared-memory offset `addr` of cluster CTA `rank` (DSMEM)
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(ra)
+               : "memory");
+  return v;
+}
+
 constexpr int kPfRows = 64;  // q rows per CTA
 constexpr int kPfThreads = 128;
 
@@ -289,17 +311,19 @@ prefill_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
 }
 
 // ------------------------------------------------------------------ decode attention --------
+// One CTA per (sequence, group of 4 q heads, KV split); the n_splits CTAs of a (sequence, head
+// group) form a thread-block CLUSTER: every CTA reduces its slice of the context to (m, l, o)
+// in shared memory, then rank 0 pulls the partials of its peers through distributed shared
+// memory and writes the bf16 output — no global workspace, no atomics, no second kernel.
+// K/V rows are prefetched 64 tokens (one page) ahead: 16 x 16-byte loads per lane in flight.
 constexpr int kDecHeads = 4;     // q heads per CTA (all share one kv head)
 constexpr int kDecThreads = 128;
 
-struct DecWs {  // workspace layout helper
-  float* o;        // [seq][head][split][128]
-  float* ml;       // [seq][head][split][2]
-  int32_t* ticket; // [seq][head/4]
+struct DecPartial {               // per-CTA result, read by the cluster leader
+  float o[kDecHeads][kHeadDim];
+  float m[kDecHeads];
+  float l[kDecHeads];
 };
-__host__ __device__ inline size_t dec_ws_floats(uint32_t n_seqs, uint32_t n_heads, uint32_t sp) {
-  return size_t(n_seqs) * n_heads * sp * (kHeadDim + 2);
-}
 
 __global__ void __launch_bounds__(kDecThreads)
 decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_pages,
@@ -307,12 +331,11 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
                         uint32_t bt_stride, const int32_t* __restrict__ bt_rows,
                         const int32_t* __restrict__ seq_lens,
                         const float2* __restrict__ rope, __nv_bfloat16* __restrict__ out,
-                        uint32_t n_heads, uint32_t n_kv, uint32_t n_splits, float* ws_o,
-                        float* ws_ml, int32_t* ws_ticket) {
+                        uint32_t n_heads, uint32_t n_kv, uint32_t n_splits) {
   __shared__ float q_s[kDecHeads][kHeadDim];
   __shared__ float mrg_o[4][kDecHeads][kHeadDim];
   __shared__ float mrg_ml[4][kDecHeads][2];
-  __shared__ int is_last;
+  __shared__ DecPartial part;
 
   const uint32_t z = blockIdx.x, hb = blockIdx.y, s = blockIdx.z;
   const uint32_t h0 = hb * kDecHeads, kvh = h0 / (n_heads / n_kv);
@@ -325,9 +348,13 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   const __nv_bfloat16* row = qkv + size_t(s) * width;
 
   const uint32_t n_pages = (uint32_t(L) + kPageTokens - 1) / kPageTokens;
-  const uint32_t chunk = ((n_pages + n_splits - 1) / n_splits) * kPageTokens;
-  const uint32_t t_begin = z * chunk;
-  const uint32_t t_end = min(uint32_t(L), t_begin + chunk);
+  const uint32_t pages_per_split = (n_pages + n_splits - 1) / n_splits;
+  const uint32_t p_begin = z * pages_per_split;
+  const uint32_t p_end = min(n_pages, p_begin + pages_per_split);
+  const uint32_t t_begin = p_begin * kPageTokens;
+  const uint32_t t_end = min(uint32_t(L), p_end * kPageTokens);
+  // first page id of this split: fetch early (the K/V addresses depend on it)
+  int32_t page_next = (p_begin < p_end) ? bt[p_begin] : 0;
 
   // rotate q (4 heads x 64 pairs = 256 pairs over 128 threads), pre-scaled for exp2
   const float scale = rsqrtf(float(kHeadDim)) * kLog2e;
@@ -382,43 +409,54 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     for (int d = 0; d < 16; ++d) acc[h][d] = 0.f;
   }
 
-  for (uint32_t tb = t_begin; tb < t_end; tb += 16) {
-    const uint32_t tok = tb + warp * 4 + grp;
-    const bool valid = tok < t_end;
-    const uint32_t tokc = valid ? tok : t_begin;
-    const int32_t page = bt[tokc / kPageTokens];
-    const size_t off = ((size_t(page) * n_kv + kvh) * kPageTokens + tokc % kPageTokens) * kHeadDim +
-                       sub * 16;
-    const uint4 k0 = *reinterpret_cast<const uint4*>(k_pages + off);
-    const uint4 k1 = *reinterpret_cast<const uint4*>(k_pages + off + 8);
-    const uint4 v0 = *reinterpret_cast<const uint4*>(v_pages + off);
-    const uint4 v1 = *reinterpret_cast<const uint4*>(v_pages + off + 8);
-    float kf[16], vf[16];
-    {
-      const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-      const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  for (uint32_t pg = p_begin; pg < p_end; ++pg) {
+    const int32_t page = page_next;
+    if (pg + 1 < p_end) page_next = bt[pg + 1];
+    const size_t pbase = (size_t(page) * n_kv + kvh) * kPageTokens * kHeadDim + sub * 16;
+    // one page = 64 tokens = 4 rounds of 16; all 16 loads of this lane issued before use
+    uint4 kq[4][2], vq[4][2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        kf[2 * i] = bf16_lo(kw[i]); kf[2 * i + 1] = bf16_hi(kw[i]);
-        vf[2 * i] = bf16_lo(vw[i]); vf[2 * i + 1] = bf16_hi(vw[i]);
-      }
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t tin = r * 16 + warp * 4 + grp;  // token within page
+      const size_t off = pbase + size_t(tin) * kHeadDim;
+      kq[r][0] = *reinterpret_cast<const uint4*>(k_pages + off);
+      kq[r][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
+      vq[r][0] = *reinterpret_cast<const uint4*>(v_pages + off);
+      vq[r][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
     }
 #pragma unroll
-    for (int h = 0; h < kDecHeads; ++h) {
-      float sc = 0.f;
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t tok = pg * kPageTokens + r * 16 + warp * 4 + grp;
+      const bool valid = tok < t_end;
+      float kf[16], vf[16];
+      {
+        const uint32_t kw[8] = {kq[r][0].x, kq[r][0].y, kq[r][0].z, kq[r][0].w,
+                                kq[r][1].x, kq[r][1].y, kq[r][1].z, kq[r][1].w};
+        const uint32_t vw[8] = {vq[r][0].x, vq[r][0].y, vq[r][0].z, vq[r][0].w,
+                                vq[r][1].x, vq[r][1].y, vq[r][1].z, vq[r][1].w};
 #pragma unroll
-      for (int d = 0; d < 16; ++d) sc = fmaf(q_r[h][d], kf[d], sc);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-      if (valid) {
-        float mn = fmaxf(m_r[h], sc);
-        float corr = exp2f(m_r[h] - mn);
-        float p = exp2f(sc - mn);
-        m_r[h] = mn;
-        l_r[h] = l_r[h] * corr + p;
+        for (int i = 0; i < 8; ++i) {
+          kf[2 * i] = bf16_lo(kw[i]); kf[2 * i + 1] = bf16_hi(kw[i]);
+          vf[2 * i] = bf16_lo(vw[i]); vf[2 * i + 1] = bf16_hi(vw[i]);
+        }
+      }
 #pragma unroll
-        for (int d = 0; d < 16; ++d) acc[h][d] = fmaf(p, vf[d], acc[h][d] * corr);
+      for (int h = 0; h < kDecHeads; ++h) {
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) sc = fmaf(q_r[h][d], kf[d], sc);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        if (valid) {
+          float mn = fmaxf(m_r[h], sc);
+          float corr = exp2f(m_r[h] - mn);
+          float p = exp2f(sc - mn);
+          m_r[h] = mn;
+          l_r[h] = l_r[h] * corr + p;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) acc[h][d] = fmaf(p, vf[d], acc[h][d] * corr);
+        }
       }
     }
   }
@@ -455,67 +493,55 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   }
   __syncthreads();
   // merge the 4 warps: thread -> (head = tid/32, 4 dims)
-  {
-    const uint32_t h = tid >> 5, d0 = (tid & 31) * 4;
-    float mn = -INFINITY;
+  const uint32_t h = tid >> 5, d0 = (tid & 31) * 4;
+  float mn = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) mn = fmaxf(mn, mrg_ml[w][h][0]);
-    float l = 0.f, ov[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int w = 0; w < 4; ++w) mn = fmaxf(mn, mrg_ml[w][h][0]);
+  float l = 0.f, ov[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      float mw = mrg_ml[w][h][0];
-      float c = (mw == -INFINITY) ? 0.f : exp2f(mw - mn);
-      l += mrg_ml[w][h][1] * c;
+  for (int w = 0; w < 4; ++w) {
+    float mw = mrg_ml[w][h][0];
+    float c = (mw == -INFINITY) ? 0.f : exp2f(mw - mn);
+    l += mrg_ml[w][h][1] * c;
 #pragma unroll
-      for (int d = 0; d < 4; ++d) ov[d] += mrg_o[w][h][d0 + d] * c;
-    }
-    if (n_splits == 1) {
-      float inv = 1.f / l;
-      __nv_bfloat16* dst = out + size_t(s) * n_heads * kHeadDim + size_t(h0 + h) * kHeadDim + d0;
-      uint2 o2;
-      o2.x = pack_bf16(ov[0] * inv, ov[1] * inv);
-      o2.y = pack_bf16(ov[2] * inv, ov[3] * inv);
-      *reinterpret_cast<uint2*>(dst) = o2;
-      return;
-    }
-    const size_t pidx = (size_t(s) * n_heads + h0 + h) * n_splits + z;
-    *reinterpret_cast<float4*>(ws_o + pidx * kHeadDim + d0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-    if ((tid & 31) == 0) {
-      ws_ml[pidx * 2] = mn;
-      ws_ml[pidx * 2 + 1] = l;
-    }
+    for (int d = 0; d < 4; ++d) ov[d] += mrg_o[w][h][d0 + d] * c;
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    int32_t* tk = ws_ticket + size_t(s) * (n_heads / kDecHeads) + hb;
-    int prev = atomicAdd(tk, 1);
-    is_last = (prev == int(n_splits) - 1);
-    if (is_last) *tk = 0;  // self-cleaning for the next launch
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  {
-    const uint32_t h = tid >> 5, d0 = (tid & 31) * 4;
-    const size_t base = (size_t(s) * n_heads + h0 + h) * n_splits;
-    float mn = -INFINITY;
-    for (uint32_t zz = 0; zz < n_splits; ++zz) mn = fmaxf(mn, __ldcg(ws_ml + (base + zz) * 2));
-    float l = 0.f, ov[4] = {0.f, 0.f, 0.f, 0.f};
-    for (uint32_t zz = 0; zz < n_splits; ++zz) {
-      float mw = __ldcg(ws_ml + (base + zz) * 2);
-      float c = (mw == -INFINITY) ? 0.f : exp2f(mw - mn);
-      l += __ldcg(ws_ml + (base + zz) * 2 + 1) * c;
-      float4 pv = __ldcg(reinterpret_cast<const float4*>(ws_o + (base + zz) * kHeadDim + d0));
-      ov[0] += pv.x * c; ov[1] += pv.y * c; ov[2] += pv.z * c; ov[3] += pv.w * c;
-    }
+  __nv_bfloat16* dst = out + size_t(s) * n_heads * kHeadDim + size_t(h0 + h) * kHeadDim + d0;
+  if (n_splits == 1) {
     float inv = 1.f / l;
-    __nv_bfloat16* dst = out + size_t(s) * n_heads * kHeadDim + size_t(h0 + h) * kHeadDim + d0;
     uint2 o2;
     o2.x = pack_bf16(ov[0] * inv, ov[1] * inv);
     o2.y = pack_bf16(ov[2] * inv, ov[3] * inv);
     *reinterpret_cast<uint2*>(dst) = o2;
+    return;
   }
+  // publish this CTA's partial, then the cluster leader folds all of them
+  *reinterpret_cast<float4*>(&part.o[h][d0]) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+  if ((tid & 31) == 0) { part.m[h] = mn; part.l[h] = l; }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (z == 0) {
+    const uint32_t my = smem_addr_u32(&part);
+    float gm = -INFINITY;
+    for (uint32_t r = 0; r < n_splits; ++r)
+      gm = fmaxf(gm, ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r));
+    float gl = 0.f, go[4] = {0.f, 0.f, 0.f, 0.f};
+    for (uint32_t r = 0; r < n_splits; ++r) {
+      const float pm = ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r);
+      const float c = (pm == -INFINITY) ? 0.f : exp2f(pm - gm);
+      gl += ld_dsmem_f32(my + offsetof(DecPartial, l) + h * 4, r) * c;
+      const float4 po = ld_dsmem_f4(my + offsetof(DecPartial, o) + (h * kHeadDim + d0) * 4, r);
+      go[0] += po.x * c; go[1] += po.y * c; go[2] += po.z * c; go[3] += po.w * c;
+    }
+    const float inv = 1.f / gl;
+    uint2 o2;
+    o2.x = pack_bf16(go[0] * inv, go[1] * inv);
+    o2.y = pack_bf16(go[2] * inv, go[3] * inv);
+    *reinterpret_cast<uint2*>(dst) = o2;
+  }
+  // peers must keep their shared memory alive until the leader has read it
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace llmlb
@@ -576,13 +602,8 @@ extern "C" int llmlb_op_prefill_attention(const void* qkv, const void* k_pages,
   return LLMLB_OK;
 }
 
-static size_t dec_ticket_bytes(uint32_t ws_seqs, uint32_t n_heads) {
-  size_t b = size_t(ws_seqs) * (n_heads / kDecHeads) * 4;
-  return (b + 255) & ~size_t(255);
-}
-extern "C" size_t llmlb_op_decode_attention_ws(uint32_t n_seqs, uint32_t n_heads,
-                                               uint32_t max_splits) {
-  return dec_ticket_bytes(n_seqs, n_heads) + dec_ws_floats(n_seqs, n_heads, max_splits) * 4;
+extern "C" size_t llmlb_op_decode_attention_ws(uint32_t, uint32_t, uint32_t) {
+  return 256;  // kept for ABI stability: the split merge now happens in cluster shared memory
 }
 
 extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v_pages,
@@ -590,25 +611,32 @@ extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v
                                          const int32_t* bt_rows, const int32_t* seq_lens,
                                          uint32_t n_seqs, void* out, uint32_t n_heads,
                                          uint32_t n_kv, const float* rope_table,
-                                         uint32_t n_splits, uint32_t ws_seqs, void* workspace,
-                                         void* stream) {
+                                         uint32_t n_splits, uint32_t, void*, void* stream) {
   if (!qkv || !k_pages || !v_pages || !block_tables || !seq_lens || !out || !rope_table ||
       n_kv == 0 || n_heads % n_kv || n_heads % kDecHeads || (n_heads / n_kv) % kDecHeads ||
-      n_splits == 0 || (n_splits > 1 && !workspace) || ws_seqs < n_seqs) {
+      n_splits == 0) {
     set_error("llmlb_op_decode_attention: bad argument (GQA group must be a multiple of 4)");
     return LLMLB_E_INVALID_ARG;
   }
   if (n_seqs == 0) return LLMLB_OK;
-  // workspace: [tickets (zeroed once by the caller; the kernel re-zeroes them)] [o] [m,l]
-  int32_t* ws_t = (int32_t*)workspace;
-  float* ws_o = workspace ? (float*)((uint8_t*)workspace + dec_ticket_bytes(ws_seqs, n_heads))
-                          : nullptr;
-  float* ws_ml = ws_o ? ws_o + size_t(ws_seqs) * n_heads * n_splits * kHeadDim : nullptr;
-  dim3 grid(n_splits, n_heads / kDecHeads, n_seqs);
-  decode_attention_kernel<<<grid, kDecThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages, block_tables,
-      bt_stride, bt_rows, seq_lens, (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv,
-      n_splits, ws_o, ws_ml, ws_t);
+  // splits form a cluster: round down to a portable cluster size
+  uint32_t sp = n_splits >= 8 ? 8 : n_splits >= 4 ? 4 : n_splits >= 2 ? 2 : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sp, n_heads / kDecHeads, n_seqs);
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = sp;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(
+      &cfg, decode_attention_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages,
+      (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows, seq_lens,
+      (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, sp));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }

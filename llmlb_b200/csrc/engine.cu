@@ -592,6 +592,10 @@ int llmlb_engine::launch_decode_step(uint32_t nb) {
 }
 
 // ------------------------------------------------------------------ steps -------------------
+__global__ void iota_kernel(int32_t* p, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = int32_t(i);
+}
 __global__ void slot_init_kernel(SlotState S, int32_t slot, float temperature, float top_p,
                                  int32_t top_k, uint64_t seed) {
   S.seq_len[slot] = 0;
@@ -1049,11 +1053,15 @@ extern "C" int llmlb_engine_pause(llmlb_engine* e, uint32_t paused) {
 // graph capture and surfaces launch errors at create time), then clear the state it touched.
 int llmlb_engine::warmup() {
   const uint32_t widths[9] = {1, 2, 3, 4, 5, 17, 33, 65, 129};
+  const size_t ms = cfg.max_seqs;
+  iota_kernel<<<ceil_div(cfg.max_seqs, 128), 128, 0, st>>>(B.slots, cfg.max_seqs);  // slot b for row b
+  LLMLB_LAUNCH_CHECK();
   for (uint32_t w : widths) {
     if (w > cfg.max_seqs) break;
+    LLMLB_CUDA_CHECK(cudaMemsetAsync(S.seq_len, 0, ms * 4, st));  // every row: empty cache, position 0
     RC(layer_stack_decode(w));
   }
-  const size_t ms = cfg.max_seqs;
+  cur_batch_slots.clear();
   LLMLB_CUDA_CHECK(cudaMemsetAsync(S.seq_len, 0, ms * 4, st));
   LLMLB_CUDA_CHECK(cudaMemsetAsync(S.last_token, 0, ms * 4, st));
   LLMLB_CUDA_CHECK(cudaMemsetAsync(S.step, 0, ms * 8, st));

@@ -238,6 +238,10 @@ int dispatch_epi(uint32_t epi, bool norm, const void* w, const void* x, const vo
   return LLMLB_E_INVALID_ARG;
 }
 
+int gemv_ks_try(const void* w, const void* x, const void* gain, float eps, void* out,
+                uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
+                cudaStream_t st);
+
 }  // namespace llmlb
 
 using namespace llmlb;
@@ -259,6 +263,11 @@ extern "C" int llmlb_op_gemv(const void* w, const void* x, const void* gain, flo
   }
   cudaStream_t st = (cudaStream_t)stream;
   bool norm = gain != nullptr;
+  if (n_tokens >= 1 && n_tokens <= 4 && epilogue <= LLMLB_EPI_STORE_F32) {
+    // K-split variant first (all SMs busy for any n_out); row-owner variant for odd shapes
+    int rc = gemv_ks_try(w, x, gain, eps, out, n_tokens, n_out, k, epilogue, out_stride, st);
+    if (rc != LLMLB_E_UNSUPPORTED) return rc;
+  }
   switch (n_tokens) {
     case 0: return LLMLB_OK;
     case 1: return dispatch_epi<1>(epilogue, norm, w, x, gain, eps, out, n_out, k, out_stride, st);

@@ -1,0 +1,251 @@
+// Decode GEMV, K-split variant (the one the engine's batch-1 decode runs).
+//
+// Why: with "a warp owns whole rows" the work quantum is a 4-row group, and 7168 groups over
+// 2368 resident warps leaves some warps 4 trips and most 3 (25% tail), while N=4096 outputs only
+// fill 64 CTAs.  Here the quantum is one row PAIR per CTA: rows are dealt to the 148 CTAs in
+// contiguous, near-equal ranges and every warp of a CTA streams its own K slice of EVERY row of
+// the CTA, so all SMs pull from HBM for the whole kernel regardless of N.
+//   * CTA = 16 warps.  K is cut into 256-element chunks (one 16-byte load per lane); a "team" of
+//     TW warps covers a row, each warp CW chunks (TW*CW*256 == K).  16/TW teams take alternate
+//     row batches.
+//   * The x slice of a lane never changes -> it lives in registers (fp32), RMSNorm fused: the CTA
+//     reduces sum(x^2) once, each lane normalises only its own slice.
+//   * Row batches of RB = 8/CW rows are software-pipelined: the next batch's 16-byte streaming
+//     loads are issued before the current batch is reduced, so ~16 loads/lane stay in flight.
+//   * Per batch: per-row warp shuffle tree -> partial[buf][row][warp] in smem -> team-scoped named
+//     barrier -> team warp 0 finishes the sum and applies the epilogue (residual add / SiLU*up / ...).
+// Algorithmic bytes: n_out * k * 2 per launch.
+#include "../../include/llmlb_b200.h"
+#include "common.cuh"
+
+namespace llmlb {
+
+constexpr int kKsThreads = 512;
+constexpr int kKsWarps = 16;
+
+__device__ __forceinline__ void team_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int B, int EPI, bool NORM, int CW>
+__global__ void __launch_bounds__(kKsThreads)
+gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin,
+               const __nv_bfloat16* __restrict__ gain, float eps, void* __restrict__ out,
+               uint32_t n_out, uint32_t K, uint32_t out_stride, uint32_t TW) {
+  constexpr int RB = 8 / CW;  // rows per batch (even)
+  __shared__ float partial[2][kKsWarps][RB * B];  // [buf][warp][row*B + b]
+  __shared__ float red[B][kKsWarps];
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t teams = kKsWarps / TW;
+  const uint32_t team = warp / TW, wt = warp % TW;  // team index, warp within team
+  const bool active = team < teams;                  // spare warps (16 % TW) only help the prologue
+
+  // rows of this CTA, in row pairs so SiLU(gate)*up pairs never straddle CTAs
+  const uint32_t n_pairs = (n_out + 1) / 2;
+  const uint32_t row_begin = uint32_t((uint64_t(blockIdx.x) * n_pairs) / gridDim.x) * 2;
+  const uint32_t row_end = min(n_out, uint32_t((uint64_t(blockIdx.x + 1) * n_pairs) / gridDim.x) * 2);
+  const uint32_t n_batches = (row_end - row_begin + RB - 1) / RB;
+
+  // element offset of this lane's chunk c: chunks are interleaved over the team's warps
+  auto koff = [&](int c) { return (uint32_t(c) * TW + wt) * 256u + lane * 8u; };
+
+  uint4 wf[RB][CW];
+  auto load_batch = [&](uint32_t batch) {
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const uint32_t row = min(row_begin + batch * RB + r, n_out - 1);
+      const __nv_bfloat16* p = W + size_t(row) * K;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) wf[r][c] = ldg_stream(p + koff(c));
+    }
+  };
+  uint32_t batch = team;
+  if (active && batch < n_batches) load_batch(batch);
+
+  // ---- prologue: this lane's slice of x in fp32 registers (RMSNorm fused) ----
+  float xr[B][CW][8];
+  if constexpr (NORM) {
+    const float* xf = reinterpret_cast<const float*>(xin);
+    float ss[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) ss[b] = 0.f;
+    for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        float4 v = reinterpret_cast<const float4*>(xf + size_t(b) * K)[i];
+        ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      float s = warp_sum(ss[b]);
+      if (lane == 0) red[b][warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kKsWarps; ++w) tot += red[b][w];
+      const float rs = rsqrtf(tot / float(K) + eps);
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+          const uint32_t k0 = koff(c);
+          const float4 v0 = *reinterpret_cast<const float4*>(xf + size_t(b) * K + k0);
+          const float4 v1 = *reinterpret_cast<const float4*>(xf + size_t(b) * K + k0 + 4);
+          const uint4 g = __ldg(reinterpret_cast<const uint4*>(gain + k0));
+          // same rounding point as the standalone rmsnorm kernel: y is bf16
+          xr[b][c][0] = __bfloat162float(__float2bfloat16_rn(v0.x * rs * bf16_lo(g.x)));
+          xr[b][c][1] = __bfloat162float(__float2bfloat16_rn(v0.y * rs * bf16_hi(g.x)));
+          xr[b][c][2] = __bfloat162float(__float2bfloat16_rn(v0.z * rs * bf16_lo(g.y)));
+          xr[b][c][3] = __bfloat162float(__float2bfloat16_rn(v0.w * rs * bf16_hi(g.y)));
+          xr[b][c][4] = __bfloat162float(__float2bfloat16_rn(v1.x * rs * bf16_lo(g.z)));
+          xr[b][c][5] = __bfloat162float(__float2bfloat16_rn(v1.y * rs * bf16_hi(g.z)));
+          xr[b][c][6] = __bfloat162float(__float2bfloat16_rn(v1.z * rs * bf16_lo(g.w)));
+          xr[b][c][7] = __bfloat162float(__float2bfloat16_rn(v1.w * rs * bf16_hi(g.w)));
+        }
+      }
+    }
+  } else {
+    if (active) {
+      const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xin);
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(xb + size_t(b) * K + koff(c));
+          xr[b][c][0] = bf16_lo(v.x); xr[b][c][1] = bf16_hi(v.x);
+          xr[b][c][2] = bf16_lo(v.y); xr[b][c][3] = bf16_hi(v.y);
+          xr[b][c][4] = bf16_lo(v.z); xr[b][c][5] = bf16_hi(v.z);
+          xr[b][c][6] = bf16_lo(v.w); xr[b][c][7] = bf16_hi(v.w);
+        }
+    }
+  }
+  if (!active) return;
+
+  // ---- main loop: this team's row batches ----
+  uint32_t buf = 0;
+  for (; batch < n_batches; batch += teams, buf ^= 1) {
+    uint4 wc[RB][CW];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int c = 0; c < CW; ++c) wc[r][c] = wf[r][c];
+    if (batch + teams < n_batches) load_batch(batch + teams);
+
+    float acc[RB][B];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) acc[r][b] = 0.f;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        const uint4 w = wc[r][c];
+        const float w0 = bf16_lo(w.x), w1 = bf16_hi(w.x), w2 = bf16_lo(w.y), w3 = bf16_hi(w.y);
+        const float w4 = bf16_lo(w.z), w5 = bf16_hi(w.z), w6 = bf16_lo(w.w), w7 = bf16_hi(w.w);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          float a = acc[r][b];
+          a = fmaf(w0, xr[b][c][0], a); a = fmaf(w1, xr[b][c][1], a);
+          a = fmaf(w2, xr[b][c][2], a); a = fmaf(w3, xr[b][c][3], a);
+          a = fmaf(w4, xr[b][c][4], a); a = fmaf(w5, xr[b][c][5], a);
+          a = fmaf(w6, xr[b][c][6], a); a = fmaf(w7, xr[b][c][7], a);
+          acc[r][b] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const float s = warp_sum(acc[r][b]);
+        if (lane == 0) partial[buf][warp][r * B + b] = s;
+      }
+    team_barrier(1 + int(team), int(TW) * 32);
+    if (wt == 0) {
+      // lanes 0 .. RB*B-1: one (row, token) each; sum the team's partials in warp order
+      const uint32_t r = lane / B, b = lane % B;
+      float v = 0.f;
+      if (lane < RB * B)
+        for (uint32_t w = 0; w < TW; ++w) v += partial[buf][team * TW + w][lane];
+      const uint32_t row = row_begin + batch * RB + r;
+      if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
+        const float up = __shfl_down_sync(0xffffffffu, v, B);  // row r+1, same token
+        if (lane < RB * B && (r & 1) == 0 && row + 1 < row_end) {
+          const float s = v / (1.f + __expf(-v));
+          reinterpret_cast<__nv_bfloat16*>(out)[size_t(b) * out_stride + (row >> 1)] =
+              __float2bfloat16_rn(s * up);
+        }
+      } else if (lane < RB * B && row < row_end) {
+        const size_t idx = size_t(b) * out_stride + row;
+        if constexpr (EPI == LLMLB_EPI_STORE_BF16)
+          reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+        else if constexpr (EPI == LLMLB_EPI_RESID_F32)
+          reinterpret_cast<float*>(out)[idx] += v;
+        else
+          reinterpret_cast<float*>(out)[idx] = v;
+      }
+    }
+  }
+}
+
+// picks (TW, CW): TW*CW*256 == K, TW <= 16, CW in {1,2,4}, B*CW <= 4.  Returns false if none.
+static bool ks_pick(uint32_t n_tokens, uint32_t K, uint32_t* tw, uint32_t* cw) {
+  if (K % 256) return false;
+  const uint32_t chunks = K / 256;
+  for (uint32_t c : {1u, 2u, 4u}) {
+    if (chunks % c) continue;
+    uint32_t t = chunks / c;
+    if (t <= 16 && n_tokens * c <= 4) { *tw = t; *cw = c; return true; }
+  }
+  return false;
+}
+
+template <int B, int EPI, bool NORM, int CW>
+static int ks_launch(const void* w, const void* x, const void* gain, float eps, void* out,
+                     uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t tw, cudaStream_t st) {
+  uint32_t n_pairs = (n_out + 1) / 2;
+  uint32_t grid = n_pairs < (uint32_t)kNumSMs ? n_pairs : (uint32_t)kNumSMs;
+  gemv_ks_kernel<B, EPI, NORM, CW><<<grid, kKsThreads, 0, st>>>(
+      (const __nv_bfloat16*)w, x, (const __nv_bfloat16*)gain, eps, out, n_out, k, out_stride, tw);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
+template <int B, int CW>
+static int ks_dispatch(uint32_t epi, bool norm, const void* w, const void* x, const void* gain,
+                       float eps, void* out, uint32_t n_out, uint32_t k, uint32_t out_stride,
+                       uint32_t tw, cudaStream_t st) {
+#define KS_CASE(E)                                                                              \
+  case E:                                                                                       \
+    return norm ? ks_launch<B, E, true, CW>(w, x, gain, eps, out, n_out, k, out_stride, tw, st) \
+                : ks_launch<B, E, false, CW>(w, x, gain, eps, out, n_out, k, out_stride, tw, st);
+  switch (epi) {
+    KS_CASE(LLMLB_EPI_STORE_BF16)
+    KS_CASE(LLMLB_EPI_RESID_F32)
+    KS_CASE(LLMLB_EPI_SILU_MUL)
+    KS_CASE(LLMLB_EPI_STORE_F32)
+  }
+#undef KS_CASE
+  set_error("gemv_ks: unknown epilogue");
+  return LLMLB_E_INVALID_ARG;
+}
+
+// returns LLMLB_E_UNSUPPORTED when the shape does not fit this variant (caller falls back)
+int gemv_ks_try(const void* w, const void* x, const void* gain, float eps, void* out,
+                uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
+                cudaStream_t st) {
+  uint32_t tw = 0, cw = 0;
+  if (n_tokens == 0 || n_tokens > 4 || !ks_pick(n_tokens, k, &tw, &cw)) return LLMLB_E_UNSUPPORTED;
+  const bool norm = gain != nullptr;
+#define KS_GO(BB, CC) return ks_dispatch<BB, CC>(epi, norm, w, x, gain, eps, out, n_out, k, out_stride, tw, st)
+  if (n_tokens == 1) { if (cw == 1) KS_GO(1, 1); if (cw == 2) KS_GO(1, 2); KS_GO(1, 4); }
+  if (n_tokens == 2) { if (cw == 1) KS_GO(2, 1); KS_GO(2, 2); }
+  if (n_tokens == 3) KS_GO(3, 1);
+  KS_GO(4, 1);
+#undef KS_GO
+}
+
+}  // namespace llmlb
