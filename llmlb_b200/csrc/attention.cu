@@ -113,7 +113,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t addr, uint32_t rank) {
   uint32_t ra;
   float v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
   return v;
 }
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t rank) {
@@ -122,8 +122,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
   asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(ra)
-               : "memory");
+               : "r"(ra));
   return v;
 }
 
@@ -337,6 +336,8 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   __shared__ float mrg_ml[4][kDecHeads][2];
   __shared__ DecPartial part;
 
+  // PDL: the O-projection GEMV that follows may start prefetching its weights now
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t z = blockIdx.x, hb = blockIdx.y, s = blockIdx.z;
   const uint32_t h0 = hb * kDecHeads, kvh = h0 / (n_heads / n_kv);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -521,17 +522,29 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (z == 0) {
+    // all DSMEM loads are issued before any is consumed (8 ranks max): one latency, not 24
     const uint32_t my = smem_addr_u32(&part);
+    float pm[8], pl[8];
+    float4 po[8];
+#pragma unroll
+    for (uint32_t r = 0; r < 8; ++r) {
+      if (r < n_splits) {
+        pm[r] = ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r);
+        pl[r] = ld_dsmem_f32(my + offsetof(DecPartial, l) + h * 4, r);
+        po[r] = ld_dsmem_f4(my + offsetof(DecPartial, o) + (h * kHeadDim + d0) * 4, r);
+      } else {
+        pm[r] = -INFINITY; pl[r] = 0.f; po[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float gm = -INFINITY;
-    for (uint32_t r = 0; r < n_splits; ++r)
-      gm = fmaxf(gm, ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r));
+#pragma unroll
+    for (uint32_t r = 0; r < 8; ++r) gm = fmaxf(gm, pm[r]);
     float gl = 0.f, go[4] = {0.f, 0.f, 0.f, 0.f};
-    for (uint32_t r = 0; r < n_splits; ++r) {
-      const float pm = ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r);
-      const float c = (pm == -INFINITY) ? 0.f : exp2f(pm - gm);
-      gl += ld_dsmem_f32(my + offsetof(DecPartial, l) + h * 4, r) * c;
-      const float4 po = ld_dsmem_f4(my + offsetof(DecPartial, o) + (h * kHeadDim + d0) * 4, r);
-      go[0] += po.x * c; go[1] += po.y * c; go[2] += po.z * c; go[3] += po.w * c;
+#pragma unroll
+    for (uint32_t r = 0; r < 8; ++r) {
+      const float c = (pm[r] == -INFINITY) ? 0.f : exp2f(pm[r] - gm);
+      gl += pl[r] * c;
+      go[0] += po[r].x * c; go[1] += po[r].y * c; go[2] += po[r].z * c; go[3] += po[r].w * c;
     }
     const float inv = 1.f / gl;
     uint2 o2;

@@ -60,8 +60,12 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
       for (int c = 0; c < CW; ++c) wf[r][c] = ldg_stream(p + koff(c));
     }
   };
+  // PDL: let the next kernel in the stream start its own weight prefetch right away ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   uint32_t batch = team;
   if (active && batch < n_batches) load_batch(batch);
+  // ... and only now wait for the producer of x / out (weights above never depend on it)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- prologue: this lane's slice of x in fp32 registers (RMSNorm fused) ----
   float xr[B][CW][8];
@@ -208,8 +212,17 @@ static int ks_launch(const void* w, const void* x, const void* gain, float eps, 
                      uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t tw, cudaStream_t st) {
   uint32_t n_pairs = (n_out + 1) / 2;
   uint32_t grid = n_pairs < (uint32_t)kNumSMs ? n_pairs : (uint32_t)kNumSMs;
-  gemv_ks_kernel<B, EPI, NORM, CW><<<grid, kKsThreads, 0, st>>>(
-      (const __nv_bfloat16*)w, x, (const __nv_bfloat16*)gain, eps, out, n_out, k, out_stride, tw);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kKsThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // programmatic dependent launch
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemv_ks_kernel<B, EPI, NORM, CW>, (const __nv_bfloat16*)w, x,
+                                      (const __nv_bfloat16*)gain, eps, out, n_out, k, out_stride, tw));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
