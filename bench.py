@@ -31,6 +31,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would precede the JSON line
 
 PROMPT, GEN = 512, 128
 
@@ -206,6 +208,7 @@ def run_ours(args):
     tp = world
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
