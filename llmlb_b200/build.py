@@ -69,5 +69,29 @@ def build(verbose=False, force=False):
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libllmlb_host.so")
+SERVER = os.path.join(HERE, "llmlb_b200_server")
+
+
+def _newer(target, deps):
+    return (not os.path.exists(target)) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+def build_host():
+    """Gateway-side C++ (no CUDA): libllmlb_host.so, plus the HTTP shim linked to the engine."""
+    hd = os.path.join(HERE, "host")
+    deps = [os.path.join(hd, f) for f in ("gateway.cpp", "gateway.hpp", "json.hpp")]
+    if _newer(HOST_LIB, deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread",
+                               os.path.join(hd, "gateway.cpp"), "-o", HOST_LIB])
+    sdeps = deps + [os.path.join(hd, "server.cpp"), LIB, os.path.join(HERE, "..", "include", "llmlb_b200.h")]
+    if os.path.exists(LIB) and _newer(SERVER, sdeps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", os.path.join(hd, "server.cpp"),
+                               os.path.join(hd, "gateway.cpp"), "-o", SERVER, "-L" + HERE, "-lllmlb_b200",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + "/usr/local/cuda/lib64"])
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build_host())

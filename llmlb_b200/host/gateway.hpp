@@ -1,0 +1,154 @@
+// Gateway-side hot path above the C ABI, in C++ because the reference is
+// compiled (Rust) code and no cargo exists in this image.  Names and semantics mirror the
+// reference so the tests read like its own:
+//   ModelTpsState::update_tps            llmlb/src/balancer/types.rs:102-118
+//   LoadManager::{update_tps, select_endpoint_by_tps_ready_for_model, begin_request, finish_request}
+//                                        llmlb/src/balancer/mod.rs:1770,1873-1985,2273-2425,2949
+//   EndpointRegistry::find_by_model      llmlb/src/registry/endpoints.rs:16-73,209-231
+//   StreamingTokenAccumulator, extract_usage_from_response   llmlb/src/token/mod.rs:41-206
+//   process_sse_lines                    llmlb/src/api/proxy.rs:104-116
+//   parse_quantized_model_name           llmlb/src/api/model_name.rs:19-40
+//   openai_error_response_with_type      llmlb/src/api/openai_util.rs:242-257
+//   InferenceGate                        llmlb/src/inference_gate.rs:17-230
+//   extract_api_key                      llmlb/src/auth/middleware.rs:292-321
+#pragma once
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "json.hpp"
+
+namespace llmlb_host {
+
+enum class TpsApiKind { ChatCompletions = 0, Completions = 1, Responses = 2 };
+
+struct ModelTpsState {
+  bool has_ema = false;
+  double tps_ema = 0.0;
+  uint64_t request_count = 0, total_output_tokens = 0, total_duration_ms = 0;
+  void update_tps(uint64_t output_tokens, uint64_t duration_ms);
+};
+
+struct ModelMapping { std::string canonical; std::vector<std::string> aliases; };
+struct EndpointModel { std::string model_id; std::string canonical_name; };  // "" = none
+struct Endpoint {
+  std::string id;
+  bool online = true;
+  bool initializing = false;
+  std::vector<EndpointModel> models;
+  // LoadManager state (balancer/types.rs:157-173)
+  uint32_t active_requests = 0;
+  uint64_t total_requests = 0, success = 0, errors = 0, latency_ms_sum = 0, output_tokens = 0;
+};
+
+enum SelectError { kSelectOk = 0, kNoCapableEndpoints = 1, kNoEndpointsAvailable = 2 };
+
+class LoadManager {
+ public:
+  void add_mapping(const std::string& canonical, const std::string& alias);
+  std::vector<std::string> model_lookup_keys(const std::string& model_id) const;
+  void add_endpoint(const std::string& id, bool online, bool initializing);
+  bool add_model(const std::string& endpoint_id, const std::string& model_id, const std::string& canonical);
+  bool set_status(const std::string& endpoint_id, bool online);       // offline clears its TPS
+  bool set_initializing(const std::string& endpoint_id, bool v);
+  std::vector<std::string> find_by_model(const std::string& model_id) const;
+  void update_tps(const std::string& endpoint_id, const std::string& model_id, TpsApiKind kind,
+                  uint64_t output_tokens, uint64_t duration_ms);
+  bool get_tps(const std::string& endpoint_id, const std::string& model_id, TpsApiKind kind,
+               ModelTpsState* out) const;
+  // model == nullptr: aggregate routing (select_endpoint_by_tps_direct); kind < 0: none
+  SelectError select(const std::string* model, int kind, std::string* out_id);
+  bool begin_request(const std::string& endpoint_id);
+  bool finish_request(const std::string& endpoint_id, bool success, uint64_t duration_ms,
+                      uint64_t output_tokens);
+  uint32_t active_requests(const std::string& endpoint_id) const;
+
+ private:
+  double score(const Endpoint& ep, const std::string* model, int kind) const;
+  const ModelMapping* find_mapping(const std::string& model_id) const;
+  Endpoint* find(const std::string& id);
+  const Endpoint* find(const std::string& id) const;
+  mutable std::mutex mu_;
+  std::vector<Endpoint> endpoints_;  // registration order
+  std::vector<ModelMapping> mappings_;
+  std::map<std::tuple<std::string, std::string, int>, ModelTpsState> tps_;
+  std::atomic<uint64_t> round_robin_{0};
+};
+
+struct TokenUsage { bool has_in = false, has_out = false, has_total = false; uint32_t in = 0, out = 0, total = 0; };
+bool extract_usage_from_response(const Json& body, TokenUsage* usage);
+
+class StreamingTokenAccumulator {
+ public:
+  explicit StreamingTokenAccumulator(const std::string& model) : model_(model) {}
+  void set_input_tokens(uint32_t n) { has_input_ = true; input_ = n; }
+  void process_chunk(const std::string& chunk);
+  // process_sse_lines with carry-over between network chunks
+  void feed(const char* data, size_t n);
+  const std::string& accumulated_content() const { return content_; }
+  bool is_done() const { return done_; }
+  // estimate: tokens for the accumulated text when the stream carried no usage (the reference
+  // uses tiktoken there; hosts of this engine always get usage so the hook is rarely used)
+  TokenUsage finalize(uint32_t (*estimate)(const std::string&) = nullptr) const;
+
+ private:
+  std::string model_, content_, line_buf_;
+  bool has_input_ = false, has_usage_ = false, done_ = false;
+  uint32_t input_ = 0;
+  TokenUsage usage_;
+};
+
+struct ParsedModelName { std::string raw, base, quantization; bool has_quant = false; };
+bool parse_quantized_model_name(const std::string& model, ParsedModelName* out);
+
+std::string openai_error_body(const std::string& message, const std::string& type, int status);
+std::string model_unavailable_body(const std::string& message, const std::string& code);
+
+// 0 ok; 1 invalid Authorization format; 2 missing  (messages as auth/middleware.rs:292-321)
+int extract_api_key(const char* x_api_key, const char* authorization, std::string* key, std::string* err);
+std::string sha256_hex(const std::string& data);
+
+class InferenceGate {  // inference_gate.rs: reject-when-draining + in-flight count
+ public:
+  bool try_begin() { if (rejecting_.load()) return false; in_flight_.fetch_add(1); return true; }
+  void end() { in_flight_.fetch_sub(1); }
+  void set_rejecting(bool v) { rejecting_.store(v); }
+  uint32_t in_flight() const { return in_flight_.load(); }
+  static std::string rejection_body() { return openai_error_body("Server is updating. Please retry.", "service_unavailable", 503); }
+ private:
+  std::atomic<bool> rejecting_{false};
+  std::atomic<uint32_t> in_flight_{0};
+};
+
+// ---- wire format writers (shapes pinned by the reference's fixtures) ----
+std::string sse_event(const Json& j);                       // "data: {...}\n\n"
+inline std::string sse_done() { return "data: [DONE]\n\n"; }
+Json chat_chunk(const std::string& id, const std::string& model, int64_t created,
+                const std::string* role, const std::string* content, const char* finish_reason);
+Json chat_usage_chunk(const std::string& id, const std::string& model, int64_t created,
+                      uint32_t prompt_tokens, uint32_t completion_tokens);
+Json chat_completion_body(const std::string& id, const std::string& model, int64_t created,
+                          const std::string& content, const char* finish_reason,
+                          uint32_t prompt_tokens, uint32_t completion_tokens);
+Json completion_body(const std::string& id, const std::string& model, int64_t created,
+                     const std::string& text, const char* finish_reason, uint32_t prompt_tokens,
+                     uint32_t completion_tokens);
+Json responses_body(const std::string& id, const std::string& model, int64_t created,
+                    const std::string& text, uint32_t input_tokens, uint32_t output_tokens,
+                    const char* status);
+Json responses_event_created(const std::string& id, const std::string& model);
+Json responses_event_item_added();
+Json responses_event_part_added();
+Json responses_event_delta(const std::string& delta);
+Json responses_event_text_done(const std::string& text);
+Json responses_event_done(const std::string& id, uint32_t input_tokens, uint32_t output_tokens);
+
+// Byte-level placeholder tokenizer (no tokenizer assets exist on the box): ids 0..255 are raw
+// bytes shifted by 3 reserved ids; anything else renders as "<|id|>".
+std::vector<int32_t> byte_tokenize(const std::string& text, uint32_t vocab);
+std::string byte_detokenize(int32_t id);
+
+}  // namespace llmlb_host

@@ -1,0 +1,340 @@
+// llmlb_b200_server — the endpoint contract llmlb already consumes, served
+// straight from the in-process engine through the C ABI.  An unmodified llmlb registers it with
+// POST /api/endpoints {"name","base_url"} (llmlb/src/api/endpoints.rs:505): detection sees
+// /api/system with "xllm_version" (detection/xllm.rs:27-66), health pulls /api/health
+// (health/endpoint_checker.rs:515-557), sync reads /v1/models (sync/parser.rs:78-110).
+//
+// Plain blocking HTTP/1.1 (thread per connection, keep-alive, chunked SSE).  Tokenisation is the
+// byte-level placeholder of gateway.hpp unless the request carries "prompt_token_ids".
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <signal.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/llmlb_b200.h"
+#include "gateway.hpp"
+
+using namespace llmlb_host;
+
+struct Server {
+  llmlb_engine* eng = nullptr;
+  std::string model_id, api_key;
+  uint32_t vocab = 0, max_ctx = 0;
+  LoadManager lm;
+  InferenceGate gate;
+  std::atomic<uint64_t> seq{0};
+};
+static Server G;
+
+struct Request {
+  std::string method, path, body;
+  std::map<std::string, std::string> headers;  // lower-cased names
+};
+
+static bool read_request(int fd, std::string& buf, Request* rq) {
+  size_t hdr_end;
+  while ((hdr_end = buf.find("\r\n\r\n")) == std::string::npos) {
+    char tmp[8192];
+    ssize_t n = recv(fd, tmp, sizeof tmp, 0);
+    if (n <= 0) return false;
+    buf.append(tmp, size_t(n));
+    if (buf.size() > (1u << 20)) return false;
+  }
+  std::string head = buf.substr(0, hdr_end);
+  size_t line_end = head.find("\r\n");
+  std::string first = head.substr(0, line_end);
+  size_t a = first.find(' '), b = first.rfind(' ');
+  if (a == std::string::npos || b == a) return false;
+  rq->method = first.substr(0, a);
+  rq->path = first.substr(a + 1, b - a - 1);
+  rq->headers.clear();
+  size_t pos = line_end == std::string::npos ? head.size() : line_end + 2;
+  while (pos < head.size()) {
+    size_t e = head.find("\r\n", pos);
+    if (e == std::string::npos) e = head.size();
+    std::string line = head.substr(pos, e - pos);
+    size_t c = line.find(':');
+    if (c != std::string::npos) {
+      std::string k = line.substr(0, c), v = line.substr(c + 1);
+      for (auto& ch : k) if (ch >= 'A' && ch <= 'Z') ch = char(ch - 'A' + 'a');
+      while (!v.empty() && v[0] == ' ') v.erase(0, 1);
+      rq->headers[k] = v;
+    }
+    pos = e + 2;
+  }
+  size_t need = 0;
+  auto it = rq->headers.find("content-length");
+  if (it != rq->headers.end()) need = size_t(strtoull(it->second.c_str(), nullptr, 10));
+  if (need > (20u << 20)) return false;  // DefaultBodyLimit 20 MiB (api/mod.rs:58)
+  size_t have = buf.size() - (hdr_end + 4);
+  while (have < need) {
+    char tmp[65536];
+    ssize_t n = recv(fd, tmp, sizeof tmp, 0);
+    if (n <= 0) return false;
+    buf.append(tmp, size_t(n));
+    have += size_t(n);
+  }
+  rq->body = buf.substr(hdr_end + 4, need);
+  buf.erase(0, hdr_end + 4 + need);
+  return true;
+}
+
+static bool send_all(int fd, const std::string& s) {
+  size_t off = 0;
+  while (off < s.size()) {
+    ssize_t n = send(fd, s.data() + off, s.size() - off, MSG_NOSIGNAL);
+    if (n <= 0) return false;
+    off += size_t(n);
+  }
+  return true;
+}
+static const char* reason(int st) {
+  switch (st) { case 200: return "OK"; case 400: return "Bad Request"; case 401: return "Unauthorized";
+    case 404: return "Not Found"; case 405: return "Method Not Allowed"; case 502: return "Bad Gateway";
+    case 503: return "Service Unavailable"; case 504: return "Gateway Timeout"; default: return "Error"; }
+}
+static bool send_json(int fd, int status, const std::string& body, const char* extra = "") {
+  std::string h = "HTTP/1.1 " + std::to_string(status) + " " + reason(status) +
+                  "\r\nContent-Type: application/json\r\nContent-Length: " + std::to_string(body.size()) + "\r\n" + extra + "\r\n";
+  return send_all(fd, h + body);
+}
+static bool send_chunk(int fd, const std::string& data) {
+  char hdr[32];
+  snprintf(hdr, sizeof hdr, "%zx\r\n", data.size());
+  return send_all(fd, std::string(hdr) + data + "\r\n");
+}
+static int map_error(int rc) {  // LbError -> status (api/error.rs:31-110)
+  switch (rc) { case LLMLB_E_INVALID_ARG: return 400; case LLMLB_E_MODEL_NOT_FOUND: return 404;
+    case LLMLB_E_QUEUE_FULL: return 503; case LLMLB_E_TIMEOUT: return 504; default: return 502; }
+}
+
+static std::string content_text(const Json& c) {  // string or [{type:text,text}] parts
+  if (c.is_string()) return c.str();
+  std::string s;
+  if (c.is_array())
+    for (auto& p : c.items()) { const Json* t = p.get("text"); if (t && t->is_string()) s += t->str(); }
+  return s;
+}
+
+// kind: 0 chat, 1 responses, 2 completions
+static void handle_generate(int fd, const Request& rq, int kind) {
+  if (!G.gate.try_begin()) { send_json(fd, 503, InferenceGate::rejection_body(), "Retry-After: 30\r\n"); return; }
+  struct GateGuard { ~GateGuard() { G.gate.end(); } } guard;
+  Json req;
+  if (!Json::parse(rq.body, &req) || !req.is_object()) { send_json(fd, 400, openai_error_body("invalid JSON body", "invalid_request_error", 400)); return; }
+  const Json* jm = req.get("model");
+  if (!jm || !jm->is_string() || jm->str().empty()) { send_json(fd, 400, openai_error_body("model is required", "invalid_request_error", 400)); return; }
+  ParsedModelName pm;
+  if (!parse_quantized_model_name(jm->str(), &pm)) { send_json(fd, 400, openai_error_body("Invalid model name (quantization format): " + jm->str(), "invalid_request_error", 400)); return; }
+  std::string ep;
+  const TpsApiKind api = kind == 0 ? TpsApiKind::ChatCompletions : kind == 1 ? TpsApiKind::Responses : TpsApiKind::Completions;
+  if (G.lm.select(&pm.base, int(api), &ep) != kSelectOk) {
+    send_json(fd, 404, openai_error_body("The model '" + jm->str() + "' does not exist", "invalid_request_error", 404));
+    return;
+  }
+  // prompt
+  std::vector<int32_t> ids;
+  if (const Json* raw = req.get("prompt_token_ids")) {
+    if (raw->is_array()) for (auto& v : raw->items()) ids.push_back(int32_t(v.as_int()));
+  } else if (kind == 0) {
+    const Json* msgs = req.get("messages");
+    if (!msgs || !msgs->is_array()) { send_json(fd, 400, openai_error_body("messages is required", "invalid_request_error", 400)); return; }
+    std::string text;
+    for (auto& m : msgs->items()) {
+      const Json* role = m.get("role"); const Json* c = m.get("content");
+      // image parts are rejected by the gateway before the boundary (openai.rs:617); mirror it
+      if (c && c->is_array()) for (auto& p : c->items()) { const Json* t = p.get("type"); if (t && t->is_string() && t->str() == "image_url") { send_json(fd, 400, openai_error_body("image inputs are not supported", "invalid_request_error", 400)); return; } }
+      text += (role && role->is_string() ? role->str() : "user") + ": " + (c ? content_text(*c) : "") + "\n";
+    }
+    text += "assistant: ";
+    ids = byte_tokenize(text, G.vocab);
+  } else if (kind == 1) {
+    const Json* in = req.get("input");
+    std::string text;
+    if (in && in->is_string()) text = in->str();
+    else if (in && in->is_array()) for (auto& m : in->items()) { const Json* c = m.get("content"); if (c) text += content_text(*c) + "\n"; }
+    ids = byte_tokenize(text, G.vocab);
+  } else {
+    const Json* p = req.get("prompt");
+    ids = byte_tokenize(p && p->is_string() ? p->str() : "", G.vocab);
+  }
+  llmlb_sampling s{};
+  const Json* mt = req.get(kind == 1 ? "max_output_tokens" : "max_tokens");
+  if (!mt && kind == 0) mt = req.get("max_completion_tokens");
+  s.max_tokens = mt && mt->is_number() ? uint32_t(std::max<int64_t>(1, mt->as_int())) : 128;
+  const Json* t = req.get("temperature");
+  s.temperature = t && t->is_number() ? float(t->as_double()) : 1.0f;
+  const Json* tp = req.get("top_p");
+  s.top_p = tp && tp->is_number() ? float(tp->as_double()) : 1.0f;
+  const Json* tk = req.get("top_k");
+  s.top_k = tk && tk->is_number() ? uint32_t(tk->as_int()) : 0;
+  const Json* sd = req.get("seed");
+  s.seed = sd && sd->is_number() ? uint64_t(sd->as_int()) : G.seq.load();
+  const Json* ie = req.get("ignore_eos");
+  s.ignore_eos = ie && ie->as_bool() ? 1 : 0;
+  const bool stream = req.get("stream") && req.get("stream")->as_bool();
+  bool include_usage = kind != 0;
+  if (const Json* so = req.get("stream_options")) if (const Json* iu = so->get("include_usage")) include_usage = iu->as_bool();
+  if (ids.size() + s.max_tokens > G.max_ctx) s.max_tokens = ids.size() < G.max_ctx ? uint32_t(G.max_ctx - ids.size()) : 0;
+
+  const auto t0 = std::chrono::steady_clock::now();
+  uint64_t rid = 0;
+  int rc = s.max_tokens ? llmlb_request_submit(G.eng, ids.data(), uint32_t(ids.size()), &s, &rid) : LLMLB_E_INVALID_ARG;
+  if (rc != LLMLB_OK) {
+    int st = map_error(rc);
+    send_json(fd, st, openai_error_body(s.max_tokens ? llmlb_last_error() : "prompt exceeds the context length", st == 400 ? "invalid_request_error" : "endpoint_request_error", st));
+    return;
+  }
+  G.lm.begin_request(ep);
+  const uint64_t n = G.seq.fetch_add(1);
+  const std::string id = std::string(kind == 0 ? "chatcmpl-" : kind == 1 ? "resp_" : "cmpl-") + std::to_string(n);
+  const int64_t created = int64_t(std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch()).count());
+  const std::string role = "assistant";
+  bool ok = true, client_gone = false;
+  if (stream) {
+    ok = send_all(fd, "HTTP/1.1 200 OK\r\nContent-Type: text/event-stream\r\nCache-Control: no-cache\r\nTransfer-Encoding: chunked\r\n\r\n");
+    if (kind == 0) ok = ok && send_chunk(fd, sse_event(chat_chunk(id, jm->str(), created, &role, nullptr, nullptr)));
+    if (kind == 1) ok = ok && send_chunk(fd, sse_event(responses_event_created(id, jm->str())) + sse_event(responses_event_item_added()) + sse_event(responses_event_part_added()));
+  }
+  std::string text;
+  uint32_t prompt_tokens = uint32_t(ids.size()), completion_tokens = 0, finish = LLMLB_FINISH_NONE;
+  while (finish == LLMLB_FINISH_NONE) {
+    llmlb_token_event ev[64];
+    uint32_t got = 0;
+    rc = llmlb_request_poll(G.eng, rid, ev, 64, &got, 100);
+    if (rc != LLMLB_OK && rc != LLMLB_E_TIMEOUT) { finish = LLMLB_FINISH_ERROR; break; }
+    std::string out;
+    for (uint32_t i = 0; i < got; ++i) {
+      if (ev[i].token_id >= 0) {
+        const std::string piece = byte_detokenize(ev[i].token_id);
+        text += piece;
+        if (stream) out += kind == 1 ? sse_event(responses_event_delta(piece))
+                                     : sse_event(chat_chunk(id, jm->str(), created, nullptr, &piece, nullptr));
+      }
+      prompt_tokens = ev[i].prompt_tokens; completion_tokens = ev[i].completion_tokens;
+      if (ev[i].finish_reason) finish = ev[i].finish_reason;
+    }
+    if (stream && !out.empty() && ok && !send_chunk(fd, out)) { ok = false; client_gone = true; llmlb_request_cancel(G.eng, rid); }
+  }
+  llmlb_request_release(G.eng, rid);
+  const uint64_t ms = uint64_t(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count());
+  // streaming drop still counts as success when tokens flowed (openai.rs:2556-2648)
+  const bool success = finish == LLMLB_FINISH_STOP || finish == LLMLB_FINISH_LENGTH || (client_gone && completion_tokens > 0);
+  G.lm.finish_request(ep, success, ms, completion_tokens);
+  if (success && completion_tokens) G.lm.update_tps(ep, pm.base, api, completion_tokens, ms);
+  const char* fr = finish == LLMLB_FINISH_STOP ? "stop" : "length";
+  if (finish == LLMLB_FINISH_ERROR && !stream) { send_json(fd, 502, openai_error_body("engine failure", "endpoint_request_error", 502)); return; }
+  if (stream) {
+    if (!ok) return;
+    std::string tail;
+    if (kind == 0) {
+      tail += sse_event(chat_chunk(id, jm->str(), created, nullptr, nullptr, fr));
+      if (include_usage) tail += sse_event(chat_usage_chunk(id, jm->str(), created, prompt_tokens, completion_tokens));
+    } else if (kind == 1) {
+      tail += sse_event(responses_event_text_done(text)) + sse_event(responses_event_done(id, prompt_tokens, completion_tokens));
+    }
+    tail += sse_done();
+    send_chunk(fd, tail);
+    send_all(fd, "0\r\n\r\n");
+  } else {
+    Json body = kind == 0 ? chat_completion_body(id, jm->str(), created, text, fr, prompt_tokens, completion_tokens)
+              : kind == 1 ? responses_body(id, jm->str(), created, text, prompt_tokens, completion_tokens, "completed")
+                          : completion_body(id, jm->str(), created, text, fr, prompt_tokens, completion_tokens);
+    send_json(fd, 200, body.dump());
+  }
+}
+
+static void handle(int fd, const Request& rq) {
+  const std::string path = rq.path.substr(0, rq.path.find('?'));
+  if (!G.api_key.empty()) {  // endpoint registered with an api_key => every call carries Bearer (proxy.rs:390-392)
+    std::string key, err;
+    auto xa = rq.headers.find("x-api-key"); auto au = rq.headers.find("authorization");
+    int rc = extract_api_key(xa != rq.headers.end() ? xa->second.c_str() : nullptr, au != rq.headers.end() ? au->second.c_str() : nullptr, &key, &err);
+    if (rc != 0 || key != G.api_key) { send_json(fd, 401, openai_error_body(rc ? err : "Invalid API key", "invalid_request_error", 401)); return; }
+  }
+  if (rq.method == "GET" && path == "/v1/models") {
+    Json m = Json::object(); m.set("id", G.model_id); m.set("object", "model"); m.set("created", 0); m.set("owned_by", "llmlb_b200");
+    Json data = Json::array(); data.push(m);
+    Json root = Json::object(); root.set("object", "list"); root.set("data", data);
+    send_json(fd, 200, root.dump());
+  } else if (rq.method == "GET" && path == "/api/system") {
+    Json root = Json::object(); root.set("xllm_version", "llmlb_b200-0.1"); root.set("engine", "llmlb_b200"); root.set("device", "NVIDIA B200");
+    send_json(fd, 200, root.dump());
+  } else if (rq.method == "GET" && path == "/api/health") {
+    llmlb_health h; llmlb_engine_health(G.eng, &h);
+    Json gpu = Json::object(); gpu.set("device_count", h.device_count); gpu.set("total_memory_bytes", h.total_memory_bytes);
+    gpu.set("used_memory_bytes", h.used_memory_bytes); gpu.set("capability_score", 100);
+    Json load = Json::object(); load.set("active_requests", h.active_requests); load.set("queued_requests", h.queued_requests);
+    load.set("in_flight_http", G.gate.in_flight());
+    Json kv = Json::object(); kv.set("free_pages", h.free_kv_pages); kv.set("total_pages", h.total_kv_pages);
+    Json root = Json::object(); root.set("status", "ok"); root.set("gpu", gpu); root.set("load", load); root.set("kv", kv);
+    send_json(fd, 200, root.dump());
+  } else if (rq.method == "GET" && path.compare(0, 12, "/api/models/") == 0 && path.size() > 17 && path.compare(path.size() - 5, 5, "/info") == 0) {
+    const std::string name = path.substr(12, path.size() - 17);
+    if (name != G.model_id) { send_json(fd, 404, openai_error_body("model not found", "invalid_request_error", 404)); return; }
+    llmlb_model_info mi; llmlb_engine_model_info(G.eng, &mi);
+    Json root = Json::object(); root.set("model", G.model_id); root.set("context_length", mi.context_length);
+    root.set("vocab_size", mi.vocab); root.set("num_layers", mi.n_layers); root.set("hidden_size", mi.hidden);
+    send_json(fd, 200, root.dump());
+  } else if (rq.method == "POST" && path == "/v1/chat/completions") handle_generate(fd, rq, 0);
+  else if (rq.method == "POST" && path == "/v1/responses") handle_generate(fd, rq, 1);
+  else if (rq.method == "POST" && path == "/v1/completions") handle_generate(fd, rq, 2);
+  else if (rq.method == "POST" && path == "/admin/drain") { G.gate.set_rejecting(rq.body.find("true") != std::string::npos); send_json(fd, 200, "{\"ok\":true}"); }
+  else send_json(fd, 404, openai_error_body("not found", "invalid_request_error", 404));
+}
+
+static void serve_conn(int fd) {
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  std::string buf;
+  Request rq;
+  while (read_request(fd, buf, &rq)) {
+    handle(fd, rq);
+    auto c = rq.headers.find("connection");
+    if (c != rq.headers.end() && c->second == "close") break;
+  }
+  close(fd);
+}
+
+int main(int argc, char** argv) {
+  signal(SIGPIPE, SIG_IGN);
+  int port = 8011; std::string geometry = "8b";
+  uint32_t max_seqs = 64, max_ctx = 2048;
+  G.model_id = "llama-3-8b";
+  for (int i = 1; i + 1 < argc; i += 2) {
+    std::string k = argv[i], v = argv[i + 1];
+    if (k == "--port") port = atoi(v.c_str()); else if (k == "--model") geometry = v;
+    else if (k == "--model-id") G.model_id = v; else if (k == "--max-seqs") max_seqs = uint32_t(atoi(v.c_str()));
+    else if (k == "--max-ctx") max_ctx = uint32_t(atoi(v.c_str())); else if (k == "--api-key") G.api_key = v;
+  }
+  llmlb_engine_config cfg; memset(&cfg, 0, sizeof cfg);
+  cfg.abi_version = LLMLB_ABI_VERSION;
+  if (geometry == "tiny") cfg.model = {512, 2, 8, 2, 128, 1024, 2048, 500000.f, 1e-5f};
+  else cfg.model = {4096, 32, 32, 8, 128, 14336, 128256, 500000.f, 1e-5f};
+  strncpy(cfg.model_id, G.model_id.c_str(), sizeof cfg.model_id - 1);
+  cfg.tp_size = 1; cfg.max_seqs = max_seqs; cfg.max_ctx = max_ctx; cfg.kv_block_tokens = 64; cfg.use_cuda_graphs = 1;
+  if (llmlb_engine_create(&cfg, &G.eng) != LLMLB_OK) { fprintf(stderr, "engine: %s\n", llmlb_last_error()); return 2; }
+  G.vocab = cfg.model.vocab; G.max_ctx = max_ctx;
+  G.lm.add_endpoint("local", true, false);
+  G.lm.add_model("local", G.model_id, "");
+  int ls = socket(AF_INET, SOCK_STREAM, 0), one = 1;
+  setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+  sockaddr_in addr{}; addr.sin_family = AF_INET; addr.sin_port = htons(uint16_t(port)); addr.sin_addr.s_addr = htonl(INADDR_LOOPBACK);
+  if (bind(ls, (sockaddr*)&addr, sizeof addr) != 0 || listen(ls, 256) != 0) { perror("bind/listen"); return 3; }
+  fprintf(stderr, "llmlb_b200_server listening on 127.0.0.1:%d model=%s\n", port, G.model_id.c_str());
+  fflush(stderr);
+  for (;;) {
+    int fd = accept(ls, nullptr, nullptr);
+    if (fd < 0) continue;
+    std::thread(serve_conn, fd).detach();
+  }
+}

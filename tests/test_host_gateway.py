@@ -1,0 +1,313 @@
+"""The C++ gateway-side code (llmlb_b200/host, libllmlb_host.so) against (a) the known-answer
+vectors of the reference's own tests and (b) the Python oracle restatement, on CPU."""
+import ctypes as C
+import json
+import os
+import random
+
+import pytest
+
+from oracle import gateway_ref as G
+
+V = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gateway_vectors.json")))
+KIND = {"chat": 0, "completions": 1, "responses": 2, None: -1}
+
+
+@pytest.fixture(scope="module")
+def H():
+    from llmlb_b200 import build
+    lib = C.CDLL(build.build_host())
+    vp, cp, u64, i64 = C.c_void_p, C.c_char_p, C.c_uint64, C.c_int64
+    sig = {
+        "llmlb_lm_create": (vp, []), "llmlb_lm_destroy": (None, [vp]),
+        "llmlb_lm_add_mapping": (None, [vp, cp, cp]), "llmlb_lm_add_endpoint": (None, [vp, cp, C.c_int, C.c_int]),
+        "llmlb_lm_add_model": (C.c_int, [vp, cp, cp, cp]), "llmlb_lm_set_status": (C.c_int, [vp, cp, C.c_int]),
+        "llmlb_lm_set_initializing": (C.c_int, [vp, cp, C.c_int]),
+        "llmlb_lm_update_tps": (None, [vp, cp, cp, C.c_int, u64, u64]),
+        "llmlb_lm_get_tps": (C.c_int, [vp, cp, cp, C.c_int, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "llmlb_lm_select": (C.c_int, [vp, cp, C.c_int, C.c_char_p, C.c_size_t]),
+        "llmlb_lm_lookup_keys": (C.c_size_t, [vp, cp, C.c_char_p, C.c_size_t]),
+        "llmlb_lm_begin_request": (C.c_int, [vp, cp]), "llmlb_lm_finish_request": (C.c_int, [vp, cp, C.c_int, u64, u64]),
+        "llmlb_lm_active": (C.c_uint32, [vp, cp]),
+        "llmlb_extract_usage": (C.c_int, [cp, C.POINTER(i64)]),
+        "llmlb_acc_create": (vp, [cp]), "llmlb_acc_destroy": (None, [vp]), "llmlb_acc_set_input_tokens": (None, [vp, C.c_uint32]),
+        "llmlb_acc_process_chunk": (None, [vp, cp]), "llmlb_acc_feed": (None, [vp, cp, C.c_size_t]),
+        "llmlb_acc_content": (C.c_size_t, [vp, C.c_char_p, C.c_size_t]), "llmlb_acc_done": (C.c_int, [vp]),
+        "llmlb_acc_finalize": (None, [vp, C.POINTER(i64)]),
+        "llmlb_parse_model_name": (C.c_int, [cp, C.c_char_p, C.c_char_p, C.c_size_t]),
+        "llmlb_error_body": (C.c_size_t, [cp, cp, C.c_int, C.c_char_p, C.c_size_t]),
+        "llmlb_gate_rejection_body": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+        "llmlb_extract_api_key": (C.c_int, [cp, cp, C.c_char_p, C.c_size_t]),
+        "llmlb_sha256_hex": (None, [cp, C.c_size_t, C.c_char_p]),
+        "llmlb_gate_create": (vp, []), "llmlb_gate_destroy": (None, [vp]), "llmlb_gate_try_begin": (C.c_int, [vp]),
+        "llmlb_gate_end": (None, [vp]), "llmlb_gate_set_rejecting": (None, [vp, C.c_int]), "llmlb_gate_in_flight": (C.c_uint32, [vp]),
+        "llmlb_frame": (C.c_size_t, [C.c_int, cp, cp, i64, C.POINTER(cp), C.c_uint32, C.c_uint32, cp, C.c_char_p, C.c_size_t]),
+        "llmlb_json_roundtrip": (C.c_size_t, [cp, C.c_char_p, C.c_size_t]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def b(s):
+    return s.encode() if s is not None else None
+
+
+def usage3(arr):
+    return [None if v < 0 else int(v) for v in arr]
+
+
+class Lm:
+    def __init__(self, H, mappings=()):
+        self.H, self.p = H, H.llmlb_lm_create()
+        for m in mappings:
+            for a in m["aliases"]:
+                H.llmlb_lm_add_mapping(self.p, b(m["canonical"]), b(a))
+
+    def add(self, eid, models, online=True, initializing=False):
+        self.H.llmlb_lm_add_endpoint(self.p, b(eid), int(online), int(initializing))
+        for m in models:
+            self.H.llmlb_lm_add_model(self.p, b(eid), b(m), None)
+
+    def select(self, model, kind):
+        out = C.create_string_buffer(128)
+        rc = self.H.llmlb_lm_select(self.p, b(model), KIND[kind], out, 128)
+        return rc, out.value.decode()
+
+    def __del__(self):
+        self.H.llmlb_lm_destroy(self.p)
+
+
+@pytest.mark.parametrize("v", V["ema"], ids=lambda v: v["cite"].split()[-1])
+def test_ema_vectors(H, v):
+    lm = Lm(H)
+    lm.add("e", ["m"])
+    for tok, dur in v["updates"]:
+        H.llmlb_lm_update_tps(lm.p, b"e", b"m", 0, tok, dur)
+    ema, cnt, tk, ms = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    found = H.llmlb_lm_get_tps(lm.p, b"e", b"m", 0, ema, cnt, tk, ms)
+    if v["ema"] is None:
+        assert (not found) or ema.value < 0
+        assert cnt.value == 0
+    else:
+        assert found and abs(ema.value - v["ema"]) < 0.01
+        assert (cnt.value, tk.value, ms.value) == (v["request_count"], v["total_output_tokens"], v["total_duration_ms"])
+
+
+def test_ema_matches_oracle_bit_for_bit(H):
+    rnd = random.Random(1)
+    for _ in range(200):
+        lm, ref = Lm(H), G.ModelTpsState()
+        lm.add("e", ["m"])
+        for _ in range(rnd.randrange(1, 12)):
+            t, d = rnd.randrange(0, 5000), rnd.randrange(0, 20000)
+            H.llmlb_lm_update_tps(lm.p, b"e", b"m", 2, t, d)
+            ref.update_tps(t, d)
+        ema, cnt, tk, ms = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        found = H.llmlb_lm_get_tps(lm.p, b"e", b"m", 2, ema, cnt, tk, ms)
+        if ref.tps_ema is None:
+            assert (not found) or ema.value < 0
+        else:
+            assert ema.value == ref.tps_ema  # same IEEE-754 double operations in the same order
+            assert cnt.value == ref.request_count
+
+
+@pytest.mark.parametrize("v", V["routing"], ids=lambda v: v["cite"].split()[-1])
+def test_routing_vectors(H, v):
+    lm = Lm(H)
+    for eid, models in v["endpoints"]:
+        lm.add(eid, models)
+    for eid, model, kind, tok, dur in v["tps"]:
+        H.llmlb_lm_update_tps(lm.p, b(eid), b(model), KIND[kind], tok, dur)
+    for model, kind, want in v["selects"]:
+        assert lm.select(model, kind) == (0, want)
+
+
+def test_routing_random_against_oracle(H):
+    rnd = random.Random(7)
+    for _ in range(100):
+        lm, ref = Lm(H, V["mappings"]), G.LoadManager(V["mappings"])
+        names = ["m1", "m2", "llama3.3:70b", "meta-llama/Llama-3.3-70B-Instruct"]
+        for i in range(rnd.randrange(1, 6)):
+            models = rnd.sample(names, rnd.randrange(1, 3))
+            online, init = rnd.random() > 0.2, rnd.random() < 0.15
+            lm.add("e%d" % i, models, online, init)
+            ref.add_endpoint("e%d" % i, models, "online" if online else "offline", init)
+            for m in models:
+                if rnd.random() < 0.6:
+                    k = rnd.choice(["chat", "responses"])
+                    t, d = rnd.randrange(1, 500), rnd.randrange(1, 3000)
+                    H.llmlb_lm_update_tps(lm.p, b("e%d" % i), b(m), KIND[k], t, d)
+                    ref.update_tps("e%d" % i, m, k, t, d)
+        for _ in range(8):
+            model = rnd.choice(names + ["unknown", None])
+            kind = rnd.choice(["chat", "responses", None])
+            try:
+                want = (0, ref.select(model, kind))
+            except LookupError as e:
+                want = ({"no_capable_endpoints": 1, "no_endpoints_available": 2}[str(e)], "")
+            assert lm.select(model, kind) == want
+
+
+def test_offline_clears_tps_and_lease_counts(H):
+    lm = Lm(H)
+    lm.add("a", ["m"]); lm.add("b", ["m"])
+    H.llmlb_lm_update_tps(lm.p, b"a", b"m", 0, 100, 1000)
+    assert lm.select("m", "chat") == (0, "a")
+    H.llmlb_lm_set_status(lm.p, b"a", 0)
+    assert lm.select("m", "chat") == (0, "b")
+    H.llmlb_lm_set_status(lm.p, b"a", 1)           # back online: TPS restarted from zero
+    ema, c1, c2, c3 = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert H.llmlb_lm_get_tps(lm.p, b"a", b"m", 0, ema, c1, c2, c3) == 0
+    H.llmlb_lm_begin_request(lm.p, b"b"); H.llmlb_lm_begin_request(lm.p, b"b")
+    assert H.llmlb_lm_active(lm.p, b"b") == 2
+    H.llmlb_lm_finish_request(lm.p, b"b", 1, 50, 10)
+    assert H.llmlb_lm_active(lm.p, b"b") == 1
+
+
+def test_lookup_keys(H):
+    lm = Lm(H, V["mappings"])
+    out = C.create_string_buffer(512)
+    H.llmlb_lm_lookup_keys(lm.p, b"llama3.3:70b", out, 512)
+    assert out.value.decode().split("\n") == G.model_lookup_keys("llama3.3:70b", V["mappings"])
+
+
+@pytest.mark.parametrize("v", V["usage"], ids=lambda v: v["cite"])
+def test_usage_vectors(H, v):
+    out = (C.c_int64 * 3)()
+    found = H.llmlb_extract_usage(b(json.dumps(v["body"])), out)
+    if v["want"] is None:
+        assert not found
+    else:
+        assert found and usage3(out) == v["want"]
+
+
+@pytest.mark.parametrize("v", V["accumulator"], ids=lambda v: v["cite"].split()[-1])
+def test_accumulator_vectors(H, v):
+    a = H.llmlb_acc_create(b"m")
+    for c in v["chunks"]:
+        H.llmlb_acc_process_chunk(a, b(c))
+    buf = C.create_string_buffer(4096)
+    H.llmlb_acc_content(a, buf, 4096)
+    assert buf.value.decode() == v["content"] and bool(H.llmlb_acc_done(a)) == v["done"]
+    if "usage" in v:
+        out = (C.c_int64 * 3)()
+        H.llmlb_acc_finalize(a, out)
+        assert usage3(out) == v["usage"]
+    H.llmlb_acc_destroy(a)
+
+
+def test_feed_handles_any_chunk_boundary(H):
+    body = "".join(c + "\n" for c in V["accumulator"][-2]["chunks"]).encode()
+    for cut in range(1, len(body), 7):
+        a = H.llmlb_acc_create(b"m")
+        H.llmlb_acc_feed(a, body[:cut], cut)
+        H.llmlb_acc_feed(a, body[cut:], len(body) - cut)
+        buf = C.create_string_buffer(256)
+        H.llmlb_acc_content(a, buf, 256)
+        assert buf.value.decode() == "Hello from streaming!" and H.llmlb_acc_done(a)
+        H.llmlb_acc_destroy(a)
+
+
+@pytest.mark.parametrize("v", V["model_names"], ids=lambda v: v["in"])
+def test_model_names(H, v):
+    base, q = C.create_string_buffer(128), C.create_string_buffer(128)
+    rc = H.llmlb_parse_model_name(b(v["in"]), base, q, 128)
+    if v.get("error"):
+        assert rc == -1
+    else:
+        assert base.value.decode() == v["base"] and (q.value.decode() or None) == v["quant"]
+
+
+@pytest.mark.parametrize("v", V["errors"], ids=lambda v: v["cite"])
+def test_error_bodies(H, v):
+    out = C.create_string_buffer(1024)
+    H.llmlb_error_body(b(v["message"]), b(v["type"]), v["status"], out, 1024)
+    assert json.loads(out.value) == v["body"]
+    H.llmlb_gate_rejection_body(out, 1024)
+    assert json.loads(out.value) == V["errors"][1]["body"]
+
+
+@pytest.mark.parametrize("v", V["api_keys"], ids=lambda v: str(v["headers"]))
+def test_api_key(H, v):
+    out = C.create_string_buffer(256)
+    rc = H.llmlb_extract_api_key(b(v["headers"].get("X-API-Key")), b(v["headers"].get("Authorization")), out, 256)
+    if "error" in v:
+        assert rc != 0 and out.value.decode() == v["error"]
+    else:
+        assert rc == 0 and out.value.decode() == v["key"]
+
+
+def test_sha256_matches_hashlib(H):
+    import hashlib
+    for s in [b"", b"sk_debug", b"a" * 55, b"a" * 56, b"a" * 64, os.urandom(1000)]:
+        out = C.create_string_buffer(65)
+        H.llmlb_sha256_hex(s, len(s), out)
+        assert out.value.decode() == hashlib.sha256(s).hexdigest()
+
+
+def test_gate(H):
+    g = H.llmlb_gate_create()
+    assert H.llmlb_gate_try_begin(g) == 0 and H.llmlb_gate_in_flight(g) == 1
+    H.llmlb_gate_set_rejecting(g, 1)
+    assert H.llmlb_gate_try_begin(g) == 503 and H.llmlb_gate_in_flight(g) == 1   # drain: no new work
+    H.llmlb_gate_end(g)
+    assert H.llmlb_gate_in_flight(g) == 0
+    H.llmlb_gate_destroy(g)
+
+
+def _frame(H, kind, pieces, prompt_tokens=7, finish=b"length"):
+    arr = (C.c_char_p * len(pieces))(*[p.encode() for p in pieces])
+    out = C.create_string_buffer(1 << 16)
+    n = H.llmlb_frame(kind, b"id-1", b"llama-3-8b", 1704067200, arr, len(pieces), prompt_tokens, finish, out, 1 << 16)
+    return out.raw[:n].decode()
+
+
+def test_chat_sse_is_what_the_reference_accumulator_expects(H):
+    pieces = ["Hello", " wor", "ld", "!\n", "é\"q\""]
+    sse = _frame(H, 0, pieces)
+    assert sse.startswith("data: ") and sse.endswith("data: [DONE]\n\n")     # bats tests/e2e/test-openai-api.bats:225,251
+    acc = G.StreamingTokenAccumulator("m")
+    rest = G.process_sse_lines(sse, acc)                                     # the gateway's own accounting
+    assert rest == "" and acc.done and acc.accumulated_content == "".join(pieces)
+    u = acc.finalize()
+    assert u == {"input_tokens": 7, "output_tokens": 5, "total_tokens": 12}
+    first = json.loads(sse.split("\n\n")[0][6:])
+    assert first["object"] == "chat.completion.chunk" and first["choices"][0]["delta"]["role"] == "assistant"
+
+
+def test_responses_sse_event_sequence_matches_golden(H):
+    sse = _frame(H, 2, ["Hello", " from", " streaming!"], prompt_tokens=5)
+    types = [json.loads(e[6:]).get("type") for e in sse.split("\n\n") if e.startswith("data: {")]
+    # llmlb/tests/integration/responses_streaming_test.rs:64-136
+    assert types == ["response.created", "response.output_item.added", "response.content_part.added",
+                     "response.output_text.delta", "response.output_text.delta", "response.output_text.delta",
+                     "response.output_text.done", "response.done"]
+    acc = G.StreamingTokenAccumulator("m")
+    G.process_sse_lines(sse, acc)
+    assert acc.accumulated_content == "Hello from streaming!" and acc.done
+    assert acc.finalize() == {"input_tokens": 5, "output_tokens": 3, "total_tokens": 8}   # nested response.usage
+
+
+def test_non_stream_bodies(H):
+    chat = json.loads(_frame(H, 1, ["a", "b"], finish=b"stop"))
+    assert chat["object"] == "chat.completion" and chat["choices"][0]["message"] == {"role": "assistant", "content": "ab"}
+    assert chat["choices"][0]["finish_reason"] == "stop"
+    assert G.extract_usage_from_response(chat) == {"input_tokens": 7, "output_tokens": 2, "total_tokens": 9}
+    resp = json.loads(_frame(H, 3, ["x", "y", "z"]))
+    # shape of llmlb/tests/integration/responses_api_test.rs:58-82
+    assert resp["object"] == "response" and resp["output"][0]["content"][0] == {"type": "output_text", "text": "xyz"}
+    assert G.extract_usage_from_response(resp) == {"input_tokens": 7, "output_tokens": 3, "total_tokens": 10}
+    comp = json.loads(_frame(H, 4, ["t"]))
+    assert comp["choices"][0]["text"] == "t" and comp["usage"]["completion_tokens"] == 1
+
+
+def test_json_roundtrip(H):
+    for doc in [{"a": [1, 2.5, -3, True, None, "x\n\"\\é😀"], "b": {"c": {}}, "d": []}, [1e20, 0, -0.5], "s", 12345678901234]:
+        out = C.create_string_buffer(4096)
+        n = H.llmlb_json_roundtrip(json.dumps(doc).encode(), out, 4096)
+        assert n and json.loads(out.value) == doc
+    out = C.create_string_buffer(64)
+    for bad in [b"{", b"[1,]", b'{"a":}', b"nul", b'"\\x"', b"1 2"]:
+        assert H.llmlb_json_roundtrip(bad, out, 64) == 0

@@ -1,0 +1,141 @@
+"""-m gpu: the HTTP shim (llmlb_b200_server) that exposes the engine behind the endpoint
+contract llmlb consumes.  The gateway's own accounting (oracle restatement of
+llmlb/src/token/mod.rs + api/proxy.rs) is run over the bytes the server produces."""
+import http.client
+import json
+import os
+import socket
+import subprocess
+import time
+
+import pytest
+
+from oracle import gateway_ref as G
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(os.path.dirname(HERE), "llmlb_b200", "llmlb_b200_server")
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+@pytest.fixture(scope="module")
+def server(built_lib):
+    from llmlb_b200 import build
+    build.build_host()
+    port = _free_port()
+    proc = subprocess.Popen([BIN, "--port", str(port), "--model", "tiny", "--model-id", "tiny-llama",
+                             "--max-seqs", "8", "--max-ctx", "512"], stderr=subprocess.PIPE)
+    deadline = time.time() + 120
+    while time.time() < deadline:
+        try:
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=2); c.request("GET", "/v1/models"); c.getresponse().read(); c.close()
+            break
+        except OSError:
+            assert proc.poll() is None, proc.stderr.read().decode()
+            time.sleep(0.2)
+    yield port
+    proc.terminate()
+    proc.wait(timeout=20)
+
+
+def call(port, method, path, body=None, headers=None):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=60)
+    c.request(method, path, json.dumps(body) if body is not None else None,
+              {"Content-Type": "application/json", **(headers or {})})
+    r = c.getresponse()
+    data = r.read()
+    c.close()
+    return r.status, dict(r.getheaders()), data
+
+
+def test_probe_endpoints(server):
+    st, _, d = call(server, "GET", "/v1/models")
+    assert st == 200 and json.loads(d)["data"][0]["id"] == "tiny-llama"          # sync/parser.rs:78-110
+    st, _, d = call(server, "GET", "/api/system")
+    assert st == 200 and "xllm_version" in json.loads(d)                          # detection/xllm.rs:27-66
+    st, _, d = call(server, "GET", "/api/health")
+    h = json.loads(d)
+    assert st == 200 and h["gpu"]["device_count"] == 1 and "active_requests" in h["load"]
+    st, _, d = call(server, "GET", "/api/models/tiny-llama/info")
+    assert st == 200 and json.loads(d)["context_length"] == 512                   # metadata/xllm.rs:48-61
+
+
+def test_chat_completion_non_stream(server):
+    st, _, d = call(server, "POST", "/v1/chat/completions",
+                    {"model": "tiny-llama", "messages": [{"role": "user", "content": "Hi"}], "max_tokens": 9, "temperature": 0, "ignore_eos": True})
+    j = json.loads(d)
+    assert st == 200 and j["object"] == "chat.completion" and j["choices"][0]["message"]["role"] == "assistant"
+    assert G.extract_usage_from_response(j)["output_tokens"] == 9 and j["choices"][0]["finish_reason"] == "length"
+
+
+def test_chat_completion_stream_accounting(server):
+    body = {"model": "tiny-llama", "messages": [{"role": "user", "content": "stream please"}], "max_tokens": 12,
+            "temperature": 0, "stream": True, "stream_options": {"include_usage": True}, "ignore_eos": True}
+    st, hdr, d = call(server, "POST", "/v1/chat/completions", body)
+    assert st == 200 and hdr["Content-Type"].startswith("text/event-stream")
+    text = d.decode()
+    assert text.startswith("data: ") and text.rstrip().endswith("data: [DONE]")
+    acc = G.StreamingTokenAccumulator("tiny-llama")
+    assert G.process_sse_lines(text, acc) == "" and acc.done
+    u = acc.finalize()
+    assert u["output_tokens"] == 12 and u["total_tokens"] == u["input_tokens"] + 12
+    # greedy stream == greedy non-stream
+    st, _, d2 = call(server, "POST", "/v1/chat/completions", {**body, "stream": False})
+    assert json.loads(d2)["choices"][0]["message"]["content"] == acc.accumulated_content
+
+
+def test_responses_stream_and_body(server):
+    body = {"model": "tiny-llama", "input": "hello", "max_output_tokens": 6, "temperature": 0, "stream": True, "ignore_eos": True}
+    st, _, d = call(server, "POST", "/v1/responses", body)
+    events = [json.loads(e[6:]) for e in d.decode().split("\n\n") if e.startswith("data: {")]
+    assert [e["type"] for e in events][:3] == ["response.created", "response.output_item.added", "response.content_part.added"]
+    assert events[-1]["type"] == "response.done" and events[-1]["response"]["usage"]["output_tokens"] == 6
+    st, _, d = call(server, "POST", "/v1/responses", {**body, "stream": False})
+    j = json.loads(d)
+    assert st == 200 and j["object"] == "response" and j["usage"]["output_tokens"] == 6
+
+
+def test_prompt_token_ids_and_completions(server):
+    st, _, d = call(server, "POST", "/v1/completions", {"model": "tiny-llama", "prompt_token_ids": list(range(5, 45)), "max_tokens": 5, "temperature": 0, "ignore_eos": True})
+    j = json.loads(d)
+    assert st == 200 and j["usage"]["prompt_tokens"] == 40 and j["usage"]["completion_tokens"] == 5
+
+
+def test_errors(server):
+    st, _, d = call(server, "POST", "/v1/chat/completions", {"model": "nope", "messages": []})
+    assert st == 404 and json.loads(d)["error"]["code"] == 404                      # openai.rs:813-817
+    st, _, d = call(server, "POST", "/v1/chat/completions", {"messages": []})
+    assert st == 400
+    st, _, d = call(server, "POST", "/v1/chat/completions", {"model": "a:b:c", "messages": []})
+    assert st == 400 and "quantization format" in json.loads(d)["error"]["message"]
+    st, _, d = call(server, "POST", "/v1/chat/completions", {"model": "tiny-llama", "messages": [{"role": "user", "content": [{"type": "image_url", "image_url": {"url": "x"}}]}]})
+    assert st == 400
+    st, _, _ = call(server, "GET", "/nothing")
+    assert st == 404
+
+
+def test_drain_gate(server):
+    call(server, "POST", "/admin/drain", True)
+    st, hdr, d = call(server, "POST", "/v1/chat/completions", {"model": "tiny-llama", "messages": [], "max_tokens": 2})
+    call(server, "POST", "/admin/drain", False)
+    assert st == 503 and hdr.get("Retry-After") == "30"                              # inference_gate.rs:177-197
+    assert json.loads(d) == G.gate_rejection()[2]
+
+
+def test_concurrent_streams(server):
+    import threading
+    outs = [None] * 12
+
+    def run(i):
+        st, _, d = call(server, "POST", "/v1/responses", {"model": "tiny-llama", "prompt_token_ids": list(range(3 + i, 60 + 3 * i)),
+                                                           "max_output_tokens": 16, "temperature": 0, "stream": True, "ignore_eos": True})
+        acc = G.StreamingTokenAccumulator("m")
+        G.process_sse_lines(d.decode(), acc)
+        outs[i] = (st, acc.finalize()["output_tokens"], acc.done)
+    th = [threading.Thread(target=run, args=(i,)) for i in range(12)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert all(o == (200, 16, True) for o in outs), outs
