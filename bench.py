@@ -112,8 +112,8 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, verb
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     t0 = time.time()
-    sd = synth_native.synth_state_dict_bf16(model, seed=0)
-    ref = LlamaRef(model, sd, weight_dtype=torch.bfloat16)
+    sd = synth_native.synth_state_dict_bits(model, seed=0)
+    ref = LlamaRef(model, sd)
     t_load = time.time() - t0
     dec_tok = dec_s = pre_tok = pre_s = 0.0
     for it in range(warmup + steps):
@@ -132,7 +132,7 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, verb
             dec_tok += sample_gen; dec_s += c - b
     return {"decode_tok_s": dec_tok / dec_s, "prefill_tok_s": pre_tok / pre_s, "cores": cores,
             "weights_s": t_load, "ms_per_step": 1e3 * (pre_s + dec_s) / max(1, steps),
-            "sample": "%d prompt + %d decoded tokens per step, full Llama-3-8B geometry, bf16 weights, torch CPU matmul, %d threads" % (sample_prompt, sample_gen, cores)}
+            "sample": "%d prompt + %d decoded tokens per step, full Llama-3-8B geometry, bf16 weights, C/OpenMP fp32-accumulate linears (oracle/llama_cpu.c), %d threads" % (sample_prompt, sample_gen, cores)}
 
 
 def run_reference(args):
@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-prompt", type=int, default=32)
-    ap.add_argument("--cpu-gen", type=int, default=4)
+    ap.add_argument("--cpu-gen", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -35,8 +35,13 @@ class LlamaRef:
         self.wd = weight_dtype
         if threads:
             torch.set_num_threads(threads)
-        self.w = {k: (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v)
-                  .to(weight_dtype) for k, v in state_dict.items()}
+        self.w = {}
+        for k, v in state_dict.items():
+            if getattr(v, "dtype", None) == "bf16_bits":   # oracle.synth_native.Bf16Weight: C kernel path
+                self.w[k] = v
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v
+                self.w[k] = t.to(weight_dtype)
         hd = cfg["head_dim"]
         self.inv_freq = 1.0 / (cfg["rope_theta"] ** (torch.arange(0, hd, 2, dtype=torch.float64) / hd))
         self.reset()
@@ -54,7 +59,9 @@ class LlamaRef:
         return _bf16_round(y) if self.emulate else y
 
     def _mm(self, x, w):
-        # weights may be held in bf16 (CPU-baseline timing mode); accumulate in that dtype's matmul
+        if getattr(w, "dtype", None) == "bf16_bits":  # CPU-baseline mode: bf16 weights, C/OpenMP GEMV
+            from .synth_native import linear_bf16
+            return torch.from_numpy(linear_bf16(w.bits, x.numpy()))
         if w.dtype == torch.float32:
             return x @ w.t()
         return (x.to(w.dtype) @ w.t()).to(torch.float32)
@@ -75,7 +82,12 @@ class LlamaRef:
         ids = torch.as_tensor(ids, dtype=torch.long)
         T = ids.numel()
         positions = torch.arange(self.pos, self.pos + T)
-        x = self.w["model.embed_tokens.weight"][ids].to(torch.float32)
+        emb = self.w["model.embed_tokens.weight"]
+        if getattr(emb, "dtype", None) == "bf16_bits":
+            from .synth import bf16_bits_to_f32
+            x = torch.from_numpy(bf16_bits_to_f32(emb.bits[ids.numpy()]).copy())
+        else:
+            x = emb[ids].to(torch.float32)
         for l in range(c["n_layers"]):
             p = "model.layers.%d." % l
             y = self._norm(x, self.w[p + "input_layernorm.weight"])

@@ -17,6 +17,31 @@ def build():
     return LIB
 
 
+CPU_LIB = os.path.join(HERE, "liboracle_cpu.so")
+_cpu = None
+
+
+def build_cpu():
+    src = os.path.join(HERE, "llama_cpu.c")
+    if not os.path.exists(CPU_LIB) or os.path.getmtime(CPU_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", src, "-o", CPU_LIB])
+    return CPU_LIB
+
+
+def linear_bf16(w_bits, x):
+    """y = x @ W^T with W as bf16 bit patterns (numpy uint16 [n, k]) and x fp32 [T, k]."""
+    global _cpu
+    if _cpu is None:
+        _cpu = C.CDLL(build_cpu())
+        _cpu.oracle_linear_bf16.restype = None
+        _cpu.oracle_linear_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, k = w_bits.shape
+    y = np.empty((x.shape[0], n), dtype=np.float32)
+    _cpu.oracle_linear_bf16(w_bits.ctypes.data, x.ctypes.data, y.ctypes.data, n, k, x.shape[0])
+    return y
+
+
 _lib = None
 
 
@@ -35,6 +60,35 @@ def synth_bits(seed, tensor_id, rows, cols, std=0.02, row0=0, col0=0, ld=None):
     _get().oracle_synth_bf16(out.ctypes.data, rows, cols, row0, col0, cols if ld is None else ld,
                              seed, tensor_id, std)
     return out
+
+
+class Bf16Weight:
+    """bf16 weight kept as its bit pattern; llama_ref._mm dispatches to the C kernel for it."""
+
+    def __init__(self, bits):
+        self.bits = bits
+        self.dtype = "bf16_bits"
+
+
+def synth_state_dict_bits(cfg, seed=0):
+    """HF-named weights for the CPU baseline: matmul weights as Bf16Weight, the rest fp32."""
+    import torch
+    from .synth import ID_EMBED, ID_LM_HEAD, KIND, bf16_bits_to_f32
+    H, nh, nkv, hd, F, V = (cfg["hidden"], cfg["n_heads"], cfg["n_kv_heads"], cfg["head_dim"],
+                            cfg["ffn"], cfg["vocab"])
+    sd = {"model.embed_tokens.weight": Bf16Weight(synth_bits(seed, ID_EMBED, V, H)),
+          "lm_head.weight": Bf16Weight(synth_bits(seed, ID_LM_HEAD, V, H)),
+          "model.norm.weight": torch.ones(H)}
+    shapes = {"self_attn.q_proj.weight": (nh * hd, H), "self_attn.k_proj.weight": (nkv * hd, H),
+              "self_attn.v_proj.weight": (nkv * hd, H), "self_attn.o_proj.weight": (H, nh * hd),
+              "mlp.gate_proj.weight": (F, H), "mlp.up_proj.weight": (F, H),
+              "mlp.down_proj.weight": (H, F)}
+    for l in range(cfg["n_layers"]):
+        for k, (r, c) in shapes.items():
+            sd["model.layers.%d.%s" % (l, k)] = Bf16Weight(synth_bits(seed, l * 16 + KIND[k], r, c))
+        sd["model.layers.%d.input_layernorm.weight" % l] = torch.ones(H)
+        sd["model.layers.%d.post_attention_layernorm.weight" % l] = torch.ones(H)
+    return sd
 
 
 def synth_state_dict_bf16(cfg, seed=0):
