@@ -202,7 +202,8 @@ class Json {
           if (p < end && *p == '}') { ++p; return true; }
           for (;;) {
             std::string k; ws(); if (!string(&k)) return false; ws();
-            if (p >= end || *p != ':') return false; ++p; ws();
+            if (p >= end || *p != ':') return false;
+            ++p; ws();
             Json v; if (!value(&v, depth + 1)) return false; out->set(k, std::move(v)); ws();
             if (p < end && *p == ',') { ++p; continue; }
             if (p < end && *p == '}') { ++p; return true; }
