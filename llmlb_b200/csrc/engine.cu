@@ -31,7 +31,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
                    uint32_t box_rows);
 uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
-                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
+                   const CUtensorMap* tx_half = nullptr);
 int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,
                     uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
 
@@ -480,7 +481,7 @@ int llmlb_engine::proj(const LayerW*, int, const void* w, const CUtensorMap& mw,
   if (T <= 4) return llmlb_op_gemv(w, xin, gain, M.rms_eps, out, T, n_out, k, epi, out_stride, st);
   // callers pass bf16 activations (already normalised) on this path
   if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, out, T, n_out, k, epi, out_stride, st);
-  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st);
+  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)]);
 }
 
 // Runs the layer stack over T rows already embedded in x.  decode: rows are one new token per
@@ -548,7 +549,7 @@ int llmlb_engine::logits_for_rows(uint32_t R, bool from_x_rows) {
     if (cfg.gemm_impl == 1)
       RC(gemm_mma_launch(lm_head, y, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
     else
-      RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
+      RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st, &m_y[bn_index(128)]));
   }
   if (tp > 1) RC(ar_allgather_cols(peers, 2, logits, R, vocab_l, st));
   return LLMLB_OK;

@@ -14,7 +14,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
                    uint32_t box_rows);
 uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
-                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
+                   const CUtensorMap* tx_half = nullptr);
 
 constexpr int kMT = 128, kMN = 128, kMK = 32, kMStages = 3, kMThreads = 256;
 
@@ -195,5 +196,8 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   if (rc) return rc;
   rc = make_tmap_bf16(&tx, x, n_tokens, k, tc_pick_bn(n_tokens));
   if (rc) return rc;
-  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st);
+  CUtensorMap txh;
+  rc = make_tmap_bf16(&txh, x, n_tokens, k, 128);
+  if (rc) return rc;
+  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh);
 }

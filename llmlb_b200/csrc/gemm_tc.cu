@@ -13,97 +13,13 @@
 // Split-K (residual epilogue only) uses fp32 red.global.add.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace llmlb {
-
-constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
-constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row
-constexpr int kTcThreads = 256;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
-                                            int32_t c0, int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
-      "{%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                       uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO),
-// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B), LBO unused (=1).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
-  d |= uint64_t(1) << 16;
-  d |= uint64_t(1024 >> 4) << 32;
-  d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
-  return d;
-}
 
 template <int BN>
 struct TcCfg {
@@ -175,12 +91,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      // L2 prefetch cursor: runs kPrefetchAhead K-slabs ahead of the smem loads (weights only —
+      // the activation operand is small and L2-resident).  The smem ring holds 3 slabs in flight
+      // (~1.5k MMA cycles); an HBM miss costs 3-4k, an L2 hit ~1k.
+      constexpr uint32_t kPrefetchAhead = 12;
+      uint32_t p_tile = blockIdx.x, p_kb = 0, p_kb1 = 0, p_mt = 0;
+      auto p_load = [&]() {
+        if (p_tile < n_tiles) {
+          uint32_t tt, ks;
+          decode_tile(p_tile, p_mt, tt, ks);
+          p_kb = ks * k_per_split;
+          p_kb1 = min(k_blocks_total, p_kb + k_per_split);
+        }
+      };
+      auto p_step = [&]() {
+        if (p_tile >= n_tiles) return;
+        tma_prefetch_l2_2d(&tmap_w, int32_t(p_kb * kBK), int32_t(p_mt * kBM));
+        if (++p_kb >= p_kb1) { p_tile += gridDim.x; p_load(); }
+      };
+      p_load();
+      for (uint32_t i = 0; i < kPrefetchAhead; ++i) p_step();
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t mt, tt, ks;
         decode_tile(tile, mt, tt, ks);
         const uint32_t kb0 = ks * k_per_split;
         const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
         for (uint32_t kb = kb0; kb < kb1; ++kb) {
+          p_step();
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kBM * kBK * 2;
@@ -381,10 +318,18 @@ uint32_t tc_pick_bn(uint32_t n_tokens) {
 
 // Launch with prebuilt tensor maps (the engine caches them: weights never move, activation
 // buffers are fixed).  The X map's box rows must equal tc_pick_bn(n_tokens).
+int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens,
+                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+
+// tx_half (optional): the activation map with a 128-row box; when given and the step is wide
+// enough for 256-token tiles the CTA-pair kernel (gemm_tc2.cu) runs instead.
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
-                   cudaStream_t st) {
+                   cudaStream_t st, const CUtensorMap* tx_half) {
   const uint32_t bn = tc_pick_bn(n_tokens);
+  static const bool no_2cta = getenv("LLMLB_GEMM_NO_2CTA") != nullptr;
+  if (tx_half && bn == 256 && n_out >= 256 && !no_2cta)
+    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st);
   // split K for the residual epilogue when the tile count cannot fill the GPU
   uint32_t split_k = 1;
   if (epi == LLMLB_EPI_RESID_F32) {

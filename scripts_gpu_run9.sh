@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 300 python -m pytest -q -x --timeout 60 -p no:cacheprovider tests/test_ops_gpu.py -k "test_gemm and tc" > gpurun_out/t1_ops.log 2>&1; echo "gemm_tc rc=$?" > gpurun_out/summary.txt
+timeout 300 python -m pytest -q --timeout 120 -p no:cacheprovider tests/test_engine_gpu.py -k "tcgen05" > gpurun_out/t2_engine.log 2>&1; echo "engine rc=$?" >> gpurun_out/summary.txt
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/summary.txt
+LLMLB_GEMM_NO_2CTA=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/bench_1cta.json 2> gpurun_out/bench_1cta.err; echo "bench 1cta rc=$?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt; tail -n 15 gpurun_out/t1_ops.log; tail -n 5 gpurun_out/t2_engine.log
+python - <<'PY'
+import json
+for f in ['bench','bench_1cta']:
+    try:
+        d=json.load(open('gpurun_out/%s.json'%f))
+        print(f,'decode',round(d['value'],1),'prefill',round(d['prefill']['value']),'pf frac',round(d['prefill']['roofline']['frac'],3))
+    except Exception as e: print(f,'ERR',e)
+PY
+tail -n 3 gpurun_out/bench.err
