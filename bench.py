@@ -109,12 +109,25 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, verb
     import torch
     from oracle import synth_native
     from oracle.llama_ref import LlamaRef
-    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    cores = synth_native.effective_cpus()
     torch.set_num_threads(cores)
+    synth_native.set_threads(cores)
     t0 = time.time()
     sd = synth_native.synth_state_dict_bits(model, seed=0)
     ref = LlamaRef(model, sd)
     t_load = time.time() - t0
+    # probe one lm_head-sized GEMV and shrink the sample if this host is slow, so the run stays
+    # inside its time box (~30 s of CPU work per step) whatever the core quota is
+    import numpy as np
+    probe_w = sd["lm_head.weight"].bits
+    px = np.zeros((1, probe_w.shape[1]), dtype=np.float32)
+    synth_native.linear_bf16(probe_w, px)
+    tp0 = time.time(); synth_native.linear_bf16(probe_w, px); probe = time.time() - tp0
+    est_token_s = probe * (algorithmic_bytes_per_decode_step(model, 0, 0) / (probe_w.size * 2.0))
+    if est_token_s * (sample_prompt / 4.0 + sample_gen) > 30.0:
+        sample_gen = max(1, min(sample_gen, int(10.0 / max(est_token_s, 1e-3))))
+        sample_prompt = max(4, min(sample_prompt, int(4 * 15.0 / max(est_token_s, 1e-3))))
     dec_tok = dec_s = pre_tok = pre_s = 0.0
     for it in range(warmup + steps):
         prompt = make_prompt(it, model["vocab"], sample_prompt)
@@ -207,8 +220,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     tp = world
     dist = None
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # NCCL prints its version banner on stdout at communicator creation: keep fd 1 clean for
+        # the ONE JSON line by pointing it at stderr until the wiring collectives are done
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -222,6 +240,10 @@ def run_ours(args):
         dist.all_gather_object(handles, eng.tp_export())
         eng.tp_import(handles)
         dist.barrier()
+        t = torch.zeros(1, device="cuda"); dist.all_reduce(t); torch.cuda.synchronize()  # create the NCCL communicator now
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     def one_step(i):
         """One request per stream in the batch; returns per-request event lists."""
@@ -255,12 +277,15 @@ def run_ours(args):
     t0 = time.perf_counter()
     first_to_last_ms, n_dec_tokens, req_tps = 0.0, 0, []
     for i in range(args.steps):
+        lo, hi = [], []
         for ev in one_step(i):
             toks = [e for e in ev if e["token_id"] >= 0]
             assert len(toks) == GEN, "request produced %d tokens" % len(toks)
-            first_to_last_ms += toks[-1]["t_ms"] - toks[0]["t_ms"]
+            lo.append(toks[0]["t_ms"]); hi.append(toks[-1]["t_ms"])
             n_dec_tokens += len(toks) - 1
             req_tps.append(len(toks) / (toks[-1]["t_ms"] / 1e3))
+        # all streams of a step are submitted together: decode phase = first first-token .. last last-token
+        first_to_last_ms += max(hi) - min(lo)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None

@@ -5,6 +5,7 @@
  *   gcc -O3 -march=native -fopenmp -shared -fPIC oracle/llama_cpu.c -o oracle/liboracle_cpu.so
  *
  *   y[t, n] = sum_k x[t, k] * W[n, k]      W bf16 [n_out, k] row-major, x/y fp32, T <= 64     */
+#include <omp.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -16,6 +17,8 @@ static inline float bf16_to_f32(uint16_t v) {
   memcpy(&f, &u, 4);
   return f;
 }
+
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 void oracle_linear_bf16(const uint16_t* W, const float* X, float* Y, int64_t n_out, int64_t k,
                         int64_t T) {

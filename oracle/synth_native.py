@@ -28,6 +28,33 @@ def build_cpu():
     return CPU_LIB
 
 
+def effective_cpus():
+    """Cores this process may actually use: affinity mask and cgroup CPU quota (a container can
+    report 128 CPUs while being throttled to a fraction; spinning OpenMP threads then thrash)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def set_threads(n):
+    global _cpu
+    if _cpu is None:
+        linear_bf16(np.zeros((1, 8), dtype=np.uint16), np.zeros((1, 8), dtype=np.float32))
+    _cpu.oracle_set_threads(int(n))
+
+
 def linear_bf16(w_bits, x):
     """y = x @ W^T with W as bf16 bit patterns (numpy uint16 [n, k]) and x fp32 [T, k]."""
     global _cpu
@@ -35,6 +62,8 @@ def linear_bf16(w_bits, x):
         _cpu = C.CDLL(build_cpu())
         _cpu.oracle_linear_bf16.restype = None
         _cpu.oracle_linear_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+        _cpu.oracle_set_threads.restype = None
+        _cpu.oracle_set_threads.argtypes = [C.c_int]
     x = np.ascontiguousarray(x, dtype=np.float32)
     n, k = w_bits.shape
     y = np.empty((x.shape[0], n), dtype=np.float32)
