@@ -318,6 +318,9 @@ prefill_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
 constexpr int kDecHeads = 4;     // q heads per CTA (all share one kv head)
 constexpr int kDecThreads = 128;
 
+static __device__ TraceBuf d_trace_attn;
+void attn_set_trace(const TraceBuf& tb) { cudaMemcpyToSymbol(d_trace_attn, &tb, sizeof(tb)); }
+
 struct DecPartial {               // per-CTA result, read by the cluster leader
   float o[kDecHeads][kHeadDim];
   float m[kDecHeads];
@@ -332,10 +335,14 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
                         const float2* __restrict__ rope, __nv_bfloat16* __restrict__ out,
                         uint32_t n_heads, uint32_t n_kv, uint32_t n_splits) {
   __shared__ float q_s[kDecHeads][kHeadDim];
+  __shared__ float kv_new[2][kHeadDim];  // rotated k and v of the new token (owner CTA only)
   __shared__ float mrg_o[4][kDecHeads][kHeadDim];
   __shared__ float mrg_ml[4][kDecHeads][2];
   __shared__ DecPartial part;
 
+  const TraceBuf tb = d_trace_attn;
+  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+  if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
   // PDL: the O-projection GEMV that follows may start prefetching its weights now
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t z = blockIdx.x, hb = blockIdx.y, s = blockIdx.z;
@@ -354,15 +361,32 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   const uint32_t p_end = min(n_pages, p_begin + pages_per_split);
   const uint32_t t_begin = p_begin * kPageTokens;
   const uint32_t t_end = min(uint32_t(L), p_end * kPageTokens);
-  // first page id of this split: fetch early (the K/V addresses depend on it)
+  // ---- before the dependency wait: everything that does not read this step's qkv ----
+  // (seq_lens / block tables were written at the start of the step; old K/V long before)
+  const uint32_t grp = lane >> 3, sub = lane & 7;
   int32_t page_next = (p_begin < p_end) ? bt[p_begin] : 0;
+  uint4 kq[4][2], vq[4][2];
+  auto load_page = [&](int32_t page) {
+    const size_t pbase = (size_t(page) * n_kv + kvh) * kPageTokens * kHeadDim + sub * 16;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const size_t off = pbase + size_t(r * 16 + warp * 4 + grp) * kHeadDim;
+      kq[r][0] = *reinterpret_cast<const uint4*>(k_pages + off);
+      kq[r][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
+      vq[r][0] = *reinterpret_cast<const uint4*>(v_pages + off);
+      vq[r][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
+    }
+  };
+  if (p_begin < p_end) load_page(page_next);   // 16 x 16-byte loads per lane in flight
+  const float2 cs_lane0 = cs[tid & 63];        // rope row of the new position
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // rotate q (4 heads x 64 pairs = 256 pairs over 128 threads), pre-scaled for exp2
   const float scale = rsqrtf(float(kHeadDim)) * kLog2e;
 #pragma unroll
   for (uint32_t p = tid; p < kDecHeads * 64; p += kDecThreads) {
     uint32_t h = p / 64, i = p % 64;
-    float2 c = cs[i];
+    float2 c = cs_lane0;  // p % 64 == tid % 64 for both trips (128 threads, stride 128)
     const __nv_bfloat16* hp = row + size_t(h0 + h) * kHeadDim;
     float a = __bfloat162float(hp[i]), b = __bfloat162float(hp[i + 64]);
     // round through bf16 like the prefill path (q is stored as bf16 there)
@@ -371,8 +395,10 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     q_s[h][i] = ra * scale;
     q_s[h][i + 64] = rb * scale;
   }
-  // the CTA whose range holds the new position rotates k and appends k,v
-  if (t_begin <= pos && pos < t_end) {
+  // the CTA whose range holds the new position rotates k and appends k,v; the values it uses
+  // for that token come from shared memory (the page was prefetched before they existed)
+  const bool owns_new = (t_begin <= pos && pos < t_end);
+  if (owns_new) {
     const int32_t page = bt[pos / kPageTokens];
     const uint32_t slot = pos % kPageTokens;
     __nv_bfloat16* kd = k_pages + ((size_t(page) * n_kv + kvh) * kPageTokens + slot) * kHeadDim;
@@ -380,21 +406,22 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     const __nv_bfloat16* kp = row + size_t(n_heads + kvh) * kHeadDim;
     const __nv_bfloat16* vp = row + size_t(n_heads + n_kv + kvh) * kHeadDim;
     if (tid < 64) {
-      float2 c = cs[tid];
+      float2 c = cs_lane0;
       float a = __bfloat162float(kp[tid]), b = __bfloat162float(kp[tid + 64]);
-      kd[tid] = __float2bfloat16_rn(a * c.x - b * c.y);
-      kd[tid + 64] = __float2bfloat16_rn(b * c.x + a * c.y);
+      __nv_bfloat16 ra = __float2bfloat16_rn(a * c.x - b * c.y), rb = __float2bfloat16_rn(b * c.x + a * c.y);
+      kd[tid] = ra; kd[tid + 64] = rb;
+      kv_new[0][tid] = __bfloat162float(ra); kv_new[0][tid + 64] = __bfloat162float(rb);
     } else {
       uint32_t i = tid - 64;
-      vd[i] = vp[i];
-      vd[i + 64] = vp[i + 64];
+      __nv_bfloat16 v0 = vp[i], v1 = vp[i + 64];
+      vd[i] = v0; vd[i + 64] = v1;
+      kv_new[1][i] = __bfloat162float(v0); kv_new[1][i + 64] = __bfloat162float(v1);
     }
-    __threadfence_block();
   }
   __syncthreads();
+  if (tb.data && threadIdx.x == 0) tr1 = gtime_ns();
 
   // each 8-lane group walks its own token stream; lane owns 16 dims
-  const uint32_t grp = lane >> 3, sub = lane & 7;
   float q_r[kDecHeads][16];
 #pragma unroll
   for (int h = 0; h < kDecHeads; ++h)
@@ -411,26 +438,17 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   }
 
   for (uint32_t pg = p_begin; pg < p_end; ++pg) {
-    const int32_t page = page_next;
+    if (pg != p_begin) load_page(page_next);          // first page is already in registers
     if (pg + 1 < p_end) page_next = bt[pg + 1];
-    const size_t pbase = (size_t(page) * n_kv + kvh) * kPageTokens * kHeadDim + sub * 16;
-    // one page = 64 tokens = 4 rounds of 16; all 16 loads of this lane issued before use
-    uint4 kq[4][2], vq[4][2];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t tin = r * 16 + warp * 4 + grp;  // token within page
-      const size_t off = pbase + size_t(tin) * kHeadDim;
-      kq[r][0] = *reinterpret_cast<const uint4*>(k_pages + off);
-      kq[r][1] = *reinterpret_cast<const uint4*>(k_pages + off + 8);
-      vq[r][0] = *reinterpret_cast<const uint4*>(v_pages + off);
-      vq[r][1] = *reinterpret_cast<const uint4*>(v_pages + off + 8);
-    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const uint32_t tok = pg * kPageTokens + r * 16 + warp * 4 + grp;
       const bool valid = tok < t_end;
       float kf[16], vf[16];
-      {
+      if (tok == pos) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) { kf[d] = kv_new[0][sub * 16 + d]; vf[d] = kv_new[1][sub * 16 + d]; }
+      } else {
         const uint32_t kw[8] = {kq[r][0].x, kq[r][0].y, kq[r][0].z, kq[r][0].w,
                                 kq[r][1].x, kq[r][1].y, kq[r][1].z, kq[r][1].w};
         const uint32_t vw[8] = {vq[r][0].x, vq[r][0].y, vq[r][0].z, vq[r][0].w,
@@ -462,6 +480,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     }
   }
 
+  if (tb.data && threadIdx.x == 0) tr2 = gtime_ns();
   // merge the 4 token groups of the warp (lanes with equal `sub`)
 #pragma unroll
   for (int h = 0; h < kDecHeads; ++h) {
@@ -522,12 +541,12 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (z == 0) {
-    // all DSMEM loads are issued before any is consumed (8 ranks max): one latency, not 24
+    // all DSMEM loads are issued before any is consumed (16 ranks max): one latency, not 48
     const uint32_t my = smem_addr_u32(&part);
-    float pm[8], pl[8];
-    float4 po[8];
+    float pm[16], pl[16];
+    float4 po[16];
 #pragma unroll
-    for (uint32_t r = 0; r < 8; ++r) {
+    for (uint32_t r = 0; r < 16; ++r) {
       if (r < n_splits) {
         pm[r] = ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r);
         pl[r] = ld_dsmem_f32(my + offsetof(DecPartial, l) + h * 4, r);
@@ -538,10 +557,10 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     }
     float gm = -INFINITY;
 #pragma unroll
-    for (uint32_t r = 0; r < 8; ++r) gm = fmaxf(gm, pm[r]);
+    for (uint32_t r = 0; r < 16; ++r) gm = fmaxf(gm, pm[r]);
     float gl = 0.f, go[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (uint32_t r = 0; r < 8; ++r) {
+    for (uint32_t r = 0; r < 16; ++r) {
       const float c = (pm[r] == -INFINITY) ? 0.f : exp2f(pm[r] - gm);
       gl += pl[r] * c;
       go[0] += po[r].x * c; go[1] += po[r].y * c; go[2] += po[r].z * c; go[3] += po[r].w * c;
@@ -555,6 +574,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   // peers must keep their shared memory alive until the leader has read it
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tb.data && threadIdx.x == 0) trace_emit(tb, 1ull, tr0, tr1, tr2, gtime_ns());
 }
 
 }  // namespace llmlb
@@ -619,12 +639,15 @@ extern "C" size_t llmlb_op_decode_attention_ws(uint32_t, uint32_t, uint32_t) {
   return 256;  // kept for ABI stability: the split merge now happens in cluster shared memory
 }
 
-extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v_pages,
-                                         const int32_t* block_tables, uint32_t bt_stride,
-                                         const int32_t* bt_rows, const int32_t* seq_lens,
-                                         uint32_t n_seqs, void* out, uint32_t n_heads,
-                                         uint32_t n_kv, const float* rope_table,
-                                         uint32_t n_splits, uint32_t, void*, void* stream) {
+namespace llmlb {
+// pdl: launch with programmatic stream serialization (the kernel prefetches its first K/V page
+// and then waits on the producer of qkv).  Only safe when everything the prologue reads
+// (seq_lens, block tables, old K/V) was written by kernels that are already complete: the engine
+// uses it for layers >= 1 of a decode step.
+int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const int32_t* block_tables,
+                            uint32_t bt_stride, const int32_t* bt_rows, const int32_t* seq_lens, uint32_t n_seqs,
+                            void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
+                            bool pdl, cudaStream_t st) {
   if (!qkv || !k_pages || !v_pages || !block_tables || !seq_lens || !out || !rope_table ||
       n_kv == 0 || n_heads % n_kv || n_heads % kDecHeads || (n_heads / n_kv) % kDecHeads ||
       n_splits == 0) {
@@ -632,24 +655,43 @@ extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v
     return LLMLB_E_INVALID_ARG;
   }
   if (n_seqs == 0) return LLMLB_OK;
-  // splits form a cluster: round down to a portable cluster size
-  uint32_t sp = n_splits >= 8 ? 8 : n_splits >= 4 ? 4 : n_splits >= 2 ? 2 : 1;
+  static bool configured = false, allow16 = false;
+  if (!configured) {
+    allow16 = cudaFuncSetAttribute(decode_attention_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+    configured = true;
+  }
+  // splits form a cluster: round down to a supported cluster size
+  uint32_t sp = (n_splits >= 16 && allow16) ? 16 : n_splits >= 8 ? 8 : n_splits >= 4 ? 4 : n_splits >= 2 ? 2 : 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sp, n_heads / kDecHeads, n_seqs);
   cfg.blockDim = dim3(kDecThreads);
   cfg.dynamicSmemBytes = 0;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = sp;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(
       &cfg, decode_attention_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages,
       (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows, seq_lens,
       (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, sp));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
+}
+}  // namespace llmlb
+
+extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v_pages,
+                                         const int32_t* block_tables, uint32_t bt_stride,
+                                         const int32_t* bt_rows, const int32_t* seq_lens,
+                                         uint32_t n_seqs, void* out, uint32_t n_heads,
+                                         uint32_t n_kv, const float* rope_table,
+                                         uint32_t n_splits, uint32_t, void*, void* stream) {
+  return decode_attention_launch(qkv, k_pages, v_pages, block_tables, bt_stride, bt_rows, seq_lens, n_seqs, out,
+                                 n_heads, n_kv, rope_table, n_splits, false, (cudaStream_t)stream);
 }

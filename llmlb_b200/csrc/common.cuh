@@ -53,7 +53,31 @@ __host__ __device__ __forceinline__ float synth_value(uint64_t seed, uint32_t te
   return float(s) * scale;
 }
 
+// ---- optional in-kernel timeline (debug): thread 0 of a CTA appends one record ----
+struct TraceBuf {
+  unsigned long long* data;  // records of 6 u64: tag, blockIdx|smid<<32, t0..t3 (globaltimer ns)
+  unsigned int* count;
+  unsigned int cap;
+};
+
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_emit(const TraceBuf& tb, unsigned long long tag, unsigned long long t0,
+                                           unsigned long long t1, unsigned long long t2, unsigned long long t3) {
+  if (!tb.data) return;
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  unsigned int i = atomicAdd(tb.count, 1u);
+  if (i < tb.cap) {
+    unsigned long long* r = tb.data + size_t(i) * 6;
+    r[0] = tag; r[1] = (unsigned long long)blockIdx.x | ((unsigned long long)smid << 32) | ((unsigned long long)blockIdx.y << 16);
+    r[2] = t0; r[3] = t1; r[4] = t2; r[5] = t3;
+  }
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -35,6 +36,19 @@ int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint
                    const CUtensorMap* tx_half = nullptr);
 int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,
                     uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+
+int gemv_decode(const void* w, const void* x, const void* gain, float eps, void* out, uint32_t n_tokens,
+                uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
+                const void* next_w, size_t next_bytes);
+int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const int32_t* block_tables,
+                            uint32_t bt_stride, const int32_t* bt_rows, const int32_t* seq_lens, uint32_t n_seqs,
+                            void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
+                            bool pdl, cudaStream_t st);
+void ks_set_trace(const TraceBuf& tb);
+void attn_set_trace(const TraceBuf& tb);
+struct ChainOpHost { const void* w; const void* x; const void* gain; void* out; uint32_t n_out, k, out_stride, epi; };
+bool gemv_chain_shape_ok(uint32_t n_out, uint32_t k);
+int gemv_chain_launch(const ChainOpHost* ops, uint32_t n_ops, float eps, uint32_t* state, cudaStream_t st);
 
 constexpr int kArMaxRanks = 8;
 struct ArPeers {
@@ -234,6 +248,9 @@ struct llmlb_engine {
   std::unordered_map<uint32_t, uint64_t> graph_nodes;  // kernels per captured step
   bool paused = false;
   std::string fatal_error;
+  size_t pf_head_bytes = 0;  // LLMLB_PF_MB: next-projection bytes prefetched into L2 per tail (measured: 0 best)
+  uint32_t* chain_state = nullptr;  // [n_layers][8] barrier counters of the decode GEMV chains
+  bool use_chain = false;
   int warmup();
   std::vector<int32_t> cur_batch_slots;  // what d B.slots currently holds
 
@@ -268,7 +285,8 @@ struct llmlb_engine {
            uint32_t k, uint32_t epi, uint32_t out_stride);
   int layer_stack_decode(uint32_t nb);
   int launch_decode_step(uint32_t nb);
-  int forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles);
+  int forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, bool* logits_done = nullptr);
+  int forward_decode_chain(bool* logits_done);
   int logits_for_rows(uint32_t R, bool from_x_rows);
   int run_prefill(const std::vector<ReqPtr>& reqs, const std::vector<uint32_t>& take);
   int run_decode(const std::vector<ReqPtr>& batch);
@@ -422,6 +440,14 @@ int llmlb_engine::alloc_all() {
     LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_stage[i], stage_bytes, cudaHostAllocDefault));
     LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_out[i], ms * 4, cudaHostAllocDefault));
   }
+  RC(dmalloc(&chain_state, size_t(M.n_layers) * 8));
+  {
+    if (const char* pm = getenv("LLMLB_PF_MB")) pf_head_bytes = size_t(atoi(pm)) << 20;
+    const char* ev = getenv("LLMLB_DECODE_CHAIN");
+    const bool want = ev && ev[0] == '1';  // measured round 1: 211 tok/s chained vs 351 unchained -> opt-in
+    use_chain = want && tp == 1 && gemv_chain_shape_ok(H, nq_l * kHeadDim) && gemv_chain_shape_ok(2 * ffn_l, H) &&
+                gemv_chain_shape_ok(H, ffn_l) && gemv_chain_shape_ok(qkv_w, H) && gemv_chain_shape_ok(vocab_l, H);
+  }
   if (tp > 1) {
     size_t slot = std::max(size_t(t_cap) * H * 4, size_t(cfg.max_seqs) * vocab_l * 4);
     slot = (slot + 255) & ~size_t(255);
@@ -486,30 +512,59 @@ int llmlb_engine::proj(const LayerW*, int, const void* w, const CUtensorMap& mw,
 
 // Runs the layer stack over T rows already embedded in x.  decode: rows are one new token per
 // sequence (nb of them); else rows are prefill tokens described by d_pos/d_page_of_tok/d_tiles.
-int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles) {
+// Batch-1 decode: QKV(0) alone, then per layer [attention] + one persistent chain kernel running
+// O-proj -> gate/up -> down -> next layer's QKV (or the lm_head after the last layer).
+int llmlb_engine::forward_decode_chain(bool* logits_done) {
+  const uint32_t H = M.hidden, ko = nq_l * kHeadDim;
+  RC(llmlb_op_gemv(layers[0].wqkv, x, layers[0].attn_norm, M.rms_eps, qkv, 1, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st));
+  for (uint32_t l = 0; l < M.n_layers; ++l) {
+    LayerW& L = layers[l];
+    RC(llmlb_op_decode_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, 1,
+                                 attn, nq_l, nkv_l, rope, decode_splits(1), cfg.max_seqs, attn_ws, st));
+    ChainOpHost ops[4];
+    ops[0] = {L.wo, attn, nullptr, x, H, ko, H, LLMLB_EPI_RESID_F32};
+    ops[1] = {L.wgu, x, L.ffn_norm, h, 2 * ffn_l, H, ffn_l, LLMLB_EPI_SILU_MUL};
+    ops[2] = {L.wdown, h, nullptr, x, H, ffn_l, H, LLMLB_EPI_RESID_F32};
+    if (l + 1 < M.n_layers) ops[3] = {layers[l + 1].wqkv, x, layers[l + 1].attn_norm, qkv, qkv_w, H, qkv_w, LLMLB_EPI_STORE_BF16};
+    else ops[3] = {lm_head, x, final_norm, logits, vocab_l, H, vocab_l, LLMLB_EPI_STORE_F32};
+    RC(gemv_chain_launch(ops, 4, M.rms_eps, chain_state + size_t(l) * 8, st));
+  }
+  *logits_done = true;
+  return LLMLB_OK;
+}
+
+int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, bool* logits_done) {
   const uint32_t H = M.hidden;
+  if (decode && T == 1 && use_chain && logits_done) return forward_decode_chain(logits_done);
   const bool small = T <= 4;
   uint32_t coll = 0;
   for (uint32_t l = 0; l < M.n_layers; ++l) {
     LayerW& L = layers[l];
     // --- attention block ---
+    const size_t kHead = pf_head_bytes;  // bytes of the next projection pulled into L2 at each tail
+    const uint32_t ko_ = nq_l * kHeadDim;
     if (small) {
-      RC(llmlb_op_gemv(L.wqkv, x, L.attn_norm, M.rms_eps, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st));
+      // QKV's tail prefetches ALL of O-proj: the attention kernel in between leaves HBM idle
+      RC(gemv_decode(L.wqkv, x, L.attn_norm, M.rms_eps, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st,
+                     (decode && kHead) ? L.wo : nullptr, size_t(H) * ko_ * 2));
     } else {
       RC(llmlb_op_rmsnorm(x, L.attn_norm, y, T, H, M.rms_eps, st));
       RC(proj(&L, 0, L.wqkv, L.m_wqkv, y, m_y, nullptr, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
     }
     if (decode) {
-      RC(llmlb_op_decode_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots,
-                                   B.seq_lens, nb, attn, nq_l, nkv_l, rope, decode_splits(nb),
-                                   cfg.max_seqs, attn_ws, st));
+      // layers >= 1: PDL launch (its K/V prefetch overlaps the QKV GEMV's tail); layer 0 is a
+      // plain launch so that decode_prepare (seq_lens) is complete before any early prologue
+      RC(decode_attention_launch(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, nb,
+                                 attn, nq_l, nkv_l, rope, decode_splits(nb), l > 0 && small && tp == 1, st));
     } else {
       RC(llmlb_op_rope_append(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, st));
       RC(llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles,
                                     n_tiles, attn, nq_l, nkv_l, st));
     }
     const uint32_t ko = nq_l * kHeadDim;
-    if (tp == 1) {
+    if (tp == 1 && small) {
+      RC(gemv_decode(L.wo, attn, nullptr, M.rms_eps, x, T, H, ko, LLMLB_EPI_RESID_F32, H, st, L.wgu, kHead));
+    } else if (tp == 1) {
       RC(proj(&L, 1, L.wo, L.m_wo, attn, m_attn, nullptr, x, T, H, ko, LLMLB_EPI_RESID_F32, H));
     } else {
       float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
@@ -519,12 +574,15 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
     }
     // --- feed-forward block ---
     if (small) {
-      RC(llmlb_op_gemv(L.wgu, x, L.ffn_norm, M.rms_eps, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, st));
+      RC(gemv_decode(L.wgu, x, L.ffn_norm, M.rms_eps, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, st, L.wdown, kHead));
     } else {
       RC(llmlb_op_rmsnorm(x, L.ffn_norm, y, T, H, M.rms_eps, st));
       RC(proj(&L, 2, L.wgu, L.m_wgu, y, m_y, nullptr, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
     }
-    if (tp == 1) {
+    if (tp == 1 && small) {
+      const void* nxt = (l + 1 < M.n_layers) ? (const void*)layers[l + 1].wqkv : (const void*)lm_head;
+      RC(gemv_decode(L.wdown, h, nullptr, M.rms_eps, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H, st, nxt, kHead));
+    } else if (tp == 1) {
       RC(proj(&L, 3, L.wdown, L.m_wdown, h, m_h, nullptr, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H));
     } else {
       float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
@@ -559,8 +617,9 @@ int llmlb_engine::layer_stack_decode(uint32_t nb) {
   decode_prepare_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(S, B, nb);
   LLMLB_LAUNCH_CHECK();
   RC(llmlb_op_embed(embed, B.ids, x, nb, M.hidden, M.vocab, st));
-  RC(forward_tokens(nb, true, nb, 0));
-  RC(logits_for_rows(nb, true));
+  bool logits_done = false;
+  RC(forward_tokens(nb, true, nb, 0, &logits_done));
+  if (!logits_done) RC(logits_for_rows(nb, true));
   RC(llmlb_op_sample(logits, nb, M.vocab, B.temperature, B.top_p, B.top_k, B.seed, B.step, B.out_ids, st));
   step_finish_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(S, B, nb);
   LLMLB_LAUNCH_CHECK();
@@ -930,7 +989,7 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
   if (e->tp_ready)
     for (uint32_t r = 0; r < e->tp; ++r)
       if (r != e->rank && e->peers.base[r]) cudaIpcCloseMemHandle(e->peers.base[r]);
-  F(e->xchg);
+  F(e->xchg); F(e->chain_state);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
@@ -1259,10 +1318,40 @@ extern "C" int llmlb_debug_decode_logits(llmlb_engine* e, int32_t token, float* 
   decode_prepare_kernel<<<1, 128, 0, st>>>(e->S, e->B, 1);
   LLMLB_LAUNCH_CHECK();
   RC(llmlb_op_embed(e->embed, e->B.ids, e->x, 1, e->M.hidden, e->M.vocab, st));
-  RC(e->forward_tokens(1, true, 1, 0));
-  RC(e->logits_for_rows(1, true));
+  bool logits_done = false;
+  RC(e->forward_tokens(1, true, 1, 0, &logits_done));
+  if (!logits_done) RC(e->logits_for_rows(1, true));
   LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
   LLMLB_CUDA_CHECK(cudaMemcpy(logits_out, e->logits, size_t(e->M.vocab) * 4, cudaMemcpyDeviceToHost));
   e->debug_len += 1;
+  return LLMLB_OK;
+}
+
+// ------------------------------------------------------------------ in-kernel timeline ------
+// Debug-only (not in the public header): records per-CTA globaltimer stamps of the decode GEMV and
+// attention kernels.  enable(cap) allocates, dump() copies records (6 x u64 each) and resets.
+static TraceBuf g_tb{};
+extern "C" int llmlb_debug_trace_enable(uint32_t cap) {
+  if (g_tb.data) { cudaFree(g_tb.data); cudaFree(g_tb.count); g_tb = TraceBuf{}; }
+  if (cap) {
+    LLMLB_CUDA_CHECK(cudaMalloc((void**)&g_tb.data, size_t(cap) * 48));
+    LLMLB_CUDA_CHECK(cudaMalloc((void**)&g_tb.count, 4));
+    LLMLB_CUDA_CHECK(cudaMemset(g_tb.count, 0, 4));
+    g_tb.cap = cap;
+  }
+  ks_set_trace(g_tb);
+  attn_set_trace(g_tb);
+  return LLMLB_OK;
+}
+extern "C" int llmlb_debug_trace_dump(unsigned long long* out, uint32_t cap_records, uint32_t* n) {
+  if (!g_tb.data) { *n = 0; return LLMLB_OK; }
+  LLMLB_CUDA_CHECK(cudaDeviceSynchronize());
+  uint32_t cnt = 0;
+  LLMLB_CUDA_CHECK(cudaMemcpy(&cnt, g_tb.count, 4, cudaMemcpyDeviceToHost));
+  if (cnt > g_tb.cap) cnt = g_tb.cap;
+  if (cnt > cap_records) cnt = cap_records;
+  LLMLB_CUDA_CHECK(cudaMemcpy(out, g_tb.data, size_t(cnt) * 48, cudaMemcpyDeviceToHost));
+  LLMLB_CUDA_CHECK(cudaMemset(g_tb.count, 0, 4));
+  *n = cnt;
   return LLMLB_OK;
 }

@@ -245,7 +245,17 @@ int gemv_bulk_try(const void* w, const void* x, const void* gain, float eps, voi
                   cudaStream_t st);
 int gemv_ks_try(const void* w, const void* x, const void* gain, float eps, void* out,
                 uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
-                cudaStream_t st);
+                cudaStream_t st, const void* pf_ptr = nullptr, uint32_t pf_bytes = 0);
+
+// Decode projection with a hint of what streams next (engine-internal: the public op has no hint)
+int gemv_decode(const void* w, const void* x, const void* gain, float eps, void* out, uint32_t n_tokens,
+                uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
+                const void* next_w, size_t next_bytes) {
+  uint32_t pfb = (uint32_t)(next_bytes > (48u << 20) ? (48u << 20) : next_bytes);
+  int rc = gemv_ks_try(w, x, gain, eps, out, n_tokens, n_out, k, epi, out_stride, st, next_w, next_w ? pfb : 0);
+  if (rc != LLMLB_E_UNSUPPORTED) return rc;
+  return llmlb_op_gemv(w, x, gain, eps, out, n_tokens, n_out, k, epi, out_stride, st);
+}
 
 }  // namespace llmlb
 

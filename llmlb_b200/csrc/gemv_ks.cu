@@ -22,6 +22,8 @@ namespace llmlb {
 
 constexpr int kKsThreads = 512;
 constexpr int kKsWarps = 16;
+static __device__ TraceBuf d_trace_ks;
+void ks_set_trace(const TraceBuf& tb) { cudaMemcpyToSymbol(d_trace_ks, &tb, sizeof(tb)); }
 
 __device__ __forceinline__ void team_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -31,7 +33,8 @@ template <int B, int EPI, bool NORM, int CW>
 __global__ void __launch_bounds__(kKsThreads)
 gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin,
                const __nv_bfloat16* __restrict__ gain, float eps, void* __restrict__ out,
-               uint32_t n_out, uint32_t K, uint32_t out_stride, uint32_t TW) {
+               uint32_t n_out, uint32_t K, uint32_t out_stride, uint32_t TW,
+               const uint8_t* __restrict__ pf_ptr, uint32_t pf_bytes) {
   constexpr int RB = 8 / CW;  // rows per batch (even)
   __shared__ float partial[2][kKsWarps][RB * B];  // [buf][warp][row*B + b]
   __shared__ float red[B][kKsWarps];
@@ -60,12 +63,16 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
       for (int c = 0; c < CW; ++c) wf[r][c] = ldg_stream(p + koff(c));
     }
   };
+  const TraceBuf tb = d_trace_ks;
+  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+  if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
   // PDL: let the next kernel in the stream start its own weight prefetch right away ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   uint32_t batch = team;
   if (active && batch < n_batches) load_batch(batch);
   // ... and only now wait for the producer of x / out (weights above never depend on it)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tb.data && threadIdx.x == 0) tr1 = gtime_ns();
 
   // ---- prologue: this lane's slice of x in fp32 registers (RMSNorm fused) ----
   float xr[B][CW][8];
@@ -127,10 +134,10 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
         }
     }
   }
-  if (!active) return;
-
+  if (tb.data && threadIdx.x == 0) tr2 = gtime_ns();
   // ---- main loop: this team's row batches ----
   uint32_t buf = 0;
+  if (active)
   for (; batch < n_batches; batch += teams, buf ^= 1) {
     uint4 wc[RB][CW];
 #pragma unroll
@@ -193,6 +200,11 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
       }
     }
   }
+  // ---- tail: pull the head of the NEXT projection's weights into L2 while this kernel drains
+  // and the next one launches (the boundary otherwise leaves HBM idle for ~2-3 us) ----
+  for (uint32_t off = (blockIdx.x * kKsThreads + threadIdx.x) * 128u; off < pf_bytes; off += gridDim.x * kKsThreads * 128u)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + off));
+  if (tb.data && threadIdx.x == 0) trace_emit(tb, (unsigned long long)n_out << 32 | K, tr0, tr1, tr2, gtime_ns());
 }
 
 // picks (TW, CW): TW*CW*256 == K, TW <= 16, CW in {1,2,4}, B*CW <= 4.  Returns false if none.
@@ -209,7 +221,8 @@ static bool ks_pick(uint32_t n_tokens, uint32_t K, uint32_t* tw, uint32_t* cw) {
 
 template <int B, int EPI, bool NORM, int CW>
 static int ks_launch(const void* w, const void* x, const void* gain, float eps, void* out,
-                     uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t tw, cudaStream_t st) {
+                     uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t tw, cudaStream_t st,
+                     const void* pf_ptr, uint32_t pf_bytes) {
   uint32_t n_pairs = (n_out + 1) / 2;
   uint32_t grid = n_pairs < (uint32_t)kNumSMs ? n_pairs : (uint32_t)kNumSMs;
   cudaLaunchConfig_t cfg{};
@@ -222,7 +235,8 @@ static int ks_launch(const void* w, const void* x, const void* gain, float eps, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemv_ks_kernel<B, EPI, NORM, CW>, (const __nv_bfloat16*)w, x,
-                                      (const __nv_bfloat16*)gain, eps, out, n_out, k, out_stride, tw));
+                                      (const __nv_bfloat16*)gain, eps, out, n_out, k, out_stride, tw,
+                                      (const uint8_t*)pf_ptr, pf_bytes));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
@@ -230,11 +244,11 @@ static int ks_launch(const void* w, const void* x, const void* gain, float eps, 
 template <int B, int CW>
 static int ks_dispatch(uint32_t epi, bool norm, const void* w, const void* x, const void* gain,
                        float eps, void* out, uint32_t n_out, uint32_t k, uint32_t out_stride,
-                       uint32_t tw, cudaStream_t st) {
-#define KS_CASE(E)                                                                              \
-  case E:                                                                                       \
-    return norm ? ks_launch<B, E, true, CW>(w, x, gain, eps, out, n_out, k, out_stride, tw, st) \
-                : ks_launch<B, E, false, CW>(w, x, gain, eps, out, n_out, k, out_stride, tw, st);
+                       uint32_t tw, cudaStream_t st, const void* pf, uint32_t pfb) {
+#define KS_CASE(E)                                                                                       \
+  case E:                                                                                                \
+    return norm ? ks_launch<B, E, true, CW>(w, x, gain, eps, out, n_out, k, out_stride, tw, st, pf, pfb) \
+                : ks_launch<B, E, false, CW>(w, x, gain, eps, out, n_out, k, out_stride, tw, st, pf, pfb);
   switch (epi) {
     KS_CASE(LLMLB_EPI_STORE_BF16)
     KS_CASE(LLMLB_EPI_RESID_F32)
@@ -249,11 +263,11 @@ static int ks_dispatch(uint32_t epi, bool norm, const void* w, const void* x, co
 // returns LLMLB_E_UNSUPPORTED when the shape does not fit this variant (caller falls back)
 int gemv_ks_try(const void* w, const void* x, const void* gain, float eps, void* out,
                 uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
-                cudaStream_t st) {
+                cudaStream_t st, const void* pf_ptr, uint32_t pf_bytes) {
   uint32_t tw = 0, cw = 0;
   if (n_tokens == 0 || n_tokens > 4 || !ks_pick(n_tokens, k, &tw, &cw)) return LLMLB_E_UNSUPPORTED;
   const bool norm = gain != nullptr;
-#define KS_GO(BB, CC) return ks_dispatch<BB, CC>(epi, norm, w, x, gain, eps, out, n_out, k, out_stride, tw, st)
+#define KS_GO(BB, CC) return ks_dispatch<BB, CC>(epi, norm, w, x, gain, eps, out, n_out, k, out_stride, tw, st, pf_ptr, pf_bytes)
   if (n_tokens == 1) { if (cw == 1) KS_GO(1, 1); if (cw == 2) KS_GO(1, 2); KS_GO(1, 4); }
   if (n_tokens == 2) { if (cw == 1) KS_GO(2, 1); KS_GO(2, 2); }
   if (n_tokens == 3) KS_GO(3, 1);

@@ -143,6 +143,12 @@ LLAMA_TINY = dict(hidden=512, n_layers=2, n_heads=8, n_kv_heads=2, head_dim=128,
                   vocab=2048, rope_theta=500000.0, rms_eps=1e-5)
 
 
+# mid geometry whose projections fit the persistent decode chain kernel (K multiple of 2048, 7
+# chunks per warp on the down projection like Llama-3-8B) while the oracle still runs in seconds
+LLAMA_MID = dict(hidden=2048, n_layers=2, n_heads=16, n_kv_heads=4, head_dim=128, ffn=14336,
+                 vocab=4096, rope_theta=500000.0, rms_eps=1e-5)
+
+
 class Engine:
     """Thin owner of an llmlb_engine*; methods map 1:1 onto the C ABI."""
 

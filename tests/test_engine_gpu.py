@@ -272,3 +272,32 @@ def test_8b_batched_equals_single_and_is_deterministic(eng8b):
             assert lg[a[0]] >= lg.max() - 0.05 and lg[b[0]] >= lg.max() - 0.05, (a[0], b[0], lg[a[0]], lg[b[0]], lg.max())
     h = eng8b.health()
     assert h["active_requests"] == 0 and h["free_kv_pages"] == h["total_kv_pages"]
+
+
+# ---- mid geometry: exercises the persistent decode chain kernel (gemv_chain.cu) ----
+def test_decode_chain_vs_oracle_and_vs_unchained(built_lib):
+    import os
+    cfg = ffi.LLAMA_MID
+    sdm = synth_state_dict(cfg, seed=3)
+    rs = np.random.RandomState(17)
+    prompt = rs.randint(0, cfg["vocab"], 70).tolist()
+    forced = rs.randint(0, cfg["vocab"], 6).tolist()
+    ref = LlamaRef(cfg, sdm)
+    want = [ref.forward(prompt).numpy()[-1]] + [ref.forward([t]).numpy()[-1] for t in forced]
+    got = {}
+    for chain in ("1", "0"):
+        os.environ["LLMLB_DECODE_CHAIN"] = chain
+        with ffi.Engine(cfg, max_seqs=4, max_ctx=256, seed=3) as e:
+            lg = [e.debug_prefill_logits(prompt)] + [e.debug_decode_logits(t) for t in forced]
+            e.debug_reset()
+            toks, _ = e.generate(prompt, 20, ignore_eos=True)   # CUDA-graph replay of the chain
+            got[chain] = (lg, toks)
+    os.environ.pop("LLMLB_DECODE_CHAIN", None)
+    sigma = float(want[0].std())
+    for chain in ("1", "0"):
+        for a, b in zip(got[chain][0], want):
+            assert np.abs(a - b).max() < 0.08 * sigma + 0.02, chain   # bf16 activations vs fp32 oracle
+    # chained and unchained kernels share rounding points; only accumulation order differs
+    for a, b in zip(got["1"][0], got["0"][0]):
+        assert np.abs(a - b).max() < 0.03 * sigma + 0.01
+    assert got["1"][1][:3] == got["0"][1][:3] and len(got["1"][1]) == 20
