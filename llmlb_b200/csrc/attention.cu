@@ -126,6 +126,18 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t rank) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void st_dsmem_f4(uint32_t ra, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_dsmem_f32(uint32_t ra, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
 constexpr int kPfRows = 64;  // q rows per CTA
 constexpr int kPfThreads = 128;
 
@@ -338,13 +350,15 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   __shared__ float kv_new[2][kHeadDim];  // rotated k and v of the new token (owner CTA only)
   __shared__ float mrg_o[4][kDecHeads][kHeadDim];
   __shared__ float mrg_ml[4][kDecHeads][2];
-  __shared__ DecPartial part;
+  __shared__ DecPartial parts[16];  // only the cluster leader's copy is filled (peers push into it)
 
   const TraceBuf tb = d_trace_attn;
   unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
   if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
   // PDL: the O-projection GEMV that follows may start prefetching its weights now
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // cluster phase 1 (arrive now, wait just before the first DSMEM store): every CTA has started
+  if (n_splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   const uint32_t z = blockIdx.x, hb = blockIdx.y, s = blockIdx.z;
   const uint32_t h0 = hb * kDecHeads, kvh = h0 / (n_heads / n_kv);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -535,35 +549,32 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     *reinterpret_cast<uint2*>(dst) = o2;
     return;
   }
-  // publish this CTA's partial, then the cluster leader folds all of them
-  *reinterpret_cast<float4*>(&part.o[h][d0]) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-  if ((tid & 31) == 0) { part.m[h] = mn; part.l[h] = l; }
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (z == 0) {
-    // all DSMEM loads are issued before any is consumed (16 ranks max): one latency, not 48
-    const uint32_t my = smem_addr_u32(&part);
-    float pm[16], pl[16];
-    float4 po[16];
-#pragma unroll
-    for (uint32_t r = 0; r < 16; ++r) {
-      if (r < n_splits) {
-        pm[r] = ld_dsmem_f32(my + offsetof(DecPartial, m) + h * 4, r);
-        pl[r] = ld_dsmem_f32(my + offsetof(DecPartial, l) + h * 4, r);
-        po[r] = ld_dsmem_f4(my + offsetof(DecPartial, o) + (h * kHeadDim + d0) * 4, r);
-      } else {
-        pm[r] = -INFINITY; pl[r] = 0.f; po[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  // push this CTA's partial into the LEADER's shared memory, one cluster barrier, peers leave
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // phase 1: leader's smem is live
+  {
+    const uint32_t slot = dsmem_addr(smem_addr_u32(&parts[z]), 0);
+    st_dsmem_f4(slot + offsetof(DecPartial, o) + (h * kHeadDim + d0) * 4, make_float4(ov[0], ov[1], ov[2], ov[3]));
+    if ((tid & 31) == 0) {
+      st_dsmem_f32(slot + offsetof(DecPartial, m) + h * 4, mn);
+      st_dsmem_f32(slot + offsetof(DecPartial, l) + h * 4, l);
     }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  if (z != 0) {
+    if (tb.data && threadIdx.x == 0) trace_emit(tb, 1ull, tr0, tr1, tr2, gtime_ns());
+    return;
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {
     float gm = -INFINITY;
-#pragma unroll
-    for (uint32_t r = 0; r < 16; ++r) gm = fmaxf(gm, pm[r]);
+    for (uint32_t r = 0; r < n_splits; ++r) gm = fmaxf(gm, parts[r].m[h]);
     float gl = 0.f, go[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (uint32_t r = 0; r < 16; ++r) {
-      const float c = (pm[r] == -INFINITY) ? 0.f : exp2f(pm[r] - gm);
-      gl += pl[r] * c;
-      go[0] += po[r].x * c; go[1] += po[r].y * c; go[2] += po[r].z * c; go[3] += po[r].w * c;
+    for (uint32_t r = 0; r < n_splits; ++r) {
+      const float pm = parts[r].m[h];
+      const float c = (pm == -INFINITY) ? 0.f : exp2f(pm - gm);
+      gl += parts[r].l[h] * c;
+      const float4 po = *reinterpret_cast<const float4*>(&parts[r].o[h][d0]);
+      go[0] += po.x * c; go[1] += po.y * c; go[2] += po.z * c; go[3] += po.w * c;
     }
     const float inv = 1.f / gl;
     uint2 o2;
@@ -571,9 +582,6 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
     o2.y = pack_bf16(go[2] * inv, go[3] * inv);
     *reinterpret_cast<uint2*>(dst) = o2;
   }
-  // peers must keep their shared memory alive until the leader has read it
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (tb.data && threadIdx.x == 0) trace_emit(tb, 1ull, tr0, tr1, tr2, gtime_ns());
 }
 

@@ -45,6 +45,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
                             void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
                             bool pdl, cudaStream_t st);
 void ks_set_trace(const TraceBuf& tb);
+void tc_set_trace(const TraceBuf& tb);
 void attn_set_trace(const TraceBuf& tb);
 struct ChainOpHost { const void* w; const void* x; const void* gain; void* out; uint32_t n_out, k, out_stride, epi; };
 bool gemv_chain_shape_ok(uint32_t n_out, uint32_t k);
@@ -1341,6 +1342,7 @@ extern "C" int llmlb_debug_trace_enable(uint32_t cap) {
   }
   ks_set_trace(g_tb);
   attn_set_trace(g_tb);
+  tc_set_trace(g_tb);
   return LLMLB_OK;
 }
 extern "C" int llmlb_debug_trace_dump(unsigned long long* out, uint32_t cap_records, uint32_t* n) {

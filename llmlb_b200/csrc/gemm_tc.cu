@@ -5,11 +5,12 @@
 // "Weights-as-M" tiling: a CTA owns a 128-row slab of W as the MMA's M operand and BN tokens
 // as the N operand (BN = 16..256 picked from T), so one kernel serves 16-token batched decode
 // (HBM-bound: W streamed once through a deep TMA ring) and 512-token prefill (tensor-bound).
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0 lane 0 : TMA producer   — cp.async.bulk.tensor 2D, 128B-swizzled 64-wide K slabs
 //   warp 1 lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, fp32 accum in TMEM
 //   warp 2        : TMEM allocator — 2 accumulator stages (epilogue of tile i overlaps MMA of i+1)
-//   warps 4..7    : epilogue       — tcgen05.ld 32x32b, fused residual-add / SiLU*up / store
+//   warps 4..11   : epilogue       — tcgen05.ld 32x32b (two warps per TMEM lane quarter, half the
+//                                    columns each), fused residual-add / SiLU*up / store
 // Split-K (residual epilogue only) uses fp32 red.global.add.
 #include <cuda.h>
 
@@ -20,6 +21,9 @@
 #include "tc_common.cuh"
 
 namespace llmlb {
+
+static __device__ TraceBuf d_trace_tc;
+void tc_set_trace(const TraceBuf& tb) { cudaMemcpyToSymbol(d_trace_tc, &tb, sizeof(tb)); }
 
 template <int BN>
 struct TcCfg {
@@ -64,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
-      mbar_init(tempty_bar + i, 4);
+      mbar_init(tempty_bar + i, 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -79,6 +83,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // debug timeline: cycles each role spent blocked (producer on free slots, MMA issuer on data,
+  // epilogue on finished accumulators) — see tools/gemm_stalls.py
+  const TraceBuf tb = d_trace_tc;
+  __shared__ long long stall[4];
+  const long long c_begin = clock64();
+  long long c_wait = 0;
 
   // tile -> (m_tile, t_tile, split): t fastest so consecutive CTAs share the W slab in L2
   auto decode_tile = [&](uint32_t tile, uint32_t& mt, uint32_t& tt, uint32_t& ks) {
@@ -118,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
         for (uint32_t kb = kb0; kb < kb1; ++kb) {
           p_step();
-          mbar_wait(empty_bar + stage, phase ^ 1);
+          { const long long c0 = clock64(); mbar_wait(empty_bar + stage, phase ^ 1); c_wait += clock64() - c0; }
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kBM * kBK * 2;
           mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
@@ -140,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (uint32_t kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar + stage, phase);
+          { const long long c0 = clock64(); mbar_wait(full_bar + stage, phase); c_wait += clock64() - c0; }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kBM * kBK * 2;
@@ -165,12 +175,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       uint32_t mt, tt, ks;
       decode_tile(tile, mt, tt, ks);
-      mbar_wait(tfull_bar + acc, acc_phase);
+      { const long long c0 = clock64(); mbar_wait(tfull_bar + acc, acc_phase); c_wait += clock64() - c0; }
       tc_fence_after();
       const uint32_t n = mt * kBM + q * 32 + lane;      // output feature of this thread
       const uint32_t t0 = tt * BN;
+      // two warps share a TMEM lane quarter: each takes half of the token columns
+      constexpr uint32_t kColsPerWarp = (BN / 2 >= 16) ? BN / 2 : 16;
+      const uint32_t c_begin = ((warp - 4) >> 2) * kColsPerWarp;
 #pragma unroll 1
-      for (uint32_t c = 0; c < BN; c += 16) {
+      for (uint32_t c = c_begin; c < c_begin + kColsPerWarp && c < BN; c += 16) {
         if (t0 + c >= n_tokens) break;                  // warp-uniform
         uint32_t r[16];
         tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
@@ -179,11 +192,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float v = __uint_as_float(r[j]);
-            float other = __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 1) == 0 && n + 1 < n_out && t0 + c + j < n_tokens) {
-              float s = v / (1.f + __expf(-v));
-              o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(s * other);
+            const float v = __uint_as_float(r[j]);
+            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            // lanes (2i, 2i+1) hold (gate_i, up_i); even lanes finish even columns, odd lanes odd ones
+            if (((j ^ lane) & 1) == 0 && (n | 1) < n_out && t0 + c + j < n_tokens) {
+              const float g = (lane & 1) ? other : v, u = (lane & 1) ? v : other;
+              const float s = g / (1.f + __expf(-g));
+              o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(s * u);
             }
           }
         } else {
@@ -214,8 +229,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
   }
 
+  if (tb.data) {
+    if (warp == 0 && lane == 0) stall[0] = c_wait;
+    if (warp == 1 && lane == 0) stall[1] = c_wait;
+    if (warp == 4 && lane == 0) stall[2] = c_wait;  // epilogue warp 4: first column half
+  }
   tc_fence_before();
   __syncthreads();
+  if (tb.data && threadIdx.x == 0)
+    trace_emit(tb, (2ull << 60) | ((unsigned long long)n_out << 32) | ((unsigned long long)EPI << 28) | K,
+               (unsigned long long)(clock64() - c_begin), (unsigned long long)stall[0], (unsigned long long)stall[1],
+               (unsigned long long)stall[2]);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),

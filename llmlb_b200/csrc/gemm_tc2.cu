@@ -11,7 +11,7 @@
 //   barriers                    : full[stage]   leader, count 2 (leader expect_tx + peer arrive)
 //                                 empty[stage]  per CTA, count 1, tcgen05.commit multicast 0b11
 //                                 tfull[acc]    per CTA, count 1, commit multicast 0b11
-//                                 tempty[acc]   leader, count 8 (4 epilogue warps x 2 CTAs)
+//                                 tempty[acc]   leader, count 16 (8 epilogue warps x 2 CTAs)
 #include <cuda.h>
 
 #include "../../include/llmlb_b200.h"
@@ -104,7 +104,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
-      mbar_init(tempty_bar + i, 8);
+      mbar_init(tempty_bar + i, 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -184,8 +184,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       tc_fence_after();
       const uint32_t n = mt * 256 + rank * kBM + q * 32 + lane;
       const uint32_t t0 = tt * BN;
+      // two warps share a TMEM lane quarter: each takes half of the token columns
+      constexpr uint32_t kColsPerWarp = (BN / 2 >= 16) ? BN / 2 : 16;
+      const uint32_t c_begin = ((warp - 4) >> 2) * kColsPerWarp;
 #pragma unroll 1
-      for (uint32_t c = 0; c < BN; c += 16) {
+      for (uint32_t c = c_begin; c < c_begin + kColsPerWarp && c < BN; c += 16) {
         if (t0 + c >= n_tokens) break;
         uint32_t r[16];
         tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
@@ -194,11 +197,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float v = __uint_as_float(r[j]);
-            float other = __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 1) == 0 && n + 1 < n_out && t0 + c + j < n_tokens) {
-              float s = v / (1.f + __expf(-v));
-              o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(s * other);
+            const float v = __uint_as_float(r[j]);
+            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            // lanes (2i, 2i+1) hold (gate_i, up_i); even lanes finish even columns, odd lanes odd ones
+            if (((j ^ lane) & 1) == 0 && (n | 1) < n_out && t0 + c + j < n_tokens) {
+              const float g = (lane & 1) ? other : v, u = (lane & 1) ? v : other;
+              const float s = g / (1.f + __expf(-g));
+              o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(s * u);
             }
           }
         } else if (n < n_out) {

@@ -49,6 +49,7 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
   const uint32_t row_begin = uint32_t((uint64_t(blockIdx.x) * n_pairs) / gridDim.x) * 2;
   const uint32_t row_end = min(n_out, uint32_t((uint64_t(blockIdx.x + 1) * n_pairs) / gridDim.x) * 2);
   const uint32_t n_batches = (row_end - row_begin + RB - 1) / RB;
+  const uint32_t rows_base = row_begin, rows_lim = row_end;
 
   // element offset of this lane's chunk c: chunks are interleaved over the team's warps
   auto koff = [&](int c) { return (uint32_t(c) * TW + wt) * 256u + lane * 8u; };
@@ -57,7 +58,7 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
   auto load_batch = [&](uint32_t batch) {
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const uint32_t row = min(row_begin + batch * RB + r, n_out - 1);
+      const uint32_t row = min(rows_base + batch * RB + r, n_out - 1);
       const __nv_bfloat16* p = W + size_t(row) * K;
 #pragma unroll
       for (int c = 0; c < CW; ++c) wf[r][c] = ldg_stream(p + koff(c));
@@ -68,7 +69,10 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
   if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
   // PDL: let the next kernel in the stream start its own weight prefetch right away ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // this CTA's batches: team, team+teams, ...  (a dynamically dealt variant was measured in round 1:
+  // slower — the per-trip atomic + publish costs more than the ~6 % tail spread it removes)
   uint32_t batch = team;
+  const uint32_t stride0 = teams;
   if (active && batch < n_batches) load_batch(batch);
   // ... and only now wait for the producer of x / out (weights above never depend on it)
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -137,14 +141,15 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
   if (tb.data && threadIdx.x == 0) tr2 = gtime_ns();
   // ---- main loop: this team's row batches ----
   uint32_t buf = 0;
+  uint32_t next = batch + stride0;      // batch after the current one
   if (active)
-  for (; batch < n_batches; batch += teams, buf ^= 1) {
+  for (; batch < n_batches; buf ^= 1) {
     uint4 wc[RB][CW];
 #pragma unroll
     for (int r = 0; r < RB; ++r)
 #pragma unroll
       for (int c = 0; c < CW; ++c) wc[r][c] = wf[r][c];
-    if (batch + teams < n_batches) load_batch(batch + teams);
+    if (next < n_batches) load_batch(next);
 
     float acc[RB][B];
 #pragma unroll
@@ -181,15 +186,15 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
       float v = 0.f;
       if (lane < RB * B)
         for (uint32_t w = 0; w < TW; ++w) v += partial[buf][team * TW + w][lane];
-      const uint32_t row = row_begin + batch * RB + r;
+      const uint32_t row = rows_base + batch * RB + r;
       if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
         const float up = __shfl_down_sync(0xffffffffu, v, B);  // row r+1, same token
-        if (lane < RB * B && (r & 1) == 0 && row + 1 < row_end) {
+        if (lane < RB * B && (r & 1) == 0 && row + 1 < rows_lim) {
           const float s = v / (1.f + __expf(-v));
           reinterpret_cast<__nv_bfloat16*>(out)[size_t(b) * out_stride + (row >> 1)] =
               __float2bfloat16_rn(s * up);
         }
-      } else if (lane < RB * B && row < row_end) {
+      } else if (lane < RB * B && row < rows_lim) {
         const size_t idx = size_t(b) * out_stride + row;
         if constexpr (EPI == LLMLB_EPI_STORE_BF16)
           reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
@@ -199,6 +204,8 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
           reinterpret_cast<float*>(out)[idx] = v;
       }
     }
+    batch = next;
+    next += stride0;
   }
   // ---- tail: pull the head of the NEXT projection's weights into L2 while this kernel drains
   // and the next one launches (the boundary otherwise leaves HBM idle for ~2-3 us) ----

@@ -9,7 +9,7 @@ namespace llmlb {
 
 constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
 constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 384;    // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
