@@ -345,7 +345,8 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
                         uint32_t bt_stride, const int32_t* __restrict__ bt_rows,
                         const int32_t* __restrict__ seq_lens,
                         const float2* __restrict__ rope, __nv_bfloat16* __restrict__ out,
-                        uint32_t n_heads, uint32_t n_kv, uint32_t n_splits) {
+                        uint32_t n_heads, uint32_t n_kv, uint32_t n_splits,
+                        const uint8_t* __restrict__ pf_ptr, uint32_t pf_bytes) {
   __shared__ float q_s[kDecHeads][kHeadDim];
   __shared__ float kv_new[2][kHeadDim];  // rotated k and v of the new token (owner CTA only)
   __shared__ float mrg_o[4][kDecHeads][kHeadDim];
@@ -359,6 +360,14 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // cluster phase 1 (arrive now, wait just before the first DSMEM store): every CTA has started
   if (n_splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  // HBM is idle while this latency-bound kernel runs: pull the O-projection's weights (constant
+  // data, safe before the dependency wait) into L2 so the GEMV that follows streams from L2
+  {
+    const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const uint32_t n_cta = gridDim.x * gridDim.y * gridDim.z;
+    for (uint32_t off = (cta * kDecThreads + threadIdx.x) * 128u; off < pf_bytes; off += n_cta * kDecThreads * 128u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + off));
+  }
   const uint32_t z = blockIdx.x, hb = blockIdx.y, s = blockIdx.z;
   const uint32_t h0 = hb * kDecHeads, kvh = h0 / (n_heads / n_kv);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -655,7 +664,7 @@ namespace llmlb {
 int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const int32_t* block_tables,
                             uint32_t bt_stride, const int32_t* bt_rows, const int32_t* seq_lens, uint32_t n_seqs,
                             void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
-                            bool pdl, cudaStream_t st) {
+                            bool pdl, cudaStream_t st, const void* pf_ptr, uint32_t pf_bytes) {
   if (!qkv || !k_pages || !v_pages || !block_tables || !seq_lens || !out || !rope_table ||
       n_kv == 0 || n_heads % n_kv || n_heads % kDecHeads || (n_heads / n_kv) % kDecHeads ||
       n_splits == 0) {
@@ -688,7 +697,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(
       &cfg, decode_attention_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages,
       (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows, seq_lens,
-      (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, sp));
+      (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, sp, (const uint8_t*)pf_ptr, pf_ptr ? pf_bytes : 0u));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
@@ -701,5 +710,5 @@ extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v
                                          uint32_t n_kv, const float* rope_table,
                                          uint32_t n_splits, uint32_t, void*, void* stream) {
   return decode_attention_launch(qkv, k_pages, v_pages, block_tables, bt_stride, bt_rows, seq_lens, n_seqs, out,
-                                 n_heads, n_kv, rope_table, n_splits, false, (cudaStream_t)stream);
+                                 n_heads, n_kv, rope_table, n_splits, false, (cudaStream_t)stream, nullptr, 0);
 }

@@ -43,7 +43,7 @@ int gemv_decode(const void* w, const void* x, const void* gain, float eps, void*
 int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const int32_t* block_tables,
                             uint32_t bt_stride, const int32_t* bt_rows, const int32_t* seq_lens, uint32_t n_seqs,
                             void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
-                            bool pdl, cudaStream_t st);
+                            bool pdl, cudaStream_t st, const void* pf_ptr = nullptr, uint32_t pf_bytes = 0);
 void ks_set_trace(const TraceBuf& tb);
 void tc_set_trace(const TraceBuf& tb);
 void attn_set_trace(const TraceBuf& tb);
@@ -249,6 +249,7 @@ struct llmlb_engine {
   std::unordered_map<uint32_t, uint64_t> graph_nodes;  // kernels per captured step
   bool paused = false;
   std::string fatal_error;
+  uint32_t attn_pf_mb = 0;    // LLMLB_ATTN_PF_MB: O-proj bytes the decode attention kernel pulls into L2 (measured: 64 -> -3 %)
   size_t pf_head_bytes = 0;  // LLMLB_PF_MB: next-projection bytes prefetched into L2 per tail (measured: 0 best)
   uint32_t* chain_state = nullptr;  // [n_layers][8] barrier counters of the decode GEMV chains
   bool use_chain = false;
@@ -363,6 +364,9 @@ int llmlb_engine::init() {
   return LLMLB_OK;
 }
 
+// NOTE: zero-fill must be ordered with the engine's (non-blocking) stream: a cudaMemset on the
+// legacy default stream is NOT ordered with it and raced with the first kernels (rope table).
+static thread_local cudaStream_t g_alloc_stream = nullptr;
 template <class T>
 static int dmalloc(T** p, size_t n_elems, bool zero = true) {
   size_t bytes = n_elems * sizeof(T);
@@ -372,12 +376,13 @@ static int dmalloc(T** p, size_t n_elems, bool zero = true) {
     set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
     return LLMLB_E_DEVICE;
   }
-  if (zero) cudaMemset(*p, 0, bytes);
+  if (zero) cudaMemsetAsync(*p, 0, bytes, g_alloc_stream);
   return LLMLB_OK;
 }
 
 int llmlb_engine::alloc_all() {
   const size_t H = M.hidden;
+  g_alloc_stream = st;
   RC(dmalloc(&embed, size_t(M.vocab) * H, false));
   RC(dmalloc(&final_norm, H, false));
   RC(dmalloc(&lm_head, size_t(vocab_l) * H, false));
@@ -444,6 +449,7 @@ int llmlb_engine::alloc_all() {
   RC(dmalloc(&chain_state, size_t(M.n_layers) * 8));
   {
     if (const char* pm = getenv("LLMLB_PF_MB")) pf_head_bytes = size_t(atoi(pm)) << 20;
+    if (const char* am = getenv("LLMLB_ATTN_PF_MB")) attn_pf_mb = (uint32_t)atoi(am);
     const char* ev = getenv("LLMLB_DECODE_CHAIN");
     const bool want = ev && ev[0] == '1';  // measured round 1: 211 tok/s chained vs 351 unchained -> opt-in
     use_chain = want && tp == 1 && gemv_chain_shape_ok(H, nq_l * kHeadDim) && gemv_chain_shape_ok(2 * ffn_l, H) &&
@@ -556,7 +562,9 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
       // layers >= 1: PDL launch (its K/V prefetch overlaps the QKV GEMV's tail); layer 0 is a
       // plain launch so that decode_prepare (seq_lens) is complete before any early prologue
       RC(decode_attention_launch(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, nb,
-                                 attn, nq_l, nkv_l, rope, decode_splits(nb), l > 0 && small && tp == 1, st));
+                                 attn, nq_l, nkv_l, rope, decode_splits(nb), l > 0 && small && tp == 1, st,
+                                 (small && attn_pf_mb) ? (const void*)L.wo : nullptr,
+                                 (uint32_t)std::min<size_t>(size_t(H) * nq_l * kHeadDim * 2, size_t(attn_pf_mb) << 20)));
     } else {
       RC(llmlb_op_rope_append(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, st));
       RC(llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles,
