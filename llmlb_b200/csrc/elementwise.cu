@@ -54,6 +54,57 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   }
 }
 
+// x[t,:] += sum_p parts[p][t,:] (p ascending: deterministic), then optionally y = RMSNorm(x)*g.
+// This is where the K-split partial products of the O / down projections are folded into the
+// residual stream — a fixed-order replacement for fp32 atomics (and the hook for TP partials).
+__global__ void __launch_bounds__(256) rmsnorm_parts_kernel(float* __restrict__ x,
+                                                            const float* __restrict__ parts,
+                                                            uint32_t n_parts, size_t part_stride,
+                                                            const __nv_bfloat16* __restrict__ gain,
+                                                            __nv_bfloat16* __restrict__ y,
+                                                            uint32_t hidden, float eps) {
+  __shared__ float red[8];
+  const uint32_t t = blockIdx.x;
+  float4* xr = reinterpret_cast<float4*>(x + size_t(t) * hidden);
+  float ss = 0.f;
+  for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
+    float4 v = xr[i];
+    for (uint32_t p = 0; p < n_parts; ++p) {
+      const float4 a = reinterpret_cast<const float4*>(parts + p * part_stride + size_t(t) * hidden)[i];
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    xr[i] = v;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (!gain) return;
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float r = rsqrtf(tot / float(hidden) + eps);
+  uint2* dst = reinterpret_cast<uint2*>(y + size_t(t) * hidden);
+  const uint2* g2 = reinterpret_cast<const uint2*>(gain);
+  for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
+    float4 v = xr[i];  // own writes, same thread
+    uint2 g = __ldg(g2 + i);
+    uint2 o;
+    o.x = pack_bf16(v.x * r * bf16_lo(g.x), v.y * r * bf16_hi(g.x));
+    o.y = pack_bf16(v.z * r * bf16_lo(g.y), v.w * r * bf16_hi(g.y));
+    dst[i] = o;
+  }
+}
+
+int rmsnorm_parts_launch(float* x, const float* parts, uint32_t n_parts, size_t part_stride, const void* gain,
+                         void* y, uint32_t n_tokens, uint32_t hidden, float eps, cudaStream_t st) {
+  if (n_tokens == 0) return LLMLB_OK;
+  rmsnorm_parts_kernel<<<n_tokens, 256, 0, st>>>(x, parts, n_parts, part_stride, (const __nv_bfloat16*)gain,
+                                                 (__nv_bfloat16*)y, hidden, eps);
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+
 __global__ void __launch_bounds__(256) synth_kernel(__nv_bfloat16* __restrict__ out,
                                                     uint64_t rows, uint64_t cols, uint64_t row0,
                                                     uint64_t col0, uint64_t ld, uint64_t seed,

@@ -33,10 +33,13 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
 uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                   const CUtensorMap* tx_half = nullptr);
+                   const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr);
 int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,
                     uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
 
+int rmsnorm_parts_launch(float* x, const float* parts, uint32_t n_parts, size_t part_stride, const void* gain,
+                         void* y, uint32_t n_tokens, uint32_t hidden, float eps, cudaStream_t st);
+constexpr int kEpiPartialF32 = 4;  // internal GEMM epilogue: fp32 K-split partials (tc_common.cuh)
 int gemv_decode(const void* w, const void* x, const void* gain, float eps, void* out, uint32_t n_tokens,
                 uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
                 const void* next_w, size_t next_bytes);
@@ -251,6 +254,7 @@ struct llmlb_engine {
   std::string fatal_error;
   uint32_t attn_pf_mb = 0;    // LLMLB_ATTN_PF_MB: O-proj bytes the decode attention kernel pulls into L2 (measured: 64 -> -3 %)
   size_t pf_head_bytes = 0;  // LLMLB_PF_MB: next-projection bytes prefetched into L2 per tail (measured: 0 best)
+  float* part_ws = nullptr;         // [8 splits][t_cap][hidden] fp32: K-split partials of O / down
   uint32_t* chain_state = nullptr;  // [n_layers][8] barrier counters of the decode GEMV chains
   bool use_chain = false;
   int warmup();
@@ -447,6 +451,7 @@ int llmlb_engine::alloc_all() {
     LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_out[i], ms * 4, cudaHostAllocDefault));
   }
   RC(dmalloc(&chain_state, size_t(M.n_layers) * 8));
+  if (tp == 1) RC(dmalloc(&part_ws, size_t(8) * t_cap * H, false));
   {
     if (const char* pm = getenv("LLMLB_PF_MB")) pf_head_bytes = size_t(atoi(pm)) << 20;
     if (const char* am = getenv("LLMLB_ATTN_PF_MB")) attn_pf_mb = (uint32_t)atoi(am);
@@ -545,17 +550,31 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
   if (decode && T == 1 && use_chain && logits_done) return forward_decode_chain(logits_done);
   const bool small = T <= 4;
   uint32_t coll = 0;
+  // T > 4, single GPU: the O / down projections write fp32 K-split partials into part_ws and the
+  // NEXT normalisation folds them into the residual in slot order (deterministic; no atomics)
+  const bool parts_mode = !small && tp == 1;
+  const size_t part_stride = size_t(T) * H;
+  uint32_t pending = 0;  // partial slots of the previous down projection not yet folded into x
+  auto big_proj_parts = [&](const void* w, const CUtensorMap& mw, const void* xin, const CUtensorMap* mx,
+                            uint32_t k, uint32_t* n_parts) -> int {
+    *n_parts = 1;
+    if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, part_ws, T, H, k, LLMLB_EPI_STORE_F32, H, st);
+    return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], part_ws, T, H, k, kEpiPartialF32, H, st,
+                          &mx[bn_index(128)], n_parts);
+  };
   for (uint32_t l = 0; l < M.n_layers; ++l) {
     LayerW& L = layers[l];
-    // --- attention block ---
     const size_t kHead = pf_head_bytes;  // bytes of the next projection pulled into L2 at each tail
-    const uint32_t ko_ = nq_l * kHeadDim;
+    const uint32_t ko = nq_l * kHeadDim;
+    // --- attention block ---
     if (small) {
       // QKV's tail prefetches ALL of O-proj: the attention kernel in between leaves HBM idle
       RC(gemv_decode(L.wqkv, x, L.attn_norm, M.rms_eps, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st,
-                     (decode && kHead) ? L.wo : nullptr, size_t(H) * ko_ * 2));
+                     (decode && kHead) ? L.wo : nullptr, size_t(H) * ko * 2));
     } else {
-      RC(llmlb_op_rmsnorm(x, L.attn_norm, y, T, H, M.rms_eps, st));
+      if (parts_mode) RC(rmsnorm_parts_launch(x, part_ws, pending, part_stride, L.attn_norm, y, T, H, M.rms_eps, st));
+      else RC(llmlb_op_rmsnorm(x, L.attn_norm, y, T, H, M.rms_eps, st));
+      pending = 0;
       RC(proj(&L, 0, L.wqkv, L.m_wqkv, y, m_y, nullptr, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
     }
     if (decode) {
@@ -570,11 +589,11 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
       RC(llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles,
                                     n_tiles, attn, nq_l, nkv_l, st));
     }
-    const uint32_t ko = nq_l * kHeadDim;
+    uint32_t n_o = 0;
     if (tp == 1 && small) {
       RC(gemv_decode(L.wo, attn, nullptr, M.rms_eps, x, T, H, ko, LLMLB_EPI_RESID_F32, H, st, L.wgu, kHead));
     } else if (tp == 1) {
-      RC(proj(&L, 1, L.wo, L.m_wo, attn, m_attn, nullptr, x, T, H, ko, LLMLB_EPI_RESID_F32, H));
+      RC(big_proj_parts(L.wo, L.m_wo, attn, m_attn, ko, &n_o));
     } else {
       float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
       RC(proj(&L, 1, L.wo, L.m_wo, attn, m_attn, nullptr, part, T, H, ko, LLMLB_EPI_STORE_F32, H));
@@ -585,14 +604,15 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
     if (small) {
       RC(gemv_decode(L.wgu, x, L.ffn_norm, M.rms_eps, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, st, L.wdown, kHead));
     } else {
-      RC(llmlb_op_rmsnorm(x, L.ffn_norm, y, T, H, M.rms_eps, st));
+      if (parts_mode) RC(rmsnorm_parts_launch(x, part_ws, n_o, part_stride, L.ffn_norm, y, T, H, M.rms_eps, st));
+      else RC(llmlb_op_rmsnorm(x, L.ffn_norm, y, T, H, M.rms_eps, st));
       RC(proj(&L, 2, L.wgu, L.m_wgu, y, m_y, nullptr, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
     }
     if (tp == 1 && small) {
       const void* nxt = (l + 1 < M.n_layers) ? (const void*)layers[l + 1].wqkv : (const void*)lm_head;
       RC(gemv_decode(L.wdown, h, nullptr, M.rms_eps, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H, st, nxt, kHead));
     } else if (tp == 1) {
-      RC(proj(&L, 3, L.wdown, L.m_wdown, h, m_h, nullptr, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H));
+      RC(big_proj_parts(L.wdown, L.m_wdown, h, m_h, ffn_l, &pending));
     } else {
       float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
       RC(proj(&L, 3, L.wdown, L.m_wdown, h, m_h, nullptr, part, T, H, ffn_l, LLMLB_EPI_STORE_F32, H));
@@ -600,6 +620,8 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
       ++coll;
     }
   }
+  // the last down projection's partials: fold into x (no normalisation: the logits path has its own)
+  if (parts_mode && pending) RC(rmsnorm_parts_launch(x, part_ws, pending, part_stride, nullptr, nullptr, T, H, M.rms_eps, st));
   return LLMLB_OK;
 }
 
@@ -998,7 +1020,7 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
   if (e->tp_ready)
     for (uint32_t r = 0; r < e->tp; ++r)
       if (r != e->rank && e->peers.base[r]) cudaIpcCloseMemHandle(e->peers.base[r]);
-  F(e->xchg); F(e->chain_state);
+  F(e->xchg); F(e->chain_state); F(e->part_ws);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;

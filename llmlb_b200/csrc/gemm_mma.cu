@@ -15,7 +15,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
 uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                   const CUtensorMap* tx_half = nullptr);
+                   const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr);
 
 constexpr int kMT = 128, kMN = 128, kMK = 32, kMStages = 3, kMThreads = 256;
 

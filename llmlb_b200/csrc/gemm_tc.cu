@@ -213,6 +213,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                   reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
                 else if constexpr (EPI == LLMLB_EPI_STORE_F32)
                   reinterpret_cast<float*>(out)[idx] = v;
+                else if constexpr (EPI == kEpiPartialF32)  // deterministic split-K: slot ks of the workspace
+                  reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
                 else {
                   if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
                   else reinterpret_cast<float*>(out)[idx] += v;
@@ -327,6 +329,8 @@ static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMa
       return launch_tc<BN, LLMLB_EPI_SILU_MUL>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
     case LLMLB_EPI_STORE_F32:
       return launch_tc<BN, LLMLB_EPI_STORE_F32>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+    case kEpiPartialF32:
+      return launch_tc<BN, kEpiPartialF32>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
   }
   set_error("gemm_tc: unknown epilogue");
   return LLMLB_E_INVALID_ARG;
@@ -343,24 +347,27 @@ uint32_t tc_pick_bn(uint32_t n_tokens) {
 // Launch with prebuilt tensor maps (the engine caches them: weights never move, activation
 // buffers are fixed).  The X map's box rows must equal tc_pick_bn(n_tokens).
 int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens,
-                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
+                    uint32_t* n_parts);
 
 // tx_half (optional): the activation map with a 128-row box; when given and the step is wide
 // enough for 256-token tiles the CTA-pair kernel (gemm_tc2.cu) runs instead.
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
-                   cudaStream_t st, const CUtensorMap* tx_half) {
+                   cudaStream_t st, const CUtensorMap* tx_half, uint32_t* n_parts) {
   const uint32_t bn = tc_pick_bn(n_tokens);
   static const bool no_2cta = getenv("LLMLB_GEMM_NO_2CTA") != nullptr;
+  if (n_parts) *n_parts = 1;
   if (tx_half && bn == 256 && n_out >= 256 && !no_2cta)
-    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st);
+    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts);
   // split K for the residual epilogue when the tile count cannot fill the GPU
   uint32_t split_k = 1;
-  if (epi == LLMLB_EPI_RESID_F32) {
+  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32) {
     uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
     uint32_t kblocks = (k + kBK - 1) / kBK;
-    while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8) split_k *= 2;
+    while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8 && split_k < 8) split_k *= 2;
   }
+  if (n_parts) *n_parts = split_k;
   switch (bn) {
     case 16: return dispatch_tc_epi<16>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
     case 32: return dispatch_tc_epi<32>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);

@@ -215,6 +215,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               const size_t idx = size_t(t) * out_stride + n;
               if constexpr (EPI == LLMLB_EPI_STORE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
               else if constexpr (EPI == LLMLB_EPI_STORE_F32) reinterpret_cast<float*>(out)[idx] = v;
+              else if constexpr (EPI == kEpiPartialF32) reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
               else {
                 if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
                 else reinterpret_cast<float*>(out)[idx] += v;
@@ -271,18 +272,20 @@ static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* o
 
 // BN = 256 only (n_tokens > 128).  tx_half: activation tensor map with a 128-row box.
 int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens, uint32_t n_out,
-                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st) {
+                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st, uint32_t* n_parts) {
   uint32_t split_k = 1;
-  if (epi == LLMLB_EPI_RESID_F32) {
+  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32) {
     uint32_t tiles = ((n_out + 255) / 256) * ((n_tokens + 255) / 256);
     uint32_t kblocks = (k + kBK - 1) / kBK;
-    while (tiles * split_k * 2 <= (uint32_t)(kNumSMs / 2) && kblocks / (split_k * 2) >= 8) split_k *= 2;
+    while (tiles * split_k * 2 <= (uint32_t)(kNumSMs / 2) && kblocks / (split_k * 2) >= 8 && split_k < 8) split_k *= 2;
   }
+  if (n_parts) *n_parts = split_k;
   switch (epi) {
     case LLMLB_EPI_STORE_BF16: return launch_tc2<256, LLMLB_EPI_STORE_BF16>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
     case LLMLB_EPI_RESID_F32: return launch_tc2<256, LLMLB_EPI_RESID_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
     case LLMLB_EPI_SILU_MUL: return launch_tc2<256, LLMLB_EPI_SILU_MUL>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
     case LLMLB_EPI_STORE_F32: return launch_tc2<256, LLMLB_EPI_STORE_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
+    case kEpiPartialF32: return launch_tc2<256, kEpiPartialF32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
   }
   set_error("gemm_tc2: unknown epilogue");
   return LLMLB_E_INVALID_ARG;

@@ -7,6 +7,9 @@
 
 namespace llmlb {
 
+// internal epilogue (not in the public header): fp32 partial product of K-split `ks` stored at
+// out + ks * n_tokens * out_stride; the consumer adds the slots in a fixed order (deterministic)
+constexpr int kEpiPartialF32 = 4;
 constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
 constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row
 constexpr int kTcThreads = 384;    // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps

@@ -246,9 +246,8 @@ def test_8b_batched_equals_single_and_is_deterministic(eng8b):
     prompts = [rs.randint(0, cfg["vocab"], n).tolist() for n in (512, 77, 300)]
     alone = [eng8b.generate(p, 12, ignore_eos=True)[0] for p in prompts]
     again = eng8b.generate(prompts[0], 12, ignore_eos=True)[0]
-    # the prefill's split-K residual epilogue adds fp32 partials with red.global.add: a 1-ulp
-    # run-to-run difference can flip a near-tie among 128256 random logits later in the sequence
-    assert again[:4] == alone[0][:4]
+    # K-split partials are folded into the residual in slot order (no atomics): bit-reproducible
+    assert again == alone[0]
     rids = [eng8b.submit(p, 12, ignore_eos=True) for p in prompts]
     outs = []
     for r in rids:
