@@ -207,8 +207,12 @@ def gemv_microbench(model, hbm_peak):
     torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / iters
     bytes_ = n_out * H * 2
-    return {"kernel": "gemv_kernel<1,SILU_MUL,NORM> %dx%d" % (n_out, H), "bytes_per_launch": bytes_, "us_per_launch": us,
-            "achieved": bytes_ / us / 1e3, "unit": "GB/s", "frac": bytes_ / us / 1e3 / hbm_peak}
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel (one launch) from the
+    # committed `ncu --set full` capture profiles/r1_final_gemv_ks_ncu_full.txt (241.20 + 3.24 MB)
+    traffic = 244.44e6 if (n_out, H) == (28672, 4096) else None
+    return {"kernel": "gemv_ks_kernel<1,SILU_MUL,NORM,1> %dx%d (gate/up, fused RMSNorm + SiLU*up)" % (n_out, H),
+            "bytes_per_launch": bytes_, "us_per_launch": us, "achieved": bytes_ / us / 1e3, "unit": "GB/s",
+            "frac": bytes_ / us / 1e3 / hbm_peak, "traffic": traffic}
 
 
 def run_ours(args):
@@ -319,7 +323,10 @@ def run_ours(args):
                         "roofline": {"bound": "tensor", "achieved": pre_tf, "peak": tf_burst, "unit": "TFLOP/s",
                                      "frac": pre_tf / tf_burst, "peak_source": peak_src + " (burst cuBLAS bf16)"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         # per decode step: 32 x (QKV 50.39 + O 33.60 + gate/up 244.44 + down 120.83 MB) of DRAM traffic in the
+                         # ncu captures under profiles/ (lm_head not captured: its 1050.7 MB algorithmic) vs 15.08 GB algorithmic
+                         "traffic": (32 * (50.39e6 + 33.60e6 + 244.44e6 + 120.83e6) + 1050.7e6) if (args.model == "8b" and tp == 1 and args.batch == 1) else None,
+                         "peak_source": peak_src,
                          "what": "whole decode step (%.2f GB algorithmic per step per GPU / %.3f ms CUDA-event step time)" % (bytes_step / 1e9, step_s * 1e3),
                          "kernel": kern},
             "e2e": {"value": e2e_decode_tok_s, "unit": "tok/s", "h2d_bytes_per_step": PROMPT * 4 * args.batch,
