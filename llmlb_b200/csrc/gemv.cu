@@ -272,12 +272,25 @@ extern "C" int llmlb_op_gemv(const void* w, const void* x, const void* gain, flo
     set_error("llmlb_op_gemv: SILU_MUL needs interleaved gate/up rows (even n_out)");
     return LLMLB_E_INVALID_ARG;
   }
-  if (size_t(n_tokens) * k * 2 > 200 * 1024) {
-    set_error("llmlb_op_gemv: n_tokens*k too large for the shared-memory activation stage");
+  if (size_t(k) * 2 > 200 * 1024) {
+    set_error("llmlb_op_gemv: k too large for the shared-memory activation stage");
     return LLMLB_E_INVALID_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
   bool norm = gain != nullptr;
+  if (n_tokens > 1 && n_tokens <= 4 && size_t(n_tokens) * k * 2 > 200 * 1024) {
+    // very wide K (e.g. an un-sharded 70B down projection): one token per pass — the weights are
+    // streamed once per token on this rare path
+    const size_t x_step = size_t(k) * (norm ? 4 : 2);
+    const size_t o_elems = epilogue == LLMLB_EPI_SILU_MUL ? out_stride : out_stride;
+    const size_t o_step = o_elems * ((epilogue == LLMLB_EPI_STORE_BF16 || epilogue == LLMLB_EPI_SILU_MUL) ? 2 : 4);
+    for (uint32_t t = 0; t < n_tokens; ++t) {
+      int rc = llmlb_op_gemv(w, (const uint8_t*)x + t * x_step, gain, eps, (uint8_t*)out + t * o_step, 1, n_out, k,
+                             epilogue, out_stride, stream);
+      if (rc != LLMLB_OK) return rc;
+    }
+    return LLMLB_OK;
+  }
   if (n_tokens >= 1 && n_tokens <= 4 && epilogue <= LLMLB_EPI_STORE_F32) {
     // 1) bulk-copy ring (deep smem prefetch across PDL-chained kernels), 2) K-split with
     // register-staged loads, 3) row-owner variant for odd shapes

@@ -300,3 +300,33 @@ def test_decode_chain_vs_oracle_and_vs_unchained(built_lib):
     for a, b in zip(got["1"][0], got["0"][0]):
         assert np.abs(a - b).max() < 0.03 * sigma + 0.01
     assert got["1"][1][:3] == got["0"][1][:3] and len(got["1"][1]) == 20
+
+
+def test_70b_geometry_parity_4_layers(built_lib):
+    """Llama-3-70B shapes (hidden 8192, 64/8 heads -> GQA group 8, ffn 28672) on 4 layers: covers
+    the kernels' other template / fallback paths (two head groups per KV head in attention,
+    K=8192 and K=28672 projections) against the CPU oracle.  A geometry test, not a benchmark."""
+    from oracle import synth_native
+    cfg = dict(ffi.LLAMA3_70B)
+    cfg["n_layers"] = 4
+    rs = np.random.RandomState(23)
+    prompt = rs.randint(0, cfg["vocab"], 37).tolist()
+    try:
+        e = ffi.Engine(cfg, max_seqs=4, max_ctx=512, seed=2)
+    except ffi.LlmlbError as ex:
+        pytest.skip("not creatable here: %s" % ex)
+    with e:
+        lg = e.debug_prefill_logits(prompt)
+        d1 = e.debug_decode_logits(777)
+        e.debug_reset()
+        toks, _ = e.generate(prompt, 6, ignore_eos=True)
+    synth_native.set_threads(synth_native.effective_cpus())
+    ref = LlamaRef(cfg, synth_native.synth_state_dict_bits(cfg, seed=2), emulate_bf16=True)
+    rl = ref.forward(prompt).numpy()[-1]
+    r1 = ref.forward([777]).numpy()[-1]
+    sigma = float(rl.std())
+    assert np.abs(lg - rl).mean() < 0.02 * sigma + 0.005 and np.abs(lg - rl).max() < 0.25 * sigma
+    assert np.abs(d1 - r1).mean() < 0.02 * sigma + 0.005 and np.abs(d1 - r1).max() < 0.25 * sigma
+    assert np.corrcoef(lg, rl)[0, 1] > 0.999
+    # the engine's first generated token is the (near-)arg-max of the oracle's prefill logits
+    assert rl[toks[0]] >= rl.max() - 0.1 * sigma and len(toks) == 6
