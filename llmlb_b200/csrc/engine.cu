@@ -24,6 +24,7 @@
 
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace llmlb {
 
@@ -33,13 +34,15 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
 uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                   const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr);
+                   const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr,
+                   const SkWorkspace* sk = nullptr, const CUtensorMap* tw_pf = nullptr);
+int sk_workspace_create(SkWorkspace* sk, cudaStream_t st);
+void sk_workspace_destroy(SkWorkspace* sk);
 int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,
                     uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
 
 int rmsnorm_parts_launch(float* x, const float* parts, uint32_t n_parts, size_t part_stride, const void* gain,
                          void* y, uint32_t n_tokens, uint32_t hidden, float eps, cudaStream_t st);
-constexpr int kEpiPartialF32 = 4;  // internal GEMM epilogue: fp32 K-split partials (tc_common.cuh)
 int gemv_decode(const void* w, const void* x, const void* gain, float eps, void* out, uint32_t n_tokens,
                 uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
                 const void* next_w, size_t next_bytes);
@@ -49,6 +52,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
                             bool pdl, cudaStream_t st, const void* pf_ptr = nullptr, uint32_t pf_bytes = 0);
 void ks_set_trace(const TraceBuf& tb);
 void tc_set_trace(const TraceBuf& tb);
+void sk_set_trace(const TraceBuf& tb);
 void attn_set_trace(const TraceBuf& tb);
 struct ChainOpHost { const void* w; const void* x; const void* gain; void* out; uint32_t n_out, k, out_stride, epi; };
 bool gemv_chain_shape_ok(uint32_t n_out, uint32_t k);
@@ -255,6 +259,7 @@ struct llmlb_engine {
   uint32_t attn_pf_mb = 0;    // LLMLB_ATTN_PF_MB: O-proj bytes the decode attention kernel pulls into L2 (measured: 64 -> -3 %)
   size_t pf_head_bytes = 0;  // LLMLB_PF_MB: next-projection bytes prefetched into L2 per tail (measured: 0 best)
   float* part_ws = nullptr;         // [8 splits][t_cap][hidden] fp32: K-split partials of O / down
+  SkWorkspace sk;                   // stream-K scratch of the one-N-tile GEMMs (batched decode)
   uint32_t* chain_state = nullptr;  // [n_layers][8] barrier counters of the decode GEMV chains
   bool use_chain = false;
   int warmup();
@@ -452,6 +457,7 @@ int llmlb_engine::alloc_all() {
   }
   RC(dmalloc(&chain_state, size_t(M.n_layers) * 8));
   if (tp == 1) RC(dmalloc(&part_ws, size_t(8) * t_cap * H, false));
+  RC(sk_workspace_create(&sk, st));
   {
     if (const char* pm = getenv("LLMLB_PF_MB")) pf_head_bytes = size_t(atoi(pm)) << 20;
     if (const char* am = getenv("LLMLB_ATTN_PF_MB")) attn_pf_mb = (uint32_t)atoi(am);
@@ -519,7 +525,7 @@ int llmlb_engine::proj(const LayerW*, int, const void* w, const CUtensorMap& mw,
   if (T <= 4) return llmlb_op_gemv(w, xin, gain, M.rms_eps, out, T, n_out, k, epi, out_stride, st);
   // callers pass bf16 activations (already normalised) on this path
   if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, out, T, n_out, k, epi, out_stride, st);
-  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)]);
+  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &sk);
 }
 
 // Runs the layer stack over T rows already embedded in x.  decode: rows are one new token per
@@ -560,7 +566,7 @@ int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t 
     *n_parts = 1;
     if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, part_ws, T, H, k, LLMLB_EPI_STORE_F32, H, st);
     return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], part_ws, T, H, k, kEpiPartialF32, H, st,
-                          &mx[bn_index(128)], n_parts);
+                          &mx[bn_index(128)], n_parts, &sk);
   };
   for (uint32_t l = 0; l < M.n_layers; ++l) {
     LayerW& L = layers[l];
@@ -638,7 +644,7 @@ int llmlb_engine::logits_for_rows(uint32_t R, bool from_x_rows) {
     if (cfg.gemm_impl == 1)
       RC(gemm_mma_launch(lm_head, y, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
     else
-      RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st, &m_y[bn_index(128)]));
+      RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st, &m_y[bn_index(128)], nullptr, &sk));
   }
   if (tp > 1) RC(ar_allgather_cols(peers, 2, logits, R, vocab_l, st));
   return LLMLB_OK;
@@ -1021,6 +1027,7 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
     for (uint32_t r = 0; r < e->tp; ++r)
       if (r != e->rank && e->peers.base[r]) cudaIpcCloseMemHandle(e->peers.base[r]);
   F(e->xchg); F(e->chain_state); F(e->part_ws);
+  sk_workspace_destroy(&e->sk);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
@@ -1373,6 +1380,7 @@ extern "C" int llmlb_debug_trace_enable(uint32_t cap) {
   ks_set_trace(g_tb);
   attn_set_trace(g_tb);
   tc_set_trace(g_tb);
+  sk_set_trace(g_tb);
   return LLMLB_OK;
 }
 extern "C" int llmlb_debug_trace_dump(unsigned long long* out, uint32_t cap_records, uint32_t* n) {

@@ -5,8 +5,11 @@
 // CTA tile 128 tokens x 128 outputs x 32 k, 8 warps (2 x 4), warp tile 64 x 32, 3 stages.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace llmlb {
 
@@ -15,7 +18,10 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
 uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                   const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr);
+                   const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr,
+                   const SkWorkspace* sk = nullptr, const CUtensorMap* tw_pf = nullptr);
+int make_tmap_bf16_pf(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols);
+int sk_workspace_create(SkWorkspace* sk, cudaStream_t st);
 
 constexpr int kMT = 128, kMN = 128, kMK = 32, kMStages = 3, kMThreads = 256;
 
@@ -187,9 +193,24 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   if (n_tokens == 0) return LLMLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) return gemm_mma_launch(w, x, out, n_tokens, n_out, k, epilogue, out_stride, st);
-  if (impl != 0) {
-    set_error("llmlb_op_gemm: impl must be 0 (tcgen05) or 1 (mma.sync)");
+  if (impl > 2) {
+    set_error("llmlb_op_gemm: impl must be 0 (tcgen05 tiles), 1 (mma.sync) or 2 (tcgen05 stream-K)");
     return LLMLB_E_INVALID_ARG;
+  }
+  // impl 2: stream-K work split (gemm_sk.cu for one token tile, gemm_tc2.cu above); scratch is per device and the
+  // op-level entry point is synchronous test/bench surface, so one static workspace is enough
+  const SkWorkspace* sk = nullptr;
+  if (impl == 2) {
+    static SkWorkspace sk_dev[64];
+    int dev = 0;
+    LLMLB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("llmlb_op_gemm: device index"); return LLMLB_E_INVALID_ARG; }
+    if (!sk_dev[dev].ws) {
+      int rc = sk_workspace_create(&sk_dev[dev], st);
+      if (rc) return rc;
+      sk_dev[dev].force = true;
+    }
+    sk = &sk_dev[dev];
   }
   CUtensorMap tw, tx;
   int rc = make_tmap_bf16(&tw, w, n_out, k, 128);
@@ -199,5 +220,11 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   CUtensorMap txh;
   rc = make_tmap_bf16(&txh, x, n_tokens, k, 128);
   if (rc) return rc;
-  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh);
+  CUtensorMap twpf;
+  static const bool wide = getenv("LLMLB_GEMM_PF_WIDE") != nullptr;
+  if (wide) {
+    rc = make_tmap_bf16_pf(&twpf, w, n_out, k);
+    if (rc) return rc;
+  }
+  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, sk, wide ? &twpf : nullptr);
 }

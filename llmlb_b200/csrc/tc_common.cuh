@@ -102,5 +102,36 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// stream-K flag / barrier helpers
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void epi_bar() {  // the 8 epilogue warps only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+// tile configuration shared by the 1-CTA kernels (gemm_tc.cu, gemm_sk.cu)
+template <int BN>
+struct TcCfg {
+  static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in set
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // bf16 x bf16 -> f32, A and B K-major, M=128, N=BN
+  static constexpr uint32_t kIdesc =
+      (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+};
+
+// stream-K scratch: one fp32 partial tile per CTA + one ready flag per CTA (zero between launches)
+struct SkWorkspace {
+  float* ws = nullptr;        // [kNumSMs][<= 256 tokens][kBM] fp32
+  uint32_t* flags = nullptr;  // [kNumSMs]
+  bool force = false;         // op-level impl = 2: stream-K even where the engine's default is tiles
+};
+constexpr size_t kSkWsBytes = size_t(kNumSMs) * 256 * kBM * sizeof(float);
 
 }  // namespace llmlb

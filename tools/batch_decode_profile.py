@@ -54,6 +54,26 @@ def main():
         tot = rows[:, 2]
         print("%-40s %7d %9.0f %8.1f %8.1f%% %8.1f%% %8.1f%%" % (nm, len(rows), tot.mean(), tot.mean() / 1.9e3, 100 * (rows[:, 3] / tot).mean(),
                                                                100 * (rows[:, 4] / tot).mean(), 100 * (rows[:, 5] / tot).mean()))
+    k = r[(r[:, 0] >> np.uint64(60)) == 3]
+    if len(k):
+        print("%-40s %7s %8s %8s %8s %9s %9s %9s" % ("gemm_sk (stream-K) kernel", "ctas", "span_us", "life_us", "min_life", "prod_wait", "flag_wait", "epi_wait"))
+    for tag in np.unique(k[:, 0]):
+        rows = k[k[:, 0] == tag].astype(np.int64)
+        t = int(tag)
+        nm = "n_out=%d k=%d %s" % ((t >> 32) & 0xFFFFFFF, t & 0xFFFFFFF, names.get((t >> 28) & 0xF, "?"))
+        # launches are separated in time: split the records of this tag into launches by start gaps
+        order = np.argsort(rows[:, 2]); rows = rows[order]
+        cuts = np.where(np.diff(rows[:, 2]) > 20000)[0] + 1
+        spans, lifes, mins = [], [], []
+        for grp in np.split(rows, cuts):
+            spans.append((grp[:, 5].max() - grp[:, 2].min()) / 1e3)
+            lifes.append((grp[:, 5] - grp[:, 2]).mean() / 1e3)
+            mins.append((grp[:, 5] - grp[:, 2]).min() / 1e3)
+        life_cyc = (rows[:, 5] - rows[:, 2]) * 1.9
+        print("%-40s %7d %8.1f %8.1f %8.1f %8.1f%% %8.1f%% %8.1f%%" % (
+            nm, len(rows) // max(1, len(spans)), np.mean(spans), np.mean(lifes), np.mean(mins),
+            100 * ((rows[:, 3] >> 32) / life_cyc).mean(), 100 * ((rows[:, 3] & 0xFFFFFFFF) / life_cyc).mean(),
+            100 * (rows[:, 4] / life_cyc).mean()))
     a = r[r[:, 0] == 1].astype(np.int64)
     if len(a):
         print("decode attention: %d CTAs, lifetime mean %.1f us max %.1f us; loop %.1f us; merge %.1f us" % (
