@@ -205,8 +205,8 @@ int llmlb_op_gemv(const void* w_bf16, const void* x, const void* gain_bf16, floa
                   uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epilogue,
                   uint32_t out_stride, void* stream);
 /* prefill / batched path: out[t,n] = sum_k x[t,k]*W[n,k] on tensor cores.
- * impl 0 = tcgen05+TMEM+TMA tiles, 1 = mma.sync, 2 = tcgen05 with the stream-K work split (what the
- * engine runs for prefill-sized steps). x is bf16 [n_tokens,k]. */
+ * impl 0 = tcgen05+TMEM+TMA tiles, 1 = mma.sync, 2 = tcgen05 with the stream-K work split
+ * (n_tokens <= 128; opt-in experiment). x is bf16 [n_tokens,k]. */
 int llmlb_op_gemm(const void* w_bf16, const void* x_bf16, void* out, uint32_t n_tokens,
                   uint32_t n_out, uint32_t k, uint32_t epilogue, uint32_t out_stride,
                   uint32_t impl, void* stream);

@@ -35,7 +35,7 @@ uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
                    const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr,
-                   const SkWorkspace* sk = nullptr, const CUtensorMap* tw_pf = nullptr);
+                   const SkWorkspace* sk = nullptr);
 int sk_workspace_create(SkWorkspace* sk, cudaStream_t st);
 void sk_workspace_destroy(SkWorkspace* sk);
 int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,

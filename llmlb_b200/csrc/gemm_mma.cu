@@ -19,8 +19,7 @@ uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
                    const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr,
-                   const SkWorkspace* sk = nullptr, const CUtensorMap* tw_pf = nullptr);
-int make_tmap_bf16_pf(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols);
+                   const SkWorkspace* sk = nullptr);
 int sk_workspace_create(SkWorkspace* sk, cudaStream_t st);
 
 constexpr int kMT = 128, kMN = 128, kMK = 32, kMStages = 3, kMThreads = 256;
@@ -193,11 +192,11 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   if (n_tokens == 0) return LLMLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) return gemm_mma_launch(w, x, out, n_tokens, n_out, k, epilogue, out_stride, st);
-  if (impl > 2) {
-    set_error("llmlb_op_gemm: impl must be 0 (tcgen05 tiles), 1 (mma.sync) or 2 (tcgen05 stream-K)");
+  if (impl > 2 || (impl == 2 && n_tokens > 128)) {
+    set_error("llmlb_op_gemm: impl must be 0 (tcgen05 tiles), 1 (mma.sync) or 2 (tcgen05 stream-K, n_tokens <= 128)");
     return LLMLB_E_INVALID_ARG;
   }
-  // impl 2: stream-K work split (gemm_sk.cu for one token tile, gemm_tc2.cu above); scratch is per device and the
+  // impl 2: stream-K work split (gemm_sk.cu, one token tile); scratch is per device and the
   // op-level entry point is synchronous test/bench surface, so one static workspace is enough
   const SkWorkspace* sk = nullptr;
   if (impl == 2) {
@@ -220,11 +219,5 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   CUtensorMap txh;
   rc = make_tmap_bf16(&txh, x, n_tokens, k, 128);
   if (rc) return rc;
-  CUtensorMap twpf;
-  static const bool wide = getenv("LLMLB_GEMM_PF_WIDE") != nullptr;
-  if (wide) {
-    rc = make_tmap_bf16_pf(&twpf, w, n_out, k);
-    if (rc) return rc;
-  }
-  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, sk, wide ? &twpf : nullptr);
+  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, sk);
 }

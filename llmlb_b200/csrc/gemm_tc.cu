@@ -29,8 +29,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K,
-               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k,
-               const __grid_constant__ CUtensorMap tmap_wpf, uint32_t wide_pf) {
+               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -94,29 +93,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       // L2 prefetch cursor: runs kPrefetchAhead K-slabs ahead of the smem loads (weights only —
       // the activation operand is small and L2-resident).  The smem ring holds 3 slabs in flight
       // (~1.5k MMA cycles); an HBM miss costs 3-4k, an L2 hit ~1k.
-      // wide_pf: the cursor asks for 4 K blocks (512 B of every row) per request through a second,
-      // unswizzled map, so HBM sees longer contiguous runs per row than the 128 B the smem loads take
-      const uint32_t kPrefetchAhead = wide_pf ? 16 : 12;
+      // (a 512-byte-per-row prefetch view through a second, unswizzled map measured slower:
+      // lm_head at 64 tokens 188 -> 203 us)
+      constexpr uint32_t kPrefetchAhead = 12;
       uint32_t p_tile = blockIdx.x, p_kb = 0, p_kb1 = 0, p_mt = 0;
-      bool p_first = true;
       auto p_load = [&]() {
         if (p_tile < n_tiles) {
           uint32_t tt, ks;
           decode_tile(p_tile, p_mt, tt, ks);
           p_kb = ks * k_per_split;
           p_kb1 = min(k_blocks_total, p_kb + k_per_split);
-          p_first = true;
         }
       };
       auto p_step = [&]() {
         if (p_tile >= n_tiles) return;
-        if (wide_pf) {
-          if (p_first || (p_kb & 3) == 0)
-            tma_prefetch_l2_2d(&tmap_wpf, int32_t((p_kb & ~3u) * kBK), int32_t(p_mt * kBM));
-          p_first = false;
-        } else {
-          tma_prefetch_l2_2d(&tmap_w, int32_t(p_kb * kBK), int32_t(p_mt * kBM));
-        }
+        tma_prefetch_l2_2d(&tmap_w, int32_t(p_kb * kBK), int32_t(p_mt * kBM));
         if (++p_kb >= p_kb1) { p_tile += gridDim.x; p_load(); }
       };
       p_load();
@@ -293,29 +284,6 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
   return LLMLB_OK;
 }
 
-// L2-prefetch view of a weight matrix: box = {256 cols, 128 rows}, no swizzle (never lands in smem)
-int make_tmap_bf16_pf(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled not available from the driver");
-    return LLMLB_E_DEVICE;
-  }
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {cols * 2};
-  cuuint32_t box[2] = {256, 128};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (prefetch view) failed: " + std::to_string((int)r));
-    return LLMLB_E_DEVICE;
-  }
-  return LLMLB_OK;
-}
-
-static thread_local const CUtensorMap* g_tw_pf = nullptr;  // set by gemm_tc_launch for the launch below
-
 template <int BN, int EPI>
 static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                      uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t split_k,
@@ -332,9 +300,8 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, ui
   uint32_t t_tiles = (n_tokens + BN - 1) / BN;
   uint32_t tiles = m_tiles * t_tiles * split_k;
   uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
-  const bool wide = g_tw_pf != nullptr && BN <= 128;
   kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tw, tx, out, n_tokens, n_out, k, out_stride,
-                                                  m_tiles, t_tiles, split_k, wide ? *g_tw_pf : tw, wide ? 1u : 0u);
+                                                  m_tiles, t_tiles, split_k);
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
@@ -372,7 +339,7 @@ uint32_t tc_pick_bn(uint32_t n_tokens) {
 // buffers are fixed).  The X map's box rows must equal tc_pick_bn(n_tokens).
 int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens,
                     uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                    uint32_t* n_parts, const SkWorkspace* sk);
+                    uint32_t* n_parts);
 int gemm_sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
                    const SkWorkspace& sk, cudaStream_t st);
@@ -382,8 +349,7 @@ int gemm_sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
                    cudaStream_t st, const CUtensorMap* tx_half, uint32_t* n_parts,
-                   const SkWorkspace* sk, const CUtensorMap* tw_pf) {
-  g_tw_pf = tw_pf;
+                   const SkWorkspace* sk) {
   const uint32_t bn = tc_pick_bn(n_tokens);
   static const bool no_2cta = getenv("LLMLB_GEMM_NO_2CTA") != nullptr;
   static const bool no_sk = getenv("LLMLB_GEMM_NO_SK") != nullptr;
@@ -395,8 +361,7 @@ int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint
   if (sk && sk->ws && n_tokens <= 128 && !no_sk && (sk_small || sk->force))
     return gemm_sk_launch(tw, tx, out, n_tokens, n_out, k, epi, out_stride, *sk, st);
   if (tx_half && bn == 256 && n_out >= 256 && !no_2cta)
-    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts,
-                           (sk && sk->ws && !no_sk) ? sk : nullptr);
+    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts);
   // split K for the residual epilogue when the tile count cannot fill the GPU
   uint32_t split_k = 1;
   if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32) {

@@ -14,8 +14,6 @@
 //                                 tempty[acc]   leader, count 16 (8 epilogue warps x 2 CTAs)
 #include <cuda.h>
 
-#include <cstdlib>
-
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -76,8 +74,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                 void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K, uint32_t out_stride,
-                uint32_t m_tiles /*256-row slabs*/, uint32_t t_tiles, uint32_t split_k,
-                float* __restrict__ sk_ws, uint32_t* __restrict__ sk_flags) {
+                uint32_t m_tiles /*256-row slabs*/, uint32_t t_tiles, uint32_t split_k) {
   using Cfg = Tc2Cfg<BN>;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -122,69 +119,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Work list of this pair as segments (slab mt, token tile tt, K blocks [kb0, kb1)).
-  //   tiled mode   : tiles pair, pair + n_pairs, ... ; a tile is one (mt, tt, K split ks)
-  //   stream-K mode: (sk_ws != nullptr) hybrid schedule.  The first sk_tiles tiles (between one and
-  //                  two waves' worth, or everything when there is less than a wave) are cut, as a
-  //                  flat list of (tile, K block) units, into n_pairs equal contiguous ranges — the
-  //                  piece / head protocol of gemm_sk.cu; the remaining whole waves run as plain
-  //                  round-robin tiles afterwards.  Neighbouring pairs therefore sit on neighbouring
-  //                  tiles at all times (shared W slab / token tile in L2), and nobody idles through
-  //                  a ragged last wave.
-  const bool sk = sk_ws != nullptr;
-  const uint32_t tiles_all = m_tiles * t_tiles;
-  const uint32_t dp_waves = (sk && tiles_all >= n_pairs) ? tiles_all / n_pairs - 1 : 0u;
-  const uint32_t sk_tiles = tiles_all - dp_waves * n_pairs;
-  const uint32_t units = sk_tiles * k_blocks_total;
-  const uint32_t u0 = sk ? uint32_t(uint64_t(pair) * units / n_pairs) : 0u;
-  const uint32_t u1 = sk ? uint32_t(uint64_t(pair + 1) * units / n_pairs) : 0u;
-  struct Seg { uint32_t mt, tt, ks, kb0, kb1; };
-  constexpr uint32_t kDpPhase = 0x80000000u;  // cursor values >= this count whole-tile waves
-  const uint32_t cur0 = sk ? u0 : pair;
-  auto next_seg = [&](uint32_t& cur, Seg& g) -> bool {
-    if (sk) {
-      if (cur < kDpPhase) {
-        if (cur < u1) {
-          const uint32_t tile = cur / k_blocks_total;
-          g.kb0 = cur - tile * k_blocks_total;
-          g.kb1 = min(k_blocks_total, g.kb0 + (u1 - cur));
-          g.tt = tile % t_tiles;
-          g.mt = tile / t_tiles;
-          g.ks = 0;
-          cur += g.kb1 - g.kb0;
-          return true;
-        }
-        cur = kDpPhase;
-      }
-      const uint32_t wave = cur - kDpPhase;
-      if (wave >= dp_waves) return false;
-      const uint32_t tile = sk_tiles + wave * n_pairs + pair;
-      g.tt = tile % t_tiles;
-      g.mt = tile / t_tiles;
-      g.ks = 0;
-      g.kb0 = 0;
-      g.kb1 = k_blocks_total;
-      ++cur;
-      return true;
-    }
-    if (cur >= n_tiles) return false;
-    g.tt = cur % t_tiles;
-    const uint32_t r = cur / t_tiles;
-    g.ks = r % split_k;
-    g.mt = r / split_k;
-    g.kb0 = g.ks * k_per_split;
-    g.kb1 = min(k_blocks_total, g.kb0 + k_per_split);
-    cur += n_pairs;
-    return true;
+  auto decode_tile = [&](uint32_t tile, uint32_t& mt, uint32_t& tt, uint32_t& ks) {
+    tt = tile % t_tiles;
+    uint32_t r = tile / t_tiles;
+    ks = r % split_k;
+    mt = r / split_k;
   };
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer (both CTAs) ----
-      uint32_t stage = 0, phase = 0, cur = cur0;
-      Seg g;
-      while (next_seg(cur, g)) {
-        const uint32_t mt = g.mt, tt = g.tt;
-        for (uint32_t kb = g.kb0; kb < g.kb1; ++kb) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs) {
+        uint32_t mt, tt, ks;
+        decode_tile(tile, mt, tt, ks);
+        const uint32_t kb0 = ks * k_per_split;
+        const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kBM * kBK * 2;
@@ -198,10 +148,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {  // ---- MMA issuer for the pair ----
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, cur = cur0;
-      Seg g;
-      while (next_seg(cur, g)) {
-        const uint32_t kb0 = g.kb0, kb1 = g.kb1;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs) {
+        uint32_t mt, tt, ks;
+        decode_tile(tile, mt, tt, ks);
+        const uint32_t kb0 = ks * k_per_split;
+        const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -224,119 +176,58 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
   } else if (warp >= 4) {  // ---- epilogue (both CTAs, own TMEM lanes = own 128 weight rows) ----
     const uint32_t q = warp & 3;
-    uint32_t acc = 0, acc_phase = 0, cur = cur0;
-    Seg g;
-    while (next_seg(cur, g)) {
-      const uint32_t mt = g.mt, tt = g.tt, ks = g.ks;
-      // stream-K: a segment that starts inside a tile is parked for the pair that owns the tile's
-      // head; the head adds the parked pieces (pair order) before the fused epilogue
-      const bool piece = sk && g.kb0 > 0;
-      const bool head = sk && g.kb0 == 0 && g.kb1 < k_blocks_total;
-      uint32_t f_lo = pair + 1, f_hi = f_lo;
-      if (head) {
-        const uint32_t tile_end = (mt * t_tiles + tt + 1) * k_blocks_total;
-        while (f_hi < n_pairs && uint32_t(uint64_t(f_hi) * units / n_pairs) < tile_end) ++f_hi;
-        if (lane == 0)
-          for (uint32_t f = f_lo; f < f_hi; ++f)
-            while (ld_acquire_u32(sk_flags + f * 2 + rank) == 0) {}
-        __syncwarp();
-      }
-      const uint32_t row = q * 32 + lane;
-      const uint32_t n = mt * 256 + rank * kBM + row;
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs) {
+      uint32_t mt, tt, ks;
+      decode_tile(tile, mt, tt, ks);
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t n = mt * 256 + rank * kBM + q * 32 + lane;
       const uint32_t t0 = tt * BN;
       // two warps share a TMEM lane quarter: each takes half of the token columns
       constexpr uint32_t kColsPerWarp = (BN / 2 >= 16) ? BN / 2 : 16;
-      constexpr uint32_t kGroup = kColsPerWarp < 64 ? kColsPerWarp : 64;  // columns gathered per round
       const uint32_t c_begin = ((warp - 4) >> 2) * kColsPerWarp;
-      bool waited = false;
 #pragma unroll 1
-      for (uint32_t cg = c_begin; cg < c_begin + kColsPerWarp && cg < BN; cg += kGroup) {
-        if (t0 + cg >= n_tokens) break;
-        // head: sum of the parked pieces for this thread's row x kGroup columns, every load of a
-        // piece in flight at once (a dependent 16-column round trip per piece cost ~10 us per tile);
-        // the first round is issued before the accumulator is awaited
-        float p[kGroup];
-        if (head) {
+      for (uint32_t c = c_begin; c < c_begin + kColsPerWarp && c < BN; c += 16) {
+        if (t0 + c >= n_tokens) break;
+        uint32_t r[16];
+        tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
+        tc_wait_ld();
+        if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll
-          for (uint32_t j = 0; j < kGroup; ++j) p[j] = 0.f;
-          for (uint32_t f = f_lo; f < f_hi; ++f) {
-            const float* slot = sk_ws + (size_t(f * 2 + rank) * BN + cg) * kBM + row;
-#pragma unroll
-            for (uint32_t j = 0; j < kGroup; ++j) p[j] += __ldcg(slot + size_t(j) * kBM);
+          for (int j = 0; j < 16; ++j) {
+            const float v = __uint_as_float(r[j]);
+            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            // lanes (2i, 2i+1) hold (gate_i, up_i); even lanes finish even columns, odd lanes odd ones
+            if (((j ^ lane) & 1) == 0 && (n | 1) < n_out && t0 + c + j < n_tokens) {
+              const float g = (lane & 1) ? other : v, u = (lane & 1) ? v : other;
+              const float s = __fdividef(g, 1.f + __expf(-g));  // IEEE division was ~half of the epilogue's instructions
+              o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(s * u);
+            }
           }
-        }
-        if (!waited) {
-          mbar_wait(tfull_bar + acc, acc_phase);
-          tc_fence_after();
-          waited = true;
-        }
+        } else if (n < n_out) {
 #pragma unroll
-        for (uint32_t cc = 0; cc < kGroup; cc += 16) {
-          const uint32_t c = cg + cc;
-          if (t0 + c < n_tokens) {                 // warp-uniform
-            uint32_t r[16];
-            tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
-            tc_wait_ld();
-            if (piece) {
-              float* slot = sk_ws + (size_t(blockIdx.x) * BN + c) * kBM + row;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) slot[size_t(j) * kBM] = __uint_as_float(r[j]);
-            } else {
-              if (head) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + p[cc + j]);
-              }
-              if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float v = __uint_as_float(r[j]);
-                  const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-                  // lanes (2i, 2i+1) hold (gate_i, up_i); even lanes finish even columns, odd lanes odd ones
-                  if (((j ^ lane) & 1) == 0 && (n | 1) < n_out && t0 + c + j < n_tokens) {
-                    const float gt = (lane & 1) ? other : v, up = (lane & 1) ? v : other;
-                    const float sg = __fdividef(gt, 1.f + __expf(-gt));  // IEEE division was ~half of the epilogue's instructions
-                    o[size_t(t0 + c + j) * out_stride + (n >> 1)] = __float2bfloat16_rn(sg * up);
-                  }
-                }
-              } else if (n < n_out) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const uint32_t t = t0 + c + j;
-                  if (t < n_tokens) {
-                    const float v = __uint_as_float(r[j]);
-                    const size_t idx = size_t(t) * out_stride + n;
-                    if constexpr (EPI == LLMLB_EPI_STORE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
-                    else if constexpr (EPI == LLMLB_EPI_STORE_F32) reinterpret_cast<float*>(out)[idx] = v;
-                    else if constexpr (EPI == kEpiPartialF32) reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
-                    else {
-                      if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
-                      else reinterpret_cast<float*>(out)[idx] += v;
-                    }
-                  }
-                }
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t t = t0 + c + j;
+            if (t < n_tokens) {
+              const float v = __uint_as_float(r[j]);
+              const size_t idx = size_t(t) * out_stride + n;
+              if constexpr (EPI == LLMLB_EPI_STORE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+              else if constexpr (EPI == LLMLB_EPI_STORE_F32) reinterpret_cast<float*>(out)[idx] = v;
+              else if constexpr (EPI == kEpiPartialF32) reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
+              else {
+                if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
+                else reinterpret_cast<float*>(out)[idx] += v;
               }
             }
           }
         }
       }
-      if (!waited) {  // no live columns for this warp: still observe the accumulator phase
-        mbar_wait(tfull_bar + acc, acc_phase);
-        tc_fence_after();
-      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar + acc);  // leader's MMA thread reuses the accumulator
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (piece) {
-        __threadfence();
-        epi_bar();
-        if (warp == 4 && lane == 0) st_release_u32(sk_flags + blockIdx.x, 1u);
-      } else if (head) {
-        epi_bar();                                   // every warp has consumed the parked pieces
-        if (warp == 4 && lane == 0)
-          for (uint32_t f = f_lo; f < f_hi; ++f) sk_flags[f * 2 + rank] = 0;   // clean for the next launch
-      }
     }
   }
 
@@ -351,7 +242,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 
 template <int BN, int EPI>
 static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens, uint32_t n_out,
-                      uint32_t k, uint32_t out_stride, uint32_t split_k, cudaStream_t st, const SkWorkspace* sk) {
+                      uint32_t k, uint32_t out_stride, uint32_t split_k, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN>;
   auto kern = gemm_tc2_kernel<BN, EPI>;
   static bool configured = false;
@@ -362,18 +253,6 @@ static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* o
   const uint32_t m_tiles = (n_out + 255) / 256, t_tiles = (n_tokens + BN - 1) / BN;
   const uint32_t tiles = m_tiles * t_tiles * split_k;
   uint32_t pairs = tiles < (uint32_t)(kNumSMs / 2) ? tiles : (uint32_t)(kNumSMs / 2);
-  float* sk_ws = nullptr;
-  uint32_t* sk_flags = nullptr;
-  if (sk) {  // stream-K: every pair gets an equal, non-empty (>= 4 K blocks) share of the unit list
-    const uint32_t units = m_tiles * t_tiles * ((k + kBK - 1) / kBK);
-    pairs = units / 4;
-    if (pairs < 1) pairs = 1;
-    if (pairs > (uint32_t)(kNumSMs / 2)) pairs = kNumSMs / 2;
-    if ((m_tiles * t_tiles) % pairs != 0) {  // whole waves need no fix-up: plain tiles
-      sk_ws = sk->ws;
-      sk_flags = sk->flags;
-    }
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(pairs * 2);
   cfg.blockDim = dim3(kTcThreads);
@@ -386,36 +265,27 @@ static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* o
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx_half, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k,
-                                      sk_ws, sk_flags));
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx_half, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
 
 // BN = 256 only (n_tokens > 128).  tx_half: activation tensor map with a 128-row box.
 int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens, uint32_t n_out,
-                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st, uint32_t* n_parts,
-                    const SkWorkspace* sk) {
+                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st, uint32_t* n_parts) {
   uint32_t split_k = 1;
-  // Stream-K is opt-in for the engine: on Llama-3-8B at T = 512 it measured 0-9 % SLOWER end to end
-  // than whole tiles + K-split partials (DESIGN.md, round-1 negative results), although it removes
-  // the ragged last wave.  LLMLB_GEMM_SK_MODE = 1: all epilogues, 2: only where K-split partials
-  // are not available (bf16 / SiLU stores), 0 (default): off.  llmlb_op_gemm(impl = 2) forces it.
-  static const int sk_mode = getenv("LLMLB_GEMM_SK_MODE") ? atoi(getenv("LLMLB_GEMM_SK_MODE")) : 0;
-  const bool partial_ok = epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32;
-  if (sk && !sk->force && (sk_mode == 0 || (sk_mode == 2 && partial_ok))) sk = nullptr;
-  if (!sk && partial_ok) {
+  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32) {
     uint32_t tiles = ((n_out + 255) / 256) * ((n_tokens + 255) / 256);
     uint32_t kblocks = (k + kBK - 1) / kBK;
     while (tiles * split_k * 2 <= (uint32_t)(kNumSMs / 2) && kblocks / (split_k * 2) >= 8 && split_k < 8) split_k *= 2;
   }
   if (n_parts) *n_parts = split_k;
   switch (epi) {
-    case LLMLB_EPI_STORE_BF16: return launch_tc2<256, LLMLB_EPI_STORE_BF16>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st, sk);
-    case LLMLB_EPI_RESID_F32: return launch_tc2<256, LLMLB_EPI_RESID_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st, sk);
-    case LLMLB_EPI_SILU_MUL: return launch_tc2<256, LLMLB_EPI_SILU_MUL>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st, sk);
-    case LLMLB_EPI_STORE_F32: return launch_tc2<256, LLMLB_EPI_STORE_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st, sk);
-    case kEpiPartialF32: return launch_tc2<256, kEpiPartialF32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st, sk);
+    case LLMLB_EPI_STORE_BF16: return launch_tc2<256, LLMLB_EPI_STORE_BF16>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
+    case LLMLB_EPI_RESID_F32: return launch_tc2<256, LLMLB_EPI_RESID_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case LLMLB_EPI_SILU_MUL: return launch_tc2<256, LLMLB_EPI_SILU_MUL>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
+    case LLMLB_EPI_STORE_F32: return launch_tc2<256, LLMLB_EPI_STORE_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
+    case kEpiPartialF32: return launch_tc2<256, kEpiPartialF32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
   }
   set_error("gemm_tc2: unknown epilogue");
   return LLMLB_E_INVALID_ARG;

@@ -128,10 +128,10 @@ struct TcCfg {
 
 // stream-K scratch: one fp32 partial tile per CTA + one ready flag per CTA (zero between launches)
 struct SkWorkspace {
-  float* ws = nullptr;        // [kNumSMs][<= 256 tokens][kBM] fp32
+  float* ws = nullptr;        // [kNumSMs][<= 128 tokens][kBM] fp32
   uint32_t* flags = nullptr;  // [kNumSMs]
   bool force = false;         // op-level impl = 2: stream-K even where the engine's default is tiles
 };
-constexpr size_t kSkWsBytes = size_t(kNumSMs) * 256 * kBM * sizeof(float);
+constexpr size_t kSkWsBytes = size_t(kNumSMs) * 128 * kBM * sizeof(float);
 
 }  // namespace llmlb

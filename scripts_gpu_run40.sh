@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 300 python tools/gemm_pair_timeline.py 512 > gpurun_out/pair_timeline.txt 2>&1
+timeout 300 python tools/gemm_pair_timeline.py 2048 > gpurun_out/pair_timeline_2048.txt 2>&1
+timeout 300 python tools/gemm_pair_timeline.py 512 6144 4096 > gpurun_out/pair_timeline_qkv.txt 2>&1
+grep "segments\|span" gpurun_out/pair_timeline.txt gpurun_out/pair_timeline_2048.txt gpurun_out/pair_timeline_qkv.txt

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 300 python tools/gemm_pair_timeline.py 512 6144 4096 > gpurun_out/pair_timeline_qkv.txt 2>&1
+grep "epilogue\|span\|rounds" gpurun_out/pair_timeline_qkv.txt | head; tail -3 gpurun_out/pair_timeline_qkv.txt

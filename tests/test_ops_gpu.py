@@ -107,6 +107,8 @@ GEMM_SHAPES = [(512, 6144, 4096), (512, 4096, 14336), (64, 4096, 4096), (16, 102
 def test_gemm(L, impl, T, N, K, epi):
     if epi == ffi.EPI_SILU_MUL and N % 2:
         pytest.skip("odd N")
+    if impl == 2 and T > 128:
+        pytest.skip("stream-K serves one token tile (T <= 128)")
     w = bf16_randn((N, K), std=0.02, seed=7)
     x = bf16_randn((T, K), seed=8)
     n_cols = N // 2 if epi == ffi.EPI_SILU_MUL else N
@@ -122,8 +124,7 @@ def test_gemm(L, impl, T, N, K, epi):
     assert bool((err <= lim).all()), "max err %g at %s" % (err.max().item(), (err - lim).argmax().item())
 
 
-@pytest.mark.parametrize("T,N,K", [(64, 28672, 4096), (64, 6144, 4096), (33, 4096, 14336), (16, 128, 4096),
-                                   (512, 28672, 4096), (512, 4096, 14336), (300, 6144, 4096)])
+@pytest.mark.parametrize("T,N,K", [(64, 28672, 4096), (64, 6144, 4096), (33, 4096, 14336), (16, 128, 4096)])
 def test_gemm_streamk_reproducible(L, T, N, K):
     """Stream-K sums the parked pieces in CTA order: repeated launches (flags recycled) agree bit for bit."""
     w = bf16_randn((N, K), std=0.02, seed=17)

@@ -33,7 +33,9 @@ def main():
     print("%-8s %5s %-8s %9s %9s %6s" % ("shape", "T", "impl", "us", "TFLOP/s", "frac"))
     tot = {}
     for name, n, k, epi in SHAPES:
-        w = torch.empty(n, k, dtype=torch.bfloat16, device="cuda").normal_(0, 0.02)
+        # rotate over > 2x L2 of weight copies: in a real prefill every layer's weights are cold
+        copies = max(2, int(400e6 // (n * k * 2)) + 1)
+        w = [torch.empty(n, k, dtype=torch.bfloat16, device="cuda").normal_(0, 0.02) for _ in range(copies)]
         for T in Ts:
             x = torch.randn(T, k, device="cuda").bfloat16()
             cols = n // 2 if epi == ffi.EPI_SILU_MUL else n
@@ -42,16 +44,16 @@ def main():
                 side = torch.cuda.Stream()
                 with torch.cuda.stream(side):
                     st = C.c_void_p(side.cuda_stream)
-                    run = lambda: ffi.check(L.llmlb_op_gemm(vp(w), vp(x), vp(out), T, n, k, epi, cols, impl, st))
-                    for _ in range(3):
-                        run()
+                    run = lambda i=0: ffi.check(L.llmlb_op_gemm(vp(w[i % copies]), vp(x), vp(out), T, n, k, epi, cols, impl, st))
+                    for i in range(3):
+                        run(i)
                     side.synchronize()
                     gr = torch.cuda.CUDAGraph()
                     iters = 20
                     with torch.cuda.graph(gr, stream=side):
                         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-                        for _ in range(iters):
-                            run()
+                        for i in range(iters):
+                            run(i)
                     gr.replay()
                     side.synchronize()
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
