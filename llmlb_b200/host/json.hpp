@@ -204,7 +204,10 @@ class Json {
             std::string k; ws(); if (!string(&k)) return false; ws();
             if (p >= end || *p != ':') return false;
             ++p; ws();
-            Json v; if (!value(&v, depth + 1)) return false; out->set(k, std::move(v)); ws();
+            Json v; if (!value(&v, depth + 1)) return false;
+            // big objects (a 128k-entry vocab) skip the duplicate-key scan of set(): first key wins
+            if (out->o_.size() < 64) out->set(k, std::move(v)); else out->o_.emplace_back(std::move(k), std::move(v));
+            ws();
             if (p < end && *p == ',') { ++p; continue; }
             if (p < end && *p == '}') { ++p; return true; }
             return false;

@@ -4,8 +4,11 @@
 // /api/system with "xllm_version" (detection/xllm.rs:27-66), health pulls /api/health
 // (health/endpoint_checker.rs:515-557), sync reads /v1/models (sync/parser.rs:78-110).
 //
-// Plain blocking HTTP/1.1 (thread per connection, keep-alive, chunked SSE).  Tokenisation is the
-// byte-level placeholder of gateway.hpp unless the request carries "prompt_token_ids".
+// Plain blocking HTTP/1.1 (thread per connection, keep-alive, chunked SSE).  With
+// `--tokenizer tokenizer.json` prompts go through the native Llama-3 BPE tokenizer + chat template
+// (tokenizer.hpp) and SSE deltas through its UTF-8-safe streaming detokenizer; without it (no
+// tokenizer assets exist on the build box) the byte-level placeholder of gateway.hpp is used.
+// A request may always carry "prompt_token_ids" instead of text.
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
@@ -15,13 +18,17 @@
 
 #include <chrono>
 #include <cstring>
+#include <fstream>
 #include <map>
+#include <memory>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/llmlb_b200.h"
 #include "gateway.hpp"
+#include "tokenizer.hpp"
 
 using namespace llmlb_host;
 
@@ -32,6 +39,8 @@ struct Server {
   LoadManager lm;
   InferenceGate gate;
   std::atomic<uint64_t> seq{0};
+  std::unique_ptr<BpeTokenizer> tok;   // null: byte-level placeholder
+  std::vector<int32_t> stop_ids;       // <|eot_id|>, <|end_of_text|>, <|eom_id|> when a tokenizer is loaded
 };
 static Server G;
 
@@ -149,24 +158,33 @@ static void handle_generate(int fd, const Request& rq, int kind) {
     const Json* msgs = req.get("messages");
     if (!msgs || !msgs->is_array()) { send_json(fd, 400, openai_error_body("messages is required", "invalid_request_error", 400)); return; }
     std::string text;
+    std::vector<ChatMessage> chat;
     for (auto& m : msgs->items()) {
       const Json* role = m.get("role"); const Json* c = m.get("content");
       // image parts are rejected by the gateway before the boundary (openai.rs:617); mirror it
       if (c && c->is_array()) for (auto& p : c->items()) { const Json* t = p.get("type"); if (t && t->is_string() && t->str() == "image_url") { send_json(fd, 400, openai_error_body("image inputs are not supported", "invalid_request_error", 400)); return; } }
-      text += (role && role->is_string() ? role->str() : "user") + ": " + (c ? content_text(*c) : "") + "\n";
+      chat.push_back(ChatMessage{role && role->is_string() ? role->str() : "user", c ? content_text(*c) : ""});
+      text += chat.back().role + ": " + chat.back().content + "\n";
     }
     text += "assistant: ";
-    ids = byte_tokenize(text, G.vocab);
+    ids = G.tok ? G.tok->encode_chat(chat) : byte_tokenize(text, G.vocab);
   } else if (kind == 1) {
     const Json* in = req.get("input");
     std::string text;
-    if (in && in->is_string()) text = in->str();
-    else if (in && in->is_array()) for (auto& m : in->items()) { const Json* c = m.get("content"); if (c) text += content_text(*c) + "\n"; }
-    ids = byte_tokenize(text, G.vocab);
+    std::vector<ChatMessage> chat;
+    if (in && in->is_string()) { text = in->str(); chat.push_back(ChatMessage{"user", text}); }
+    else if (in && in->is_array()) for (auto& m : in->items()) {
+      const Json* role = m.get("role"); const Json* c = m.get("content");
+      if (c) { text += content_text(*c) + "\n"; chat.push_back(ChatMessage{role && role->is_string() ? role->str() : "user", content_text(*c)}); }
+    }
+    ids = G.tok ? G.tok->encode_chat(chat) : byte_tokenize(text, G.vocab);
   } else {
     const Json* p = req.get("prompt");
-    ids = byte_tokenize(p && p->is_string() ? p->str() : "", G.vocab);
+    const std::string text = p && p->is_string() ? p->str() : "";
+    ids = G.tok ? G.tok->encode(text, /*add_bos=*/true, /*parse_special=*/false) : byte_tokenize(text, G.vocab);
   }
+  for (int32_t t : ids)
+    if (t < 0 || uint32_t(t) >= G.vocab) { send_json(fd, 400, openai_error_body("prompt token id outside the model vocabulary", "invalid_request_error", 400)); return; }
   llmlb_sampling s{};
   const Json* mt = req.get(kind == 1 ? "max_output_tokens" : "max_tokens");
   if (!mt && kind == 0) mt = req.get("max_completion_tokens");
@@ -181,6 +199,7 @@ static void handle_generate(int fd, const Request& rq, int kind) {
   s.seed = sd && sd->is_number() ? uint64_t(sd->as_int()) : G.seq.load();
   const Json* ie = req.get("ignore_eos");
   s.ignore_eos = ie && ie->as_bool() ? 1 : 0;
+  if (!G.stop_ids.empty()) { s.stop_ids = G.stop_ids.data(); s.n_stop_ids = uint32_t(G.stop_ids.size()); }
   const bool stream = req.get("stream") && req.get("stream")->as_bool();
   bool include_usage = kind != 0;
   if (const Json* so = req.get("stream_options")) if (const Json* iu = so->get("include_usage")) include_usage = iu->as_bool();
@@ -206,6 +225,7 @@ static void handle_generate(int fd, const Request& rq, int kind) {
     if (kind == 1) ok = ok && send_chunk(fd, sse_event(responses_event_created(id, jm->str())) + sse_event(responses_event_item_added()) + sse_event(responses_event_part_added()));
   }
   std::string text;
+  BpeTokenizer::Stream detok;
   uint32_t prompt_tokens = uint32_t(ids.size()), completion_tokens = 0, finish = LLMLB_FINISH_NONE;
   while (finish == LLMLB_FINISH_NONE) {
     llmlb_token_event ev[64];
@@ -215,15 +235,24 @@ static void handle_generate(int fd, const Request& rq, int kind) {
     std::string out;
     for (uint32_t i = 0; i < got; ++i) {
       if (ev[i].token_id >= 0) {
-        const std::string piece = byte_detokenize(ev[i].token_id);
+        // with a tokenizer a delta only carries complete UTF-8 (a character split over tokens waits)
+        const std::string piece = G.tok ? G.tok->decode_next(&detok, ev[i].token_id, /*skip_special=*/true)
+                                        : byte_detokenize(ev[i].token_id);
         text += piece;
-        if (stream) out += kind == 1 ? sse_event(responses_event_delta(piece))
+        if (stream && !piece.empty()) out += kind == 1 ? sse_event(responses_event_delta(piece))
                                      : sse_event(chat_chunk(id, jm->str(), created, nullptr, &piece, nullptr));
       }
       prompt_tokens = ev[i].prompt_tokens; completion_tokens = ev[i].completion_tokens;
       if (ev[i].finish_reason) finish = ev[i].finish_reason;
     }
     if (stream && !out.empty() && ok && !send_chunk(fd, out)) { ok = false; client_gone = true; llmlb_request_cancel(G.eng, rid); }
+  }
+  if (G.tok) {  // generation ended inside a multi-byte character: U+FFFD, like from_utf8_lossy
+    const std::string rest = BpeTokenizer::flush(&detok);
+    if (!rest.empty()) {
+      text += rest;
+      if (stream && ok) send_chunk(fd, kind == 1 ? sse_event(responses_event_delta(rest)) : sse_event(chat_chunk(id, jm->str(), created, nullptr, &rest, nullptr)));
+    }
   }
   llmlb_request_release(G.eng, rid);
   const uint64_t ms = uint64_t(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count());
@@ -307,23 +336,36 @@ static void serve_conn(int fd) {
 
 int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
-  int port = 8011; std::string geometry = "8b";
-  uint32_t max_seqs = 64, max_ctx = 2048;
+  int port = 8011; std::string geometry = "8b", tokenizer_path;
+  uint32_t max_seqs = 64, max_ctx = 2048, vocab_override = 0;
   G.model_id = "llama-3-8b";
   for (int i = 1; i + 1 < argc; i += 2) {
     std::string k = argv[i], v = argv[i + 1];
     if (k == "--port") port = atoi(v.c_str()); else if (k == "--model") geometry = v;
     else if (k == "--model-id") G.model_id = v; else if (k == "--max-seqs") max_seqs = uint32_t(atoi(v.c_str()));
     else if (k == "--max-ctx") max_ctx = uint32_t(atoi(v.c_str())); else if (k == "--api-key") G.api_key = v;
+    else if (k == "--tokenizer") tokenizer_path = v;
+    else if (k == "--vocab") vocab_override = uint32_t(atoi(v.c_str()));
   }
   llmlb_engine_config cfg; memset(&cfg, 0, sizeof cfg);
   cfg.abi_version = LLMLB_ABI_VERSION;
   if (geometry == "tiny") cfg.model = {512, 2, 8, 2, 128, 1024, 2048, 500000.f, 1e-5f};
   else cfg.model = {4096, 32, 32, 8, 128, 14336, 128256, 500000.f, 1e-5f};
+  if (vocab_override) cfg.model.vocab = vocab_override;   // synthetic weights: any vocabulary size works
   strncpy(cfg.model_id, G.model_id.c_str(), sizeof cfg.model_id - 1);
   cfg.tp_size = 1; cfg.max_seqs = max_seqs; cfg.max_ctx = max_ctx; cfg.kv_block_tokens = 64; cfg.use_cuda_graphs = 1;
   if (llmlb_engine_create(&cfg, &G.eng) != LLMLB_OK) { fprintf(stderr, "engine: %s\n", llmlb_last_error()); return 2; }
   G.vocab = cfg.model.vocab; G.max_ctx = max_ctx;
+  if (!tokenizer_path.empty()) {
+    std::ifstream f(tokenizer_path, std::ios::binary);
+    std::stringstream ss; ss << f.rdbuf();
+    std::string err;
+    G.tok.reset(new BpeTokenizer());
+    if (!f || !G.tok->load_json(ss.str(), &err)) { fprintf(stderr, "tokenizer %s: %s\n", tokenizer_path.c_str(), f ? err.c_str() : "cannot read"); return 2; }
+    if (G.tok->vocab_size() > G.vocab) { fprintf(stderr, "tokenizer has %u entries, the model only %u\n", G.tok->vocab_size(), G.vocab); return 2; }
+    for (const char* name : {"<|eot_id|>", "<|end_of_text|>", "<|eom_id|>"}) { const int32_t id = G.tok->special_id(name); if (id >= 0) G.stop_ids.push_back(id); }
+    fprintf(stderr, "tokenizer: %u entries, %zu stop ids\n", G.tok->vocab_size(), G.stop_ids.size());
+  }
   G.lm.add_endpoint("local", true, false);
   G.lm.add_model("local", G.model_id, "");
   int ls = socket(AF_INET, SOCK_STREAM, 0), one = 1;

@@ -1,0 +1,173 @@
+"""Native Llama-3-style BPE tokenizer (llmlb_b200/host/tokenizer.cpp) against
+vectors produced by the Hugging Face `tokenizers` library (tests/golden/make_tokenizer_golden.py):
+pre-token pieces, ids with / without the begin-of-text token, special tokens parsed or taken as
+text, decode, streaming decode at every split point, chat template."""
+import ctypes as C
+import json
+import os
+
+import pytest
+
+from llmlb_b200 import build
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def H():
+    lib = C.CDLL(build.build_host())
+    lib.llmlb_tok_create.restype = C.c_void_p
+    lib.llmlb_tok_create.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint32]
+    lib.llmlb_tok_destroy.argtypes = [C.c_void_p]
+    lib.llmlb_tok_vocab_size.argtypes = [C.c_void_p]
+    lib.llmlb_tok_vocab_size.restype = C.c_uint32
+    lib.llmlb_tok_bos_id.argtypes = [C.c_void_p]
+    lib.llmlb_tok_special_id.argtypes = [C.c_void_p, C.c_char_p]
+    lib.llmlb_tok_encode.restype = C.c_int64
+    lib.llmlb_tok_encode.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_uint64]
+    lib.llmlb_tok_decode.restype = C.c_int64
+    lib.llmlb_tok_decode.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_uint64, C.c_int, C.c_char_p, C.c_uint64]
+    lib.llmlb_tok_pretokenize.restype = C.c_int64
+    lib.llmlb_tok_pretokenize.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint64]
+    lib.llmlb_tok_stream_create.restype = C.c_void_p
+    lib.llmlb_tok_stream_destroy.argtypes = [C.c_void_p]
+    lib.llmlb_tok_stream_next.restype = C.c_int64
+    lib.llmlb_tok_stream_next.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_char_p, C.c_uint64]
+    lib.llmlb_tok_stream_flush.restype = C.c_int64
+    lib.llmlb_tok_stream_flush.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+    lib.llmlb_tok_chat_ids.restype = C.c_int64
+    lib.llmlb_tok_chat_ids.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64]
+    lib.llmlb_tok_chat_text.restype = C.c_int64
+    lib.llmlb_tok_chat_text.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_char_p, C.c_uint64]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def tok(H):
+    data = open(os.path.join(GOLD, "tokenizer_llama3_style.json"), "rb").read()
+    err = C.create_string_buffer(256)
+    t = H.llmlb_tok_create(data, len(data), err, 256)
+    assert t, err.value
+    yield t
+    H.llmlb_tok_destroy(t)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(GOLD, "tokenizer_vectors.json"), encoding="utf-8"))
+
+
+def encode(H, tok, text, add_bos=False, parse_special=True):
+    b = text.encode("utf-8")
+    cap = 4 * len(b) + 16
+    out = (C.c_int32 * cap)()
+    n = H.llmlb_tok_encode(tok, b, len(b), int(add_bos), int(parse_special), out, cap)
+    assert 0 <= n <= cap
+    return list(out[:n])
+
+
+def decode(H, tok, ids, skip_special=False):
+    arr = (C.c_int32 * max(1, len(ids)))(*ids)
+    cap = 64 * len(ids) + 64
+    buf = C.create_string_buffer(cap)
+    n = H.llmlb_tok_decode(tok, arr, len(ids), int(skip_special), buf, cap)
+    assert n <= cap
+    return buf.raw[:n]
+
+
+def test_loads_vocab_and_specials(H, tok):
+    assert H.llmlb_tok_vocab_size(tok) == 3011
+    assert H.llmlb_tok_bos_id(tok) == H.llmlb_tok_special_id(tok, b"<|begin_of_text|>") >= 3000
+    assert H.llmlb_tok_special_id(tok, b"<|eot_id|>") > 0
+    assert H.llmlb_tok_special_id(tok, b"<|nope|>") == -1
+
+
+def test_rejects_other_models(H):
+    bad = json.dumps({"model": {"type": "WordPiece", "vocab": {}}}).encode()
+    err = C.create_string_buffer(256)
+    assert not H.llmlb_tok_create(bad, len(bad), err, 256)
+    assert b"BPE" in err.value
+    err2 = C.create_string_buffer(256)
+    assert not H.llmlb_tok_create(b"{nope", 5, err2, 256)
+
+
+def test_pretokenizer_pieces_match_the_library(H, gold):
+    for v in gold["vectors"]:
+        b = v["text"].encode("utf-8")
+        cap = len(b) + 4
+        out = (C.c_uint32 * (2 * cap))()
+        n = H.llmlb_tok_pretokenize(b, len(b), out, cap)
+        pieces = [b[out[2 * i]:out[2 * i + 1]].decode("utf-8") for i in range(n)]
+        assert pieces == v["pieces"], repr(v["text"])
+
+
+def test_ids_match_the_library(H, tok, gold):
+    for v in gold["vectors"]:
+        assert encode(H, tok, v["text"]) == v["ids"], repr(v["text"])
+        assert encode(H, tok, v["text"], add_bos=True) == v["ids_bos"], repr(v["text"])
+
+
+def test_special_tokens_taken_as_text_when_not_parsed(H, tok, gold):
+    for v in gold["vectors"]:
+        assert encode(H, tok, v["text"], parse_special=False) == v["ids_plain"], repr(v["text"])
+
+
+def test_decode_matches_and_round_trips(H, tok, gold):
+    for v in gold["vectors"]:
+        assert decode(H, tok, v["ids"]).decode("utf-8") == v["decoded"]
+        assert decode(H, tok, v["ids"], skip_special=True).decode("utf-8") == v["decoded_skip"]
+        # byte-level BPE is lossless on text without special tokens
+        assert decode(H, tok, v["ids_plain"]).decode("utf-8") == v["text"]
+
+
+def test_streaming_decode_emits_only_complete_utf8(H, tok, gold):
+    """Token by token (what an SSE delta carries): every emitted piece is valid UTF-8 and the
+    concatenation equals the one-shot decode, also when a multi-byte character spans tokens."""
+    buf = C.create_string_buffer(4096)
+    spans = 0
+    for v in gold["vectors"]:
+        s = H.llmlb_tok_stream_create()
+        parts = []
+        for i in v["ids_plain"]:
+            n = H.llmlb_tok_stream_next(tok, s, i, 0, buf, 4096)
+            piece = buf.raw[:n]
+            piece.decode("utf-8")          # raises if a sequence was cut
+            if n == 0:
+                spans += 1
+            parts.append(piece)
+        n = H.llmlb_tok_stream_flush(s, buf, 4096)
+        assert n == 0                       # complete text leaves nothing pending
+        H.llmlb_tok_stream_destroy(s)
+        assert b"".join(parts).decode("utf-8") == v["text"]
+    assert spans > 20                       # the fixture really has characters split across tokens
+
+
+def test_streaming_flush_replaces_a_truncated_character(H, tok):
+    ids = encode(H, tok, "🦄", parse_special=False)   # not in the training corpus: several byte tokens
+    assert len(ids) >= 2
+    s = H.llmlb_tok_stream_create()
+    buf = C.create_string_buffer(64)
+    out = b""
+    for i in ids[:-1]:
+        n = H.llmlb_tok_stream_next(tok, s, i, 0, buf, 64)
+        out += buf.raw[:n]
+    assert out == b""
+    n = H.llmlb_tok_stream_flush(s, buf, 64)
+    assert buf.raw[:n].decode("utf-8") == "�"
+    H.llmlb_tok_stream_destroy(s)
+
+
+def test_chat_template_text_and_ids(H, tok, gold):
+    for c in gold["chats"]:
+        m = json.dumps(c["messages"]).encode("utf-8")
+        buf = C.create_string_buffer(8192)
+        n = H.llmlb_tok_chat_text(tok, m, len(m), 1, buf, 8192)
+        assert buf.raw[:n].decode("utf-8") == c["text"]
+        out = (C.c_int32 * 4096)()
+        k = H.llmlb_tok_chat_ids(tok, m, len(m), out, 4096)
+        assert list(out[:k]) == c["ids"]
+    # control tokens inside message content stay text: exactly one <|eot_id|> per message
+    eot = H.llmlb_tok_special_id(tok, b"<|eot_id|>")
+    smuggle = gold["chats"][2]
+    assert smuggle["ids"].count(eot) == 1
+    assert H.llmlb_tok_chat_ids(tok, b"{}", 2, (C.c_int32 * 4)(), 4) == -1

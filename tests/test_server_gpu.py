@@ -139,3 +139,65 @@ def test_concurrent_streams(server):
     th = [threading.Thread(target=run, args=(i,)) for i in range(12)]
     [t.start() for t in th]; [t.join() for t in th]
     assert all(o == (200, 16, True) for o in outs), outs
+
+
+# ---- native tokenizer on the serving path ----
+@pytest.fixture(scope="module")
+def tok_server(built_lib):
+    from llmlb_b200 import build
+    build.build_host()
+    port = _free_port()
+    proc = subprocess.Popen([BIN, "--port", str(port), "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "8",
+                             "--max-ctx", "512", "--vocab", "3072",
+                             "--tokenizer", os.path.join(HERE, "golden", "tokenizer_llama3_style.json")], stderr=subprocess.PIPE)
+    deadline = time.time() + 120
+    while time.time() < deadline:
+        try:
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=2); c.request("GET", "/v1/models"); c.getresponse().read(); c.close()
+            break
+        except OSError:
+            assert proc.poll() is None, proc.stderr.read().decode()
+            time.sleep(0.2)
+    yield port
+    proc.terminate()
+    proc.wait(timeout=20)
+
+
+def test_chat_through_the_native_tokenizer(tok_server):
+    gold = json.load(open(os.path.join(HERE, "golden", "tokenizer_vectors.json"), encoding="utf-8"))
+    conv = gold["chats"][1]
+    body = {"model": "tiny-llama", "messages": conv["messages"], "max_tokens": 48, "temperature": 0, "ignore_eos": True}
+    st, _, d = call(tok_server, "POST", "/v1/chat/completions", body)
+    assert st == 200
+    j = json.loads(d)
+    # the prompt is the chat template's ids (markers as control tokens, content as plain text)
+    assert j["usage"]["prompt_tokens"] == len(conv["ids"])
+    assert j["usage"]["completion_tokens"] == 48
+    full = j["choices"][0]["message"]["content"]
+    # same request streamed: every delta is complete UTF-8 and the pieces add up to the same text
+    st, _, d = call(tok_server, "POST", "/v1/chat/completions", dict(body, stream=True, stream_options={"include_usage": True}))
+    assert st == 200
+    acc = G.StreamingTokenAccumulator("tiny-llama")
+    pieces = []
+    for line in d.decode("utf-8").split("\n"):
+        if line.startswith("data: ") and line != "data: [DONE]":
+            ch = json.loads(line[6:])
+            for c in ch.get("choices", []):
+                if c.get("delta", {}).get("content"):
+                    pieces.append(c["delta"]["content"])
+        if line:
+            acc.process_chunk(line)
+    assert "".join(pieces) == full == acc.accumulated_content
+    assert acc.finalize()["output_tokens"] == 48 and acc.done
+
+
+def test_stop_at_end_of_turn_token(tok_server):
+    """Without ignore_eos the control tokens of the template end generation ('stop') and never
+    show up in the text; a prompt outside the vocabulary is a 400."""
+    st, _, d = call(tok_server, "POST", "/v1/completions", {"model": "tiny-llama", "prompt": "hello", "max_tokens": 400, "temperature": 1.0, "seed": 3})
+    assert st == 200
+    j = json.loads(d)
+    assert "<|eot_id|>" not in j["choices"][0]["text"]
+    assert j["choices"][0]["finish_reason"] in ("stop", "length")
+    st, _, d = call(tok_server, "POST", "/v1/completions", {"model": "tiny-llama", "prompt_token_ids": [5, 999999], "max_tokens": 4})
+    assert st == 400
