@@ -667,7 +667,13 @@ namespace llmlb {
 // one), so the kernel is bound by the K/V stream instead of by SIMT dot products
 // (round-1 profile at 64 streams: SIMT kernel 69 us/layer for 136 MB of K/V = 2 TB/s).
 constexpr int kDamThreads = 32;
-constexpr int kDamSmem = 2 * 2 * kPageTokens * kHeadDim * 2 + kDecHeads * kHeadDim * 2;  // K,V x 2 stages + q
+// K/V move through a 3-stage ring of 32-token half pages: 48 KiB + q per CTA, so FOUR one-warp CTAs
+// share an SM and the 512 CTAs of a 64-stream step are resident at once (with whole pages and
+// two stages only three fit: a second, mostly empty wave doubled the kernel's time — ncu,
+// profiles/r1_decode_attn_mma_ncu_full.txt)
+constexpr int kDamChunk = 32;
+constexpr int kDamStages = 3;
+constexpr int kDamSmem = kDamStages * 2 * kDamChunk * kHeadDim * 2 + kDecHeads * kHeadDim * 2;
 
 __global__ void __launch_bounds__(kDamThreads)
 decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_pages,
@@ -676,9 +682,9 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
                             const int32_t* __restrict__ seq_lens, const float2* __restrict__ rope,
                             __nv_bfloat16* __restrict__ out, uint32_t n_heads, uint32_t n_kv) {
   extern __shared__ __align__(128) uint8_t dam_smem[];
-  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(dam_smem);            // [2][64][128] swizzled
-  __nv_bfloat16* sv = sk + 2 * kPageTokens * kHeadDim;                       // [2][64][128] swizzled
-  __nv_bfloat16* sq = sv + 2 * kPageTokens * kHeadDim;                       // [4][128] rotated q (bf16)
+  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(dam_smem);            // [3][32][128] swizzled
+  __nv_bfloat16* sv = sk + kDamStages * kDamChunk * kHeadDim;                // [3][32][128] swizzled
+  __nv_bfloat16* sq = sv + kDamStages * kDamChunk * kHeadDim;                // [4][128] rotated q (bf16)
   __shared__ __align__(16) __nv_bfloat16 s_knew[kHeadDim];
   __shared__ __align__(16) __nv_bfloat16 s_vnew[kHeadDim];
 
@@ -690,26 +696,30 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
   const uint32_t pos = uint32_t(L - 1);
   const float2* cs = rope + size_t(pos) * 64;
   const __nv_bfloat16* row = qkv + size_t(s) * width;
-  const uint32_t n_pages = (uint32_t(L) + kPageTokens - 1) / kPageTokens;
+  const uint32_t n_chunks = (uint32_t(L) + kDamChunk - 1) / kDamChunk;
   const uint32_t g = lane >> 2, t4 = lane & 3;
+  constexpr uint32_t kChunksPerPage = kPageTokens / kDamChunk;
 
-  auto load_page = [&](uint32_t pg, uint32_t buf) {
-    const int32_t page = bt[pg];
-    const __nv_bfloat16* kg = k_pages + (size_t(page) * n_kv + kvh) * kPageTokens * kHeadDim;
-    const __nv_bfloat16* vg = v_pages + (size_t(page) * n_kv + kvh) * kPageTokens * kHeadDim;
-    __nv_bfloat16* dk = sk + buf * kPageTokens * kHeadDim;
-    __nv_bfloat16* dv = sv + buf * kPageTokens * kHeadDim;
-    const uint32_t rows = min(uint32_t(kPageTokens), uint32_t(L) - pg * kPageTokens);
+  auto load_chunk = [&](uint32_t c, uint32_t buf) {
+    const int32_t page = bt[c / kChunksPerPage];
+    const size_t base = ((size_t(page) * n_kv + kvh) * kPageTokens + (c % kChunksPerPage) * kDamChunk) * kHeadDim;
+    const __nv_bfloat16* kg = k_pages + base;
+    const __nv_bfloat16* vg = v_pages + base;
+    __nv_bfloat16* dk = sk + buf * kDamChunk * kHeadDim;
+    __nv_bfloat16* dv = sv + buf * kDamChunk * kHeadDim;
+    const uint32_t rows = min(uint32_t(kDamChunk), uint32_t(L) - c * kDamChunk);
 #pragma unroll 4
-    for (uint32_t i = 0; i < 32; ++i) {
-      const uint32_t c = lane + i * 32;  // 1024 16-byte chunks per tile
-      const uint32_t r = c >> 4, ch = c & 15;
+    for (uint32_t i = 0; i < kDamChunk / 2; ++i) {
+      const uint32_t x = lane + i * 32;  // 512 16-byte pieces per tile
+      const uint32_t r = x >> 4, ch = x & 15;
       const bool valid = r < rows;
       cp_async16(dk + swz(r, ch), kg + r * kHeadDim + ch * 8, valid);
       cp_async16(dv + swz(r, ch), vg + r * kHeadDim + ch * 8, valid);
     }
   };
-  load_page(0, 0);
+  load_chunk(0, 0);
+  cp_async_commit();
+  if (n_chunks > 1) load_chunk(1, 1);
   cp_async_commit();
 
   // rotate q (4 heads x 64 pairs), rotate + append the new k, append v
@@ -757,25 +767,25 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
   float m_run = -INFINITY, l_run = 0.f;   // row g (rows g+8 are padding)
   const float scale = rsqrtf(float(kHeadDim)) * kLog2e;
 
-  for (uint32_t pg = 0; pg < n_pages; ++pg) {
-    const uint32_t buf = pg & 1;
-    if (pg + 1 < n_pages) load_page(pg + 1, buf ^ 1);
+  for (uint32_t c = 0; c < n_chunks; ++c) {
+    const uint32_t buf = c % kDamStages;
+    if (c + 2 < n_chunks) load_chunk(c + 2, (c + 2) % kDamStages);   // the buffer chunk c-1 just left
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<2>();
     __syncwarp();
-    __nv_bfloat16* tk = sk + buf * kPageTokens * kHeadDim;
-    __nv_bfloat16* tv = sv + buf * kPageTokens * kHeadDim;
-    if (pg == pos / kPageTokens) {  // the new token's row was fetched before it was written: patch it
-      const uint32_t r = pos % kPageTokens;
+    __nv_bfloat16* tk = sk + buf * kDamChunk * kHeadDim;
+    __nv_bfloat16* tv = sv + buf * kDamChunk * kHeadDim;
+    if (c == pos / kDamChunk) {  // the new token's row was fetched before it was written: patch it
+      const uint32_t r = pos % kDamChunk;
       for (uint32_t ch = lane; ch < 16; ch += 32) {
         *reinterpret_cast<uint4*>(tk + swz(r, ch)) = *reinterpret_cast<const uint4*>(s_knew + ch * 8);
         *reinterpret_cast<uint4*>(tv + swz(r, ch)) = *reinterpret_cast<const uint4*>(s_vnew + ch * 8);
       }
       __syncwarp();
     }
-    float sc[8][4];
+    float sc[kDamChunk / 8][4];
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+    for (int nb = 0; nb < kDamChunk / 8; ++nb) {
       sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
 #pragma unroll
       for (int kp = 0; kp < 4; ++kp) {
@@ -786,10 +796,10 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
         mma_bf16_16816(sc[nb], qf[kp * 2 + 1], kb[2], kb[3]);
       }
     }
-    const uint32_t kv0 = pg * kPageTokens;
+    const uint32_t kv0 = c * kDamChunk;
     float m_new = m_run;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
+    for (int nb = 0; nb < kDamChunk / 8; ++nb)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float v = sc[nb][e] * scale;
@@ -803,7 +813,7 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     m_run = m_new;
     float rsum = 0.f;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+    for (int nb = 0; nb < kDamChunk / 8; ++nb) {
       const float p0 = exp2f(sc[nb][0] - m_new), p1 = exp2f(sc[nb][1] - m_new);
       sc[nb][0] = p0; sc[nb][1] = p1;
       rsum += p0 + p1;
@@ -812,7 +822,7 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 #pragma unroll
     for (int nb = 0; nb < 16; ++nb) { o[nb][0] *= corr; o[nb][1] *= corr; }
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < kDamChunk / 16; ++ks) {
       uint32_t pa[4];
       pa[0] = pack_bf16(sc[2 * ks][0], sc[2 * ks][1]);
       pa[1] = 0;
