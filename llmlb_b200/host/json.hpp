@@ -97,7 +97,11 @@ class Json {
       case Int: out += std::to_string(i_); break;
       case Double: {
         if (!std::isfinite(d_)) { out += "null"; break; }
-        char b[40]; snprintf(b, sizeof b, "%.17g", d_);
+        char b[40];
+        for (int prec = 1; prec <= 17; ++prec) {  // shortest text that reads back exactly (0.2, not 0.20000000000000001)
+          snprintf(b, sizeof b, "%.*g", prec, d_);
+          if (strtod(b, nullptr) == d_) break;
+        }
         std::string s(b);
         if (s.find_first_of(".eE") == std::string::npos) s += ".0";
         out += s; break;

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/llmlb_b200.h"
+#include "anthropic.hpp"
 #include "gateway.hpp"
 #include "tokenizer.hpp"
 
@@ -134,20 +135,41 @@ static std::string content_text(const Json& c) {  // string or [{type:text,text}
   return s;
 }
 
-// kind: 0 chat, 1 responses, 2 completions
-static void handle_generate(int fd, const Request& rq, int kind) {
-  if (!G.gate.try_begin()) { send_json(fd, 503, InferenceGate::rejection_body(), "Retry-After: 30\r\n"); return; }
+// Anthropic error types by status (anthropic.rs:1594-1611 anthropic_error_from_lb_error)
+static std::string anthropic_error_body(int status, const std::string& message) {
+  AnthropicError e;
+  e.status = status;
+  e.type = status == 400 ? "invalid_request_error" : status == 401 ? "authentication_error" : status == 403 ? "permission_error"
+         : status == 404 ? "not_found_error" : "api_error";
+  e.message = message;
+  return e.body();
+}
+
+// kind: 0 chat, 1 responses, 2 completions.  anthropic: the request came in through /v1/messages
+// (already translated to the chat form in `pre`); errors, the body and the SSE events leave in
+// Anthropic shape — the chat chunks produced below are run through AnthropicStreamTransformer,
+// the same transformation the reference applies to an upstream's OpenAI stream.
+static void handle_generate(int fd, const Request& rq, int kind, const Json* pre = nullptr, bool anthropic = false) {
+  auto send_err = [&](int status, const std::string& message, const char* type, const char* extra = "") {
+    send_json(fd, status, anthropic ? anthropic_error_body(status, message) : openai_error_body(message, type, status), extra);
+  };
+  if (!G.gate.try_begin()) {
+    if (anthropic) send_err(503, "Server is updating. Please retry.", "service_unavailable", "Retry-After: 30\r\n");
+    else send_json(fd, 503, InferenceGate::rejection_body(), "Retry-After: 30\r\n");
+    return;
+  }
   struct GateGuard { ~GateGuard() { G.gate.end(); } } guard;
   Json req;
-  if (!Json::parse(rq.body, &req) || !req.is_object()) { send_json(fd, 400, openai_error_body("invalid JSON body", "invalid_request_error", 400)); return; }
+  if (pre) req = *pre;
+  else if (!Json::parse(rq.body, &req) || !req.is_object()) { send_err(400, "invalid JSON body", "invalid_request_error"); return; }
   const Json* jm = req.get("model");
-  if (!jm || !jm->is_string() || jm->str().empty()) { send_json(fd, 400, openai_error_body("model is required", "invalid_request_error", 400)); return; }
+  if (!jm || !jm->is_string() || jm->str().empty()) { send_err(400, "model is required", "invalid_request_error"); return; }
   ParsedModelName pm;
-  if (!parse_quantized_model_name(jm->str(), &pm)) { send_json(fd, 400, openai_error_body("Invalid model name (quantization format): " + jm->str(), "invalid_request_error", 400)); return; }
+  if (!parse_quantized_model_name(jm->str(), &pm)) { send_err(400, "Invalid model name (quantization format): " + jm->str(), "invalid_request_error"); return; }
   std::string ep;
   const TpsApiKind api = kind == 0 ? TpsApiKind::ChatCompletions : kind == 1 ? TpsApiKind::Responses : TpsApiKind::Completions;
   if (G.lm.select(&pm.base, int(api), &ep) != kSelectOk) {
-    send_json(fd, 404, openai_error_body("The model '" + jm->str() + "' does not exist", "invalid_request_error", 404));
+    send_err(404, "The model '" + jm->str() + "' does not exist", "invalid_request_error");
     return;
   }
   // prompt
@@ -156,13 +178,13 @@ static void handle_generate(int fd, const Request& rq, int kind) {
     if (raw->is_array()) for (auto& v : raw->items()) ids.push_back(int32_t(v.as_int()));
   } else if (kind == 0) {
     const Json* msgs = req.get("messages");
-    if (!msgs || !msgs->is_array()) { send_json(fd, 400, openai_error_body("messages is required", "invalid_request_error", 400)); return; }
+    if (!msgs || !msgs->is_array()) { send_err(400, "messages is required", "invalid_request_error"); return; }
     std::string text;
     std::vector<ChatMessage> chat;
     for (auto& m : msgs->items()) {
       const Json* role = m.get("role"); const Json* c = m.get("content");
       // image parts are rejected by the gateway before the boundary (openai.rs:617); mirror it
-      if (c && c->is_array()) for (auto& p : c->items()) { const Json* t = p.get("type"); if (t && t->is_string() && t->str() == "image_url") { send_json(fd, 400, openai_error_body("image inputs are not supported", "invalid_request_error", 400)); return; } }
+      if (c && c->is_array()) for (auto& p : c->items()) { const Json* t = p.get("type"); if (t && t->is_string() && t->str() == "image_url") { send_err(400, "image inputs are not supported", "invalid_request_error"); return; } }
       chat.push_back(ChatMessage{role && role->is_string() ? role->str() : "user", c ? content_text(*c) : ""});
       text += chat.back().role + ": " + chat.back().content + "\n";
     }
@@ -184,7 +206,7 @@ static void handle_generate(int fd, const Request& rq, int kind) {
     ids = G.tok ? G.tok->encode(text, /*add_bos=*/true, /*parse_special=*/false) : byte_tokenize(text, G.vocab);
   }
   for (int32_t t : ids)
-    if (t < 0 || uint32_t(t) >= G.vocab) { send_json(fd, 400, openai_error_body("prompt token id outside the model vocabulary", "invalid_request_error", 400)); return; }
+    if (t < 0 || uint32_t(t) >= G.vocab) { send_err(400, "prompt token id outside the model vocabulary", "invalid_request_error"); return; }
   llmlb_sampling s{};
   const Json* mt = req.get(kind == 1 ? "max_output_tokens" : "max_tokens");
   if (!mt && kind == 0) mt = req.get("max_completion_tokens");
@@ -210,7 +232,7 @@ static void handle_generate(int fd, const Request& rq, int kind) {
   int rc = s.max_tokens ? llmlb_request_submit(G.eng, ids.data(), uint32_t(ids.size()), &s, &rid) : LLMLB_E_INVALID_ARG;
   if (rc != LLMLB_OK) {
     int st = map_error(rc);
-    send_json(fd, st, openai_error_body(s.max_tokens ? llmlb_last_error() : "prompt exceeds the context length", st == 400 ? "invalid_request_error" : "endpoint_request_error", st));
+    send_err(st, s.max_tokens ? llmlb_last_error() : "prompt exceeds the context length", st == 400 ? "invalid_request_error" : "endpoint_request_error");
     return;
   }
   G.lm.begin_request(ep);
@@ -219,9 +241,17 @@ static void handle_generate(int fd, const Request& rq, int kind) {
   const int64_t created = int64_t(std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch()).count());
   const std::string role = "assistant";
   bool ok = true, client_gone = false;
+  AnthropicStreamTransformer to_anthropic(jm->str(), int64_t(ids.size()), "msg_" + std::to_string(n));
+  // every SSE chunk leaves through here: verbatim, or re-framed as Anthropic events
+  auto send_sse = [&](const std::string& openai_sse) -> bool {
+    if (!anthropic) return send_chunk(fd, openai_sse);
+    to_anthropic.feed(openai_sse);
+    const std::string out = to_anthropic.take_output();
+    return out.empty() ? true : send_chunk(fd, out);
+  };
   if (stream) {
     ok = send_all(fd, "HTTP/1.1 200 OK\r\nContent-Type: text/event-stream\r\nCache-Control: no-cache\r\nTransfer-Encoding: chunked\r\n\r\n");
-    if (kind == 0) ok = ok && send_chunk(fd, sse_event(chat_chunk(id, jm->str(), created, &role, nullptr, nullptr)));
+    if (kind == 0) ok = ok && send_sse(sse_event(chat_chunk(id, jm->str(), created, &role, nullptr, nullptr)));
     if (kind == 1) ok = ok && send_chunk(fd, sse_event(responses_event_created(id, jm->str())) + sse_event(responses_event_item_added()) + sse_event(responses_event_part_added()));
   }
   std::string text;
@@ -245,13 +275,13 @@ static void handle_generate(int fd, const Request& rq, int kind) {
       prompt_tokens = ev[i].prompt_tokens; completion_tokens = ev[i].completion_tokens;
       if (ev[i].finish_reason) finish = ev[i].finish_reason;
     }
-    if (stream && !out.empty() && ok && !send_chunk(fd, out)) { ok = false; client_gone = true; llmlb_request_cancel(G.eng, rid); }
+    if (stream && !out.empty() && ok && !send_sse(out)) { ok = false; client_gone = true; llmlb_request_cancel(G.eng, rid); }
   }
   if (G.tok) {  // generation ended inside a multi-byte character: U+FFFD, like from_utf8_lossy
     const std::string rest = BpeTokenizer::flush(&detok);
     if (!rest.empty()) {
       text += rest;
-      if (stream && ok) send_chunk(fd, kind == 1 ? sse_event(responses_event_delta(rest)) : sse_event(chat_chunk(id, jm->str(), created, nullptr, &rest, nullptr)));
+      if (stream && ok) send_sse(kind == 1 ? sse_event(responses_event_delta(rest)) : sse_event(chat_chunk(id, jm->str(), created, nullptr, &rest, nullptr)));
     }
   }
   llmlb_request_release(G.eng, rid);
@@ -261,7 +291,7 @@ static void handle_generate(int fd, const Request& rq, int kind) {
   G.lm.finish_request(ep, success, ms, completion_tokens);
   if (success && completion_tokens) G.lm.update_tps(ep, pm.base, api, completion_tokens, ms);
   const char* fr = finish == LLMLB_FINISH_STOP ? "stop" : "length";
-  if (finish == LLMLB_FINISH_ERROR && !stream) { send_json(fd, 502, openai_error_body("engine failure", "endpoint_request_error", 502)); return; }
+  if (finish == LLMLB_FINISH_ERROR && !stream) { send_err(502, "engine failure", "endpoint_request_error"); return; }
   if (stream) {
     if (!ok) return;
     std::string tail;
@@ -272,8 +302,18 @@ static void handle_generate(int fd, const Request& rq, int kind) {
       tail += sse_event(responses_event_text_done(text)) + sse_event(responses_event_done(id, prompt_tokens, completion_tokens));
     }
     tail += sse_done();
-    send_chunk(fd, tail);
+    if (anthropic) {  // usage always travels to the transformer (message_delta carries output_tokens)
+      if (!include_usage) to_anthropic.feed(sse_event(chat_usage_chunk(id, jm->str(), created, prompt_tokens, completion_tokens)));
+      to_anthropic.feed(tail);
+      to_anthropic.finish();
+      send_chunk(fd, to_anthropic.take_output());
+    } else {
+      send_chunk(fd, tail);
+    }
     send_all(fd, "0\r\n\r\n");
+  } else if (anthropic) {
+    const Json chat = chat_completion_body(id, jm->str(), created, text, fr, prompt_tokens, completion_tokens);
+    send_json(fd, 200, openai_to_anthropic_message_response(chat, jm->str(), prompt_tokens, completion_tokens, "msg_" + std::to_string(n)).dump());
   } else {
     Json body = kind == 0 ? chat_completion_body(id, jm->str(), created, text, fr, prompt_tokens, completion_tokens)
               : kind == 1 ? responses_body(id, jm->str(), created, text, prompt_tokens, completion_tokens, "completed")
@@ -282,13 +322,30 @@ static void handle_generate(int fd, const Request& rq, int kind) {
   }
 }
 
+// POST /v1/messages (llmlb/src/api/anthropic.rs:83-135 handle_messages): version header, request
+// translation, then the chat path with Anthropic framing.  "anthropic:" cloud models are the
+// gateway's business, not this endpoint's.
+static void handle_messages(int fd, const Request& rq) {
+  AnthropicError err;
+  auto ver = rq.headers.find("anthropic-version");
+  if (!anthropic_required_header(ver != rq.headers.end() ? ver->second.c_str() : nullptr, "anthropic-version", &err)) { send_json(fd, err.status, err.body()); return; }
+  Json payload, openai;
+  if (!Json::parse(rq.body, &payload) || !payload.is_object()) { send_json(fd, 400, anthropic_error_body(400, "invalid JSON body")); return; }
+  if (!anthropic_request_to_openai(payload, &openai, nullptr, nullptr, &err)) { send_json(fd, err.status, err.body()); return; }
+  handle_generate(fd, rq, 0, &openai, true);
+}
+
 static void handle(int fd, const Request& rq) {
   const std::string path = rq.path.substr(0, rq.path.find('?'));
   if (!G.api_key.empty()) {  // endpoint registered with an api_key => every call carries Bearer (proxy.rs:390-392)
     std::string key, err;
     auto xa = rq.headers.find("x-api-key"); auto au = rq.headers.find("authorization");
     int rc = extract_api_key(xa != rq.headers.end() ? xa->second.c_str() : nullptr, au != rq.headers.end() ? au->second.c_str() : nullptr, &key, &err);
-    if (rc != 0 || key != G.api_key) { send_json(fd, 401, openai_error_body(rc ? err : "Invalid API key", "invalid_request_error", 401)); return; }
+    if (rc != 0 || key != G.api_key) {
+      if (path == "/v1/messages") send_json(fd, 401, anthropic_error_body(401, "Invalid or missing x-api-key"));   // auth/middleware.rs:551-557
+      else send_json(fd, 401, openai_error_body(rc ? err : "Invalid API key", "invalid_request_error", 401));
+      return;
+    }
   }
   if (rq.method == "GET" && path == "/v1/models") {
     Json m = Json::object(); m.set("id", G.model_id); m.set("object", "model"); m.set("created", 0); m.set("owned_by", "llmlb_b200");
@@ -317,6 +374,7 @@ static void handle(int fd, const Request& rq) {
   } else if (rq.method == "POST" && path == "/v1/chat/completions") handle_generate(fd, rq, 0);
   else if (rq.method == "POST" && path == "/v1/responses") handle_generate(fd, rq, 1);
   else if (rq.method == "POST" && path == "/v1/completions") handle_generate(fd, rq, 2);
+  else if (rq.method == "POST" && path == "/v1/messages") handle_messages(fd, rq);
   else if (rq.method == "POST" && path == "/admin/drain") { G.gate.set_rejecting(rq.body.find("true") != std::string::npos); send_json(fd, 200, "{\"ok\":true}"); }
   else send_json(fd, 404, openai_error_body("not found", "invalid_request_error", 404));
 }

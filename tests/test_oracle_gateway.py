@@ -131,3 +131,89 @@ def test_extract_api_key(v):
         assert str(ei.value) == v["error"]
     else:
         assert G.extract_api_key(v["headers"]) == v["key"]
+
+
+# ---- Anthropic Messages front door (llmlb/src/api/anthropic.rs) ---------------------------------
+@pytest.mark.parametrize("v", V["anthropic"]["request"], ids=lambda v: v["cite"].split()[-1])
+def test_anthropic_request_conversion(v):
+    if "error_status" in v:
+        with pytest.raises(G.AnthropicError) as e:
+            G.anthropic_request_to_openai(v["payload"])
+        assert e.value.status == v["error_status"] and e.value.body()["type"] == "error"
+        return
+    body, text, stream = G.anthropic_request_to_openai(v["payload"])
+    x = v["expect"]
+    if "roles" in x:
+        assert [m["role"] for m in body["messages"]] == x["roles"]
+        assert (body["model"], body["max_tokens"], body["stream"], body["stop"]) == (x["model"], x["max_tokens"], x["stream"], x["stop"])
+        assert stream is True and x["request_text_contains"] in text
+    if "n_tools" in x:
+        assert len(body["tools"]) == x["n_tools"] and body["tools"][0]["type"] == x["tool0"]["type"]
+        assert body["tools"][0]["function"]["name"] == x["tool0"]["name"]
+        assert body["tools"][0]["function"]["description"] == x["tool0"]["description"]
+        assert body["tool_choice"] == x["tool_choice"]
+    if "tool_message" in x:
+        tm = [m for m in body["messages"] if m["role"] == "tool"]
+        assert len(tm) == 1 and tm[0]["tool_call_id"] == x["tool_message"]["tool_call_id"] and tm[0]["content"] == x["tool_message"]["content"]
+
+
+@pytest.mark.parametrize("v", V["anthropic"]["response"], ids=lambda v: v["cite"].split()[-1])
+def test_anthropic_response_conversion(v):
+    r = G.openai_to_anthropic_message_response(v["body"], v["model"], v["usage"][0], v["usage"][1])
+    x = v["expect"]
+    assert (r["type"], r["role"], r["stop_reason"]) == (x["type"], x["role"], x["stop_reason"])
+    assert r["model"] == v["model"] and r["stop_sequence"] is None and r["id"] == v["body"]["id"]
+    if "content0" in x:
+        assert r["content"][0] == x["content0"]
+        assert (r["usage"]["input_tokens"], r["usage"]["output_tokens"]) == (x["input_tokens"], x["output_tokens"])
+    if "tool_use" in x:
+        assert len(r["content"]) >= x["min_blocks"]
+        tu = [c for c in r["content"] if c["type"] == "tool_use"][0]
+        assert (tu["name"], tu["id"], tu["input"]) == (x["tool_use"]["name"], x["tool_use"]["id"], x["tool_use"]["input"])
+
+
+@pytest.mark.parametrize("v", V["anthropic"]["stream"], ids=lambda v: v["cite"].split()[-1])
+def test_anthropic_stream_transform(v):
+    t = G.AnthropicStreamTransformer("test-model", input_tokens=None)
+    # arbitrary network chunking must not matter
+    up = v["upstream"]
+    for i in range(0, len(up), 7):
+        t.feed(up[i:i + 7])
+    t.finish()
+    wire = t.wire()
+    for needle in v["contains"]:
+        assert needle in wire
+    names = [n for n, _ in t.out]
+    assert names == ["message_start", "content_block_start", "content_block_delta", "content_block_delta",
+                     "content_block_stop", "message_delta", "message_stop"]
+    assert t.out[0][1]["message"]["id"] == "msg_123"
+    assert t.out[-2][1]["delta"]["stop_reason"] == "end_turn"
+
+
+def test_anthropic_errors_and_edges():
+    for v in V["anthropic"]["errors"]:
+        with pytest.raises(G.AnthropicError) as e:
+            G.anthropic_required_header(v["headers"], "anthropic-version")
+        b = e.value.body()
+        assert (e.value.status, b["type"], b["error"]["type"]) == (v["status"], v["type"], v["error_type"])
+        assert b["error"]["message"] == "Missing required header: anthropic-version"
+    for payload, msg in [({}, "model is required"), ({"model": "  "}, "model must not be empty"),
+                         ({"model": "m", "messages": []}, "max_tokens is required"),
+                         ({"model": "m", "max_tokens": 1}, "messages must be an array"),
+                         ({"model": "m", "max_tokens": 1, "messages": [{"content": "x"}]}, "messages[0].role is required"),
+                         ({"model": "m", "max_tokens": 1, "messages": [{"role": "system", "content": "x"}]}, "messages[0].role must be 'user' or 'assistant'"),
+                         ({"model": "m", "max_tokens": 1, "messages": [{"role": "user"}]}, "messages[0].content is required"),
+                         ({"model": "m", "max_tokens": 1, "messages": [], "stop_sequences": "END"}, "stop_sequences must be an array of strings"),
+                         ({"model": "m", "max_tokens": 1, "messages": [], "tool_choice": {"type": "nope"}}, "unknown tool_choice type: nope")]:
+        with pytest.raises(G.AnthropicError) as e:
+            G.anthropic_request_to_openai(payload)
+        assert e.value.message == msg
+    assert G.map_finish_reason_to_stop_reason("length") == "max_tokens"
+    assert G.map_finish_reason_to_stop_reason("weird") == "end_turn"
+    # empty completion still yields one empty text block; stream without [DONE] is closed by finish()
+    r = G.openai_to_anthropic_message_response({"choices": [{"message": {"content": ""}, "finish_reason": "length"}]}, "m", None, None)
+    assert r["content"] == [{"type": "text", "text": ""}] and r["stop_reason"] == "max_tokens" and r["usage"] == {"input_tokens": 0, "output_tokens": 0}
+    t = G.AnthropicStreamTransformer("m", input_tokens=7)
+    t.feed('data: {"id":"chatcmpl-9","choices":[{"delta":{"content":"x"}}],"usage":{"prompt_tokens":7,"completion_tokens":1}}\n')
+    t.finish()
+    assert [n for n, _ in t.out][-2:] == ["message_delta", "message_stop"] and t.out[-2][1]["usage"]["output_tokens"] == 1

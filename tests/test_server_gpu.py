@@ -201,3 +201,57 @@ def test_stop_at_end_of_turn_token(tok_server):
     assert j["choices"][0]["finish_reason"] in ("stop", "length")
     st, _, d = call(tok_server, "POST", "/v1/completions", {"model": "tiny-llama", "prompt_token_ids": [5, 999999], "max_tokens": 4})
     assert st == 400
+
+
+# ---- Anthropic Messages front door (llmlb/src/api/anthropic.rs) ----
+def test_messages_route_non_stream_and_stream(server):
+    hdr = {"anthropic-version": "2023-06-01"}
+    body = {"model": "tiny-llama", "max_tokens": 24, "temperature": 0, "system": "be brief",
+            "messages": [{"role": "user", "content": [{"type": "text", "text": "Hello"}]}]}
+    st, _, d = call(server, "POST", "/v1/messages", body, hdr)
+    assert st == 200
+    j = json.loads(d)
+    assert (j["type"], j["role"], j["model"], j["stop_sequence"]) == ("message", "assistant", "tiny-llama", None)
+    assert j["content"][0]["type"] == "text" and j["stop_reason"] in ("end_turn", "max_tokens")
+    assert j["usage"]["input_tokens"] > 0 and 0 < j["usage"]["output_tokens"] <= 24
+    # the same prompt through /v1/chat/completions gives the same text (the route is a translation)
+    conv, _, _ = G.anthropic_request_to_openai(body)
+    st, _, d2 = call(server, "POST", "/v1/chat/completions", conv)
+    assert st == 200 and json.loads(d2)["choices"][0]["message"]["content"] == j["content"][0]["text"]
+    # streamed: Anthropic event sequence, text adds up, output_tokens in message_delta
+    st, h, d = call(server, "POST", "/v1/messages", dict(body, stream=True), hdr)
+    assert st == 200 and h.get("Content-Type", h.get("content-type")) == "text/event-stream"
+    evs = []
+    for blk in d.decode("utf-8").split("\n\n"):
+        if blk.startswith("event: "):
+            name, data = blk.split("\n", 1)
+            evs.append((name[7:], json.loads(data[6:])))
+    names = [n for n, _ in evs]
+    assert names[0] == "message_start" and names[1] == "content_block_start" and names[-3:] == ["content_block_stop", "message_delta", "message_stop"]
+    assert set(names[2:-3]) <= {"content_block_delta"}
+    text = "".join(e["delta"]["text"] for n, e in evs if n == "content_block_delta")
+    assert text == j["content"][0]["text"]
+    assert evs[0][1]["message"]["usage"]["input_tokens"] == j["usage"]["input_tokens"]
+    assert evs[-2][1]["usage"]["output_tokens"] == j["usage"]["output_tokens"]
+    assert evs[-2][1]["delta"]["stop_reason"] == j["stop_reason"]
+    # and it is exactly what the reference's transformer makes of our own chat stream
+    st, _, chat_sse = call(server, "POST", "/v1/chat/completions", dict(conv, stream=True, stream_options={"include_usage": True}))
+    ref = G.AnthropicStreamTransformer("tiny-llama", input_tokens=j["usage"]["input_tokens"])
+    ref.feed(chat_sse.decode("utf-8"))
+    ref.finish()
+    strip = lambda out: [(n, {k: v for k, v in e.items() if k != "message"} if n == "message_start" else e) for n, e in out]
+    assert strip(evs) == strip(ref.out)
+
+
+def test_messages_route_errors_in_anthropic_shape(server):
+    ok_hdr = {"anthropic-version": "2023-06-01"}
+    st, _, d = call(server, "POST", "/v1/messages", {"model": "tiny-llama", "max_tokens": 4, "messages": []})
+    j = json.loads(d)   # llmlb/tests/contract/anthropic_messages_api_test.rs:223-247
+    assert st == 400 and j["type"] == "error" and j["error"] == {"type": "invalid_request_error", "message": "Missing required header: anthropic-version"}
+    st, _, d = call(server, "POST", "/v1/messages", {"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}]}, ok_hdr)
+    assert st == 400 and json.loads(d)["error"]["message"] == "max_tokens is required"
+    st, _, d = call(server, "POST", "/v1/messages", {"model": "tiny-llama", "max_tokens": 4, "messages": [{"role": "user", "content": [{"type": "image", "source": {}}]}]}, ok_hdr)
+    assert st == 400 and "is not supported" in json.loads(d)["error"]["message"]
+    st, _, d = call(server, "POST", "/v1/messages", {"model": "nope", "max_tokens": 4, "messages": [{"role": "user", "content": "x"}]}, ok_hdr)
+    j = json.loads(d)
+    assert st == 404 and j["type"] == "error" and j["error"]["type"] == "not_found_error"
