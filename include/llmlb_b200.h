@@ -90,7 +90,12 @@ void llmlb_engine_destroy(llmlb_engine* e);
 #define LLMLB_IPC_HANDLE_BYTES 64
 int llmlb_engine_tp_export(llmlb_engine* e, uint8_t handle[LLMLB_IPC_HANDLE_BYTES]);
 int llmlb_engine_tp_import(llmlb_engine* e, const uint8_t* handles /* tp_size*64 */, uint32_t n);
-/* Rank 0 plans every step; followers execute the same plans read from a POSIX shm ring. */
+/* Serving with tp_size > 1: rank 0 owns the request queue; it logs every scheduler-state change
+ * (submit, cancel, release, pause, scheduling iteration, harvest) to a POSIX shared-memory ring
+ * `shm_name` and the follower ranks replay the log, so all ranks launch identical steps.  Call
+ * after llmlb_engine_tp_import and before any submit, on rank 0 FIRST (it creates the ring), then
+ * on the followers.  Afterwards submit/poll/cancel/pause only on rank 0 (followers return
+ * LLMLB_E_UNSUPPORTED).  No-op for tp_size == 1. */
 int llmlb_engine_tp_plan_channel(llmlb_engine* e, const char* shm_name);
 
 /* Replace a synthetic tensor with real weights (host pointer, row-major bf16, the FULL

@@ -22,6 +22,11 @@
 #include <unordered_map>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -187,6 +192,114 @@ struct InflightStep {
   uint32_t n_tokens = 0;
 };
 
+// ---- tensor-parallel plan channel ------------------------------------------------------------
+// Rank 0 owns the request queue and the scheduler.  Everything that changes scheduler state —
+// submit, cancel/release, pause, one scheduling iteration, one harvest — is appended, in the order
+// rank 0 applied it, to a byte ring in POSIX shared memory; the follower ranks replay the same
+// calls in the same order, so every rank holds the same slots, pages and batches and launches the
+// same steps (the collectives inside a step need exactly that).  Sampling is identical on every
+// rank (all-gathered logits, per-request seeds), so finishes are reproduced, not transmitted.
+struct PlanHeader {
+  std::atomic<uint64_t> head;        // bytes ever written
+  std::atomic<uint64_t> tail[8];     // bytes consumed per rank (rank 0 unused)
+  std::atomic<uint32_t> magic;       // set last by the leader
+  uint32_t n_ranks;
+  uint64_t ring_bytes;
+};
+enum PlanEvent : uint32_t { kPlanSubmit = 1, kPlanCancel = 2, kPlanRelease = 3, kPlanPause = 4, kPlanSched = 5, kPlanHarvest = 6, kPlanStop = 7 };
+constexpr uint32_t kPlanMagic = 0x4C4C5031u;   // "LLP1"
+constexpr size_t kPlanHeaderBytes = 4096, kPlanRingBytes = size_t(8) << 20;
+
+struct PlanChannel {
+  PlanHeader* h = nullptr;
+  uint8_t* ring = nullptr;
+  uint32_t rank = 0;
+  std::string name;
+  bool leader = false;
+
+  int open(const std::string& shm_name, uint32_t my_rank, uint32_t n_ranks) {
+    name = shm_name[0] == '/' ? shm_name : "/" + shm_name;
+    rank = my_rank;
+    leader = my_rank == 0;
+    const size_t total = kPlanHeaderBytes + kPlanRingBytes;
+    int fd = -1;
+    if (leader) {
+      shm_unlink(name.c_str());
+      fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+      if (fd < 0 || ftruncate(fd, off_t(total)) != 0) { if (fd >= 0) close(fd); set_error("plan channel: cannot create " + name); return LLMLB_E_INTERNAL; }
+    } else {
+      for (int tries = 0; tries < 3000 && fd < 0; ++tries) {   // the leader may still be creating it
+        fd = shm_open(name.c_str(), O_RDWR, 0600);
+        struct stat sb;
+        if (fd >= 0 && (fstat(fd, &sb) != 0 || size_t(sb.st_size) < total)) { close(fd); fd = -1; }
+        if (fd < 0) usleep(10000);
+      }
+      if (fd < 0) { set_error("plan channel: " + name + " did not appear (rank 0 calls llmlb_engine_tp_plan_channel first)"); return LLMLB_E_TIMEOUT; }
+    }
+    void* p = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { set_error("plan channel: mmap failed"); return LLMLB_E_INTERNAL; }
+    h = static_cast<PlanHeader*>(p);
+    ring = static_cast<uint8_t*>(p) + kPlanHeaderBytes;
+    if (leader) {
+      h->head.store(0);
+      for (auto& t : h->tail) t.store(0);
+      h->n_ranks = n_ranks;
+      h->ring_bytes = kPlanRingBytes;
+      h->magic.store(kPlanMagic, std::memory_order_release);
+    } else {
+      for (int tries = 0; tries < 3000 && h->magic.load(std::memory_order_acquire) != kPlanMagic; ++tries) usleep(10000);
+      if (h->magic.load(std::memory_order_acquire) != kPlanMagic) { set_error("plan channel: header never initialised"); return LLMLB_E_TIMEOUT; }
+    }
+    return LLMLB_OK;
+  }
+  void close_channel() {
+    if (h) munmap(h, kPlanHeaderBytes + kPlanRingBytes);
+    if (leader && !name.empty()) shm_unlink(name.c_str());
+    h = nullptr;
+  }
+  void copy_in(uint64_t pos, const void* src, size_t n) {
+    const size_t off = size_t(pos % kPlanRingBytes), first = std::min(n, kPlanRingBytes - off);
+    memcpy(ring + off, src, first);
+    if (n > first) memcpy(ring, static_cast<const uint8_t*>(src) + first, n - first);
+  }
+  void copy_out(uint64_t pos, void* dst, size_t n) const {
+    const size_t off = size_t(pos % kPlanRingBytes), first = std::min(n, kPlanRingBytes - off);
+    memcpy(dst, ring + off, first);
+    if (n > first) memcpy(static_cast<uint8_t*>(dst) + first, ring, n - first);
+  }
+  // leader: record = [u32 payload bytes][u32 type][payload, padded to 8]
+  void write(uint32_t type, const void* payload, uint32_t len) {
+    const uint32_t padded = (len + 7u) & ~7u;
+    const uint64_t need = 8 + padded;
+    uint64_t head = h->head.load(std::memory_order_relaxed);
+    for (;;) {   // back-pressure: never overwrite what the slowest follower has not read
+      uint64_t lo = head;
+      for (uint32_t r = 1; r < h->n_ranks; ++r) lo = std::min(lo, h->tail[r].load(std::memory_order_acquire));
+      if (head + need - lo <= kPlanRingBytes) break;
+      usleep(50);
+    }
+    const uint32_t hdr[2] = {len, type};
+    copy_in(head, hdr, 8);
+    if (len) copy_in(head + 8, payload, len);
+    h->head.store(head + need, std::memory_order_release);
+  }
+  // follower: blocks until the next record is there (0 = aborted by engine destroy)
+  uint32_t read(std::vector<uint8_t>* payload, const std::atomic<bool>& abort) {
+    const uint64_t tail = h->tail[rank].load(std::memory_order_relaxed);
+    for (uint32_t spins = 0; h->head.load(std::memory_order_acquire) == tail; ++spins) {
+      if (abort.load(std::memory_order_relaxed)) return 0;
+      if (spins > 2000) usleep(20); else std::this_thread::yield();
+    }
+    uint32_t hdr[2];
+    copy_out(tail, hdr, 8);
+    payload->resize(hdr[0]);
+    if (hdr[0]) copy_out(tail + 8, payload->data(), hdr[0]);
+    h->tail[rank].store(tail + 8 + ((hdr[0] + 7u) & ~7u), std::memory_order_release);
+    return hdr[1];
+  }
+};
+
 struct LayerW {
   __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
   CUtensorMap m_wqkv, m_wo, m_wgu, m_wdown;
@@ -271,6 +384,9 @@ struct llmlb_engine {
   std::mutex step_mu;          // held while a step (or a debug call) uses the GPU state
   std::thread worker;
   bool stop = false;
+  PlanChannel plan;               // attached by llmlb_engine_tp_plan_channel (tp > 1)
+  bool plan_on = false;           // mu: leader logs / follower replays
+  std::atomic<bool> plan_abort{false};   // engine destroy: wakes a follower blocked on the log
   uint64_t next_id = 1;
   std::map<uint64_t, ReqPtr> requests;
   std::deque<ReqPtr> waiting;
@@ -303,6 +419,11 @@ struct llmlb_engine {
   int run_decode(const std::vector<ReqPtr>& batch);
   void harvest_one();
   void loop();
+  void loop_follower();
+  bool sched_iteration(std::unique_lock<std::mutex>& lk);   // one scheduling decision + launch; lk held on entry, released inside
+  // the log has ONE writer at a time: every append happens with mu held
+  void plan_log(uint32_t type, const void* payload = nullptr, uint32_t len = 0) { if (plan_on && plan.leader) plan.write(type, payload, len); }
+  void plan_log_locked(uint32_t type) { if (plan_on && plan.leader) { std::lock_guard<std::mutex> lk(mu); plan.write(type, nullptr, 0); } }
   void finish_request(const ReqPtr& r, uint32_t reason);
   void release_resources(const ReqPtr& r);
   cudaEvent_t get_event();
@@ -902,73 +1023,141 @@ void llmlb_engine::harvest_one() {
   cv_events.notify_all();
 }
 
+// One scheduling iteration: apply cancellations, pick the next step (prefill chunks first, then
+// a decode step over every running sequence), launch it.  `lk` (mu) is held on entry and released
+// before the launch.  Deterministic in the scheduler state, which is what lets follower ranks
+// replay it (PlanChannel).
+bool llmlb_engine::sched_iteration(std::unique_lock<std::mutex>& lk) {
+  std::vector<ReqPtr> pf_reqs;
+  std::vector<uint32_t> pf_take;
+  std::vector<ReqPtr> dec;
+  // cancellations
+  for (auto it = waiting.begin(); it != waiting.end();) {
+    if ((*it)->cancel) { ReqPtr r = *it; it = waiting.erase(it); finish_request(r, LLMLB_FINISH_CANCELLED); }
+    else ++it;
+  }
+  for (size_t i = 0; i < running.size();) {
+    if (running[i]->cancel && !running[i]->finished) finish_request(running[i], LLMLB_FINISH_CANCELLED);
+    else ++i;
+  }
+  if (!paused) {
+    uint32_t budget = cfg.max_step_tokens;
+    // continue chunked prefills first
+    for (auto& r : running) {
+      if (budget == 0) break;
+      if (r->prefilled < r->prompt.size()) {
+        uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size() - r->prefilled);
+        pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
+      }
+    }
+    // admit in FIFO order while a slot, the pages for prompt+max_tokens and token budget exist
+    while (!waiting.empty() && budget > 0 && !free_slots.empty()) {
+      ReqPtr r = waiting.front();
+      uint32_t need = ceil_div((uint32_t)r->prompt.size() + r->s.max_tokens, kPageTokens);
+      if (need > free_pages.size()) break;
+      waiting.pop_front();
+      r->slot = free_slots.back(); free_slots.pop_back();
+      for (uint32_t i = 0; i < need; ++i) { r->pages.push_back(free_pages.back()); free_pages.pop_back(); }
+      running.push_back(r);
+      uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size());
+      pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
+    }
+    if (pf_reqs.empty()) {
+      for (auto& r : running)
+        if (!r->finished && r->prefilled == r->prompt.size() && r->launched < r->s.max_tokens)
+          dec.push_back(r);
+    }
+  }
+  lk.unlock();
+  if (pf_reqs.empty() && dec.empty()) return false;
+  std::lock_guard<std::mutex> sl(step_mu);
+  int rc = !pf_reqs.empty() ? run_prefill(pf_reqs, pf_take) : run_decode(dec);
+  if (rc != LLMLB_OK) {
+    std::string msg = g_err;
+    cudaStreamSynchronize(st);
+    std::lock_guard<std::mutex> lk2(mu);
+    fatal_error = msg;
+    for (auto& r : std::vector<ReqPtr>(running)) finish_request(r, LLMLB_FINISH_ERROR);
+  }
+  return true;
+}
+
 void llmlb_engine::loop() {
   cudaSetDevice(cfg.device);
   for (;;) {
-    std::vector<ReqPtr> pf_reqs;
-    std::vector<uint32_t> pf_take;
-    std::vector<ReqPtr> dec;
+    bool launched = false;
     {
       std::unique_lock<std::mutex> lk(mu);
       cv_sched.wait(lk, [&] {
-        return stop || !inflight.empty() || (!paused && (!waiting.empty() || !running.empty()));
+        return stop || (plan_on && !plan.leader) || !inflight.empty() || (!paused && (!waiting.empty() || !running.empty()));
       });
       if (stop) break;
-      // cancellations
-      for (auto it = waiting.begin(); it != waiting.end();) {
-        if ((*it)->cancel) { ReqPtr r = *it; it = waiting.erase(it); finish_request(r, LLMLB_FINISH_CANCELLED); }
-        else ++it;
-      }
-      for (size_t i = 0; i < running.size();) {
-        if (running[i]->cancel && !running[i]->finished) finish_request(running[i], LLMLB_FINISH_CANCELLED);
-        else ++i;
-      }
-      if (!paused) {
-        uint32_t budget = cfg.max_step_tokens;
-        // continue chunked prefills first
-        for (auto& r : running) {
-          if (budget == 0) break;
-          if (r->prefilled < r->prompt.size()) {
-            uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size() - r->prefilled);
-            pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
-          }
-        }
-        // admit in FIFO order while a slot, the pages for prompt+max_tokens and token budget exist
-        while (!waiting.empty() && budget > 0 && !free_slots.empty()) {
-          ReqPtr r = waiting.front();
-          uint32_t need = ceil_div((uint32_t)r->prompt.size() + r->s.max_tokens, kPageTokens);
-          if (need > free_pages.size()) break;
-          waiting.pop_front();
-          r->slot = free_slots.back(); free_slots.pop_back();
-          for (uint32_t i = 0; i < need; ++i) { r->pages.push_back(free_pages.back()); free_pages.pop_back(); }
-          running.push_back(r);
-          uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size());
-          pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
-        }
-        if (pf_reqs.empty()) {
-          for (auto& r : running)
-            if (!r->finished && r->prefilled == r->prompt.size() && r->launched < r->s.max_tokens)
-              dec.push_back(r);
-        }
-      }
-    }
-    bool launched = false;
-    if (!pf_reqs.empty() || !dec.empty()) {
-      std::lock_guard<std::mutex> sl(step_mu);
-      int rc = !pf_reqs.empty() ? run_prefill(pf_reqs, pf_take) : run_decode(dec);
-      launched = true;
-      if (rc != LLMLB_OK) {
-        std::string msg = g_err;
-        cudaStreamSynchronize(st);
-        std::lock_guard<std::mutex> lk(mu);
-        fatal_error = msg;
-        for (auto& r : std::vector<ReqPtr>(running)) finish_request(r, LLMLB_FINISH_ERROR);
-      }
+      if (plan_on && !plan.leader) { lk.unlock(); loop_follower(); return; }
+      plan_log(kPlanSched);            // followers run the same iteration, concurrently with ours
+      launched = sched_iteration(lk);
     }
     while (inflight.size() > lookahead || (!launched && !inflight.empty())) {
+      plan_log_locked(kPlanHarvest);
       harvest_one();
       launched = true;  // harvest at most until the window is back to `lookahead`
       if (inflight.size() <= lookahead) break;
+    }
+  }
+  while (!inflight.empty()) { plan_log_locked(kPlanHarvest); harvest_one(); }
+  plan_log_locked(kPlanStop);
+}
+
+// Follower rank of a tensor-parallel group: replay rank 0's log.  Nobody polls requests here, so
+// they are created already released (freed when they finish).
+void llmlb_engine::loop_follower() {
+  std::vector<uint8_t> buf;
+  for (;;) {
+    const uint32_t type = plan.read(&buf, plan_abort);
+    if (type == 0 || type == kPlanStop) break;
+    switch (type) {
+      case kPlanSubmit: {
+        if (buf.size() < sizeof(uint64_t) + sizeof(llmlb_sampling) + 8) break;
+        const uint8_t* p = buf.data();
+        auto r = std::make_shared<Request>();
+        memcpy(&r->id, p, 8); p += 8;
+        memcpy(&r->s, p, sizeof(llmlb_sampling)); p += sizeof(llmlb_sampling);
+        uint32_t n_prompt = 0, n_stop = 0;
+        memcpy(&n_prompt, p, 4); memcpy(&n_stop, p + 4, 4); p += 8;
+        r->prompt.assign(reinterpret_cast<const int32_t*>(p), reinterpret_cast<const int32_t*>(p) + n_prompt);
+        p += size_t(n_prompt) * 4;
+        r->stop_ids.assign(reinterpret_cast<const int32_t*>(p), reinterpret_cast<const int32_t*>(p) + n_stop);
+        r->s.stop_ids = nullptr;
+        r->client_released = true;
+        r->t_submit = std::chrono::steady_clock::now();
+        std::lock_guard<std::mutex> lk(mu);
+        requests[r->id] = r;
+        waiting.push_back(r);
+        break;
+      }
+      case kPlanCancel:
+      case kPlanRelease: {
+        uint64_t id = 0;
+        if (buf.size() >= 8) memcpy(&id, buf.data(), 8);
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = requests.find(id);
+        if (it != requests.end()) it->second->cancel = true;
+        break;
+      }
+      case kPlanPause: {
+        std::lock_guard<std::mutex> lk(mu);
+        paused = !buf.empty() && buf[0] != 0;
+        break;
+      }
+      case kPlanSched: {
+        std::unique_lock<std::mutex> lk(mu);
+        sched_iteration(lk);
+        break;
+      }
+      case kPlanHarvest:
+        if (!inflight.empty()) harvest_one();
+        break;
+      default:
+        break;
     }
   }
   while (!inflight.empty()) harvest_one();
@@ -1005,8 +1194,10 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
     std::lock_guard<std::mutex> lk(e->mu);
     e->stop = true;
   }
+  e->plan_abort.store(true);
   e->cv_sched.notify_all();
   if (e->worker.joinable()) e->worker.join();
+  if (e->plan_on) e->plan.close_channel();
   cudaSetDevice(e->cfg.device);
   if (e->st) cudaStreamSynchronize(e->st);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
@@ -1087,12 +1278,24 @@ extern "C" int llmlb_request_submit(llmlb_engine* e, const int32_t* prompt_ids, 
   r->t_submit = std::chrono::steady_clock::now();
   {
     std::lock_guard<std::mutex> lk(e->mu);
+    if (e->plan_on && !e->plan.leader) { set_error("follower rank of a plan channel: requests enter through rank 0"); return LLMLB_E_UNSUPPORTED; }
     if (!e->fatal_error.empty()) { set_error("engine failed: " + e->fatal_error); return LLMLB_E_DEVICE; }
     if (e->waiting.size() >= 4096) { set_error("queue full"); return LLMLB_E_QUEUE_FULL; }
     r->id = e->next_id++;
     e->requests[r->id] = r;
     e->waiting.push_back(r);
     *req_id = r->id;
+    if (e->plan_on) {   // id, sampling, prompt and stop ids travel to the followers in queue order
+      std::vector<uint8_t> rec(8 + sizeof(llmlb_sampling) + 8 + (size_t(n_prompt) + r->stop_ids.size()) * 4);
+      uint8_t* p = rec.data();
+      memcpy(p, &r->id, 8); p += 8;
+      memcpy(p, &r->s, sizeof(llmlb_sampling)); p += sizeof(llmlb_sampling);
+      const uint32_t n_stop = uint32_t(r->stop_ids.size());
+      memcpy(p, &n_prompt, 4); memcpy(p + 4, &n_stop, 4); p += 8;
+      memcpy(p, r->prompt.data(), size_t(n_prompt) * 4); p += size_t(n_prompt) * 4;
+      if (n_stop) memcpy(p, r->stop_ids.data(), size_t(n_stop) * 4);
+      e->plan_log(kPlanSubmit, rec.data(), uint32_t(rec.size()));
+    }
   }
   e->cv_sched.notify_all();
   return LLMLB_OK;
@@ -1125,6 +1328,7 @@ extern "C" int llmlb_request_cancel(llmlb_engine* e, uint64_t req_id) {
     auto it = e->requests.find(req_id);
     if (it == e->requests.end()) { set_error("unknown request id"); return LLMLB_E_NOT_FOUND; }
     it->second->cancel = true;
+    e->plan_log(kPlanCancel, &req_id, 8);
   }
   e->cv_sched.notify_all();
   return LLMLB_OK;
@@ -1136,13 +1340,19 @@ extern "C" int llmlb_request_release(llmlb_engine* e, uint64_t req_id) {
   auto it = e->requests.find(req_id);
   if (it == e->requests.end()) { set_error("unknown request id"); return LLMLB_E_NOT_FOUND; }
   if (it->second->finished) e->requests.erase(it);
-  else { it->second->client_released = true; it->second->cancel = true; e->cv_sched.notify_all(); }
+  else { it->second->client_released = true; it->second->cancel = true; e->plan_log(kPlanRelease, &req_id, 8); e->cv_sched.notify_all(); }
   return LLMLB_OK;
 }
 
 extern "C" int llmlb_engine_pause(llmlb_engine* e, uint32_t paused) {
   if (!e) { set_error("null engine"); return LLMLB_E_INVALID_ARG; }
-  { std::lock_guard<std::mutex> lk(e->mu); e->paused = paused != 0; }
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->plan_on && !e->plan.leader) { set_error("follower rank of a plan channel: rank 0 pauses the group"); return LLMLB_E_UNSUPPORTED; }
+    e->paused = paused != 0;
+    const uint8_t v = paused != 0;
+    e->plan_log(kPlanPause, &v, 1);
+  }
   e->cv_sched.notify_all();
   return LLMLB_OK;
 }
@@ -1196,10 +1406,20 @@ extern "C" int llmlb_engine_tp_import(llmlb_engine* e, const uint8_t* handles, u
   return e->warmup();
 }
 
-extern "C" int llmlb_engine_tp_plan_channel(llmlb_engine*, const char*) {
-  set_error("plan channel: not implemented yet; submit identical requests on every rank while "
-            "paused (llmlb_engine_pause) and resume after a barrier");
-  return LLMLB_E_UNSUPPORTED;
+// Rank 0 first (it creates the shared-memory ring), then the followers.  From then on requests are
+// submitted on rank 0 only; follower ranks replay its scheduler log (PlanChannel above).
+extern "C" int llmlb_engine_tp_plan_channel(llmlb_engine* e, const char* shm_name) {
+  if (!e || !shm_name || !*shm_name) { set_error("llmlb_engine_tp_plan_channel: bad argument"); return LLMLB_E_INVALID_ARG; }
+  if (e->tp == 1) return LLMLB_OK;   // nothing to coordinate
+  if (!e->tp_ready) { set_error("plan channel: import the peer handles first (llmlb_engine_tp_import)"); return LLMLB_E_UNSUPPORTED; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->plan_on) { set_error("plan channel already attached"); return LLMLB_E_INVALID_ARG; }
+  if (!e->waiting.empty() || !e->running.empty() || !e->inflight.empty()) { set_error("plan channel: attach before submitting requests"); return LLMLB_E_QUEUE_FULL; }
+  int rc = e->plan.open(shm_name, e->rank, e->tp);
+  if (rc != LLMLB_OK) return rc;
+  e->plan_on = true;
+  e->cv_sched.notify_all();
+  return LLMLB_OK;
 }
 
 extern "C" int llmlb_op_allreduce(llmlb_engine* e, float* buf, uint64_t n, void* stream) {

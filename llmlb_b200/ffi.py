@@ -296,3 +296,8 @@ class Engine:
         blob = b"".join(handles)
         arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
         check(lib().llmlb_engine_tp_import(self._h, arr, len(handles)))
+
+    def tp_plan_channel(self, name):
+        """Rank 0 first (creates the shared-memory log), then the followers; afterwards only rank 0
+        submits and the other ranks replay its scheduler."""
+        check(lib().llmlb_engine_tp_plan_channel(self._h, name.encode()))
