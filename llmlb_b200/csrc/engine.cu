@@ -1406,6 +1406,43 @@ extern "C" int llmlb_engine_tp_import(llmlb_engine* e, const uint8_t* handles, u
   return e->warmup();
 }
 
+// CPU-only self-test of the plan ring (tests/test_plan_ring_cpu.py runs it in two processes): the
+// leader writes `n_records` records of pseudo-random size (more bytes than the ring holds, so wrap
+// and back-pressure are exercised), the follower reads them back; both return an FNV-1a checksum
+// over (type, length, payload).  No GPU involved.
+extern "C" int llmlb_debug_plan_ring(const char* shm_name, uint32_t rank, uint32_t n_records, uint64_t seed, uint64_t* checksum) {
+  if (!shm_name || !checksum || rank > 1) { set_error("llmlb_debug_plan_ring: bad argument"); return LLMLB_E_INVALID_ARG; }
+  PlanChannel ch;
+  int rc = ch.open(shm_name, rank, 2);
+  if (rc != LLMLB_OK) return rc;
+  uint64_t h = 1469598103934665603ull;
+  auto mixb = [&](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+  std::atomic<bool> never{false};
+  std::vector<uint8_t> buf;
+  uint64_t state = seed;
+  for (uint32_t i = 0; i < n_records; ++i) {
+    if (rank == 0) {
+      state = mix64(state);
+      const uint32_t len = (i % 7 == 0) ? 0u : uint32_t(state % 65537);
+      const uint32_t type = 1 + uint32_t((state >> 20) % 6);
+      buf.resize(len);
+      for (uint32_t k = 0; k < len; ++k) buf[k] = uint8_t(mix64(state + k) >> 13);
+      ch.write(type, buf.data(), len);
+      mixb(&type, 4); mixb(&len, 4); mixb(buf.data(), len);
+    } else {
+      const uint32_t type = ch.read(&buf, never);
+      const uint32_t len = uint32_t(buf.size());
+      mixb(&type, 4); mixb(&len, 4); mixb(buf.data(), len);
+    }
+  }
+  if (rank == 0) {   // do not unlink the ring under a reader that is still draining it
+    for (int tries = 0; tries < 6000 && ch.h->tail[1].load(std::memory_order_acquire) != ch.h->head.load(std::memory_order_acquire); ++tries) usleep(1000);
+  }
+  ch.close_channel();
+  *checksum = h;
+  return LLMLB_OK;
+}
+
 // Rank 0 first (it creates the shared-memory ring), then the followers.  From then on requests are
 // submitted on rank 0 only; follower ranks replay its scheduler log (PlanChannel above).
 extern "C" int llmlb_engine_tp_plan_channel(llmlb_engine* e, const char* shm_name) {
