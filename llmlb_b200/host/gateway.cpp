@@ -468,6 +468,73 @@ std::string byte_detokenize(int32_t id) {
 
 }  // namespace llmlb_host
 
+// ---- outbound payload preparation --------------------------------------------------------------
+namespace llmlb_host {
+namespace {
+bool id_eq_ci(const std::string& a, const std::string& b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); ++i)
+    if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+  return true;
+}
+}  // namespace
+
+std::string resolve_engine_name(const std::string& model, const std::string& endpoint_type, const std::vector<EngineMapping>& mappings) {
+  for (const auto& m : mappings) {
+    bool knows = id_eq_ci(m.canonical, model);
+    for (const auto& a : m.aliases) knows |= id_eq_ci(a.name, model);
+    if (!knows) continue;
+    for (const auto& a : m.aliases)
+      if (a.engine == endpoint_type) return a.name;
+    return "";
+  }
+  return "";
+}
+
+std::string resolve_runtime_model_name_for_endpoint(const std::string& requested, const std::string& selected,
+                                                    const std::string& endpoint_type, const std::vector<EndpointModel>& endpoint_models,
+                                                    const std::vector<EngineMapping>& mappings) {
+  for (const auto& em : endpoint_models)
+    if (em.model_id == requested) return requested;
+  for (const auto& em : endpoint_models) {
+    if (em.model_id == selected) return em.model_id;
+    if (!em.canonical_name.empty() && (em.canonical_name == selected || em.canonical_name == requested)) return em.model_id;
+  }
+  const std::string alias = resolve_engine_name(selected, endpoint_type, mappings);
+  return alias.empty() ? selected : alias;
+}
+
+Json rewrite_payload_model_for_endpoint(const Json& payload, const std::string& selected, const std::string& endpoint_type,
+                                        const std::vector<EndpointModel>& endpoint_models, const std::vector<EngineMapping>& mappings) {
+  const Json* m = payload.get("model");
+  if (!m || !m->is_string()) return payload;
+  const std::string runtime = resolve_runtime_model_name_for_endpoint(m->str(), selected, endpoint_type, endpoint_models, mappings);
+  if (runtime == m->str()) return payload;
+  Json out = payload;
+  out.set("model", runtime);
+  return out;
+}
+
+Json prepare_upstream_payload(const Json& payload, const std::string& upstream_model, bool stream) {
+  Json out = payload;
+  if (!out.is_object()) return out;
+  out.set("model", upstream_model);
+  if (stream) {
+    const Json* opts = out.get("stream_options");
+    if (!opts) {
+      Json o = Json::object();
+      o.set("include_usage", Json(true));
+      out.set("stream_options", o);
+    } else if (opts->is_object() && !opts->get("include_usage")) {
+      Json o = *opts;
+      o.set("include_usage", Json(true));
+      out.set("stream_options", o);
+    }
+  }
+  return out;
+}
+}  // namespace llmlb_host
+
 // =============================================================================================
 // extern "C" surface for ctypes tests (tests/test_host_gateway.py)
 // =============================================================================================
@@ -586,5 +653,44 @@ size_t llmlb_json_roundtrip(const char* text, char* out, size_t cap) {
   Json j;
   if (!Json::parse(text, &j)) return 0;
   return copy_out(j.dump(), out, cap);
+}
+// spec: {"payload":{...},"selected":"..","endpoint_type":"..","endpoint_models":[[id,canonical|null],..],
+//        "mappings":[{"canonical","aliases":[..],"engines":{alias:engine}}]} -> rewritten payload JSON
+size_t llmlb_rewrite_payload(const char* spec_json, char* out, size_t cap) {
+  Json spec;
+  if (!Json::parse(spec_json, &spec)) return 0;
+  std::vector<EndpointModel> ems;
+  if (const Json* a = spec.get("endpoint_models"))
+    for (const Json& e : a->items()) {
+      EndpointModel em;
+      if (e.items().size() >= 1 && e.items()[0].is_string()) em.model_id = e.items()[0].str();
+      if (e.items().size() >= 2 && e.items()[1].is_string()) em.canonical_name = e.items()[1].str();
+      ems.push_back(em);
+    }
+  std::vector<EngineMapping> maps;
+  if (const Json* a = spec.get("mappings"))
+    for (const Json& m : a->items()) {
+      EngineMapping em;
+      if (const Json* c = m.get("canonical")) em.canonical = c->str();
+      const Json* eng = m.get("engines");
+      if (const Json* al = m.get("aliases"))
+        for (const Json& x : al->items()) {
+          EngineAlias ea;
+          ea.name = x.str();
+          if (eng) if (const Json* e = eng->get(ea.name)) ea.engine = e->str();
+          em.aliases.push_back(ea);
+        }
+      maps.push_back(em);
+    }
+  const Json* payload = spec.get("payload");
+  const Json* sel = spec.get("selected");
+  const Json* et = spec.get("endpoint_type");
+  if (!payload || !sel || !et) return 0;
+  return copy_out(rewrite_payload_model_for_endpoint(*payload, sel->str(), et->str(), ems, maps).dump(), out, cap);
+}
+size_t llmlb_prepare_upstream_payload(const char* payload_json, const char* upstream_model, int stream, char* out, size_t cap) {
+  Json p;
+  if (!Json::parse(payload_json, &p)) return 0;
+  return copy_out(prepare_upstream_payload(p, upstream_model, stream != 0).dump(), out, cap);
 }
 }  // extern "C"

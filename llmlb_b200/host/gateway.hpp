@@ -11,6 +11,9 @@
 //   openai_error_response_with_type      llmlb/src/api/openai_util.rs:242-257
 //   InferenceGate                        llmlb/src/inference_gate.rs:17-230
 //   extract_api_key                      llmlb/src/auth/middleware.rs:292-321
+//   rewrite_payload_model_for_endpoint, resolve_runtime_model_name_for_endpoint  llmlb/src/api/model_name.rs:43-108
+//   resolve_engine_name                  llmlb/src/models/mapping.rs:302-323
+//   stream_options.include_usage injection  llmlb/src/api/openai.rs:977-992
 #pragma once
 #include <atomic>
 #include <map>
@@ -122,6 +125,19 @@ class InferenceGate {  // inference_gate.rs: reject-when-draining + in-flight co
   std::atomic<bool> rejecting_{false};
   std::atomic<uint32_t> in_flight_{0};
 };
+
+// ---- outbound payload preparation (model_name.rs:43-108, openai.rs:977-992, mapping.rs:302-323) ----
+struct EngineAlias { std::string name, engine; };             // engine: "ollama", "lm_studio", "xllm", "vllm", ...
+struct EngineMapping { std::string canonical; std::vector<EngineAlias> aliases; };
+// first alias of the mapping that knows `model` (canonical or alias, case-insensitively) for that engine; "" if none
+std::string resolve_engine_name(const std::string& model, const std::string& endpoint_type, const std::vector<EngineMapping>& mappings);
+std::string resolve_runtime_model_name_for_endpoint(const std::string& requested, const std::string& selected,
+                                                    const std::string& endpoint_type, const std::vector<EndpointModel>& endpoint_models,
+                                                    const std::vector<EngineMapping>& mappings);
+Json rewrite_payload_model_for_endpoint(const Json& payload, const std::string& selected, const std::string& endpoint_type,
+                                        const std::vector<EndpointModel>& endpoint_models, const std::vector<EngineMapping>& mappings);
+// model := upstream name; streaming requests get stream_options.include_usage = true unless the client set it
+Json prepare_upstream_payload(const Json& payload, const std::string& upstream_model, bool stream);
 
 // ---- wire format writers (shapes pinned by the reference's fixtures) ----
 std::string sse_event(const Json& j);                       // "data: {...}\n\n"

@@ -549,3 +549,62 @@ class AnthropicStreamTransformer:
     def wire(self):
         """emit_event (anthropic.rs:1015-1018): 'event: <name>\\ndata: <json>\\n\\n'"""
         return "".join("event: %s\ndata: %s\n\n" % (n, json.dumps(d, separators=(",", ":"), ensure_ascii=False)) for n, d in self.out)
+
+
+# =============================================================================================
+# Outbound payload preparation (SURVEY.md §8 a1.5 / a1.10)
+# =============================================================================================
+# --- llmlb/src/models/mapping.rs:302-323 resolve_engine_name ----------------------------------
+def resolve_engine_name(model, endpoint_type, mappings):
+    """mappings: [{"canonical", "aliases": [...], "engines": {alias: endpoint_type}}] — the first
+    alias registered for `endpoint_type` of the mapping that knows `model`, else None."""
+    m = find_mapping(model, mappings)
+    if not m:
+        return None
+    engines = m.get("engines", {})
+    for a in m["aliases"]:
+        if engines.get(a) == endpoint_type:
+            return a
+    return None
+
+
+# --- llmlb/src/api/model_name.rs:43-80 resolve_runtime_model_name(_for_endpoint) -------------
+def resolve_runtime_model_name_for_endpoint(requested, selected, endpoint_type, endpoint_models, mappings):
+    """endpoint_models: [(model_id, canonical_name or None)] as the endpoint advertises them"""
+    if any(mid == requested for mid, _ in endpoint_models):
+        return requested
+    for mid, canon in endpoint_models:
+        if mid == selected:
+            return mid
+        if canon is not None and (canon == selected or canon == requested):
+            return mid
+    return resolve_engine_name(selected, endpoint_type, mappings) or selected
+
+
+# --- llmlb/src/api/model_name.rs:82-108 rewrite_payload_model_for_endpoint -------------------
+def rewrite_payload_model_for_endpoint(payload, selected, endpoint_type, endpoint_models, mappings):
+    requested = payload.get("model") if isinstance(payload, dict) else None
+    if not isinstance(requested, str):
+        return payload
+    runtime = resolve_runtime_model_name_for_endpoint(requested, selected, endpoint_type, endpoint_models, mappings)
+    if runtime == requested:
+        return payload
+    out = dict(payload)
+    out["model"] = runtime
+    return out
+
+
+# --- llmlb/src/api/openai.rs:977-992: upstream model + stream_options.include_usage -----------
+def prepare_upstream_payload(payload, upstream_model, stream):
+    out = dict(payload)
+    out["model"] = upstream_model
+    if stream:
+        opts = out.get("stream_options")
+        if opts is None or "stream_options" not in out:
+            out["stream_options"] = {"include_usage": True}
+        elif isinstance(opts, dict):
+            opts = dict(opts)
+            opts.setdefault("include_usage", True)
+            out["stream_options"] = opts
+        # a non-object stream_options is left as the client sent it (as_object_mut() is None)
+    return out

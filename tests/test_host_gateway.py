@@ -452,3 +452,32 @@ def test_anthropic_required_header(A):
         v = V["anthropic"]["errors"][0]
         assert (st.value, body["type"], body["error"]["type"]) == (v["status"], v["type"], v["error_type"])
         assert body["error"]["message"] == "Missing required header: anthropic-version"
+
+
+# ---- outbound payload preparation: C++ vs reference vectors and the oracle --------------------
+def test_payload_rewrite_and_include_usage(H):
+    H.llmlb_rewrite_payload.restype = C.c_size_t
+    H.llmlb_rewrite_payload.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    H.llmlb_prepare_upstream_payload.restype = C.c_size_t
+    H.llmlb_prepare_upstream_payload.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+    buf = C.create_string_buffer(1 << 14)
+    maps = V["payload"]["mappings"]
+    cases = list(V["payload"]["rewrite"])
+    cases += [{"payload": {"model": "a", "x": 1}, "selected": "b", "endpoint_type": "vllm", "endpoint_models": [], "model": "b"},
+              {"payload": {"model": "a"}, "selected": "b", "endpoint_type": "vllm", "endpoint_models": [["x", "b"]], "model": "x"},
+              {"payload": {"model": "a"}, "selected": "b", "endpoint_type": "vllm", "endpoint_models": [["a", None]], "model": "a"},
+              {"payload": {"model": "OPENAI/GPT-OSS-20B"}, "selected": "GPT-OSS:20B", "endpoint_type": "lm_studio", "endpoint_models": [], "model": "openai/gpt-oss-20b"},
+              {"payload": {"model": 5}, "selected": "b", "endpoint_type": "ollama", "endpoint_models": [], "model": 5}]
+    for v in cases:
+        spec = {"payload": v["payload"], "selected": v["selected"], "endpoint_type": v["endpoint_type"],
+                "endpoint_models": v["endpoint_models"], "mappings": maps}
+        n = H.llmlb_rewrite_payload(json.dumps(spec).encode(), buf, 1 << 14)
+        got = json.loads(buf.raw[:n].decode())
+        want = G.rewrite_payload_model_for_endpoint(v["payload"], v["selected"], v["endpoint_type"],
+                                                    [(m, c) for m, c in v["endpoint_models"]], maps)
+        assert got == want and got["model"] == v["model"], v
+    for payload in ({"model": "c", "messages": [], "stream": True}, {"model": "c", "stream_options": {"include_usage": False, "x": 1}},
+                    {"model": "c", "stream_options": {}}, {"model": "c", "stream_options": "bogus"}):
+        for stream in (0, 1):
+            n = H.llmlb_prepare_upstream_payload(json.dumps(payload).encode(), b"runtime-name", stream, buf, 1 << 14)
+            assert json.loads(buf.raw[:n].decode()) == G.prepare_upstream_payload(payload, "runtime-name", bool(stream)), (payload, stream)

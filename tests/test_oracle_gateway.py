@@ -217,3 +217,29 @@ def test_anthropic_errors_and_edges():
     t.feed('data: {"id":"chatcmpl-9","choices":[{"delta":{"content":"x"}}],"usage":{"prompt_tokens":7,"completion_tokens":1}}\n')
     t.finish()
     assert [n for n, _ in t.out][-2:] == ["message_delta", "message_stop"] and t.out[-2][1]["usage"]["output_tokens"] == 1
+
+
+# ---- outbound payload preparation (model_name.rs:43-108, openai.rs:977-992) -----------------------
+@pytest.mark.parametrize("v", V["payload"]["rewrite"], ids=lambda v: v["cite"].split()[-1])
+def test_rewrite_payload_model_for_endpoint(v):
+    models = [(m, c) for m, c in v["endpoint_models"]]
+    out = G.rewrite_payload_model_for_endpoint(v["payload"], v["selected"], v["endpoint_type"], models, V["payload"]["mappings"])
+    assert out["model"] == v["model"]
+    assert {k: x for k, x in out.items() if k != "model"} == {k: x for k, x in v["payload"].items() if k != "model"}
+    if v["model"] == v["payload"]["model"]:
+        assert out == v["payload"]
+
+
+def test_prepare_upstream_payload_injects_include_usage():
+    p = {"model": "client-name", "messages": [], "stream": True}
+    assert G.prepare_upstream_payload(p, "m", True) == {"model": "m", "messages": [], "stream": True, "stream_options": {"include_usage": True}}
+    assert "stream_options" not in G.prepare_upstream_payload(p, "m", False)
+    keep = G.prepare_upstream_payload(dict(p, stream_options={"include_usage": False, "x": 1}), "m", True)
+    assert keep["stream_options"] == {"include_usage": False, "x": 1}          # the client's explicit choice wins
+    assert G.prepare_upstream_payload(dict(p, stream_options={}), "m", True)["stream_options"] == {"include_usage": True}
+    assert G.prepare_upstream_payload(dict(p, stream_options="bogus"), "m", True)["stream_options"] == "bogus"
+    assert p == {"model": "client-name", "messages": [], "stream": True}       # input untouched
+    # no mapping, nothing advertised: the selected name passes through
+    assert G.resolve_runtime_model_name_for_endpoint("a", "b", "vllm", [], []) == "b"
+    assert G.resolve_runtime_model_name_for_endpoint("a", "b", "vllm", [("x", "b")], []) == "x"
+    assert G.resolve_runtime_model_name_for_endpoint("a", "b", "vllm", [("a", None)], []) == "a"
