@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(256) rmsnorm_parts_kernel(float* __restrict__ 
                                                             __nv_bfloat16* __restrict__ y,
                                                             uint32_t hidden, float eps) {
   __shared__ float red[8];
+  // lets a PDL-launched successor (the next projection GEMM) start pulling its weights now; a
+  // no-op for ordinary launches
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t t = blockIdx.x;
   float4* xr = reinterpret_cast<float4*>(x + size_t(t) * hidden);
   float ss = 0.f;

@@ -29,8 +29,12 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K,
-               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k) {
+               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k, uint32_t pdl) {
   using Cfg = TcCfg<BN>;
+  // Programmatic dependent launch: the next kernel of the stream may be
+  // scheduled as soon as SMs free up, and THIS kernel may have been scheduled before its
+  // predecessor finished: until griddepcontrol.wait it touches nothing but weights.
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~uintptr_t(1023));
@@ -112,6 +116,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       };
       p_load();
       for (uint32_t i = 0; i < kPrefetchAhead; ++i) p_step();
+      // pdl: the first ring of WEIGHT slabs is requested before the predecessor is known to be done;
+      // the activation halves of those stages follow after griddepcontrol.wait (same full barrier,
+      // its expect_tx already counts both)
+      bool dep_ready = pdl == 0;
+      uint32_t n_deferred = 0;
+      uint32_t d_stage[Cfg::kStages], d_kb[Cfg::kStages], d_tt[Cfg::kStages];
+      auto release_deferred = [&]() {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (uint32_t i = 0; i < n_deferred; ++i)
+          tma_load_2d(smem + d_stage[i] * Cfg::kStageBytes + kBM * kBK * 2, &tmap_x, full_bar + d_stage[i],
+                      int32_t(d_kb[i] * kBK), int32_t(d_tt[i] * BN));
+        dep_ready = true;
+      };
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t mt, tt, ks;
         decode_tile(tile, mt, tt, ks);
@@ -119,15 +136,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const uint32_t kb1 = min(k_blocks_total, kb0 + k_per_split);
         for (uint32_t kb = kb0; kb < kb1; ++kb) {
           p_step();
+          if (!dep_ready && n_deferred == uint32_t(Cfg::kStages)) release_deferred();   // ring full of weights
           { const long long c0 = clock64(); mbar_wait(empty_bar + stage, phase ^ 1); c_wait += clock64() - c0; }
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kBM * kBK * 2;
           mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
           tma_load_2d(sa, &tmap_w, full_bar + stage, int32_t(kb * kBK), int32_t(mt * kBM));
-          tma_load_2d(sb, &tmap_x, full_bar + stage, int32_t(kb * kBK), int32_t(tt * BN));
+          if (dep_ready) {
+            tma_load_2d(sb, &tmap_x, full_bar + stage, int32_t(kb * kBK), int32_t(tt * BN));
+          } else {
+            d_stage[n_deferred] = stage; d_kb[n_deferred] = kb; d_tt[n_deferred] = tt;
+            ++n_deferred;
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (!dep_ready) release_deferred();   // fewer K blocks than stages
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -163,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   } else if (warp >= 4) {
     const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t acc = 0, acc_phase = 0;
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs may alias what earlier kernels read
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       uint32_t mt, tt, ks;
       decode_tile(tile, mt, tt, ks);
@@ -300,8 +325,24 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, ui
   uint32_t t_tiles = (n_tokens + BN - 1) / BN;
   uint32_t tiles = m_tiles * t_tiles * split_k;
   uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tw, tx, out, n_tokens, n_out, k, out_stride,
-                                                  m_tiles, t_tiles, split_k);
+  // default on (64 streams: 12.5k -> 13.2k tok/s, 16 streams +8 %); LLMLB_GEMM_NO_PDL=1 restores plain launches
+  static const bool pdl = getenv("LLMLB_GEMM_NO_PDL") == nullptr;
+  if (!pdl) {
+    kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tw, tx, out, n_tokens, n_out, k, out_stride,
+                                                    m_tiles, t_tiles, split_k, 0u);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, 1u));
+  }
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
