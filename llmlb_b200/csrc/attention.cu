@@ -680,8 +680,10 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
                             __nv_bfloat16* v_pages, const int32_t* __restrict__ block_tables,
                             uint32_t bt_stride, const int32_t* __restrict__ bt_rows,
                             const int32_t* __restrict__ seq_lens, const float2* __restrict__ rope,
-                            __nv_bfloat16* __restrict__ out, uint32_t n_heads, uint32_t n_kv) {
+                            __nv_bfloat16* __restrict__ out, uint32_t n_heads, uint32_t n_kv, uint32_t trigger) {
   extern __shared__ __align__(128) uint8_t dam_smem[];
+  // a PDL-launched successor (the O projection) may take the SMs this grid frees and start on its weights
+  if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(dam_smem);            // [3][32][128] swizzled
   __nv_bfloat16* sv = sk + kDamStages * kDamChunk * kHeadDim;                // [3][32][128] swizzled
   __nv_bfloat16* sq = sv + kDamStages * kDamChunk * kHeadDim;                // [4][128] rotated q (bf16)
@@ -875,6 +877,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
   // splits form a cluster: round down to a supported cluster size
   uint32_t sp = (n_splits >= 16 && allow16) ? 16 : n_splits >= 8 ? 8 : n_splits >= 4 ? 4 : n_splits >= 2 ? 2 : 1;
   static const bool no_mma = getenv("LLMLB_DECODE_ATTN_SIMT") != nullptr;
+  static const bool attn_trigger = getenv("LLMLB_ATTN_NO_TRIGGER") == nullptr;
   if (sp == 1 && !no_mma) {  // wide batch: one warp per (sequence, head group), tensor cores + cp.async ring
     static bool dam_configured = false;
     if (!dam_configured) {
@@ -883,7 +886,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
     }
     decode_attention_mma_kernel<<<dim3(n_heads / kDecHeads, n_seqs), kDamThreads, kDamSmem, st>>>(
         (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows,
-        seq_lens, (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv);
+        seq_lens, (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, attn_trigger ? 1u : 0u);
     LLMLB_LAUNCH_CHECK();
     return LLMLB_OK;
   }
