@@ -76,3 +76,22 @@ def test_argument_validation_without_gpu(built_lib):
     assert L.llmlb_op_gemv(None, None, None, 0.0, None, 1, 8, 8, 0, 8, None) == ffi.E_INVALID_ARG
     assert L.llmlb_op_gemm(None, None, None, 1, 8, 8, 0, 8, 0, None) == ffi.E_INVALID_ARG
     assert b"bad argument" in L.llmlb_last_error()
+
+
+def test_host_library_exports_every_declared_symbol():
+    """include/llmlb_host.h (tokenizer + Anthropic translation, no GPU) against libllmlb_host.so, and
+    the header compiles as plain C."""
+    import subprocess
+    import tempfile
+    from llmlb_b200 import build
+    src = open(os.path.join(ROOT, "include", "llmlb_host.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    fns = sorted(set(re.findall(r"\b(llmlb_[a-z0-9_]+)\s*\(", src)))
+    assert "llmlb_tok_encode" in fns and "llmlb_anthropic_stream_feed" in fns and len(fns) >= 20
+    lib = ctypes.CDLL(build.build_host())
+    missing = [f for f in fns if not hasattr(lib, f)]
+    assert not missing, missing
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "h.c")
+        open(c, "w").write('#include "llmlb_host.h"\nvoid* (*probe)(void) = llmlb_tok_stream_create;\nint main(void){return 0;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "h.o")])
