@@ -387,12 +387,17 @@ std::vector<int32_t> BpeTokenizer::encode(const std::string& text, bool add_bos,
     encode_plain(text, &out);
     return out;
   }
-  // leftmost-longest match over the added tokens (added_ is sorted longest first)
+  // leftmost-longest match over the added tokens (added_ is sorted longest first); only positions
+  // whose byte can start one are examined (Llama-3 has 256 of them, all beginning with '<')
+  bool first_byte[256] = {false};
+  for (const auto& a : added_)
+    if (!a.first.empty()) first_byte[uint8_t(a.first[0])] = true;
   size_t start = 0, i = 0;
   const size_t n = text.size();
   while (i < n) {
     int32_t hit = -1;
     size_t hit_len = 0;
+    if (!first_byte[uint8_t(text[i])]) { ++i; continue; }
     for (const auto& a : added_) {
       if (a.first.size() <= n - i && text.compare(i, a.first.size(), a.first) == 0) { hit = a.second; hit_len = a.first.size(); break; }
     }
