@@ -171,3 +171,36 @@ def test_chat_template_text_and_ids(H, tok, gold):
     smuggle = gold["chats"][2]
     assert smuggle["ids"].count(eot) == 1
     assert H.llmlb_tok_chat_ids(tok, b"{}", 2, (C.c_int32 * 4)(), 4) == -1
+
+
+def test_random_unicode_against_the_library_at_test_time(H, tok):
+    """Beyond the committed vectors: seeded random strings over the whole code space (letters and
+    numbers of every script, every White_Space character, unassigned code points, control tokens)
+    must tokenise exactly like the `tokenizers` library loaded from the same tokenizer.json.  The
+    \\p{L} / \\p{N} tables are generated from that library's own regex engine (Unicode 16)."""
+    tk = pytest.importorskip("tokenizers")
+    import random
+    hf = tk.Tokenizer.from_file(os.path.join(GOLD, "tokenizer_llama3_style.json"))
+    rng = random.Random(20240921)
+    spaces = [0x9, 0xA, 0xB, 0xC, 0xD, 0x20, 0x85, 0xA0, 0x1680, 0x2003, 0x2028, 0x2029, 0x202F, 0x205F, 0x3000, 0x200B, 0xFEFF, 0x180E]
+    specials = ["<|eot_id|>", "<|begin_of_text|>", "<|start_header_id|>", "<|", "|>", "<|eot_id"]
+    for _ in range(20000):
+        parts = []
+        for _ in range(rng.randint(1, 14)):
+            r = rng.random()
+            if r < 0.30:
+                parts.append(chr(rng.randint(0x20, 0x7E)))
+            elif r < 0.42:
+                parts.append(chr(rng.choice(spaces)))
+            elif r < 0.45:
+                parts.append(rng.choice(specials))
+            elif r < 0.50:
+                parts.append(rng.choice(["'s", "'T", "'re", "'LL", "'d", "'", "123", "4567"]))
+            elif r < 0.85:
+                cp = rng.randint(0x80, 0xFFFF)
+                if not 0xD800 <= cp <= 0xDFFF:
+                    parts.append(chr(cp))
+            else:
+                parts.append(chr(rng.randint(0x10000, 0x10FFFF)))
+        s = "".join(parts)
+        assert encode(H, tok, s) == hf.encode(s, add_special_tokens=False).ids, [hex(ord(c)) for c in s]
