@@ -481,3 +481,40 @@ def test_payload_rewrite_and_include_usage(H):
         for stream in (0, 1):
             n = H.llmlb_prepare_upstream_payload(json.dumps(payload).encode(), b"runtime-name", stream, buf, 1 << 14)
             assert json.loads(buf.raw[:n].decode()) == G.prepare_upstream_payload(payload, "runtime-name", bool(stream)), (payload, stream)
+
+
+def test_json_fuzz_against_python(H):
+    """Seeded random documents (nesting, every escape, astral characters, integer / float edge values,
+    ensure_ascii on and off, whitespace) parse and re-serialise to the same value Python reads."""
+    rnd = random.Random(11)
+    alphabet = ['a', 'Z', ' ', '"', '\\', '/', '\b', '\f', '\n', '\r', '\t', '\x01', '\x1f', 'é', 'ß', '日', ' ', '😀', '𝄞', '﻿', '{', ']', ':', ',']
+
+    def rstr():
+        return "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 8)))
+
+    def rnum():
+        k = rnd.random()
+        if k < 0.3:
+            return rnd.randint(-1000, 1000)
+        if k < 0.45:
+            return rnd.choice([0, -1, 2 ** 31, -2 ** 31, 2 ** 53, 2 ** 62, -2 ** 62, 10 ** 17, 999999999999999999])
+        if k < 0.8:
+            return rnd.choice([0.5, -0.25, 0.1, 0.2, 1e-7, 1.5e300, -2.5e-300, 3.14159, 1 / 3, 123456.789, 1e22, 5e-324])
+        return rnd.uniform(-1e6, 1e6)
+
+    def rval(depth):
+        k = rnd.random()
+        if depth > 4 or k < 0.35:
+            return rnd.choice([None, True, False, rstr(), rnum(), rnum()])
+        if k < 0.65:
+            return [rval(depth + 1) for _ in range(rnd.randint(0, 5))]
+        return {rstr(): rval(depth + 1) for _ in range(rnd.randint(0, 5))}
+
+    out = C.create_string_buffer(1 << 16)
+    for i in range(3000):
+        doc = rval(0)
+        text = json.dumps(doc, ensure_ascii=bool(i & 1), indent=(None, 1, 3)[i % 3])
+        n = H.llmlb_json_roundtrip(text.encode("utf-8"), out, 1 << 16)
+        assert n, text
+        back = json.loads(out.raw[:n].decode("utf-8"))
+        assert back == doc, (text, out.raw[:n])
