@@ -518,3 +518,68 @@ def test_json_fuzz_against_python(H):
         assert n, text
         back = json.loads(out.raw[:n].decode("utf-8"))
         assert back == doc, (text, out.raw[:n])
+
+
+def test_accumulator_fuzz_against_oracle(H):
+    """Random SSE streams — chat deltas, Responses deltas / done events, every usage spelling,
+    comments, CRLF, garbage, truncated JSON, [DONE] in the middle — cut at random byte positions: the
+    C++ accumulator (feed) and the oracle restatement of llmlb/src/token/mod.rs agree on content,
+    done flag and usage."""
+    rnd = random.Random(23)
+    words = ["Hello", " world", "", "é", "日本", "😀", "\\n", " \"q\" ", "a" * 40]
+
+    def event():
+        k = rnd.random()
+        if k < 0.30:
+            return "data: " + json.dumps({"id": "c", "choices": [{"delta": {"content": rnd.choice(words)}, "index": 0}]}, ensure_ascii=bool(rnd.getrandbits(1)))
+        if k < 0.40:
+            return "data: " + json.dumps({"type": "response.output_text.delta", "delta": rnd.choice(words)})
+        if k < 0.45:
+            return "data: " + json.dumps({"type": "response.output_text.done", "text": "full text"})
+        if k < 0.55:
+            u = rnd.choice([{"prompt_tokens": 3, "completion_tokens": 4, "total_tokens": 7}, {"input_tokens": 5, "output_tokens": 6},
+                            {"prompt_tokens": 1}, {"output_tokens": 9, "total_tokens": 9}, {"completion_tokens": -1}, {"prompt_tokens": 2.5}])
+            return "data: " + json.dumps(rnd.choice([{"choices": [], "usage": u}, {"type": "response.done", "response": {"usage": u}}, {"usage": u, "response": {"usage": {"input_tokens": 100}}}]))
+        if k < 0.60:
+            return "data: [DONE]"
+        if k < 0.66:
+            return ": keep-alive"
+        if k < 0.72:
+            return "data:" + json.dumps({"choices": [{"delta": {"content": "nospace"}}]})
+        if k < 0.78:
+            return "event: message"
+        if k < 0.84:
+            return "data: {\"choices\": [{\"delta\": {\"content\": \"trunc"
+        if k < 0.90:
+            return "data: " + json.dumps({"choices": [{"delta": {"content": 5}}, {"delta": {"content": "second"}}, "notdict"]})
+        return rnd.choice(["", "   ", "data: 42", "data: null", "garbage line", "data: [\"a\"]"])
+
+    buf = C.create_string_buffer(1 << 14)
+    for trial in range(400):
+        lines = [event() for _ in range(rnd.randint(1, 14))]
+        sep = "\r\n" if trial % 5 == 0 else "\n"
+        body = "".join(l + sep + (sep if rnd.random() < 0.7 else "") for l in lines)
+        if rnd.random() < 0.2:
+            body = body.rstrip("\r\n")          # last line never terminated: stays in the buffer
+        ref = G.StreamingTokenAccumulator("m")
+        if trial % 3 == 0:
+            ref.input_tokens = 11
+        rest = G.process_sse_lines(body, ref)
+        a = H.llmlb_acc_create(b"m")
+        if trial % 3 == 0:
+            H.llmlb_acc_set_input_tokens(a, 11)
+        raw, pos = body.encode("utf-8"), 0
+        while pos < len(raw):
+            step = rnd.randint(1, 23)
+            H.llmlb_acc_feed(a, raw[pos:pos + step], len(raw[pos:pos + step]))
+            pos += step
+        n = H.llmlb_acc_content(a, buf, 1 << 14)
+        assert buf.raw[:n].decode("utf-8") == ref.accumulated_content, (trial, body)
+        assert bool(H.llmlb_acc_done(a)) == ref.done
+        out = (C.c_int64 * 3)()
+        H.llmlb_acc_finalize(a, out)
+        want = ref.finalize()
+        if ref.extracted_usage is not None or not ref.accumulated_content:
+            assert usage3(out) == [want["input_tokens"], want["output_tokens"], want["total_tokens"]], (trial, body)
+        H.llmlb_acc_destroy(a)
+        assert "\n" not in rest
