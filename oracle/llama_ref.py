@@ -67,11 +67,12 @@ class LlamaRef:
         return (x.to(w.dtype) @ w.t()).to(torch.float32)
 
     def _rope(self, x, positions):
-        # x [T, heads, 128]; rotate-half: (x[..., :64], x[..., 64:]) pairs
+        # x [T, heads, head_dim]; rotate-half: (x[..., :hd/2], x[..., hd/2:]) pairs
         ang = positions.to(torch.float64)[:, None] * self.inv_freq[None, :]
         cos = torch.cos(ang).to(torch.float32)[:, None, :]
         sin = torch.sin(ang).to(torch.float32)[:, None, :]
-        a, b = x[..., :64], x[..., 64:]
+        half = x.shape[-1] // 2
+        a, b = x[..., :half], x[..., half:]
         return torch.cat([a * cos - b * sin, b * cos + a * sin], dim=-1)
 
     @torch.no_grad()

@@ -70,3 +70,19 @@ def test_bf16_rounding_is_rne():
     x = np.random.RandomState(0).randn(4096).astype(np.float32)
     want = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     assert np.array_equal(f32_to_bf16_bits(x), want)
+
+
+# ---- more geometries (tests/golden/make_llama_variants_golden.py): MHA / MQA / GQA, head_dim 64 / 128 ----
+@pytest.mark.parametrize("name", ["mha64", "mqa128", "gqa4"])
+def test_variant_geometries_match_transformers(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(os.path.dirname(__file__), "golden", "make_llama_variants_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    M = mk.VARIANTS[name]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "llama_variants_golden.npz"))
+    r = LlamaRef(M, synth_state_dict(M, seed=7))
+    lg = r.forward(g["prompt_" + name]).numpy()
+    assert np.abs(lg[-6:] - g["logits_" + name]).max() < 3e-5
+    toks, _ = r.greedy(g["prompt_" + name], len(g["greedy_" + name]))
+    assert toks == g["greedy_" + name].tolist()
