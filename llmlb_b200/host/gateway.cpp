@@ -468,6 +468,41 @@ std::string byte_detokenize(int32_t id) {
 
 }  // namespace llmlb_host
 
+// ---- 60-minute request history --------------------------------------------------------------------
+namespace llmlb_host {
+void RequestHistory::record(RequestOutcome outcome, int64_t ts) {
+  const int64_t minute = align_to_minute(ts);
+  std::lock_guard<std::mutex> lk(mu_);
+  if (points_.empty() || points_.back().minute != minute) {
+    RequestHistoryPoint p;
+    p.minute = minute;
+    points_.push_back(p);
+  }
+  RequestHistoryPoint& last = points_.back();
+  if (outcome == RequestOutcome::Success) { if (last.success != UINT64_MAX) ++last.success; }
+  else if (outcome == RequestOutcome::Error) { if (last.error != UINT64_MAX) ++last.error; }
+  const int64_t cutoff = minute - 60 * (kWindowMinutes - 1);
+  size_t drop = 0;
+  while (drop < points_.size() && points_[drop].minute < cutoff) ++drop;
+  if (drop) points_.erase(points_.begin(), points_.begin() + drop);
+}
+
+std::vector<RequestHistoryPoint> RequestHistory::window(int64_t now) const {
+  now = align_to_minute(now);
+  std::vector<RequestHistoryPoint> out;
+  out.reserve(size_t(kWindowMinutes));
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int64_t m = now - 60 * (kWindowMinutes - 1); m <= now; m += 60) {
+    RequestHistoryPoint p;
+    p.minute = m;
+    for (const auto& q : points_)
+      if (q.minute == m) { p = q; break; }
+    out.push_back(p);
+  }
+  return out;
+}
+}  // namespace llmlb_host
+
 // ---- outbound payload preparation --------------------------------------------------------------
 namespace llmlb_host {
 namespace {
@@ -692,5 +727,15 @@ size_t llmlb_prepare_upstream_payload(const char* payload_json, const char* upst
   Json p;
   if (!Json::parse(payload_json, &p)) return 0;
   return copy_out(prepare_upstream_payload(p, upstream_model, stream != 0).dump(), out, cap);
+}
+void* llmlb_history_create() { return new RequestHistory(); }
+void llmlb_history_destroy(void* h) { delete static_cast<RequestHistory*>(h); }
+int64_t llmlb_history_align(int64_t ts) { return RequestHistory::align_to_minute(ts); }
+void llmlb_history_record(void* h, int outcome, int64_t ts) { static_cast<RequestHistory*>(h)->record(RequestOutcome(outcome), ts); }
+// out: triples (minute, success, error); window = 1: the zero-filled 60-minute view ending at `now`
+uint32_t llmlb_history_get(void* h, int window, int64_t now, int64_t* out, uint32_t cap_points) {
+  const auto pts = window ? static_cast<RequestHistory*>(h)->window(now) : static_cast<RequestHistory*>(h)->points();
+  for (uint32_t i = 0; i < pts.size() && i < cap_points; ++i) { out[3 * i] = pts[i].minute; out[3 * i + 1] = int64_t(pts[i].success); out[3 * i + 2] = int64_t(pts[i].error); }
+  return uint32_t(pts.size());
 }
 }  // extern "C"

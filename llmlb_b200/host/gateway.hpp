@@ -10,6 +10,7 @@
 //   parse_quantized_model_name           llmlb/src/api/model_name.rs:19-40
 //   openai_error_response_with_type      llmlb/src/api/openai_util.rs:242-257
 //   InferenceGate                        llmlb/src/inference_gate.rs:17-230
+//   RequestHistory (60-minute window)    llmlb/src/balancer/mod.rs:2643-2658,2973-3060
 //   extract_api_key                      llmlb/src/auth/middleware.rs:292-321
 //   rewrite_payload_model_for_endpoint, resolve_runtime_model_name_for_endpoint  llmlb/src/api/model_name.rs:43-108
 //   resolve_engine_name                  llmlb/src/models/mapping.rs:302-323
@@ -79,6 +80,23 @@ class LoadManager {
   std::vector<ModelMapping> mappings_;
   std::map<std::tuple<std::string, std::string, int>, ModelTpsState> tps_;
   std::atomic<uint64_t> round_robin_{0};
+};
+
+// 60-minute request history (balancer/mod.rs:2643-2658, 2973-3060): per-minute success / error
+// counts, newest minute incremented in place, points older than the window dropped on insert;
+// window(now) = exactly 60 points, oldest first, zero-filled.  Timestamps are unix seconds.
+enum class RequestOutcome { Success = 0, Error = 1, Queued = 2 };
+struct RequestHistoryPoint { int64_t minute = 0; uint64_t success = 0, error = 0; };
+class RequestHistory {
+ public:
+  static constexpr int64_t kWindowMinutes = 60;
+  static int64_t align_to_minute(int64_t ts) { return ts - ((ts % 60) + 60) % 60; }
+  void record(RequestOutcome outcome, int64_t ts);
+  std::vector<RequestHistoryPoint> window(int64_t now) const;
+  std::vector<RequestHistoryPoint> points() const { std::lock_guard<std::mutex> lk(mu_); return points_; }
+ private:
+  mutable std::mutex mu_;
+  std::vector<RequestHistoryPoint> points_;
 };
 
 struct TokenUsage { bool has_in = false, has_out = false, has_total = false; uint32_t in = 0, out = 0, total = 0; };

@@ -608,3 +608,48 @@ def prepare_upstream_payload(payload, upstream_model, stream):
             out["stream_options"] = opts
         # a non-object stream_options is left as the client sent it (as_object_mut() is None)
     return out
+
+
+# =============================================================================================
+# 60-minute request history — llmlb/src/balancer/mod.rs:2643-2658, 2973-3060
+# =============================================================================================
+REQUEST_HISTORY_WINDOW_MINUTES = 60          # balancer/types.rs:22
+
+
+def align_to_minute(ts):                     # mod.rs:2973-2975 (ts: unix seconds)
+    return ts - ts % 60
+
+
+class RequestHistory:
+    """Per-minute (success, error) counters: the newest minute is incremented in place, a new minute
+    appends a point, points older than the 60-minute window (relative to the newest) are dropped;
+    'queued' outcomes leave the counters alone.  window(now) returns exactly 60 points, oldest
+    first, ending at now's minute, zero-filled."""
+
+    def __init__(self):
+        self.points = []                     # [[minute, success, error]]
+
+    def record(self, outcome, ts):           # mod.rs:2643-2658
+        minute = align_to_minute(ts)
+        if self.points and self.points[-1][0] == minute:
+            self._inc(self.points[-1], outcome)
+        else:
+            p = [minute, 0, 0]
+            self._inc(p, outcome)
+            self.points.append(p)
+        cutoff = minute - 60 * (REQUEST_HISTORY_WINDOW_MINUTES - 1)      # prune_history :2977-2986
+        while self.points and self.points[0][0] < cutoff:
+            self.points.pop(0)
+
+    @staticmethod
+    def _inc(p, outcome):                    # increment_history :2998-3004
+        if outcome == "success":
+            p[1] += 1
+        elif outcome == "error":
+            p[2] += 1
+
+    def window(self, now):                   # build_history_window / fill_history :3024-3060
+        now = align_to_minute(now)
+        have = {p[0]: p for p in self.points}
+        start = now - 60 * (REQUEST_HISTORY_WINDOW_MINUTES - 1)
+        return [list(have.get(m, [m, 0, 0])) for m in range(start, now + 60, 60)]

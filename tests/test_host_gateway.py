@@ -583,3 +583,51 @@ def test_accumulator_fuzz_against_oracle(H):
             assert usage3(out) == [want["input_tokens"], want["output_tokens"], want["total_tokens"]], (trial, body)
         H.llmlb_acc_destroy(a)
         assert "\n" not in rest
+
+
+# ---- 60-minute request history: C++ vs reference vectors and the oracle ----------------------------
+def test_request_history_matches_vectors_and_oracle(H):
+    i64 = C.c_int64
+    H.llmlb_history_create.restype = C.c_void_p
+    H.llmlb_history_destroy.argtypes = [C.c_void_p]
+    H.llmlb_history_align.restype = i64
+    H.llmlb_history_align.argtypes = [i64]
+    H.llmlb_history_record.argtypes = [C.c_void_p, C.c_int, i64]
+    H.llmlb_history_get.restype = C.c_uint32
+    H.llmlb_history_get.argtypes = [C.c_void_p, C.c_int, i64, C.POINTER(i64), C.c_uint32]
+    NOW = 1749983445
+    code = {"success": 0, "error": 1, "queued": 2}
+
+    def get(h, window, now=0):
+        buf = (i64 * (3 * 128))()
+        n = H.llmlb_history_get(h, window, now, buf, 128)
+        return [[buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]] for i in range(n)]
+
+    for v in V["history"]:
+        if "align" in v:
+            assert H.llmlb_history_align(v["align"][0]) == v["align"][1] == G.align_to_minute(v["align"][0])
+            continue
+        h, ref = H.llmlb_history_create(), G.RequestHistory()
+        events = [(o, NOW + 60 * dm + 7) for o, dm, cnt in v.get("records", []) for _ in range(cnt)]
+        if "then" in v:
+            events.append((v["then"][0], NOW + 60 * v["then"][1]))
+        for o, ts in events:
+            H.llmlb_history_record(h, code[o], ts)
+            ref.record(o, ts)
+        assert get(h, 0) == ref.points
+        assert get(h, 1, NOW + 10) == ref.window(NOW + 10)
+        if "kept_minutes" in v:
+            assert [p[0] for p in get(h, 0)] == [G.align_to_minute(NOW) + 60 * m for m in v["kept_minutes"]]
+        if "totals" in v:
+            assert [sum(p[1] for p in get(h, 0)), sum(p[2] for p in get(h, 0))] == v["totals"]
+        H.llmlb_history_destroy(h)
+    # a long random day: both sides stay identical, the window always has 60 points
+    rnd = random.Random(3)
+    h, ref, t = H.llmlb_history_create(), G.RequestHistory(), NOW
+    for _ in range(5000):
+        t += rnd.choice([0, 1, 5, 59, 61, 600, 4000]) if rnd.random() < 0.9 else 0
+        o = rnd.choice(["success", "success", "error", "queued"])
+        H.llmlb_history_record(h, code[o], t)
+        ref.record(o, t)
+    assert get(h, 0) == ref.points and get(h, 1, t) == ref.window(t) and len(get(h, 1, t)) == 60
+    H.llmlb_history_destroy(h)

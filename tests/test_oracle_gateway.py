@@ -243,3 +243,31 @@ def test_prepare_upstream_payload_injects_include_usage():
     assert G.resolve_runtime_model_name_for_endpoint("a", "b", "vllm", [], []) == "b"
     assert G.resolve_runtime_model_name_for_endpoint("a", "b", "vllm", [("x", "b")], []) == "x"
     assert G.resolve_runtime_model_name_for_endpoint("a", "b", "vllm", [("a", None)], []) == "a"
+
+
+# ---- 60-minute request history (balancer/mod.rs:2643-2658, 2973-3060) ---------------------------
+NOW = 1749983445     # 2025-06-15T10:30:45Z
+
+
+def _play(v, H):
+    for outcome, dmin, count in v.get("records", []):
+        for _ in range(count):
+            H.record(outcome, NOW + 60 * dmin + 7)
+    if "then" in v:
+        H.record(v["then"][0], NOW + 60 * v["then"][1])
+
+
+@pytest.mark.parametrize("v", V["history"], ids=lambda v: v["cite"].split()[-1])
+def test_request_history(v):
+    if "align" in v:
+        assert G.align_to_minute(v["align"][0]) == v["align"][1] and v["align"][1] % 60 == 0
+        return
+    h = G.RequestHistory()
+    _play(v, h)
+    if "kept_minutes" in v:
+        assert [p[0] for p in h.points] == [G.align_to_minute(NOW) + 60 * m for m in v["kept_minutes"]]
+    if "totals" in v:
+        assert [sum(p[1] for p in h.points), sum(p[2] for p in h.points)] == v["totals"]
+    w = h.window(NOW + 10)
+    assert len(w) == 60 and w[-1][0] == G.align_to_minute(NOW) and w[0][0] == w[-1][0] - 59 * 60
+    assert sum(p[1] for p in w) == sum(p[1] for p in h.points if p[0] >= w[0][0])
