@@ -738,4 +738,11 @@ uint32_t llmlb_history_get(void* h, int window, int64_t now, int64_t* out, uint3
   for (uint32_t i = 0; i < pts.size() && i < cap_points; ++i) { out[3 * i] = pts[i].minute; out[3 * i + 1] = int64_t(pts[i].success); out[3 * i + 2] = int64_t(pts[i].error); }
   return uint32_t(pts.size());
 }
+// ops: 'u' value = update(value), 'r' = reset; returns for_sort() (inf when never measured) and *has
+double llmlb_latency_play(const char* ops, const double* values, uint32_t n, int* has) {
+  InferenceLatency l;
+  for (uint32_t i = 0; i < n; ++i) { if (ops[i] == 'u') l.update(values[i]); else l.reset(); }
+  if (has) *has = l.has ? 1 : 0;
+  return l.for_sort();
+}
 }  // extern "C"

@@ -82,6 +82,20 @@ class LoadManager {
   std::atomic<uint64_t> round_robin_{0};
 };
 
+// Inference latency EMA, alpha 0.2 (types/endpoint.rs:419-440): first sample or first after a reset
+// replaces the value; reset (endpoint offline) = +inf so the endpoint sorts last.
+struct InferenceLatency {
+  bool has = false;
+  double ms = 0.0;
+  void update(double new_ms) {
+    const bool finite = has && ms == ms && ms != __builtin_inf() && ms != -__builtin_inf();
+    ms = finite ? 0.2 * new_ms + (1.0 - 0.2) * ms : new_ms;
+    has = true;
+  }
+  void reset() { has = true; ms = __builtin_inf(); }
+  double for_sort() const { return has ? ms : __builtin_inf(); }
+};
+
 // 60-minute request history (balancer/mod.rs:2643-2658, 2973-3060): per-minute success / error
 // counts, newest minute incremented in place, points older than the window dropped on insert;
 // window(now) = exactly 60 points, oldest first, zero-filled.  Timestamps are unix seconds.

@@ -653,3 +653,23 @@ class RequestHistory:
         have = {p[0]: p for p in self.points}
         start = now - 60 * (REQUEST_HISTORY_WINDOW_MINUTES - 1)
         return [list(have.get(m, [m, 0, 0])) for m in range(start, now + 60, 60)]
+
+
+# =============================================================================================
+# Inference latency EMA — llmlb/src/types/endpoint.rs:419-440
+# =============================================================================================
+class InferenceLatency:
+    ALPHA = 0.2
+
+    def __init__(self):
+        self.ms = None                       # Option<f64>
+
+    def update(self, new_ms):                # endpoint.rs:419-427: first sample (or after a reset) = the sample
+        cur = self.ms
+        self.ms = (self.ALPHA * new_ms + (1.0 - self.ALPHA) * cur) if (cur is not None and cur != float("inf") and cur == cur) else new_ms
+
+    def reset(self):                         # endpoint.rs:433-435: offline => sorts last
+        self.ms = float("inf")
+
+    def for_sort(self):                      # endpoint.rs:438-440
+        return float("inf") if self.ms is None else self.ms

@@ -631,3 +631,28 @@ def test_request_history_matches_vectors_and_oracle(H):
         ref.record(o, t)
     assert get(h, 0) == ref.points and get(h, 1, t) == ref.window(t) and len(get(h, 1, t)) == 60
     H.llmlb_history_destroy(h)
+
+
+def test_inference_latency_ema_matches_vectors_and_oracle(H):
+    H.llmlb_latency_play.restype = C.c_double
+    H.llmlb_latency_play.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_int)]
+
+    def play(ops):
+        codes = bytes(ord("u") if o == "update" else ord("r") for o, _ in ops)
+        vals = (C.c_double * max(1, len(ops)))(*[x for _, x in ops])
+        has = C.c_int()
+        return H.llmlb_latency_play(codes, vals, len(ops), C.byref(has)), bool(has.value)
+
+    assert play([]) == (float("inf"), False)
+    for v in V["latency"]:
+        want = float("inf") if v["ms"] == "inf" else v["ms"]
+        assert play(v["ops"])[0] == want
+        if "ms_then" in v:
+            assert abs(play(v["ops"] + v["then"])[0] - v["ms_then"]) < 1e-9
+    rnd = random.Random(9)
+    ops, ref = [], G.InferenceLatency()
+    for _ in range(500):
+        o = ("update", rnd.uniform(1, 5000)) if rnd.random() < 0.93 else ("reset", 0.0)
+        ops.append(o)
+        ref.update(o[1]) if o[0] == "update" else ref.reset()
+        assert play(ops)[0] == ref.for_sort()          # bit-identical doubles

@@ -271,3 +271,19 @@ def test_request_history(v):
     w = h.window(NOW + 10)
     assert len(w) == 60 and w[-1][0] == G.align_to_minute(NOW) and w[0][0] == w[-1][0] - 59 * 60
     assert sum(p[1] for p in w) == sum(p[1] for p in h.points if p[0] >= w[0][0])
+
+
+@pytest.mark.parametrize("v", V["latency"], ids=lambda v: v["cite"].split()[-1])
+def test_inference_latency_ema(v):
+    l = G.InferenceLatency()
+    assert l.ms is None and l.for_sort() == float("inf")
+    for op, x in v["ops"]:
+        l.update(x) if op == "update" else l.reset()
+    assert l.ms == (float("inf") if v["ms"] == "inf" else v["ms"])
+    for op, x in v.get("then", []):
+        l.update(x)
+    if "ms_then" in v:
+        assert abs(l.ms - v["ms_then"]) < 1e-9
+    if v["ms"] == "inf":
+        l.update(50.0)                       # first sample after a reset replaces the infinity
+        assert l.ms == 50.0
