@@ -317,3 +317,51 @@ def load_gguf(engine, path):
             if e.code != ffi.E_NOT_FOUND:
                 raise
     return loaded
+
+
+# ---- the tokenizer a .gguf carries (tokenizer.ggml.*) -> tokenizer.json for the native tokenizer ----
+LLAMA3_SPLIT_PATTERN = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*"
+                        r"|\s*[\r\n]+|\s+(?!\S)|\s+")
+_TOKEN_CONTROL, _TOKEN_USER_DEFINED = 3, 4      # llama.cpp token types that are matched as whole strings
+
+
+def tokenizer_json_from_gguf(meta):
+    """A Hugging Face style tokenizer.json (dict) from GGUF metadata: model "gpt2" (byte-level BPE)
+    with the "llama-bpe" pre-tokenizer — what Llama-3 GGUF files carry.  Tokens of type CONTROL /
+    USER_DEFINED become added tokens (control ones flagged special), the rest the BPE vocabulary;
+    `tokenizer.ggml.bos_token_id` becomes the begin-of-text token of the post-processor."""
+    model = meta.get("tokenizer.ggml.model")
+    if model != "gpt2":
+        raise GGUFError("tokenizer.ggml.model is %r: only byte-level BPE (gpt2) is supported" % (model,))
+    pre = meta.get("tokenizer.ggml.pre", "llama-bpe")
+    if pre not in ("llama-bpe", "llama3", "llama-v3"):
+        raise GGUFError("tokenizer.ggml.pre is %r: only the Llama-3 pre-tokenizer is implemented" % (pre,))
+    tokens = meta.get("tokenizer.ggml.tokens")
+    merges = meta.get("tokenizer.ggml.merges")
+    if not isinstance(tokens, list) or not isinstance(merges, list):
+        raise GGUFError("tokenizer.ggml.tokens / merges missing")
+    types = meta.get("tokenizer.ggml.token_type") or [1] * len(tokens)
+    vocab, added = {}, []
+    for i, (tok, ty) in enumerate(zip(tokens, types)):
+        if ty in (_TOKEN_CONTROL, _TOKEN_USER_DEFINED):
+            added.append({"id": i, "content": tok, "single_word": False, "lstrip": False, "rstrip": False,
+                          "normalized": False, "special": ty == _TOKEN_CONTROL})
+        else:
+            vocab[tok] = i
+    out = {
+        "version": "1.0", "truncation": None, "padding": None, "added_tokens": added, "normalizer": None,
+        "pre_tokenizer": {"type": "Sequence", "pretokenizers": [
+            {"type": "Split", "pattern": {"Regex": LLAMA3_SPLIT_PATTERN}, "behavior": "Isolated", "invert": False},
+            {"type": "ByteLevel", "add_prefix_space": False, "trim_offsets": True, "use_regex": False}]},
+        "post_processor": None,
+        "decoder": {"type": "ByteLevel", "add_prefix_space": True, "trim_offsets": True, "use_regex": True},
+        "model": {"type": "BPE", "dropout": None, "unk_token": None, "continuing_subword_prefix": None,
+                  "end_of_word_suffix": None, "fuse_unk": False, "byte_fallback": False, "ignore_merges": True,
+                  "vocab": vocab, "merges": list(merges)},
+    }
+    bos = meta.get("tokenizer.ggml.bos_token_id")
+    if isinstance(bos, int) and 0 <= bos < len(tokens):
+        out["post_processor"] = {"type": "TemplateProcessing",
+                                 "single": [{"SpecialToken": {"id": tokens[bos], "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}],
+                                 "pair": [], "special_tokens": {tokens[bos]: {"id": tokens[bos], "ids": [bos], "tokens": [tokens[bos]]}}}
+    return out

@@ -215,3 +215,54 @@ def test_engine_loaded_from_gguf(tmp_path, built_lib):
     # Q8_0 weights: logits close to the unquantised model's, far from a different seed's
     assert np.abs(lg - lg_exact).max() < 0.15 * np.abs(lg_exact).max()
     assert np.corrcoef(lg.reshape(-1), lg_exact.reshape(-1))[0, 1] > 0.99
+
+
+def test_tokenizer_embedded_in_gguf(tmp_path):
+    """A .gguf alone is enough to serve text: its tokenizer.ggml.* arrays rebuild a tokenizer.json that
+    the native tokenizer loads and that tokenises the golden vectors exactly like the original."""
+    import ctypes as C
+    import json
+    import os
+    from llmlb_b200 import build
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    tj = json.load(open(os.path.join(gold_dir, "tokenizer_llama3_style.json"), encoding="utf-8"))
+    vectors = json.load(open(os.path.join(gold_dir, "tokenizer_vectors.json"), encoding="utf-8"))["vectors"]
+    n = max(max(tj["model"]["vocab"].values()), max(a["id"] for a in tj["added_tokens"])) + 1
+    tokens, types = [""] * n, [1] * n
+    for tok, i in tj["model"]["vocab"].items():
+        tokens[i] = tok
+    for a in tj["added_tokens"]:
+        tokens[a["id"]], types[a["id"]] = a["content"], 3
+    merges = [m if isinstance(m, str) else " ".join(m) for m in tj["model"]["merges"]]
+    p = tmp_path / "tok.gguf"
+    w = ref.GGUFWriter(str(p), "llama")
+    w.add_tokenizer_model("gpt2")
+    w.add_tokenizer_pre("llama-bpe")
+    w.add_token_list(tokens)
+    w.add_token_types(types)
+    w.add_token_merges(merges)
+    w.add_bos_token_id(tokens.index("<|begin_of_text|>"))
+    w.add_tensor("token_embd.weight", np.zeros((4, 32), dtype=np.float32))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    meta, _, mm = G.read_gguf(p)
+    mm.close()
+    rebuilt = json.dumps(G.tokenizer_json_from_gguf(meta), ensure_ascii=False).encode("utf-8")
+    lib = C.CDLL(build.build_host())
+    lib.llmlb_tok_create.restype = C.c_void_p
+    lib.llmlb_tok_create.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint32]
+    lib.llmlb_tok_encode.restype = C.c_int64
+    lib.llmlb_tok_encode.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_uint64]
+    lib.llmlb_tok_destroy.argtypes = [C.c_void_p]
+    err = C.create_string_buffer(256)
+    tok = lib.llmlb_tok_create(rebuilt, len(rebuilt), err, 256)
+    assert tok, err.value
+    out = (C.c_int32 * 8192)()
+    for v in vectors:
+        b = v["text"].encode("utf-8")
+        k = lib.llmlb_tok_encode(tok, b, len(b), 0, 1, out, 8192)
+        assert list(out[:k]) == v["ids"], repr(v["text"])
+        k = lib.llmlb_tok_encode(tok, b, len(b), 1, 1, out, 8192)
+        assert list(out[:k]) == v["ids_bos"], repr(v["text"])
+    lib.llmlb_tok_destroy(tok)
+    with pytest.raises(G.GGUFError):
+        G.tokenizer_json_from_gguf({"tokenizer.ggml.model": "llama"})
