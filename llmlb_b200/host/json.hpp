@@ -56,6 +56,8 @@ class Json {
     o_.emplace_back(key, std::move(v));
     return o_.back().second;
   }
+  // like set() without the duplicate-key scan: for building big objects (a 128k-entry vocabulary)
+  Json& append(const std::string& key, Json v) { t_ = Object; o_.emplace_back(key, std::move(v)); return o_.back().second; }
   Json& push(Json v) { t_ = Array; a_.push_back(std::move(v)); return a_.back(); }
   const std::vector<Json>& items() const { return a_; }
   const std::vector<std::pair<std::string, Json>>& members() const { return o_; }

@@ -28,6 +28,7 @@
 
 #include "../../include/llmlb_b200.h"
 #include "anthropic.hpp"
+#include "checkpoint.hpp"
 #include "gateway.hpp"
 #include "tokenizer.hpp"
 
@@ -395,6 +396,7 @@ static void serve_conn(int fd) {
 int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
   int port = 8011; std::string geometry = "8b", tokenizer_path;
+  std::vector<std::string> weight_files;   // --weights x.gguf | shard.safetensors (repeatable)
   uint32_t max_seqs = 64, max_ctx = 2048, vocab_override = 0;
   G.model_id = "llama-3-8b";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -403,23 +405,60 @@ int main(int argc, char** argv) {
     else if (k == "--model-id") G.model_id = v; else if (k == "--max-seqs") max_seqs = uint32_t(atoi(v.c_str()));
     else if (k == "--max-ctx") max_ctx = uint32_t(atoi(v.c_str())); else if (k == "--api-key") G.api_key = v;
     else if (k == "--tokenizer") tokenizer_path = v;
+    else if (k == "--weights") weight_files.push_back(v);
     else if (k == "--vocab") vocab_override = uint32_t(atoi(v.c_str()));
   }
   llmlb_engine_config cfg; memset(&cfg, 0, sizeof cfg);
   cfg.abi_version = LLMLB_ABI_VERSION;
   if (geometry == "tiny") cfg.model = {512, 2, 8, 2, 128, 1024, 2048, 500000.f, 1e-5f};
   else cfg.model = {4096, 32, 32, 8, 128, 14336, 128256, 500000.f, 1e-5f};
+  // real checkpoints: geometry from the first file (--model auto), tensors loaded after create
+  std::vector<std::unique_ptr<Checkpoint>> ckpts;
+  for (const auto& wf : weight_files) {
+    std::string err;
+    ckpts.emplace_back(new Checkpoint());
+    if (!ckpts.back()->open(wf, &err)) { fprintf(stderr, "weights %s: %s\n", wf.c_str(), err.c_str()); return 2; }
+  }
+  if (geometry == "auto") {
+    if (ckpts.empty() || !ckpts[0]->geometry().known) { fprintf(stderr, "--model auto needs --weights with a file that describes the model\n"); return 2; }
+    const CkptGeometry& g = ckpts[0]->geometry();
+    cfg.model = {g.hidden, g.n_layers, g.n_heads, g.n_kv_heads, g.head_dim, g.ffn, g.vocab, g.rope_theta, g.rms_eps};
+  }
   if (vocab_override) cfg.model.vocab = vocab_override;   // synthetic weights: any vocabulary size works
   strncpy(cfg.model_id, G.model_id.c_str(), sizeof cfg.model_id - 1);
   cfg.tp_size = 1; cfg.max_seqs = max_seqs; cfg.max_ctx = max_ctx; cfg.kv_block_tokens = 64; cfg.use_cuda_graphs = 1;
   if (llmlb_engine_create(&cfg, &G.eng) != LLMLB_OK) { fprintf(stderr, "engine: %s\n", llmlb_last_error()); return 2; }
   G.vocab = cfg.model.vocab; G.max_ctx = max_ctx;
+  for (size_t ci = 0; ci < ckpts.size(); ++ci) {
+    size_t loaded = 0;
+    std::vector<uint16_t> bits;
+    for (size_t i = 0; i < ckpts[ci]->tensors().size(); ++i) {
+      const CkptTensor& t = ckpts[ci]->tensors()[i];
+      std::string err;
+      if (!ckpts[ci]->read_bf16(i, &bits, &err)) { fprintf(stderr, "weights: %s\n", err.c_str()); return 2; }
+      const int rc = llmlb_engine_load_tensor(G.eng, t.name.c_str(), bits.data(), t.rows, t.cols);
+      if (rc == LLMLB_OK) ++loaded;
+      else if (rc != LLMLB_E_NOT_FOUND) { fprintf(stderr, "weights: %s: %s\n", t.name.c_str(), llmlb_last_error()); return 2; }
+    }
+    fprintf(stderr, "weights: %s: %zu tensors loaded\n", weight_files[ci].c_str(), loaded);
+    if (tokenizer_path.empty() && !G.tok) {   // a .gguf carries its tokenizer
+      const std::string tj = ckpts[ci]->tokenizer_json();
+      if (!tj.empty()) {
+        std::string err;
+        G.tok.reset(new BpeTokenizer());
+        if (!G.tok->load_json(tj, &err)) { fprintf(stderr, "tokenizer embedded in %s: %s\n", weight_files[ci].c_str(), err.c_str()); return 2; }
+      }
+    }
+  }
+  ckpts.clear();
   if (!tokenizer_path.empty()) {
     std::ifstream f(tokenizer_path, std::ios::binary);
     std::stringstream ss; ss << f.rdbuf();
     std::string err;
     G.tok.reset(new BpeTokenizer());
     if (!f || !G.tok->load_json(ss.str(), &err)) { fprintf(stderr, "tokenizer %s: %s\n", tokenizer_path.c_str(), f ? err.c_str() : "cannot read"); return 2; }
+  }
+  if (G.tok) {
     if (G.tok->vocab_size() > G.vocab) { fprintf(stderr, "tokenizer has %u entries, the model only %u\n", G.tok->vocab_size(), G.vocab); return 2; }
     for (const char* name : {"<|eot_id|>", "<|end_of_text|>", "<|eom_id|>"}) { const int32_t id = G.tok->special_id(name); if (id >= 0) G.stop_ids.push_back(id); }
     fprintf(stderr, "tokenizer: %u entries, %zu stop ids\n", G.tok->vocab_size(), G.stop_ids.size());
