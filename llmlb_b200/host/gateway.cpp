@@ -503,6 +503,50 @@ std::vector<RequestHistoryPoint> RequestHistory::window(int64_t now) const {
 }
 }  // namespace llmlb_host
 
+// ---- stop strings -------------------------------------------------------------------------------
+namespace llmlb_host {
+StopMatcher::StopMatcher(std::vector<std::string> stops) {
+  for (auto& st : stops)
+    if (!st.empty()) stops_.push_back(std::move(st));
+}
+
+std::string StopMatcher::feed(const std::string& piece) {
+  if (hit_) return "";
+  if (stops_.empty()) return piece;
+  held_ += piece;
+  // earliest complete stop string (leftmost; the longer one when two start at the same place)
+  size_t best = std::string::npos, best_len = 0;
+  for (const auto& st : stops_) {
+    const size_t p = held_.find(st);
+    if (p != std::string::npos && (p < best || (p == best && st.size() > best_len))) { best = p; best_len = st.size(); }
+  }
+  if (best != std::string::npos) {
+    hit_ = true;
+    matched_ = held_.substr(best, best_len);
+    std::string out = held_.substr(0, best);
+    held_.clear();
+    return out;
+  }
+  // longest suffix of the held text that is a proper prefix of some stop string stays held
+  size_t keep = 0;
+  for (const auto& st : stops_) {
+    const size_t max_k = std::min(held_.size(), st.size() - 1);
+    for (size_t k = max_k; k > keep; --k)
+      if (held_.compare(held_.size() - k, k, st, 0, k) == 0) { keep = k; break; }
+  }
+  std::string out = held_.substr(0, held_.size() - keep);
+  held_.erase(0, held_.size() - keep);
+  return out;
+}
+
+std::string StopMatcher::flush() {
+  std::string out;
+  if (!hit_) out.swap(held_);
+  held_.clear();
+  return out;
+}
+}  // namespace llmlb_host
+
 // ---- outbound payload preparation --------------------------------------------------------------
 namespace llmlb_host {
 namespace {
@@ -744,5 +788,21 @@ double llmlb_latency_play(const char* ops, const double* values, uint32_t n, int
   for (uint32_t i = 0; i < n; ++i) { if (ops[i] == 'u') l.update(values[i]); else l.reset(); }
   if (has) *has = l.has ? 1 : 0;
   return l.for_sort();
+}
+// stops_json: ["...", ...]
+void* llmlb_stop_create(const char* stops_json) {
+  Json j;
+  std::vector<std::string> stops;
+  if (Json::parse(stops_json, &j) && j.is_array())
+    for (const Json& x : j.items()) if (x.is_string()) stops.push_back(x.str());
+  return new StopMatcher(stops);
+}
+void llmlb_stop_destroy(void* m) { delete static_cast<StopMatcher*>(m); }
+size_t llmlb_stop_feed(void* m, const char* piece, size_t n, char* out, size_t cap) { return copy_out(static_cast<StopMatcher*>(m)->feed(std::string(piece, n)), out, cap); }
+size_t llmlb_stop_flush(void* m, char* out, size_t cap) { return copy_out(static_cast<StopMatcher*>(m)->flush(), out, cap); }
+int llmlb_stop_hit(void* m, char* matched, size_t cap) {
+  auto* sm = static_cast<StopMatcher*>(m);
+  if (sm->hit() && matched) copy_out(sm->matched(), matched, cap);
+  return sm->hit() ? 1 : 0;
 }
 }  // extern "C"

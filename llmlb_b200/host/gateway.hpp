@@ -171,6 +171,26 @@ Json rewrite_payload_model_for_endpoint(const Json& payload, const std::string& 
 // model := upstream name; streaming requests get stream_options.include_usage = true unless the client set it
 Json prepare_upstream_payload(const Json& payload, const std::string& upstream_model, bool stream);
 
+// ---- `stop` strings (OpenAI `stop`, Anthropic `stop_sequences`) on the detokenised stream ----------
+// feed() takes the next piece of generated text and returns what may be shown to the client now:
+// text that could still turn out to be the beginning of a stop string is held back; once a stop
+// string is complete the output ends right before it (the stop string itself is never emitted),
+// hit() becomes true and everything after is dropped.  flush() releases held-back text when
+// generation ends without a match.
+class StopMatcher {
+ public:
+  explicit StopMatcher(std::vector<std::string> stops);
+  std::string feed(const std::string& piece);
+  std::string flush();
+  bool hit() const { return hit_; }
+  const std::string& matched() const { return matched_; }
+  bool empty() const { return stops_.empty(); }
+ private:
+  std::vector<std::string> stops_;
+  std::string held_, matched_;
+  bool hit_ = false;
+};
+
 // ---- wire format writers (shapes pinned by the reference's fixtures) ----
 std::string sse_event(const Json& j);                       // "data: {...}\n\n"
 inline std::string sse_done() { return "data: [DONE]\n\n"; }

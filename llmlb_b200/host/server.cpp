@@ -223,6 +223,12 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   const Json* ie = req.get("ignore_eos");
   s.ignore_eos = ie && ie->as_bool() ? 1 : 0;
   if (!G.stop_ids.empty()) { s.stop_ids = G.stop_ids.data(); s.n_stop_ids = uint32_t(G.stop_ids.size()); }
+  std::vector<std::string> stop_strings;   // OpenAI `stop`: a string or up to a few strings, matched on the text
+  if (const Json* sp = req.get("stop")) {
+    if (sp->is_string()) stop_strings.push_back(sp->str());
+    else if (sp->is_array()) for (auto& x : sp->items()) if (x.is_string()) stop_strings.push_back(x.str());
+  }
+  StopMatcher stopper(stop_strings);
   const bool stream = req.get("stream") && req.get("stream")->as_bool();
   bool include_usage = kind != 0;
   if (const Json* so = req.get("stream_options")) if (const Json* iu = so->get("include_usage")) include_usage = iu->as_bool();
@@ -267,19 +273,27 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     for (uint32_t i = 0; i < got; ++i) {
       if (ev[i].token_id >= 0) {
         // with a tokenizer a delta only carries complete UTF-8 (a character split over tokens waits)
-        const std::string piece = G.tok ? G.tok->decode_next(&detok, ev[i].token_id, /*skip_special=*/true)
-                                        : byte_detokenize(ev[i].token_id);
+        const std::string raw_piece = G.tok ? G.tok->decode_next(&detok, ev[i].token_id, /*skip_special=*/true)
+                                            : byte_detokenize(ev[i].token_id);
+        // a stop string may span tokens: text that could still become one is held back
+        const std::string piece = stopper.feed(raw_piece);
         text += piece;
         if (stream && !piece.empty()) out += kind == 1 ? sse_event(responses_event_delta(piece))
                                      : sse_event(chat_chunk(id, jm->str(), created, nullptr, &piece, nullptr));
       }
       prompt_tokens = ev[i].prompt_tokens; completion_tokens = ev[i].completion_tokens;
       if (ev[i].finish_reason) finish = ev[i].finish_reason;
+      if (stopper.hit()) {   // the text ends before the stop string: stop generating, report "stop"
+        llmlb_request_cancel(G.eng, rid);
+        finish = LLMLB_FINISH_STOP;
+        break;
+      }
     }
     if (stream && !out.empty() && ok && !send_sse(out)) { ok = false; client_gone = true; llmlb_request_cancel(G.eng, rid); }
   }
-  if (G.tok) {  // generation ended inside a multi-byte character: U+FFFD, like from_utf8_lossy
-    const std::string rest = BpeTokenizer::flush(&detok);
+  if (!stopper.hit()) {  // text held back as a possible stop prefix, and a character cut by the end of generation
+    std::string rest = stopper.feed(G.tok ? BpeTokenizer::flush(&detok) : std::string());
+    if (!stopper.hit()) rest += stopper.flush();
     if (!rest.empty()) {
       text += rest;
       if (stream && ok) send_sse(kind == 1 ? sse_event(responses_event_delta(rest)) : sse_event(chat_chunk(id, jm->str(), created, nullptr, &rest, nullptr)));

@@ -656,3 +656,74 @@ def test_inference_latency_ema_matches_vectors_and_oracle(H):
         ops.append(o)
         ref.update(o[1]) if o[0] == "update" else ref.reset()
         assert play(ops)[0] == ref.for_sort()          # bit-identical doubles
+
+
+# ---- stop strings on the detokenised stream ----------------------------------------------------------
+def _stop_ref(stops, text):
+    """What a client must see: everything before the earliest complete stop string (leftmost; the
+    longer one if two start together), or all of it."""
+    best = None
+    for st in stops:
+        if st:
+            p = text.find(st)
+            if p >= 0 and (best is None or p < best[0] or (p == best[0] and len(st) > len(best[1]))):
+                best = (p, st)
+    return (text[:best[0]], best[1]) if best else (text, None)
+
+
+def test_stop_matcher(H):
+    H.llmlb_stop_create.restype = C.c_void_p
+    H.llmlb_stop_create.argtypes = [C.c_char_p]
+    H.llmlb_stop_destroy.argtypes = [C.c_void_p]
+    H.llmlb_stop_feed.restype = C.c_size_t
+    H.llmlb_stop_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    H.llmlb_stop_flush.restype = C.c_size_t
+    H.llmlb_stop_flush.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    H.llmlb_stop_hit.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    buf = C.create_string_buffer(1 << 12)
+    rnd = random.Random(4)
+
+    def run(stops, pieces):
+        m = H.llmlb_stop_create(json.dumps(stops).encode())
+        shown, emitted_after_hit = b"", False
+        for pc in pieces:
+            n = H.llmlb_stop_feed(m, pc, len(pc), buf, 1 << 12)
+            if H.llmlb_stop_hit(m, None, 0) and n and shown.endswith(buf.raw[:n]) is False and emitted_after_hit:
+                raise AssertionError("text after the stop")
+            shown += buf.raw[:n]
+            emitted_after_hit = emitted_after_hit or bool(H.llmlb_stop_hit(m, None, 0))
+        n = H.llmlb_stop_flush(m, buf, 1 << 12)
+        shown += buf.raw[:n]
+        matched = C.create_string_buffer(64)
+        hit = H.llmlb_stop_hit(m, matched, 64)
+        H.llmlb_stop_destroy(m)
+        return shown.decode("utf-8"), (matched.value.decode("utf-8") if hit else None)
+
+    # hand cases: stop split over pieces, false starts, overlapping candidates, no stop, empty list
+    assert run(["END"], [b"abc E", b"N", b"D def"]) == ("abc ", "END")
+    assert run(["END"], [b"abc EN", b"x END"]) == ("abc ENx ", "END")
+    assert run(["\n\n", "\nUser:"], [b"line\n", b"User", b": hi"]) == ("line", "\nUser:")
+    assert run(["ab", "abc"], [b"xxabcd"]) == ("xx", "abc")
+    assert run(["zzz"], [b"hello ", b"world"]) == ("hello world", None)
+    assert run([], [b"a", b"b"]) == ("ab", None)
+    assert run(["", "b"], [b"a", b"b", b"c"]) == ("a", "b")
+    # held-back text is released as soon as it cannot be a stop any more, not only at the end
+    m = H.llmlb_stop_create(b'["STOP"]')
+    assert H.llmlb_stop_feed(m, b"xS", 2, buf, 64) == 1 and buf.raw[:1] == b"x"
+    assert H.llmlb_stop_feed(m, b"Ta", 2, buf, 64) == 3 and buf.raw[:3] == b"STa"
+    H.llmlb_stop_destroy(m)
+    # random: any chunking gives the reference answer
+    alphabet = "abAB\n é"
+    for _ in range(600):
+        stops = ["".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 4))) for _ in range(rnd.randint(1, 3))]
+        text = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 40)))
+        raw = text.encode("utf-8")
+        pieces, pos = [], 0
+        while pos < len(raw):
+            step = rnd.randint(1, 6)
+            # keep UTF-8 sequences whole, as the streaming detokenizer guarantees
+            while pos + step < len(raw) and (raw[pos + step] & 0xC0) == 0x80:
+                step += 1
+            pieces.append(raw[pos:pos + step])
+            pos += step
+        assert run(stops, pieces) == _stop_ref(stops, text), (stops, text)

@@ -318,3 +318,27 @@ def test_server_from_a_single_gguf(built_lib, tmp_path):
     finally:
         proc.terminate()
         proc.wait(timeout=20)
+
+
+@pytest.mark.xfail(strict=False, reason="stop strings were wired into the shim after the round's GPU budget was spent; first run decides")
+def test_stop_strings_end_the_text_before_the_match(server):
+    body = {"model": "tiny-llama", "prompt": "abc", "max_tokens": 40, "temperature": 0, "ignore_eos": True}
+    st, _, d = call(server, "POST", "/v1/completions", body)
+    assert st == 200
+    full = json.loads(d)["choices"][0]["text"]
+    assert len(full) >= 12
+    stop = full[7:10]
+    cut = full.find(stop)
+    st, _, d = call(server, "POST", "/v1/completions", dict(body, stop=[stop, "\x00never"]))
+    j = json.loads(d)
+    assert st == 200 and j["choices"][0]["text"] == full[:cut] and j["choices"][0]["finish_reason"] == "stop"
+    assert j["usage"]["completion_tokens"] < 40
+    # chat + streaming: the deltas add up to the same truncated text and the stop string never shows
+    cbody = {"model": "tiny-llama", "messages": [{"role": "user", "content": "abc"}], "max_tokens": 40, "temperature": 0, "ignore_eos": True}
+    st, _, d = call(server, "POST", "/v1/chat/completions", cbody)
+    cfull = json.loads(d)["choices"][0]["message"]["content"]
+    cstop = cfull[5:8]
+    st, _, d = call(server, "POST", "/v1/chat/completions", dict(cbody, stop=cstop, stream=True))
+    acc = G.StreamingTokenAccumulator("tiny-llama")
+    assert G.process_sse_lines(d.decode("utf-8"), acc) == "" and acc.done
+    assert acc.accumulated_content == cfull[:cfull.find(cstop)]
