@@ -14,15 +14,15 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libllmlb_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["elementwise.cu", "gemv.cu", "gemv_ks.cu", "gemv_bulk.cu", "gemv_chain.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_sk.cu", "gemm_mma.cu", "attention.cu",
-           "sampling.cu", "allreduce.cu", "engine.cu"]
+SOURCES = ["elementwise.cu", "gemv.cu", "gemv_ks.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention.cu",
+           "sampling.cu", "tp_exchange.cu", "engine.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
 def _digest(path):
     h = hashlib.sha256()
-    for dep in [path, os.path.join(CSRC, "common.cuh"),
+    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "tp_common.cuh"),
                 os.path.join(HERE, "..", "include", "llmlb_b200.h"), __file__]:
         with open(dep, "rb") as f:
             h.update(f.read())

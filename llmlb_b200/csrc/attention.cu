@@ -10,8 +10,6 @@
 //  * decode_attention_kernel  one new token per sequence: rotate q,k, append k,v, split-KV
 //                             attention over the pages (HBM-bound: ctx*2*128*2 B per kv head),
 //                             last-arriving CTA merges the splits
-#include <cstdlib>
-
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
 
@@ -347,8 +345,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
                         uint32_t bt_stride, const int32_t* __restrict__ bt_rows,
                         const int32_t* __restrict__ seq_lens,
                         const float2* __restrict__ rope, __nv_bfloat16* __restrict__ out,
-                        uint32_t n_heads, uint32_t n_kv, uint32_t n_splits,
-                        const uint8_t* __restrict__ pf_ptr, uint32_t pf_bytes) {
+                        uint32_t n_heads, uint32_t n_kv, uint32_t n_splits) {
   __shared__ float q_s[kDecHeads][kHeadDim];
   __shared__ float kv_new[2][kHeadDim];  // rotated k and v of the new token (owner CTA only)
   __shared__ float mrg_o[4][kDecHeads][kHeadDim];
@@ -362,14 +359,6 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // cluster phase 1 (arrive now, wait just before the first DSMEM store): every CTA has started
   if (n_splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-  // HBM is idle while this latency-bound kernel runs: pull the O-projection's weights (constant
-  // data, safe before the dependency wait) into L2 so the GEMV that follows streams from L2
-  {
-    const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    const uint32_t n_cta = gridDim.x * gridDim.y * gridDim.z;
-    for (uint32_t off = (cta * kDecThreads + threadIdx.x) * 128u; off < pf_bytes; off += n_cta * kDecThreads * 128u)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + off));
-  }
   const uint32_t z = blockIdx.x, hb = blockIdx.y, s = blockIdx.z;
   const uint32_t h0 = hb * kDecHeads, kvh = h0 / (n_heads / n_kv);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -860,7 +849,7 @@ decode_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const int32_t* block_tables,
                             uint32_t bt_stride, const int32_t* bt_rows, const int32_t* seq_lens, uint32_t n_seqs,
                             void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
-                            bool pdl, cudaStream_t st, const void* pf_ptr, uint32_t pf_bytes) {
+                            bool pdl, cudaStream_t st) {
   if (!qkv || !k_pages || !v_pages || !block_tables || !seq_lens || !out || !rope_table ||
       n_kv == 0 || n_heads % n_kv || n_heads % kDecHeads || (n_heads / n_kv) % kDecHeads ||
       n_splits == 0) {
@@ -876,9 +865,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
   }
   // splits form a cluster: round down to a supported cluster size
   uint32_t sp = (n_splits >= 16 && allow16) ? 16 : n_splits >= 8 ? 8 : n_splits >= 4 ? 4 : n_splits >= 2 ? 2 : 1;
-  static const bool no_mma = getenv("LLMLB_DECODE_ATTN_SIMT") != nullptr;
-  static const bool attn_trigger = getenv("LLMLB_ATTN_NO_TRIGGER") == nullptr;
-  if (sp == 1 && !no_mma) {  // wide batch: one warp per (sequence, head group), tensor cores + cp.async ring
+  if (sp == 1) {  // wide batch: one warp per (sequence, head group), tensor cores + cp.async ring
     static bool dam_configured = false;
     if (!dam_configured) {
       LLMLB_CUDA_CHECK(cudaFuncSetAttribute(decode_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDamSmem));
@@ -886,7 +873,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
     }
     decode_attention_mma_kernel<<<dim3(n_heads / kDecHeads, n_seqs), kDamThreads, kDamSmem, st>>>(
         (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows,
-        seq_lens, (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, attn_trigger ? 1u : 0u);
+        seq_lens, (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, 1u);
     LLMLB_LAUNCH_CHECK();
     return LLMLB_OK;
   }
@@ -907,7 +894,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(
       &cfg, decode_attention_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages,
       (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows, seq_lens,
-      (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, sp, (const uint8_t*)pf_ptr, pf_ptr ? pf_bytes : 0u));
+      (const float2*)rope_table, (__nv_bfloat16*)out, n_heads, n_kv, sp));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
@@ -920,5 +907,5 @@ extern "C" int llmlb_op_decode_attention(const void* qkv, void* k_pages, void* v
                                          uint32_t n_kv, const float* rope_table,
                                          uint32_t n_splits, uint32_t, void*, void* stream) {
   return decode_attention_launch(qkv, k_pages, v_pages, block_tables, bt_stride, bt_rows, seq_lens, n_seqs, out,
-                                 n_heads, n_kv, rope_table, n_splits, false, (cudaStream_t)stream, nullptr, 0);
+                                 n_heads, n_kv, rope_table, n_splits, false, (cudaStream_t)stream);
 }

@@ -1,8 +1,6 @@
 // Embedding gather (a2.1), RMSNorm (a2.2) and the synthetic-weight generator.
 // All three are HBM-bound: 16-byte accesses, one row per CTA, no re-reads.
 #include "../../include/llmlb_b200.h"
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace llmlb {
@@ -106,27 +104,11 @@ __global__ void __launch_bounds__(256) rmsnorm_parts_kernel(float* __restrict__ 
 int rmsnorm_parts_launch(float* x, const float* parts, uint32_t n_parts, size_t part_stride, const void* gain,
                          void* y, uint32_t n_tokens, uint32_t hidden, float eps, cudaStream_t st) {
   if (n_tokens == 0) return LLMLB_OK;
-  // opt-in: launching this small kernel itself as a programmatic dependent measured SLOWER
+  // plain launch: launching this small kernel itself as a programmatic dependent measured SLOWER
   // (64 streams: 13.56k -> 12.52k tok/s) — the projection behind it then starts, and holds SMs,
   // two kernels early
-  static const bool pdl = getenv("LLMLB_NORM_PDL") != nullptr;
-  if (!pdl) {
-    rmsnorm_parts_kernel<<<n_tokens, 256, 0, st>>>(x, parts, n_parts, part_stride, (const __nv_bfloat16*)gain,
-                                                   (__nv_bfloat16*)y, hidden, eps, 0u);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_tokens);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rmsnorm_parts_kernel, x, parts, n_parts, part_stride, (const __nv_bfloat16*)gain,
-                                        (__nv_bfloat16*)y, hidden, eps, 1u));
-  }
+  rmsnorm_parts_kernel<<<n_tokens, 256, 0, st>>>(x, parts, n_parts, part_stride, (const __nv_bfloat16*)gain,
+                                                 (__nv_bfloat16*)y, hidden, eps, 0u);
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }

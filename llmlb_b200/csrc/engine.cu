@@ -30,6 +30,7 @@
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tp_common.cuh"
 
 namespace llmlb {
 
@@ -40,39 +41,29 @@ uint32_t tc_pick_bn(uint32_t n_tokens);
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
                    const CUtensorMap* tx_half = nullptr, uint32_t* n_parts = nullptr,
-                   const SkWorkspace* sk = nullptr);
-int sk_workspace_create(SkWorkspace* sk, cudaStream_t st);
-void sk_workspace_destroy(SkWorkspace* sk);
-int gemm_mma_launch(const void* w, const void* x, void* out, uint32_t n_tokens, uint32_t n_out,
-                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
+                   const TpPushRS* tpp = nullptr, uint32_t max_split = 8);
 
 int rmsnorm_parts_launch(float* x, const float* parts, uint32_t n_parts, size_t part_stride, const void* gain,
                          void* y, uint32_t n_tokens, uint32_t hidden, float eps, cudaStream_t st);
 int gemv_decode(const void* w, const void* x, const void* gain, float eps, void* out, uint32_t n_tokens,
-                uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                const void* next_w, size_t next_bytes);
+                uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st);
 int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const int32_t* block_tables,
                             uint32_t bt_stride, const int32_t* bt_rows, const int32_t* seq_lens, uint32_t n_seqs,
                             void* out, uint32_t n_heads, uint32_t n_kv, const float* rope_table, uint32_t n_splits,
-                            bool pdl, cudaStream_t st, const void* pf_ptr = nullptr, uint32_t pf_bytes = 0);
+                            bool pdl, cudaStream_t st);
 void ks_set_trace(const TraceBuf& tb);
 void tc_set_trace(const TraceBuf& tb);
-void sk_set_trace(const TraceBuf& tb);
 void attn_set_trace(const TraceBuf& tb);
-struct ChainOpHost { const void* w; const void* x; const void* gain; void* out; uint32_t n_out, k, out_stride, epi; };
-bool gemv_chain_shape_ok(uint32_t n_out, uint32_t k);
-int gemv_chain_launch(const ChainOpHost* ops, uint32_t n_ops, float eps, uint32_t* state, cudaStream_t st);
 
-constexpr int kArMaxRanks = 8;
-struct ArPeers {
-  uint8_t* base[kArMaxRanks];
-  uint32_t rank, size;
-  uint64_t slot_bytes;
-};
-size_t ar_signal_bytes();
-int ar_allreduce_add(const ArPeers& P, uint32_t slot, float* x, uint64_t n, cudaStream_t st);
-int ar_allgather_cols(const ArPeers& P, uint32_t slot, float* out, uint32_t rows,
-                      uint32_t cols_local, cudaStream_t st);
+// tensor parallel (tp_common.cuh): fused GEMV consumer / producer of protocol A, pull kernels
+int gemv_tp_consume(const TpCtx& ctx, uint32_t coll_in, const void* w, const float* x_in, float* x_out,
+                    const void* gain, float eps, void* out, uint32_t n_tokens, uint32_t n_out, uint32_t k,
+                    uint32_t epi, uint32_t out_stride, cudaStream_t st);
+int gemv_tp_push(const TpCtx& ctx, uint32_t coll_out, const void* w, const void* x_bf16, uint32_t n_tokens,
+                 uint32_t n_out, uint32_t k, cudaStream_t st);
+int ar_allreduce_add(const TpCtx& P, uint64_t off, float* x, uint64_t n, cudaStream_t st);
+int ar_allgather_cols(const TpCtx& P, uint64_t off, float* out, uint32_t rows, uint32_t cols_local, cudaStream_t st);
+constexpr uint32_t kTpMaxSplit = 4;   // K-split parts a push-RS GEMM may use (slot capacity)
 
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
@@ -358,23 +349,24 @@ struct llmlb_engine {
   uint64_t out_seq = 0;
   std::vector<cudaEvent_t> ev_pool;
 
-  // TP exchange
+  // TP exchange (tp_common.cuh): one IPC-shared region per rank
   uint8_t* xchg = nullptr;
   size_t xchg_bytes = 0;
-  ArPeers peers{};
+  TpCtx tpc{};
+  uint64_t logits_slot_off = 0, pull_slot_off = 0, pull_slot_bytes = 0;
   bool tp_ready = false;
+  uint32_t tp_coll = 0;              // collectives issued so far in the current forward pass
+  float* xb = nullptr;               // second residual buffer (protocol A ping-pong)
+  float* tp_stage = nullptr;         // [4][hidden] fp32: partial rows of projections the fused GEMV does not take
+  __nv_bfloat16* ylast = nullptr;    // [max_seqs][hidden] normalised rows that need logits (protocol B)
+  CUtensorMap m_ylast[5]{};
 
   // decode graphs by batch width
   std::unordered_map<uint32_t, cudaGraphExec_t> graphs;
   std::unordered_map<uint32_t, uint64_t> graph_nodes;  // kernels per captured step
   bool paused = false;
   std::string fatal_error;
-  uint32_t attn_pf_mb = 0;    // LLMLB_ATTN_PF_MB: O-proj bytes the decode attention kernel pulls into L2 (measured: 64 -> -3 %)
-  size_t pf_head_bytes = 0;  // LLMLB_PF_MB: next-projection bytes prefetched into L2 per tail (measured: 0 best)
-  float* part_ws = nullptr;         // [8 splits][t_cap][hidden] fp32: K-split partials of O / down
-  SkWorkspace sk;                   // stream-K scratch of the one-N-tile GEMMs (batched decode)
-  uint32_t* chain_state = nullptr;  // [n_layers][8] barrier counters of the decode GEMV chains
-  bool use_chain = false;
+  float* part_ws = nullptr;         // [8 splits][t_cap][hidden] fp32: K-split partials of O / down (tp == 1)
   int warmup();
   std::vector<int32_t> cur_batch_slots;  // what d B.slots currently holds
 
@@ -407,14 +399,29 @@ struct llmlb_engine {
   int init();
   int alloc_all();
   int gen_weights();
-  int proj(const LayerW* L, int which, const void* w, const CUtensorMap& mw, const void* xin,
-           const CUtensorMap* mx, const __nv_bfloat16* gain, void* out, uint32_t T, uint32_t n_out,
-           uint32_t k, uint32_t epi, uint32_t out_stride);
+  // where a forward pass left the final hidden state
+  struct FwdState {
+    float* xres = nullptr;     // fp32 residual rows (complete unless `pending`)
+    float* xother = nullptr;   // tp, protocol A: the other residual buffer
+    bool pending = false;      // tp, protocol A: collective `pending_coll` is pushed but not folded into xres
+    uint32_t pending_coll = 0;
+    bool y_final = false;      // tp, protocol B: y holds RMSNorm(x) * final_norm for all rows (bf16)
+  };
+  int proj(const CUtensorMap& mw, const void* w, const void* xin, const CUtensorMap* mx, void* out, uint32_t T,
+           uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride);
   int layer_stack_decode(uint32_t nb);
   int launch_decode_step(uint32_t nb);
-  int forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, bool* logits_done = nullptr);
-  int forward_decode_chain(bool* logits_done);
-  int logits_for_rows(uint32_t R, bool from_x_rows);
+  int forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs);
+  int forward_small_tp(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs);
+  int forward_big_tp(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs);
+  int attention_block(uint32_t l, uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, bool pdl);
+  int finish_small_tp(FwdState* fs, uint32_t T);                     // fold a pending collective: xres complete
+  int logits_from_x(const float* src, uint32_t R);                   // fp32 rows, final norm applied here
+  int logits_from_y(const __nv_bfloat16* src, const CUtensorMap* maps, uint32_t R);   // rows already normalised
+  int logits_tp_consume(FwdState* fs, uint32_t R);                   // protocol A: lm_head consumes the pending collective
+  int logits_gather(uint32_t R);                                     // tp > 1: vocab slices -> full rows
+  int logits_after_forward(FwdState* fs, uint32_t R, bool decode);   // rows = x[0..R) (decode) or gathered last rows
+  float* logits_dst() { return tp == 1 ? logits : reinterpret_cast<float*>(xchg + logits_slot_off); }
   int run_prefill(const std::vector<ReqPtr>& reqs, const std::vector<uint32_t>& take);
   int run_decode(const std::vector<ReqPtr>& batch);
   void harvest_one();
@@ -465,6 +472,7 @@ int llmlb_engine::init() {
     set_error("kv_block_tokens must be 64"); return LLMLB_E_INVALID_ARG;
   }
   if (!(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank >= tp) { set_error("bad tp_size/tp_rank"); return LLMLB_E_INVALID_ARG; }
+  if (cfg.gemm_impl != 0) { set_error("gemm_impl: only 0 (tcgen05 tiles) is built into the library"); return LLMLB_E_INVALID_ARG; }
   if (M.n_kv_heads == 0 || M.n_heads % M.n_kv_heads || M.n_kv_heads % tp || M.ffn % tp || M.vocab % tp ||
       ((M.n_heads / M.n_kv_heads) % 4) || M.hidden % 8 || (M.ffn / tp) % 8 || (M.vocab / tp) % 4 ||
       M.n_layers == 0 || M.vocab == 0) {
@@ -526,14 +534,12 @@ int llmlb_engine::alloc_all() {
     RC(dmalloc(&L.attn_norm, H, false));
     RC(dmalloc(&L.ffn_norm, H, false));
     param_bytes += (size_t(qkv_w) * H + H * size_t(nq_l) * kHeadDim + size_t(2) * ffn_l * H + H * size_t(ffn_l)) * 2;
-    if (cfg.gemm_impl == 0) {
-      RC(make_tmap_bf16(&L.m_wqkv, L.wqkv, qkv_w, H, 128));
-      RC(make_tmap_bf16(&L.m_wo, L.wo, H, size_t(nq_l) * kHeadDim, 128));
-      RC(make_tmap_bf16(&L.m_wgu, L.wgu, 2 * ffn_l, H, 128));
-      RC(make_tmap_bf16(&L.m_wdown, L.wdown, H, ffn_l, 128));
-    }
+    RC(make_tmap_bf16(&L.m_wqkv, L.wqkv, qkv_w, H, 128));
+    RC(make_tmap_bf16(&L.m_wo, L.wo, H, size_t(nq_l) * kHeadDim, 128));
+    RC(make_tmap_bf16(&L.m_wgu, L.wgu, 2 * ffn_l, H, 128));
+    RC(make_tmap_bf16(&L.m_wdown, L.wdown, H, ffn_l, 128));
   }
-  if (cfg.gemm_impl == 0) RC(make_tmap_bf16(&m_lm_head, lm_head, vocab_l, H, 128));
+  RC(make_tmap_bf16(&m_lm_head, lm_head, vocab_l, H, 128));
 
   layer_pool_elems = size_t(n_pages) * nkv_l * kPageTokens * kHeadDim;
   RC(dmalloc(&k_pool, layer_pool_elems * M.n_layers));
@@ -543,21 +549,47 @@ int llmlb_engine::alloc_all() {
   RC(dmalloc(&d_block_tables, size_t(cfg.max_seqs) * pages_per_seq));
 
   RC(dmalloc(&x, size_t(t_cap) * H));
-  RC(dmalloc(&y, size_t(t_cap) * H));
+  if (tp > 1) {
+    // the exchange region (tp_common.cuh): [pull barrier flags | TpFlags | slot 0 | slot 1 | logits | y]
+    const size_t al = 1024;
+    auto up = [&](size_t v) { return (v + al - 1) & ~(al - 1); };
+    const size_t slot = up(std::max(size_t(kTpMaxSplit) * (t_cap + kTpMaxRanks) * H * 4, size_t(kTpMaxRanks) * kTpSmallRows * H * 4));
+    const size_t lslot = up(size_t(cfg.max_seqs) * vocab_l * 4);
+    size_t off = up(tp_region_prefix_bytes());
+    tpc.flags_off = tp_region_prefix_bytes() - kTpFlagBytes;
+    tpc.slot_off[0] = off; off += slot;
+    tpc.slot_off[1] = off; off += slot;
+    tpc.slot_bytes = slot;
+    logits_slot_off = off; off += lslot;
+    tpc.y_off = off; off += up(size_t(t_cap) * H * 2);
+    xchg_bytes = off;
+    RC(dmalloc(&xchg, xchg_bytes));
+    y = reinterpret_cast<__nv_bfloat16*>(xchg + tpc.y_off);
+    tpc.rank = rank; tpc.size = tp;
+    for (auto& b : tpc.base) b = nullptr;
+    tpc.base[rank] = xchg;
+    // llmlb_op_allreduce (standalone pull all-reduce of the parity tests) borrows slot 0
+    pull_slot_off = tpc.slot_off[0]; pull_slot_bytes = slot;
+    RC(dmalloc(&xb, size_t(kTpSmallRows) * H));
+    RC(dmalloc(&tp_stage, size_t(kTpSmallRows) * H));
+    RC(dmalloc(&ylast, size_t(cfg.max_seqs) * H));
+  } else {
+    RC(dmalloc(&y, size_t(t_cap) * H));
+  }
   RC(dmalloc(&qkv, size_t(t_cap) * qkv_w));
   RC(dmalloc(&attn, size_t(t_cap) * nq_l * kHeadDim));
   RC(dmalloc(&h, size_t(t_cap) * ffn_l));
   RC(dmalloc(&logits, size_t(cfg.max_seqs) * M.vocab));
-  if (tp > 1) RC(dmalloc(&logits_l, size_t(cfg.max_seqs) * vocab_l));
   RC(dmalloc(&x_last, size_t(cfg.max_seqs) * H));
   size_t ws = llmlb_op_decode_attention_ws(cfg.max_seqs, nq_l, 16);
   RC(dmalloc((uint8_t**)&attn_ws, ws));
-  if (cfg.gemm_impl == 0) {
+  {
     const uint32_t boxes[5] = {16, 32, 64, 128, 256};
     for (int i = 0; i < 5; ++i) {
       RC(make_tmap_bf16(&m_y[i], y, t_cap, H, boxes[i]));
       RC(make_tmap_bf16(&m_attn[i], attn, t_cap, size_t(nq_l) * kHeadDim, boxes[i]));
       RC(make_tmap_bf16(&m_h[i], h, t_cap, ffn_l, boxes[i]));
+      if (tp > 1) RC(make_tmap_bf16(&m_ylast[i], ylast, cfg.max_seqs, H, boxes[i]));
     }
   }
   RC(dmalloc(&d_ids, t_cap));
@@ -571,30 +603,13 @@ int llmlb_engine::alloc_all() {
   RC(dmalloc(&B.slots, ms)); RC(dmalloc(&B.ids, ms)); RC(dmalloc(&B.seq_lens, ms));
   RC(dmalloc(&B.temperature, ms)); RC(dmalloc(&B.top_p, ms)); RC(dmalloc(&B.top_k, ms));
   RC(dmalloc(&B.seed, ms)); RC(dmalloc(&B.step, ms)); RC(dmalloc(&B.out_ids, ms));
-  stage_bytes = size_t(t_cap) * 4 * 3 + size_t(t_cap / 64 + ms + 1) * 16 + ms * 4 * 2 + 256;
+  // run_prefill's layout: ids, positions, pages [t_cap each] | tiles [tiles_cap x 4] | rows, slots, lens [max_seqs each]
+  stage_bytes = size_t(t_cap) * 4 * 3 + size_t(t_cap / 64 + ms + 1) * 16 + ms * 4 * 3 + 256;
   for (int i = 0; i < kRing; ++i) {
     LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_stage[i], stage_bytes, cudaHostAllocDefault));
     LLMLB_CUDA_CHECK(cudaHostAlloc((void**)&h_out[i], ms * 4, cudaHostAllocDefault));
   }
-  RC(dmalloc(&chain_state, size_t(M.n_layers) * 8));
   if (tp == 1) RC(dmalloc(&part_ws, size_t(8) * t_cap * H, false));
-  RC(sk_workspace_create(&sk, st));
-  {
-    if (const char* pm = getenv("LLMLB_PF_MB")) pf_head_bytes = size_t(atoi(pm)) << 20;
-    if (const char* am = getenv("LLMLB_ATTN_PF_MB")) attn_pf_mb = (uint32_t)atoi(am);
-    const char* ev = getenv("LLMLB_DECODE_CHAIN");
-    const bool want = ev && ev[0] == '1';  // measured round 1: 211 tok/s chained vs 351 unchained -> opt-in
-    use_chain = want && tp == 1 && gemv_chain_shape_ok(H, nq_l * kHeadDim) && gemv_chain_shape_ok(2 * ffn_l, H) &&
-                gemv_chain_shape_ok(H, ffn_l) && gemv_chain_shape_ok(qkv_w, H) && gemv_chain_shape_ok(vocab_l, H);
-  }
-  if (tp > 1) {
-    size_t slot = std::max(size_t(t_cap) * H * 4, size_t(cfg.max_seqs) * vocab_l * 4);
-    slot = (slot + 255) & ~size_t(255);
-    xchg_bytes = ar_signal_bytes() + 3 * slot;
-    RC(dmalloc(&xchg, xchg_bytes));
-    peers.rank = rank; peers.size = tp; peers.slot_bytes = slot;
-    // signal struct offset must match ar_signal_bytes(): slots start right after sizeof(ArSignals)
-  }
   return LLMLB_OK;
 }
 
@@ -639,145 +654,225 @@ int llmlb_engine::gen_weights() {
 }
 
 // ------------------------------------------------------------------ forward passes ----------
-// One projection: GEMV (<= 4 tokens, optional fused RMSNorm) or tensor-core GEMM.
-int llmlb_engine::proj(const LayerW*, int, const void* w, const CUtensorMap& mw, const void* xin,
-                       const CUtensorMap* mx, const __nv_bfloat16* gain, void* out, uint32_t T,
+// y[r, :] = src[rows[r], :]  (bf16 gather of the normalised rows that need logits; protocol B)
+__global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows,
+                                        __nv_bfloat16* __restrict__ out, uint32_t hidden) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + size_t(rows[blockIdx.x]) * hidden);
+  uint4* d4 = reinterpret_cast<uint4*>(out + size_t(blockIdx.x) * hidden);
+  for (uint32_t i = threadIdx.x; i < hidden / 8; i += blockDim.x) d4[i] = s4[i];
+}
+
+// One tensor-core projection of bf16 activations (T > 4).
+int llmlb_engine::proj(const CUtensorMap& mw, const void*, const void*, const CUtensorMap* mx, void* out, uint32_t T,
                        uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride) {
-  if (T <= 4) return llmlb_op_gemv(w, xin, gain, M.rms_eps, out, T, n_out, k, epi, out_stride, st);
-  // callers pass bf16 activations (already normalised) on this path
-  if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, out, T, n_out, k, epi, out_stride, st);
-  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &sk);
+  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)]);
+}
+
+// RoPE + KV append + attention of layer l over the rows in qkv -> attn
+int llmlb_engine::attention_block(uint32_t l, uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, bool pdl) {
+  if (decode)
+    return decode_attention_launch(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, nb,
+                                   attn, nq_l, nkv_l, rope, decode_splits(nb), pdl, st);
+  RC(llmlb_op_rope_append(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, st));
+  return llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles, n_tiles, attn,
+                                    nq_l, nkv_l, st);
 }
 
 // Runs the layer stack over T rows already embedded in x.  decode: rows are one new token per
 // sequence (nb of them); else rows are prefill tokens described by d_pos/d_page_of_tok/d_tiles.
-// Batch-1 decode: QKV(0) alone, then per layer [attention] + one persistent chain kernel running
-// O-proj -> gate/up -> down -> next layer's QKV (or the lm_head after the last layer).
-int llmlb_engine::forward_decode_chain(bool* logits_done) {
-  const uint32_t H = M.hidden, ko = nq_l * kHeadDim;
-  RC(llmlb_op_gemv(layers[0].wqkv, x, layers[0].attn_norm, M.rms_eps, qkv, 1, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st));
-  for (uint32_t l = 0; l < M.n_layers; ++l) {
-    LayerW& L = layers[l];
-    RC(llmlb_op_decode_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, 1,
-                                 attn, nq_l, nkv_l, rope, decode_splits(1), cfg.max_seqs, attn_ws, st));
-    ChainOpHost ops[4];
-    ops[0] = {L.wo, attn, nullptr, x, H, ko, H, LLMLB_EPI_RESID_F32};
-    ops[1] = {L.wgu, x, L.ffn_norm, h, 2 * ffn_l, H, ffn_l, LLMLB_EPI_SILU_MUL};
-    ops[2] = {L.wdown, h, nullptr, x, H, ffn_l, H, LLMLB_EPI_RESID_F32};
-    if (l + 1 < M.n_layers) ops[3] = {layers[l + 1].wqkv, x, layers[l + 1].attn_norm, qkv, qkv_w, H, qkv_w, LLMLB_EPI_STORE_BF16};
-    else ops[3] = {lm_head, x, final_norm, logits, vocab_l, H, vocab_l, LLMLB_EPI_STORE_F32};
-    RC(gemv_chain_launch(ops, 4, M.rms_eps, chain_state + size_t(l) * 8, st));
-  }
-  *logits_done = true;
-  return LLMLB_OK;
-}
-
-int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, bool* logits_done) {
+int llmlb_engine::forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs) {
   const uint32_t H = M.hidden;
-  if (decode && T == 1 && use_chain && logits_done) return forward_decode_chain(logits_done);
+  *fs = FwdState{};
+  fs->xres = x;
   const bool small = T <= 4;
-  uint32_t coll = 0;
-  // T > 4, single GPU: the O / down projections write fp32 K-split partials into part_ws and the
-  // NEXT normalisation folds them into the residual in slot order (deterministic; no atomics)
-  const bool parts_mode = !small && tp == 1;
+  if (tp > 1) {
+    if (!tp_ready) { set_error("tensor-parallel engine: import the peer handles first (llmlb_engine_tp_import)"); return LLMLB_E_UNSUPPORTED; }
+    RC(tp_step_begin(tpc, st));
+    tp_coll = 0;
+    return small ? forward_small_tp(T, decode, nb, n_tiles, fs) : forward_big_tp(T, decode, nb, n_tiles, fs);
+  }
+  // T > 4: the O / down projections write fp32 K-split partials into part_ws and the NEXT
+  // normalisation folds them into the residual in slot order (deterministic; no atomics)
   const size_t part_stride = size_t(T) * H;
   uint32_t pending = 0;  // partial slots of the previous down projection not yet folded into x
-  auto big_proj_parts = [&](const void* w, const CUtensorMap& mw, const void* xin, const CUtensorMap* mx,
-                            uint32_t k, uint32_t* n_parts) -> int {
-    *n_parts = 1;
-    if (cfg.gemm_impl == 1) return gemm_mma_launch(w, xin, part_ws, T, H, k, LLMLB_EPI_STORE_F32, H, st);
+  auto big_proj_parts = [&](const CUtensorMap& mw, const CUtensorMap* mx, uint32_t k, uint32_t* n_parts) -> int {
     return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], part_ws, T, H, k, kEpiPartialF32, H, st,
-                          &mx[bn_index(128)], n_parts, &sk);
+                          &mx[bn_index(128)], n_parts);
   };
   for (uint32_t l = 0; l < M.n_layers; ++l) {
     LayerW& L = layers[l];
-    const size_t kHead = pf_head_bytes;  // bytes of the next projection pulled into L2 at each tail
     const uint32_t ko = nq_l * kHeadDim;
     // --- attention block ---
     if (small) {
-      // QKV's tail prefetches ALL of O-proj: the attention kernel in between leaves HBM idle
-      RC(gemv_decode(L.wqkv, x, L.attn_norm, M.rms_eps, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st,
-                     (decode && kHead) ? L.wo : nullptr, size_t(H) * ko * 2));
+      RC(gemv_decode(L.wqkv, x, L.attn_norm, M.rms_eps, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, st));
     } else {
-      if (parts_mode) RC(rmsnorm_parts_launch(x, part_ws, pending, part_stride, L.attn_norm, y, T, H, M.rms_eps, st));
-      else RC(llmlb_op_rmsnorm(x, L.attn_norm, y, T, H, M.rms_eps, st));
+      RC(rmsnorm_parts_launch(x, part_ws, pending, part_stride, L.attn_norm, y, T, H, M.rms_eps, st));
       pending = 0;
-      RC(proj(&L, 0, L.wqkv, L.m_wqkv, y, m_y, nullptr, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
+      RC(proj(L.m_wqkv, L.wqkv, y, m_y, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
     }
-    if (decode) {
-      // layers >= 1: PDL launch (its K/V prefetch overlaps the QKV GEMV's tail); layer 0 is a
-      // plain launch so that decode_prepare (seq_lens) is complete before any early prologue
-      RC(decode_attention_launch(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, nb,
-                                 attn, nq_l, nkv_l, rope, decode_splits(nb), l > 0 && small && tp == 1, st,
-                                 (small && attn_pf_mb) ? (const void*)L.wo : nullptr,
-                                 (uint32_t)std::min<size_t>(size_t(H) * nq_l * kHeadDim * 2, size_t(attn_pf_mb) << 20)));
-    } else {
-      RC(llmlb_op_rope_append(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, st));
-      RC(llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles,
-                                    n_tiles, attn, nq_l, nkv_l, st));
-    }
+    // decode, layers >= 1: PDL launch (its K/V prefetch overlaps the QKV GEMV's tail); layer 0 is a
+    // plain launch so that decode_prepare (seq_lens) is complete before any early prologue
+    RC(attention_block(l, T, decode, nb, n_tiles, l > 0 && small));
     uint32_t n_o = 0;
-    if (tp == 1 && small) {
-      RC(gemv_decode(L.wo, attn, nullptr, M.rms_eps, x, T, H, ko, LLMLB_EPI_RESID_F32, H, st, L.wgu, kHead));
-    } else if (tp == 1) {
-      RC(big_proj_parts(L.wo, L.m_wo, attn, m_attn, ko, &n_o));
-    } else {
-      float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
-      RC(proj(&L, 1, L.wo, L.m_wo, attn, m_attn, nullptr, part, T, H, ko, LLMLB_EPI_STORE_F32, H));
-      RC(ar_allreduce_add(peers, coll & 1, x, uint64_t(T) * H, st));
-      ++coll;
-    }
+    if (small) RC(gemv_decode(L.wo, attn, nullptr, M.rms_eps, x, T, H, ko, LLMLB_EPI_RESID_F32, H, st));
+    else RC(big_proj_parts(L.m_wo, m_attn, ko, &n_o));
     // --- feed-forward block ---
     if (small) {
-      RC(gemv_decode(L.wgu, x, L.ffn_norm, M.rms_eps, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, st, L.wdown, kHead));
+      RC(gemv_decode(L.wgu, x, L.ffn_norm, M.rms_eps, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, st));
+      RC(gemv_decode(L.wdown, h, nullptr, M.rms_eps, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H, st));
     } else {
-      if (parts_mode) RC(rmsnorm_parts_launch(x, part_ws, n_o, part_stride, L.ffn_norm, y, T, H, M.rms_eps, st));
-      else RC(llmlb_op_rmsnorm(x, L.ffn_norm, y, T, H, M.rms_eps, st));
-      RC(proj(&L, 2, L.wgu, L.m_wgu, y, m_y, nullptr, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
-    }
-    if (tp == 1 && small) {
-      const void* nxt = (l + 1 < M.n_layers) ? (const void*)layers[l + 1].wqkv : (const void*)lm_head;
-      RC(gemv_decode(L.wdown, h, nullptr, M.rms_eps, x, T, H, ffn_l, LLMLB_EPI_RESID_F32, H, st, nxt, kHead));
-    } else if (tp == 1) {
-      RC(big_proj_parts(L.wdown, L.m_wdown, h, m_h, ffn_l, &pending));
-    } else {
-      float* part = reinterpret_cast<float*>(xchg + ar_signal_bytes() + size_t(coll & 1) * peers.slot_bytes);
-      RC(proj(&L, 3, L.wdown, L.m_wdown, h, m_h, nullptr, part, T, H, ffn_l, LLMLB_EPI_STORE_F32, H));
-      RC(ar_allreduce_add(peers, coll & 1, x, uint64_t(T) * H, st));
-      ++coll;
+      RC(rmsnorm_parts_launch(x, part_ws, n_o, part_stride, L.ffn_norm, y, T, H, M.rms_eps, st));
+      RC(proj(L.m_wgu, L.wgu, y, m_y, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
+      RC(big_proj_parts(L.m_wdown, m_h, ffn_l, &pending));
     }
   }
   // the last down projection's partials: fold into x (no normalisation: the logits path has its own)
-  if (parts_mode && pending) RC(rmsnorm_parts_launch(x, part_ws, pending, part_stride, nullptr, nullptr, T, H, M.rms_eps, st));
+  if (!small && pending) RC(rmsnorm_parts_launch(x, part_ws, pending, part_stride, nullptr, nullptr, T, H, M.rms_eps, st));
   return LLMLB_OK;
 }
 
-// logits[r, :] for R rows.  from_x_rows: rows are x[0..R) (decode); else x_last[0..R) (gathered).
-int llmlb_engine::logits_for_rows(uint32_t R, bool from_x_rows) {
+// Tensor parallel, T <= 4 (protocol A of tp_common.cuh): the O / down GEMVs push their partial rows
+// to every rank, the NEXT projection's RMSNorm prologue folds them into the replicated residual.
+// 5 launches per layer, all PDL-chained; no all-reduce kernel.
+int llmlb_engine::forward_small_tp(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs) {
+  const uint32_t H = M.hidden, ko = nq_l * kHeadDim;
+  float* cur = x;
+  float* oth = xb;
+  int pending = -1;   // collective pushed but not yet folded into `cur`
+  auto consume = [&](const void* w, const __nv_bfloat16* gain, void* out, uint32_t n_out, uint32_t epi, uint32_t out_stride) -> int {
+    if (pending >= 0) {
+      int rc = gemv_tp_consume(tpc, uint32_t(pending), w, cur, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, st);
+      if (rc == LLMLB_E_UNSUPPORTED) {   // odd shape: fold with its own kernel, then the plain projection
+        RC(tp_fold_rows(tpc, uint32_t(pending), cur, oth, T, H, st));
+        rc = gemv_decode(w, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, st);
+      }
+      RC(rc);
+      std::swap(cur, oth);
+      pending = -1;
+      return LLMLB_OK;
+    }
+    return gemv_decode(w, cur, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, st);
+  };
+  auto push = [&](const void* w, const void* xin_bf16, uint32_t k) -> int {
+    const uint32_t c = tp_coll++;
+    int rc = gemv_tp_push(tpc, c, w, xin_bf16, T, H, k, st);
+    if (rc == LLMLB_E_UNSUPPORTED) {
+      RC(llmlb_op_gemv(w, xin_bf16, nullptr, M.rms_eps, tp_stage, T, H, k, LLMLB_EPI_STORE_F32, H, st));
+      rc = tp_push_rows(tpc, c, tp_stage, T, H, st);
+    }
+    RC(rc);
+    pending = int(c);
+    return LLMLB_OK;
+  };
+  for (uint32_t l = 0; l < M.n_layers; ++l) {
+    LayerW& L = layers[l];
+    RC(consume(L.wqkv, L.attn_norm, qkv, qkv_w, LLMLB_EPI_STORE_BF16, qkv_w));
+    RC(attention_block(l, T, decode, nb, n_tiles, l > 0));
+    RC(push(L.wo, attn, ko));
+    RC(consume(L.wgu, L.ffn_norm, h, 2 * ffn_l, LLMLB_EPI_SILU_MUL, ffn_l));
+    RC(push(L.wdown, h, ffn_l));
+  }
+  fs->xres = cur; fs->xother = oth;
+  fs->pending = true; fs->pending_coll = uint32_t(pending);
+  return LLMLB_OK;
+}
+
+int llmlb_engine::finish_small_tp(FwdState* fs, uint32_t T) {
+  if (!fs->pending) return LLMLB_OK;
+  RC(tp_fold_rows(tpc, fs->pending_coll, fs->xres, fs->xother, T, M.hidden, st));
+  std::swap(fs->xres, fs->xother);
+  fs->pending = false;
+  return LLMLB_OK;
+}
+
+// Tensor parallel, T > 4 (protocol B): the O / down GEMM epilogues reduce-scatter their fp32 tiles by
+// address into the row owners' slots; tp_reduce_norm folds the owned rows into the (row-sharded)
+// residual, normalises and all-gathers the bf16 rows into every rank's y.
+int llmlb_engine::forward_big_tp(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs) {
+  const uint32_t H = M.hidden, ko = nq_l * kHeadDim;
+  const uint32_t rpr = ceil_div(T, tp);
+  auto push_rs = [&](const CUtensorMap& mw, const CUtensorMap* mx, uint32_t k, const __nv_bfloat16* next_gain) -> int {
+    TpPushRS tpp{};
+    tpp.ctx = tpc; tpp.coll = tp_coll++; tpp.rpr = rpr;
+    uint32_t n_parts = 1;
+    RC(gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], nullptr, T, H, k, kEpiPushRS, H, st, &mx[bn_index(128)], &n_parts,
+                      &tpp, kTpMaxSplit));
+    return tp_reduce_norm(tpc, tpp.coll, x, next_gain, T, H, M.rms_eps, n_parts, st);
+  };
+  // layer 0: the embedding rows are complete on every rank
+  RC(llmlb_op_rmsnorm(x, layers[0].attn_norm, y, T, H, M.rms_eps, st));
+  for (uint32_t l = 0; l < M.n_layers; ++l) {
+    LayerW& L = layers[l];
+    RC(proj(L.m_wqkv, L.wqkv, y, m_y, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
+    RC(attention_block(l, T, decode, nb, n_tiles, false));
+    RC(push_rs(L.m_wo, m_attn, ko, L.ffn_norm));
+    RC(proj(L.m_wgu, L.wgu, y, m_y, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
+    RC(push_rs(L.m_wdown, m_h, ffn_l, l + 1 < M.n_layers ? layers[l + 1].attn_norm : final_norm));
+  }
+  fs->y_final = true;
+  return LLMLB_OK;
+}
+
+// ---- logits ----
+int llmlb_engine::logits_gather(uint32_t R) {
+  if (tp == 1) return LLMLB_OK;
+  return ar_allgather_cols(tpc, logits_slot_off, logits, R, vocab_l, st);
+}
+// logits[r, :] for R fp32 residual rows at src (final RMSNorm applied here)
+int llmlb_engine::logits_from_x(const float* src, uint32_t R) {
   const uint32_t H = M.hidden;
-  const float* src = from_x_rows ? x : x_last;
-  float* dst = (tp == 1) ? logits
-                         : reinterpret_cast<float*>(xchg + ar_signal_bytes() + 2 * peers.slot_bytes);
+  float* dst = logits_dst();
   if (R <= 4) {
     RC(llmlb_op_gemv(lm_head, src, final_norm, M.rms_eps, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
   } else {
     RC(llmlb_op_rmsnorm(src, final_norm, y, R, H, M.rms_eps, st));
-    if (cfg.gemm_impl == 1)
-      RC(gemm_mma_launch(lm_head, y, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
-    else
-      RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st, &m_y[bn_index(128)], nullptr, &sk));
+    RC(gemm_tc_launch(m_lm_head, m_y[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st, &m_y[bn_index(128)]));
   }
-  if (tp > 1) RC(ar_allgather_cols(peers, 2, logits, R, vocab_l, st));
-  return LLMLB_OK;
+  return logits_gather(R);
+}
+// rows already normalised (bf16): the lm_head projection alone
+int llmlb_engine::logits_from_y(const __nv_bfloat16* src, const CUtensorMap* maps, uint32_t R) {
+  const uint32_t H = M.hidden;
+  float* dst = logits_dst();
+  if (R <= 4) RC(llmlb_op_gemv(lm_head, src, nullptr, M.rms_eps, dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st));
+  else RC(gemm_tc_launch(m_lm_head, maps[bn_index(tc_pick_bn(R))], dst, R, vocab_l, H, LLMLB_EPI_STORE_F32, vocab_l, st, &maps[bn_index(128)]));
+  return logits_gather(R);
+}
+// protocol A, decode: the lm_head GEMV's prologue consumes the last down projection's collective
+int llmlb_engine::logits_tp_consume(FwdState* fs, uint32_t R) {
+  int rc = gemv_tp_consume(tpc, fs->pending_coll, lm_head, fs->xres, fs->xother, final_norm, M.rms_eps, logits_dst(), R,
+                           vocab_l, M.hidden, LLMLB_EPI_STORE_F32, vocab_l, st);
+  if (rc == LLMLB_E_UNSUPPORTED) {
+    RC(finish_small_tp(fs, R));
+    return logits_from_x(fs->xres, R);
+  }
+  RC(rc);
+  std::swap(fs->xres, fs->xother);
+  fs->pending = false;
+  return logits_gather(R);
+}
+// decode: logits of rows 0..R of the step; prefill: logits of the rows listed in d_last_rows
+int llmlb_engine::logits_after_forward(FwdState* fs, uint32_t R, bool decode) {
+  if (fs->y_final) {
+    if (decode) return logits_from_y(y, m_y, R);
+    gather_rows_bf16_kernel<<<R, 128, 0, st>>>(y, d_last_rows, ylast, M.hidden);
+    LLMLB_LAUNCH_CHECK();
+    return logits_from_y(ylast, m_ylast, R);
+  }
+  if (decode) {
+    if (fs->pending) return logits_tp_consume(fs, R);
+    return logits_from_x(fs->xres, R);
+  }
+  return LLMLB_E_INTERNAL;   // prefill with fp32 residual: run_prefill gathers the rows itself
 }
 
 int llmlb_engine::layer_stack_decode(uint32_t nb) {
   decode_prepare_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(S, B, nb);
   LLMLB_LAUNCH_CHECK();
   RC(llmlb_op_embed(embed, B.ids, x, nb, M.hidden, M.vocab, st));
-  bool logits_done = false;
-  RC(forward_tokens(nb, true, nb, 0, &logits_done));
-  if (!logits_done) RC(logits_for_rows(nb, true));
+  FwdState fs;
+  RC(forward_tokens(nb, true, nb, 0, &fs));
+  RC(logits_after_forward(&fs, nb, true));
   RC(llmlb_op_sample(logits, nb, M.vocab, B.temperature, B.top_p, B.top_k, B.seed, B.step, B.out_ids, st));
   step_finish_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(S, B, nb);
   LLMLB_LAUNCH_CHECK();
@@ -905,11 +1000,17 @@ int llmlb_engine::run_prefill(const std::vector<ReqPtr>& reqs, const std::vector
   step.ev_end = get_event();
   LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_start, st));
   RC(llmlb_op_embed(embed, d_ids, x, T, M.hidden, M.vocab, st));
-  RC(forward_tokens(T, false, 0, n_tiles));
+  FwdState fs;
+  RC(forward_tokens(T, false, 0, n_tiles, &fs));
+  if (!fs.y_final) RC(finish_small_tp(&fs, T));   // tp, T <= 4: every rank folds the last collective (also when R == 0)
   if (R) {
-    gather_rows_kernel<<<R, 256, 0, st>>>(x, d_last_rows, x_last, M.hidden);
-    LLMLB_LAUNCH_CHECK();
-    RC(logits_for_rows(R, false));
+    if (fs.y_final) {
+      RC(logits_after_forward(&fs, R, false));
+    } else {
+      gather_rows_kernel<<<R, 256, 0, st>>>(fs.xres, d_last_rows, x_last, M.hidden);
+      LLMLB_LAUNCH_CHECK();
+      RC(logits_from_x(x_last, R));
+    }
     sample_prepare_kernel<<<ceil_div(R, 128), 128, 0, st>>>(S, B, R);
     LLMLB_LAUNCH_CHECK();
     RC(llmlb_op_sample(logits, R, M.vocab, B.temperature, B.top_p, B.top_k, B.seed, B.step, B.out_ids, st));
@@ -1205,7 +1306,7 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
   F(e->embed); F(e->final_norm); F(e->lm_head);
   for (auto& L : e->layers) { F(L.wqkv); F(L.wo); F(L.wgu); F(L.wdown); F(L.attn_norm); F(L.ffn_norm); }
   F(e->k_pool); F(e->v_pool); F(e->rope); F(e->d_block_tables);
-  F(e->x); F(e->y); F(e->qkv); F(e->attn); F(e->h); F(e->logits); F(e->logits_l); F(e->x_last); F(e->attn_ws);
+  F(e->x); if (e->tp == 1) F(e->y); F(e->xb); F(e->tp_stage); F(e->ylast); F(e->qkv); F(e->attn); F(e->h); F(e->logits); F(e->logits_l); F(e->x_last); F(e->attn_ws);
   F(e->d_ids); F(e->d_pos); F(e->d_page_of_tok); F(e->d_tiles); F(e->d_last_rows);
   F(e->S.seq_len); F(e->S.last_token); F(e->S.temperature); F(e->S.top_p); F(e->S.top_k); F(e->S.seed); F(e->S.step);
   F(e->B.slots); F(e->B.ids); F(e->B.seq_lens); F(e->B.temperature); F(e->B.top_p); F(e->B.top_k);
@@ -1216,9 +1317,8 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
   }
   if (e->tp_ready)
     for (uint32_t r = 0; r < e->tp; ++r)
-      if (r != e->rank && e->peers.base[r]) cudaIpcCloseMemHandle(e->peers.base[r]);
-  F(e->xchg); F(e->chain_state); F(e->part_ws);
-  sk_workspace_destroy(&e->sk);
+      if (r != e->rank && e->tpc.base[r]) cudaIpcCloseMemHandle(e->tpc.base[r]);
+  F(e->xchg); F(e->part_ws);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
@@ -1395,12 +1495,12 @@ extern "C" int llmlb_engine_tp_import(llmlb_engine* e, const uint8_t* handles, u
   cudaSetDevice(e->cfg.device);
   std::lock_guard<std::mutex> sl(e->step_mu);
   for (uint32_t r = 0; r < n; ++r) {
-    if (r == e->rank) { e->peers.base[r] = e->xchg; continue; }
+    if (r == e->rank) { e->tpc.base[r] = e->xchg; continue; }
     cudaIpcMemHandle_t hnd;
     memcpy(&hnd, handles + size_t(r) * LLMLB_IPC_HANDLE_BYTES, sizeof(hnd));
     void* p = nullptr;
     LLMLB_CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-    e->peers.base[r] = (uint8_t*)p;
+    e->tpc.base[r] = (uint8_t*)p;
   }
   e->tp_ready = true;
   return e->warmup();
@@ -1463,15 +1563,15 @@ extern "C" int llmlb_op_allreduce(llmlb_engine* e, float* buf, uint64_t n, void*
   if (!e || !buf || n % 4) { set_error("llmlb_op_allreduce: bad argument"); return LLMLB_E_INVALID_ARG; }
   if (e->tp == 1) return LLMLB_OK;
   if (!e->tp_ready) { set_error("tp handles not imported"); return LLMLB_E_UNSUPPORTED; }
-  if (n * 4 > e->peers.slot_bytes) { set_error("llmlb_op_allreduce: larger than the exchange slot"); return LLMLB_E_INVALID_ARG; }
-  // sum = buf_0 + ... ; implemented as: copy buf into slot, zero buf, then allreduce-add
+  if (n * 4 > e->pull_slot_bytes) { set_error("llmlb_op_allreduce: larger than the exchange slot"); return LLMLB_E_INVALID_ARG; }
+  // sum = buf_0 + ... : copy buf into the slot, zero buf, pull-add every rank's slot, then a second
+  // (empty) barrier so that nobody overwrites the slot while a peer still reads it
   cudaStream_t st = (cudaStream_t)stream;
-  float* part = reinterpret_cast<float*>(e->xchg + ar_signal_bytes());
+  float* part = reinterpret_cast<float*>(e->xchg + e->pull_slot_off);
   LLMLB_CUDA_CHECK(cudaMemcpyAsync(part, buf, n * 4, cudaMemcpyDeviceToDevice, st));
   LLMLB_CUDA_CHECK(cudaMemsetAsync(buf, 0, n * 4, st));
-  RC(ar_allreduce_add(e->peers, 0, buf, n, st));
-  // keep slot parity even for the engine: a second (empty) collective on slot 1
-  return ar_allreduce_add(e->peers, 1, buf, 0, st);
+  RC(ar_allreduce_add(e->tpc, e->pull_slot_off, buf, n, st));
+  return ar_allreduce_add(e->tpc, e->pull_slot_off, buf, 0, st);
 }
 
 // ------------------------------------------------------------------ tensors by HF name ------
@@ -1581,13 +1681,20 @@ extern "C" int llmlb_debug_prefill_logits(llmlb_engine* e, const int32_t* prompt
   slot_init_kernel<<<1, 1, 0, st>>>(e->S, slot, 0.f, 1.f, 0, 0);
   LLMLB_LAUNCH_CHECK();
   RC(llmlb_op_embed(e->embed, e->d_ids, e->x, n, e->M.hidden, e->M.vocab, st));
-  RC(e->forward_tokens(n, false, 0, (uint32_t)tiles.size() / 4));
+  llmlb_engine::FwdState fs;
+  RC(e->forward_tokens(n, false, 0, (uint32_t)tiles.size() / 4, &fs));
+  if (!fs.y_final) RC(e->finish_small_tp(&fs, n));
   const uint32_t chunk = e->cfg.max_seqs;
   const size_t H = e->M.hidden, V = e->M.vocab;
   for (uint32_t c0 = logits_all ? 0 : n - 1; c0 < n; c0 += chunk) {
     uint32_t R = std::min(chunk, n - c0);
-    LLMLB_CUDA_CHECK(cudaMemcpyAsync(e->x_last, e->x + size_t(c0) * H, size_t(R) * H * 4, cudaMemcpyDeviceToDevice, st));
-    RC(e->logits_for_rows(R, false));
+    if (fs.y_final) {   // tensor parallel, protocol B: the rows are already normalised (bf16)
+      LLMLB_CUDA_CHECK(cudaMemcpyAsync(e->ylast, e->y + size_t(c0) * H, size_t(R) * H * 2, cudaMemcpyDeviceToDevice, st));
+      RC(e->logits_from_y(e->ylast, e->m_ylast, R));
+    } else {
+      LLMLB_CUDA_CHECK(cudaMemcpyAsync(e->x_last, fs.xres + size_t(c0) * H, size_t(R) * H * 4, cudaMemcpyDeviceToDevice, st));
+      RC(e->logits_from_x(e->x_last, R));
+    }
     LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (logits_all) LLMLB_CUDA_CHECK(cudaMemcpy(logits_all + size_t(c0) * V, e->logits, size_t(R) * V * 4, cudaMemcpyDeviceToHost));
     if (c0 + R == n) LLMLB_CUDA_CHECK(cudaMemcpy(logits_last, e->logits + size_t(R - 1) * V, V * 4, cudaMemcpyDeviceToHost));
@@ -1613,9 +1720,9 @@ extern "C" int llmlb_debug_decode_logits(llmlb_engine* e, int32_t token, float* 
   decode_prepare_kernel<<<1, 128, 0, st>>>(e->S, e->B, 1);
   LLMLB_LAUNCH_CHECK();
   RC(llmlb_op_embed(e->embed, e->B.ids, e->x, 1, e->M.hidden, e->M.vocab, st));
-  bool logits_done = false;
-  RC(e->forward_tokens(1, true, 1, 0, &logits_done));
-  if (!logits_done) RC(e->logits_for_rows(1, true));
+  llmlb_engine::FwdState fs;
+  RC(e->forward_tokens(1, true, 1, 0, &fs));
+  RC(e->logits_after_forward(&fs, 1, true));
   LLMLB_CUDA_CHECK(cudaStreamSynchronize(st));
   LLMLB_CUDA_CHECK(cudaMemcpy(logits_out, e->logits, size_t(e->M.vocab) * 4, cudaMemcpyDeviceToHost));
   e->debug_len += 1;
@@ -1637,7 +1744,6 @@ extern "C" int llmlb_debug_trace_enable(uint32_t cap) {
   ks_set_trace(g_tb);
   attn_set_trace(g_tb);
   tc_set_trace(g_tb);
-  sk_set_trace(g_tb);
   return LLMLB_OK;
 }
 extern "C" int llmlb_debug_trace_dump(unsigned long long* out, uint32_t cap_records, uint32_t* n) {

@@ -14,8 +14,6 @@
 // Split-K (residual epilogue only) uses fp32 red.global.add.
 #include <cuda.h>
 
-#include <cstdlib>
-
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -29,8 +27,13 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K,
-               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k, uint32_t pdl) {
+               uint32_t out_stride, uint32_t m_tiles, uint32_t t_tiles, uint32_t split_k, uint32_t pdl,
+               const TpPushRS tp) {
   using Cfg = TcCfg<BN>;
+  __shared__ uint8_t* s_peer_slot[kTpMaxRanks];   // kEpiPushRS: slot base of every rank
+  if constexpr (EPI == kEpiPushRS) {
+    if (threadIdx.x < tp.ctx.size) s_peer_slot[threadIdx.x] = tp.ctx.base[threadIdx.x] + tp.ctx.slot_off[tp.coll & 1];
+  }
   // Programmatic dependent launch: the next kernel of the stream may be
   // scheduled as soon as SMs free up, and THIS kernel may have been scheduled before its
   // predecessor finished: until griddepcontrol.wait it touches nothing but weights.
@@ -231,7 +234,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                   reinterpret_cast<float*>(out)[idx] = v;
                 else if constexpr (EPI == kEpiPartialF32)  // deterministic split-K: slot ks of the workspace
                   reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
-                else {
+                else if constexpr (EPI == kEpiPushRS) {    // reduce-scatter by address into the row owner's slot
+                  const uint32_t owner = t / tp.rpr, tl = t - owner * tp.rpr;
+                  st_peer_f32(reinterpret_cast<float*>(s_peer_slot[owner]) +
+                                  (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * out_stride + n, v);
+                } else {
                   if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
                   else reinterpret_cast<float*>(out)[idx] += v;
                 }
@@ -263,6 +270,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(uint32_t(Cfg::kTmemCols))
                  : "memory");
+  }
+  if constexpr (EPI == kEpiPushRS) {
+    const uint32_t slot = tp.coll & 1;
+    tp_signal_when_grid_done(tp.ctx, &tp_flags(tp.ctx, tp.ctx.rank)->done[slot], gridDim.x, tp_epoch(tp.ctx, tp.coll),
+                             [&](TpFlags* f) { return &f->push_flag[slot][tp.ctx.rank]; });
   }
 }
 
@@ -312,7 +324,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
 template <int BN, int EPI>
 static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                      uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t split_k,
-                     cudaStream_t st) {
+                     cudaStream_t st, const TpPushRS* tpp = nullptr) {
   using Cfg = TcCfg<BN>;
   auto kern = gemm_tc_kernel<BN, EPI>;
   static bool configured = false;
@@ -325,11 +337,13 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, ui
   uint32_t t_tiles = (n_tokens + BN - 1) / BN;
   uint32_t tiles = m_tiles * t_tiles * split_k;
   uint32_t grid = tiles < (uint32_t)kNumSMs ? tiles : (uint32_t)kNumSMs;
-  // default on (64 streams: 12.5k -> 13.2k tok/s, 16 streams +8 %); LLMLB_GEMM_NO_PDL=1 restores plain launches
-  static const bool pdl = getenv("LLMLB_GEMM_NO_PDL") == nullptr;
+  // programmatic dependent launch (64 streams: 12.5k -> 13.2k tok/s, 16 streams +8 %)
+  constexpr bool pdl = true;
+  TpPushRS tp{};
+  if (tpp) tp = *tpp;
   if (!pdl) {
     kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tw, tx, out, n_tokens, n_out, k, out_stride,
-                                                    m_tiles, t_tiles, split_k, 0u);
+                                                    m_tiles, t_tiles, split_k, 0u, tp);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -341,7 +355,7 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, ui
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, 1u));
+    LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, 1u, tp));
   }
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
@@ -350,7 +364,7 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, ui
 template <int BN>
 static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMap& tx, void* out,
                            uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t out_stride,
-                           uint32_t split_k, cudaStream_t st) {
+                           uint32_t split_k, cudaStream_t st, const TpPushRS* tpp) {
   switch (epi) {
     case LLMLB_EPI_STORE_BF16:
       return launch_tc<BN, LLMLB_EPI_STORE_BF16>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
@@ -363,6 +377,8 @@ static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMa
       return launch_tc<BN, LLMLB_EPI_STORE_F32>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
     case kEpiPartialF32:
       return launch_tc<BN, kEpiPartialF32>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case kEpiPushRS:
+      return launch_tc<BN, kEpiPushRS>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
   }
   set_error("gemm_tc: unknown epilogue");
   return LLMLB_E_INVALID_ARG;
@@ -380,44 +396,72 @@ uint32_t tc_pick_bn(uint32_t n_tokens) {
 // buffers are fixed).  The X map's box rows must equal tc_pick_bn(n_tokens).
 int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens,
                     uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                    uint32_t* n_parts);
-int gemm_sk_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
-                   uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
-                   const SkWorkspace& sk, cudaStream_t st);
+                    uint32_t* n_parts, const TpPushRS* tpp, uint32_t max_split);
 
 // tx_half (optional): the activation map with a 128-row box; when given and the step is wide
 // enough for 256-token tiles the CTA-pair kernel (gemm_tc2.cu) runs instead.
+// K-split (kEpiPartialF32 / kEpiPushRS / RESID_F32 only) up to max_split parts; *n_parts = parts used.
+// (A stream-K work split of the same pipeline was built and measured in round 1 — no better than
+// slab tiles + K-split partials in either regime; it lives in tools/experiments/csrc/gemm_sk.cu.)
 int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                    uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
                    cudaStream_t st, const CUtensorMap* tx_half, uint32_t* n_parts,
-                   const SkWorkspace* sk) {
+                   const TpPushRS* tpp, uint32_t max_split) {
   const uint32_t bn = tc_pick_bn(n_tokens);
-  static const bool no_2cta = getenv("LLMLB_GEMM_NO_2CTA") != nullptr;
-  static const bool no_sk = getenv("LLMLB_GEMM_NO_SK") != nullptr;
-  // one token tile (batched decode, short chunks) is an HBM-bound weight stream; there stream-K
-  // measured no better than slab tiling + K-split partials (round-1 notes in DESIGN.md), so the
-  // engine only takes it when asked; llmlb_op_gemm(impl = 2) always does
-  static const bool sk_small = getenv("LLMLB_GEMM_SK_SMALL") != nullptr;
   if (n_parts) *n_parts = 1;
-  if (sk && sk->ws && n_tokens <= 128 && !no_sk && (sk_small || sk->force))
-    return gemm_sk_launch(tw, tx, out, n_tokens, n_out, k, epi, out_stride, *sk, st);
-  if (tx_half && bn == 256 && n_out >= 256 && !no_2cta)
-    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts);
-  // split K for the residual epilogue when the tile count cannot fill the GPU
+  if (tx_half && bn == 256 && n_out >= 256)
+    return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts, tpp, max_split);
+  // split K for the residual epilogues when the tile count cannot fill the GPU
   uint32_t split_k = 1;
-  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32) {
+  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32 || epi == (uint32_t)kEpiPushRS) {
     uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
     uint32_t kblocks = (k + kBK - 1) / kBK;
-    while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8 && split_k < 8) split_k *= 2;
+    while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8 && split_k * 2 <= max_split) split_k *= 2;
   }
   if (n_parts) *n_parts = split_k;
   switch (bn) {
-    case 16: return dispatch_tc_epi<16>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
-    case 32: return dispatch_tc_epi<32>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
-    case 64: return dispatch_tc_epi<64>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
-    case 128: return dispatch_tc_epi<128>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
-    default: return dispatch_tc_epi<256>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case 16: return dispatch_tc_epi<16>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
+    case 32: return dispatch_tc_epi<32>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
+    case 64: return dispatch_tc_epi<64>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
+    case 128: return dispatch_tc_epi<128>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
+    default: return dispatch_tc_epi<256>(epi, tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
   }
 }
 
 }  // namespace llmlb
+
+using namespace llmlb;
+
+// Kernel-level entry point of the tensor-core projections (parity tests, micro-benchmarks).
+// impl 0 = tcgen05 + TMEM + TMA tiles.  The mma.sync baseline (1) and the stream-K split (2) of
+// round 1 are no longer part of the library (tools/experiments/csrc/).
+extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n_tokens,
+                             uint32_t n_out, uint32_t k, uint32_t epilogue, uint32_t out_stride,
+                             uint32_t impl, void* stream) {
+  if (!w || !x || !out || n_out == 0 || k == 0 || k % 8 != 0) {
+    set_error("llmlb_op_gemm: bad argument (k must be a multiple of 8)");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (epilogue > LLMLB_EPI_STORE_F32) {
+    set_error("llmlb_op_gemm: unknown epilogue");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (epilogue == LLMLB_EPI_SILU_MUL && (n_out & 1)) {
+    set_error("llmlb_op_gemm: SILU_MUL needs interleaved gate/up rows (even n_out)");
+    return LLMLB_E_INVALID_ARG;
+  }
+  if (impl != 0) {
+    set_error("llmlb_op_gemm: only impl 0 (tcgen05 tiles) is built into the library");
+    return LLMLB_E_UNSUPPORTED;
+  }
+  if (n_tokens == 0) return LLMLB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tw, tx, txh;
+  int rc = make_tmap_bf16(&tw, w, n_out, k, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tx, x, n_tokens, k, tc_pick_bn(n_tokens));
+  if (rc) return rc;
+  rc = make_tmap_bf16(&txh, x, n_tokens, k, 128);
+  if (rc) return rc;
+  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, nullptr, 8);
+}

@@ -74,8 +74,12 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                 void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K, uint32_t out_stride,
-                uint32_t m_tiles /*256-row slabs*/, uint32_t t_tiles, uint32_t split_k) {
+                uint32_t m_tiles /*256-row slabs*/, uint32_t t_tiles, uint32_t split_k, const TpPushRS tp) {
   using Cfg = Tc2Cfg<BN>;
+  __shared__ uint8_t* s_peer_slot[kTpMaxRanks];   // kEpiPushRS: slot base of every rank
+  if constexpr (EPI == kEpiPushRS) {
+    if (threadIdx.x < tp.ctx.size) s_peer_slot[threadIdx.x] = tp.ctx.base[threadIdx.x] + tp.ctx.slot_off[tp.coll & 1];
+  }
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -216,7 +220,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               if constexpr (EPI == LLMLB_EPI_STORE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
               else if constexpr (EPI == LLMLB_EPI_STORE_F32) reinterpret_cast<float*>(out)[idx] = v;
               else if constexpr (EPI == kEpiPartialF32) reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
-              else {
+              else if constexpr (EPI == kEpiPushRS) {    // reduce-scatter by address into the row owner's slot
+                const uint32_t owner = t / tp.rpr, tl = t - owner * tp.rpr;
+                st_peer_f32(reinterpret_cast<float*>(s_peer_slot[owner]) +
+                                (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * out_stride + n, v);
+              } else {
                 if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
                 else reinterpret_cast<float*>(out)[idx] += v;
               }
@@ -238,11 +246,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(Cfg::kTmemCols))
                  : "memory");
   }
+  if constexpr (EPI == kEpiPushRS) {
+    const uint32_t slot = tp.coll & 1;
+    tp_signal_when_grid_done(tp.ctx, &tp_flags(tp.ctx, tp.ctx.rank)->done[slot], gridDim.x, tp_epoch(tp.ctx, tp.coll),
+                             [&](TpFlags* f) { return &f->push_flag[slot][tp.ctx.rank]; });
+  }
 }
 
 template <int BN, int EPI>
 static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens, uint32_t n_out,
-                      uint32_t k, uint32_t out_stride, uint32_t split_k, cudaStream_t st) {
+                      uint32_t k, uint32_t out_stride, uint32_t split_k, cudaStream_t st, const TpPushRS* tpp = nullptr) {
   using Cfg = Tc2Cfg<BN>;
   auto kern = gemm_tc2_kernel<BN, EPI>;
   static bool configured = false;
@@ -265,19 +278,22 @@ static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* o
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx_half, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k));
+  TpPushRS tp{};
+  if (tpp) tp = *tpp;
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx_half, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, tp));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
 
 // BN = 256 only (n_tokens > 128).  tx_half: activation tensor map with a 128-row box.
 int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out, uint32_t n_tokens, uint32_t n_out,
-                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st, uint32_t* n_parts) {
+                    uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st, uint32_t* n_parts,
+                    const TpPushRS* tpp, uint32_t max_split) {
   uint32_t split_k = 1;
-  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32) {
+  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32 || epi == (uint32_t)kEpiPushRS) {
     uint32_t tiles = ((n_out + 255) / 256) * ((n_tokens + 255) / 256);
     uint32_t kblocks = (k + kBK - 1) / kBK;
-    while (tiles * split_k * 2 <= (uint32_t)(kNumSMs / 2) && kblocks / (split_k * 2) >= 8 && split_k < 8) split_k *= 2;
+    while (tiles * split_k * 2 <= (uint32_t)(kNumSMs / 2) && kblocks / (split_k * 2) >= 8 && split_k * 2 <= max_split) split_k *= 2;
   }
   if (n_parts) *n_parts = split_k;
   switch (epi) {
@@ -286,6 +302,7 @@ int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out
     case LLMLB_EPI_SILU_MUL: return launch_tc2<256, LLMLB_EPI_SILU_MUL>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
     case LLMLB_EPI_STORE_F32: return launch_tc2<256, LLMLB_EPI_STORE_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
     case kEpiPartialF32: return launch_tc2<256, kEpiPartialF32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
+    case kEpiPushRS: return launch_tc2<256, kEpiPushRS>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
   }
   set_error("gemm_tc2: unknown epilogue");
   return LLMLB_E_INVALID_ARG;

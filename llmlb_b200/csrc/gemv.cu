@@ -8,7 +8,6 @@
 // loads are issued BEFORE the prologue so the RMSNorm (fused: a2.2) overlaps the HBM latency.
 // Algorithmic bytes per launch: n_out*k*2 (weights) — x and out are noise.
 #include "../../include/llmlb_b200.h"
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -240,19 +239,14 @@ int dispatch_epi(uint32_t epi, bool norm, const void* w, const void* x, const vo
   return LLMLB_E_INVALID_ARG;
 }
 
-int gemv_bulk_try(const void* w, const void* x, const void* gain, float eps, void* out,
-                  uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
-                  cudaStream_t st);
 int gemv_ks_try(const void* w, const void* x, const void* gain, float eps, void* out,
                 uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride,
                 cudaStream_t st, const void* pf_ptr = nullptr, uint32_t pf_bytes = 0);
 
-// Decode projection with a hint of what streams next (engine-internal: the public op has no hint)
+// Decode projection (engine-internal): the K-split kernel when the shape fits, else the public op
 int gemv_decode(const void* w, const void* x, const void* gain, float eps, void* out, uint32_t n_tokens,
-                uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st,
-                const void* next_w, size_t next_bytes) {
-  uint32_t pfb = (uint32_t)(next_bytes > (48u << 20) ? (48u << 20) : next_bytes);
-  int rc = gemv_ks_try(w, x, gain, eps, out, n_tokens, n_out, k, epi, out_stride, st, next_w, next_w ? pfb : 0);
+                uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, cudaStream_t st) {
+  int rc = gemv_ks_try(w, x, gain, eps, out, n_tokens, n_out, k, epi, out_stride, st);
   if (rc != LLMLB_E_UNSUPPORTED) return rc;
   return llmlb_op_gemv(w, x, gain, eps, out, n_tokens, n_out, k, epi, out_stride, st);
 }
@@ -292,16 +286,10 @@ extern "C" int llmlb_op_gemv(const void* w, const void* x, const void* gain, flo
     return LLMLB_OK;
   }
   if (n_tokens >= 1 && n_tokens <= 4 && epilogue <= LLMLB_EPI_STORE_F32) {
-    // 1) bulk-copy ring (deep smem prefetch across PDL-chained kernels), 2) K-split with
-    // register-staged loads, 3) row-owner variant for odd shapes
-    // (measured round 1: the bulk ring lets two CTAs share an SM, the block scheduler then packs
-    // the 148 CTAs unevenly and the kernel drops to 0.67 of HBM peak vs 0.97 for K-split, so it is
-    // opt-in until its rows are dealt dynamically: LLMLB_GEMV_BULK=1)
-    static const bool use_bulk = getenv("LLMLB_GEMV_BULK") != nullptr;
-    int rc = !use_bulk ? LLMLB_E_UNSUPPORTED
-                       : gemv_bulk_try(w, x, gain, eps, out, n_tokens, n_out, k, epilogue, out_stride, st);
-    if (rc != LLMLB_E_UNSUPPORTED) return rc;
-    rc = gemv_ks_try(w, x, gain, eps, out, n_tokens, n_out, k, epilogue, out_stride, st);
+    // K-split kernel (gemv_ks.cu) for every shape it takes; the row-owner kernel below is the
+    // fallback for odd K.  (A bulk-copy shared-memory ring variant was measured at 0.67 of HBM peak
+    // against 0.97 here and lives in tools/experiments/csrc/gemv_bulk.cu.)
+    int rc = gemv_ks_try(w, x, gain, eps, out, n_tokens, n_out, k, epilogue, out_stride, st);
     if (rc != LLMLB_E_UNSUPPORTED) return rc;
   }
   switch (n_tokens) {

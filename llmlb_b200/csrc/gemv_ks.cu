@@ -17,8 +17,22 @@
 // Algorithmic bytes: n_out * k * 2 per launch.
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
+#include "tp_common.cuh"
 
 namespace llmlb {
+
+// Tensor-parallel decode (protocol A of tp_common.cuh), fused into this kernel:
+//   TPM == 1  the RMSNorm prologue is the all-reduce's consumer: wait for the N push flags, fold the
+//             N partial rows of the slot into the replicated fp32 residual (rank order), keep the
+//             new residual in shared memory for the norm and write it to x_out (the other residual
+//             buffer: other CTAs of this grid still read x_in)
+//   TPM == 2  the epilogue is the producer: every finished output element is stored into the slot
+//             of EVERY rank, the last CTA of the grid raises the flags
+struct TpGemv {
+  TpCtx ctx;
+  uint32_t coll_in, coll_out;   // collective consumed by the prologue / produced by the epilogue
+  float* x_out;                 // TPM == 1: residual after the fold
+};
 
 constexpr int kKsThreads = 512;
 constexpr int kKsWarps = 16;
@@ -29,12 +43,14 @@ __device__ __forceinline__ void team_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int B, int EPI, bool NORM, int CW>
+template <int B, int EPI, bool NORM, int CW, int TPM>
 __global__ void __launch_bounds__(kKsThreads)
 gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin,
                const __nv_bfloat16* __restrict__ gain, float eps, void* __restrict__ out,
                uint32_t n_out, uint32_t K, uint32_t out_stride, uint32_t TW,
-               const uint8_t* __restrict__ pf_ptr, uint32_t pf_bytes) {
+               const uint8_t* __restrict__ pf_ptr, uint32_t pf_bytes, const TpGemv tp) {
+  static_assert(TPM == 0 || (TPM == 1 && NORM) || (TPM == 2 && !NORM && EPI == LLMLB_EPI_STORE_F32), "tp mode");
+  extern __shared__ float ks_dyn[];   // TPM == 1: the folded residual, [B][K] fp32
   constexpr int RB = 8 / CW;  // rows per batch (even)
   __shared__ float partial[2][kKsWarps][RB * B];  // [buf][warp][row*B + b]
   __shared__ float red[B][kKsWarps];
@@ -85,12 +101,33 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
     float ss[B];
 #pragma unroll
     for (int b = 0; b < B; ++b) ss[b] = 0.f;
+    if constexpr (TPM == 1) {
+      const uint32_t slot = tp.coll_in & 1;
+      TpFlags* mine = tp_flags(tp.ctx, tp.ctx.rank);
+      tp_wait_flags(mine, mine->push_flag[slot], tp.ctx.size, tp_epoch(tp.ctx, tp.coll_in));
+      const float4* sb = reinterpret_cast<const float4*>(tp.ctx.base[tp.ctx.rank] + tp.ctx.slot_off[slot]);
+      for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          float4 v = reinterpret_cast<const float4*>(xf + size_t(b) * K)[i];
+          for (uint32_t r = 0; r < tp.ctx.size; ++r) {   // rank order: identical sums on every rank
+            const float4 a = ld_pushed_f4(sb + (size_t(r) * kTpSmallRows + b) * (K / 4) + i);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          }
+          reinterpret_cast<float4*>(ks_dyn + size_t(b) * K)[i] = v;
+          if (i % gridDim.x == blockIdx.x) reinterpret_cast<float4*>(tp.x_out + size_t(b) * K)[i] = v;
+          ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+      xf = ks_dyn;   // generic pointer into shared memory: the slices below come from the fold
+    } else {
     for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         float4 v = reinterpret_cast<const float4*>(xf + size_t(b) * K)[i];
         ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       }
+    }
     }
 #pragma unroll
     for (int b = 0; b < B; ++b) {
@@ -194,6 +231,13 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
           reinterpret_cast<__nv_bfloat16*>(out)[size_t(b) * out_stride + (row >> 1)] =
               __float2bfloat16_rn(s * up);
         }
+      } else if constexpr (TPM == 2) {
+        if (lane < RB * B && row < rows_lim) {
+          const size_t idx = (size_t(tp.ctx.rank) * kTpSmallRows + b) * out_stride + row;
+          const uint32_t slot = tp.coll_out & 1;
+          for (uint32_t r = 0; r < tp.ctx.size; ++r)
+            st_peer_f32(reinterpret_cast<float*>(tp.ctx.base[r] + tp.ctx.slot_off[slot]) + idx, v);
+        }
       } else if (lane < RB * B && row < rows_lim) {
         const size_t idx = size_t(b) * out_stride + row;
         if constexpr (EPI == LLMLB_EPI_STORE_BF16)
@@ -211,6 +255,11 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
   // and the next one launches (the boundary otherwise leaves HBM idle for ~2-3 us) ----
   for (uint32_t off = (blockIdx.x * kKsThreads + threadIdx.x) * 128u; off < pf_bytes; off += gridDim.x * kKsThreads * 128u)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + off));
+  if constexpr (TPM == 2) {
+    const uint32_t slot = tp.coll_out & 1;
+    tp_signal_when_grid_done(tp.ctx, &tp_flags(tp.ctx, tp.ctx.rank)->done[slot], gridDim.x, tp_epoch(tp.ctx, tp.coll_out),
+                             [&](TpFlags* f) { return &f->push_flag[slot][tp.ctx.rank]; });
+  }
   if (tb.data && threadIdx.x == 0) trace_emit(tb, (unsigned long long)n_out << 32 | K, tr0, tr1, tr2, gtime_ns());
 }
 
@@ -226,24 +275,37 @@ static bool ks_pick(uint32_t n_tokens, uint32_t K, uint32_t* tw, uint32_t* cw) {
   return false;
 }
 
-template <int B, int EPI, bool NORM, int CW>
+template <int B, int EPI, bool NORM, int CW, int TPM = 0>
 static int ks_launch(const void* w, const void* x, const void* gain, float eps, void* out,
                      uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t tw, cudaStream_t st,
-                     const void* pf_ptr, uint32_t pf_bytes) {
+                     const void* pf_ptr, uint32_t pf_bytes, const TpGemv* tp = nullptr) {
   uint32_t n_pairs = (n_out + 1) / 2;
   uint32_t grid = n_pairs < (uint32_t)kNumSMs ? n_pairs : (uint32_t)kNumSMs;
+  auto kern = gemv_ks_kernel<B, EPI, NORM, CW, TPM>;
+  size_t dyn = 0;
+  if constexpr (TPM == 1) {
+    dyn = size_t(B) * k * sizeof(float);
+    static size_t configured = 0;
+    if (dyn > configured) {
+      LLMLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      configured = dyn;
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kKsThreads);
+  cfg.dynamicSmemBytes = dyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // programmatic dependent launch
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemv_ks_kernel<B, EPI, NORM, CW>, (const __nv_bfloat16*)w, x,
+  TpGemv tpv{};
+  if (tp) tpv = *tp;
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)w, x,
                                       (const __nv_bfloat16*)gain, eps, out, n_out, k, out_stride, tw,
-                                      (const uint8_t*)pf_ptr, pf_bytes));
+                                      (const uint8_t*)pf_ptr, pf_bytes, tpv));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
@@ -280,6 +342,49 @@ int gemv_ks_try(const void* w, const void* x, const void* gain, float eps, void*
   if (n_tokens == 3) KS_GO(3, 1);
   KS_GO(4, 1);
 #undef KS_GO
+}
+
+// ---- tensor-parallel variants (protocol A of tp_common.cuh) ----
+bool gemv_tp_shape_ok(uint32_t n_tokens, uint32_t k) {
+  uint32_t tw, cw;
+  return n_tokens >= 1 && n_tokens <= 4 && ks_pick(n_tokens, k, &tw, &cw);
+}
+
+// consumer: x_out = x_in + sum of the pushed partials of collective coll_in; out = epi(W . RMSNorm(x_out))
+int gemv_tp_consume(const TpCtx& ctx, uint32_t coll_in, const void* w, const float* x_in, float* x_out,
+                    const void* gain, float eps, void* out, uint32_t n_tokens, uint32_t n_out, uint32_t k,
+                    uint32_t epi, uint32_t out_stride, cudaStream_t st) {
+  uint32_t tw = 0, cw = 0;
+  if (n_tokens == 0 || n_tokens > 4 || !gain || !ks_pick(n_tokens, k, &tw, &cw)) return LLMLB_E_UNSUPPORTED;
+  TpGemv tp{};
+  tp.ctx = ctx; tp.coll_in = coll_in; tp.x_out = x_out;
+#define KS_TC(BB, CC)                                                                                                          \
+  switch (epi) {                                                                                                               \
+    case LLMLB_EPI_STORE_BF16: return ks_launch<BB, LLMLB_EPI_STORE_BF16, true, CC, 1>(w, x_in, gain, eps, out, n_out, k, out_stride, tw, st, nullptr, 0, &tp); \
+    case LLMLB_EPI_SILU_MUL: return ks_launch<BB, LLMLB_EPI_SILU_MUL, true, CC, 1>(w, x_in, gain, eps, out, n_out, k, out_stride, tw, st, nullptr, 0, &tp);     \
+    case LLMLB_EPI_STORE_F32: return ks_launch<BB, LLMLB_EPI_STORE_F32, true, CC, 1>(w, x_in, gain, eps, out, n_out, k, out_stride, tw, st, nullptr, 0, &tp);   \
+    default: set_error("gemv_tp_consume: epilogue"); return LLMLB_E_INVALID_ARG;                                               \
+  }
+  if (n_tokens == 1) { if (cw == 1) { KS_TC(1, 1) } if (cw == 2) { KS_TC(1, 2) } KS_TC(1, 4) }
+  if (n_tokens == 2) { if (cw == 1) { KS_TC(2, 1) } KS_TC(2, 2) }
+  if (n_tokens == 3) { KS_TC(3, 1) }
+  KS_TC(4, 1)
+#undef KS_TC
+}
+
+// producer: partial = W . x (bf16 x) pushed into slot[coll_out & 1][my rank] of every rank (n_out = hidden)
+int gemv_tp_push(const TpCtx& ctx, uint32_t coll_out, const void* w, const void* x_bf16, uint32_t n_tokens,
+                 uint32_t n_out, uint32_t k, cudaStream_t st) {
+  uint32_t tw = 0, cw = 0;
+  if (n_tokens == 0 || n_tokens > 4 || !ks_pick(n_tokens, k, &tw, &cw)) return LLMLB_E_UNSUPPORTED;
+  TpGemv tp{};
+  tp.ctx = ctx; tp.coll_out = coll_out;
+#define KS_TP(BB, CC) return ks_launch<BB, LLMLB_EPI_STORE_F32, false, CC, 2>(w, x_bf16, nullptr, 0.f, nullptr, n_out, k, n_out, tw, st, nullptr, 0, &tp)
+  if (n_tokens == 1) { if (cw == 1) KS_TP(1, 1); if (cw == 2) KS_TP(1, 2); KS_TP(1, 4); }
+  if (n_tokens == 2) { if (cw == 1) KS_TP(2, 1); KS_TP(2, 2); }
+  if (n_tokens == 3) KS_TP(3, 1);
+  KS_TP(4, 1);
+#undef KS_TP
 }
 
 }  // namespace llmlb

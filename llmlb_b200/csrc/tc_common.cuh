@@ -4,12 +4,21 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tp_common.cuh"
 
 namespace llmlb {
 
 // internal epilogue (not in the public header): fp32 partial product of K-split `ks` stored at
 // out + ks * n_tokens * out_stride; the consumer adds the slots in a fixed order (deterministic)
 constexpr int kEpiPartialF32 = 4;
+// tensor parallel, protocol B (tp_common.cuh): the fp32 partial of token row t, K-split ks, goes
+// straight into the slot of the rank that OWNS the row: part (rank * split_k + ks), row t % rpr
+constexpr int kEpiPushRS = 5;
+struct TpPushRS {
+  TpCtx ctx;
+  uint32_t coll;      // collective index within the step (slot = coll & 1)
+  uint32_t rpr;       // token rows per owner rank = ceil(n_tokens / size)
+};
 constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
 constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row
 constexpr int kTcThreads = 384;    // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
@@ -102,15 +111,6 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// stream-K flag / barrier helpers
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void epi_bar() {  // the 8 epilogue warps only
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
@@ -125,13 +125,5 @@ struct TcCfg {
   static constexpr uint32_t kIdesc =
       (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
 };
-
-// stream-K scratch: one fp32 partial tile per CTA + one ready flag per CTA (zero between launches)
-struct SkWorkspace {
-  float* ws = nullptr;        // [kNumSMs][<= 128 tokens][kBM] fp32
-  uint32_t* flags = nullptr;  // [kNumSMs]
-  bool force = false;         // op-level impl = 2: stream-K even where the engine's default is tiles
-};
-constexpr size_t kSkWsBytes = size_t(kNumSMs) * 128 * kBM * sizeof(float);
 
 }  // namespace llmlb

@@ -29,9 +29,9 @@ def sd():
     return synth_state_dict(TINY, seed=0)
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["tcgen05", "mma_sync"])
-def eng(request, built_lib):
-    e = ffi.Engine(TINY, max_seqs=8, max_ctx=1024, seed=0, gemm_impl=request.param)
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    e = ffi.Engine(TINY, max_seqs=8, max_ctx=1024, seed=0)
     yield e
     e.close()
 
@@ -273,9 +273,8 @@ def test_8b_batched_equals_single_and_is_deterministic(eng8b):
     assert h["active_requests"] == 0 and h["free_kv_pages"] == h["total_kv_pages"]
 
 
-# ---- mid geometry: exercises the persistent decode chain kernel (gemv_chain.cu) ----
-def test_decode_chain_vs_oracle_and_vs_unchained(built_lib):
-    import os
+# ---- mid geometry (hidden 2048): other GEMV team shapes than tiny / 8B ----
+def test_mid_geometry_vs_oracle(built_lib):
     cfg = ffi.LLAMA_MID
     sdm = synth_state_dict(cfg, seed=3)
     rs = np.random.RandomState(17)
@@ -283,23 +282,14 @@ def test_decode_chain_vs_oracle_and_vs_unchained(built_lib):
     forced = rs.randint(0, cfg["vocab"], 6).tolist()
     ref = LlamaRef(cfg, sdm)
     want = [ref.forward(prompt).numpy()[-1]] + [ref.forward([t]).numpy()[-1] for t in forced]
-    got = {}
-    for chain in ("1", "0"):
-        os.environ["LLMLB_DECODE_CHAIN"] = chain
-        with ffi.Engine(cfg, max_seqs=4, max_ctx=256, seed=3) as e:
-            lg = [e.debug_prefill_logits(prompt)] + [e.debug_decode_logits(t) for t in forced]
-            e.debug_reset()
-            toks, _ = e.generate(prompt, 20, ignore_eos=True)   # CUDA-graph replay of the chain
-            got[chain] = (lg, toks)
-    os.environ.pop("LLMLB_DECODE_CHAIN", None)
+    with ffi.Engine(cfg, max_seqs=4, max_ctx=256, seed=3) as e:
+        lg = [e.debug_prefill_logits(prompt)] + [e.debug_decode_logits(t) for t in forced]
+        e.debug_reset()
+        toks, _ = e.generate(prompt, 20, ignore_eos=True)   # CUDA-graph replay
     sigma = float(want[0].std())
-    for chain in ("1", "0"):
-        for a, b in zip(got[chain][0], want):
-            assert np.abs(a - b).max() < 0.08 * sigma + 0.02, chain   # bf16 activations vs fp32 oracle
-    # chained and unchained kernels share rounding points; only accumulation order differs
-    for a, b in zip(got["1"][0], got["0"][0]):
-        assert np.abs(a - b).max() < 0.03 * sigma + 0.01
-    assert got["1"][1][:3] == got["0"][1][:3] and len(got["1"][1]) == 20
+    for a, b in zip(lg, want):
+        assert np.abs(a - b).max() < 0.08 * sigma + 0.02   # bf16 activations vs fp32 oracle
+    assert len(toks) == 20
 
 
 def test_70b_geometry_parity_4_layers(built_lib):

@@ -101,14 +101,12 @@ GEMM_SHAPES = [(512, 6144, 4096), (512, 4096, 14336), (64, 4096, 4096), (16, 102
                (5, 256, 64), (130, 1002, 520), (300, 2048, 4096), (33, 28672, 4096)]
 
 
-@pytest.mark.parametrize("impl", [1, 0, 2], ids=["mma", "tc", "streamk"])
+@pytest.mark.parametrize("impl", [0], ids=["tc"])
 @pytest.mark.parametrize("T,N,K", GEMM_SHAPES + [(128, 6144, 4096), (100, 1002, 520), (64, 4096, 14336), (7, 128, 4096)])
 @pytest.mark.parametrize("epi", [ffi.EPI_STORE_BF16, ffi.EPI_RESID_F32, ffi.EPI_SILU_MUL, ffi.EPI_STORE_F32])
 def test_gemm(L, impl, T, N, K, epi):
     if epi == ffi.EPI_SILU_MUL and N % 2:
         pytest.skip("odd N")
-    if impl == 2 and T > 128:
-        pytest.skip("stream-K serves one token tile (T <= 128)")
     w = bf16_randn((N, K), std=0.02, seed=7)
     x = bf16_randn((T, K), seed=8)
     n_cols = N // 2 if epi == ffi.EPI_SILU_MUL else N
@@ -124,21 +122,14 @@ def test_gemm(L, impl, T, N, K, epi):
     assert bool((err <= lim).all()), "max err %g at %s" % (err.max().item(), (err - lim).argmax().item())
 
 
-@pytest.mark.parametrize("T,N,K", [(64, 28672, 4096), (64, 6144, 4096), (33, 4096, 14336), (16, 128, 4096)])
-def test_gemm_streamk_reproducible(L, T, N, K):
-    """Stream-K sums the parked pieces in CTA order: repeated launches (flags recycled) agree bit for bit."""
-    w = bf16_randn((N, K), std=0.02, seed=17)
-    x = bf16_randn((T, K), seed=18)
-    outs = []
-    for _ in range(4):
-        out = torch.zeros(T, N, dtype=torch.float32, device=dev())
-        ok(L.llmlb_op_gemm(p(w), p(x), p(out), T, N, K, ffi.EPI_STORE_F32, N, 2, stream_ptr()))
-        sync()
-        outs.append(out)
-    for o in outs[1:]:
-        assert torch.equal(o, outs[0])
-    ref = x.float() @ w.float().t()
-    assert (outs[0] - ref).abs().max().item() < 2e-3 * math.sqrt(K / 4096) + 1e-4 * ref.abs().max().item()
+def test_gemm_other_impls_are_not_in_the_library(L):
+    """The mma.sync baseline and the stream-K split of round 1 moved to tools/experiments/: asking for
+    them fails loudly instead of silently running something else."""
+    w = bf16_randn((128, 64), std=0.02, seed=1)
+    x = bf16_randn((16, 64), seed=2)
+    out = torch.zeros(16, 128, dtype=torch.float32, device=dev())
+    for impl in (1, 2):
+        assert L.llmlb_op_gemm(p(w), p(x), p(out), 16, 128, 64, ffi.EPI_STORE_F32, 128, impl, stream_ptr()) == ffi.E_UNSUPPORTED
 
 
 def _rope_ref(x, pos, theta=500000.0):
