@@ -77,7 +77,12 @@ typedef struct llmlb_engine_config {
   uint32_t use_cuda_graphs;  /* capture decode steps per batch width */
   uint32_t gemm_impl;        /* 0 = tcgen05/TMEM/TMA tiles (default), 1 = mma.sync tiles */
   uint32_t lookahead;        /* decode steps in flight before the host reads tokens (0 = 2) */
-  uint32_t reserved[8];
+  /* Back-pressure, mirroring the gateway's own queue (llmlb/src/config.rs:80-99, QueueConfig) and its
+   * per-request inference timeout (llmlb/src/types/endpoint.rs:389).  0 = no limit. */
+  uint32_t queue_max;          /* waiting requests beyond this: submit returns LLMLB_E_QUEUE_FULL (gateway: 429) */
+  uint32_t queue_timeout_ms;   /* a request still waiting for admission after this finishes QUEUE_TIMEOUT (504) */
+  uint32_t request_timeout_ms; /* a request not finished this long after submit finishes DEADLINE (504 timeout) */
+  uint32_t reserved[5];
 } llmlb_engine_config;
 
 int llmlb_engine_create(const llmlb_engine_config* cfg, llmlb_engine** out);
@@ -133,6 +138,7 @@ typedef struct llmlb_health {      /* feeds GET /api/health (endpoint_checker.rs
   double gpu_ms_prefill;           /* CUDA-event time spent in prefill steps */
   double gpu_ms_decode;            /* CUDA-event time spent in decode steps */
   uint64_t kernel_launches;        /* launches of this library's kernels so far */
+  uint64_t preemptions;            /* sequences evicted (pages reclaimed, recomputed later) so far */
 } llmlb_health;
 int llmlb_engine_health(const llmlb_engine* e, llmlb_health* out);
 
@@ -150,7 +156,9 @@ typedef struct llmlb_sampling {
 } llmlb_sampling;
 
 enum { LLMLB_FINISH_NONE = 0, LLMLB_FINISH_STOP = 1, LLMLB_FINISH_LENGTH = 2,
-       LLMLB_FINISH_CANCELLED = 3, LLMLB_FINISH_ERROR = 4 };
+       LLMLB_FINISH_CANCELLED = 3, LLMLB_FINISH_ERROR = 4,
+       LLMLB_FINISH_QUEUE_TIMEOUT = 5,   /* never admitted within queue_timeout_ms ("Queue wait timeout", openai.rs:862-882) */
+       LLMLB_FINISH_DEADLINE = 6 };      /* request_timeout_ms passed (classify_upstream_request_error: 504 "timeout") */
 
 typedef struct llmlb_token_event {
   int32_t token_id;

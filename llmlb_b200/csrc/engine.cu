@@ -163,11 +163,20 @@ struct Request {
   std::vector<int32_t> stop_ids;
   int slot = -1;
   std::vector<int32_t> pages;
-  uint32_t prefilled = 0;   // prompt tokens whose KV is (being) written
+  uint32_t prefilled = 0;   // context tokens whose KV is (being) written
   uint32_t launched = 0;    // generated tokens whose computation has been launched
   uint32_t harvested = 0;   // generated tokens seen by the host
+  // `prompt` is the context to prefill: the client's prompt, plus — after a preemption — the tokens
+  // generated so far (recompute instead of swapping KV out)
+  uint32_t n_prompt0 = 0;   // the client's prompt length (usage accounting, context arithmetic)
+  std::vector<int32_t> gen; // harvested generated tokens
+  uint32_t gen_in_prompt = 0;
+  uint32_t pages_published = 0;   // entries of `pages` already in the device block table
+  uint32_t preempted = 0;
+  bool admitted_once = false;
   bool finished = false;
   bool cancel = false;
+  uint32_t cancel_reason = LLMLB_FINISH_CANCELLED;
   bool client_released = false;
   uint32_t finish_reason = LLMLB_FINISH_NONE;
   std::deque<llmlb_token_event> events;
@@ -197,7 +206,8 @@ struct PlanHeader {
   uint32_t n_ranks;
   uint64_t ring_bytes;
 };
-enum PlanEvent : uint32_t { kPlanSubmit = 1, kPlanCancel = 2, kPlanRelease = 3, kPlanPause = 4, kPlanSched = 5, kPlanHarvest = 6, kPlanStop = 7 };
+enum PlanEvent : uint32_t { kPlanSubmit = 1, kPlanCancel = 2, kPlanRelease = 3, kPlanPause = 4, kPlanSched = 5, kPlanHarvest = 6, kPlanStop = 7,
+                            kPlanExpire = 8 /* id + finish reason: a time-based decision of rank 0's clock */ };
 constexpr uint32_t kPlanMagic = 0x4C4C5031u;   // "LLP1"
 constexpr size_t kPlanHeaderBytes = 4096, kPlanRingBytes = size_t(8) << 20;
 
@@ -433,6 +443,9 @@ struct llmlb_engine {
   void plan_log_locked(uint32_t type) { if (plan_on && plan.leader) { std::lock_guard<std::mutex> lk(mu); plan.write(type, nullptr, 0); } }
   void finish_request(const ReqPtr& r, uint32_t reason);
   void release_resources(const ReqPtr& r);
+  void preempt(const ReqPtr& r);
+  void expire_requests();     // leader / single rank: queue timeouts and request deadlines (time-based)
+  std::atomic<uint64_t> preemptions{0};
   cudaEvent_t get_event();
   uint8_t* next_stage() { return h_stage[(stage_seq++) % kRing]; }
   uint32_t decode_splits(uint32_t nb) const {
@@ -910,14 +923,14 @@ __global__ void iota_kernel(int32_t* p, uint32_t n) {
   if (i < n) p[i] = int32_t(i);
 }
 __global__ void slot_init_kernel(SlotState S, int32_t slot, float temperature, float top_p,
-                                 int32_t top_k, uint64_t seed) {
+                                 int32_t top_k, uint64_t seed, uint64_t step0) {
   S.seq_len[slot] = 0;
   S.last_token[slot] = 0;
   S.temperature[slot] = temperature;
   S.top_p[slot] = top_p;
   S.top_k[slot] = top_k;
   S.seed[slot] = seed;
-  S.step[slot] = 0;
+  S.step[slot] = step0;   // a preempted sequence resumes its sampler stream where it stopped
 }
 __global__ void prefill_finish_kernel(SlotState S, BatchView B, uint32_t n) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -959,8 +972,9 @@ int llmlb_engine::run_prefill(const std::vector<ReqPtr>& reqs, const std::vector
     if (r.prefilled == 0) {  // first chunk: publish block table + sampler state
       LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_block_tables + size_t(r.slot) * pages_per_seq, r.pages.data(),
                                        r.pages.size() * 4, cudaMemcpyHostToDevice, st));
-      slot_init_kernel<<<1, 1, 0, st>>>(S, r.slot, r.s.temperature, r.s.top_p, (int32_t)r.s.top_k, r.s.seed);
+      slot_init_kernel<<<1, 1, 0, st>>>(S, r.slot, r.s.temperature, r.s.top_p, (int32_t)r.s.top_k, r.s.seed, uint64_t(r.harvested));
       LLMLB_LAUNCH_CHECK();
+      r.pages_published = uint32_t(r.pages.size());
     }
     const uint32_t p0 = r.prefilled;
     for (uint32_t j = 0; j < take[i]; ++j) {
@@ -1024,7 +1038,7 @@ int llmlb_engine::run_prefill(const std::vector<ReqPtr>& reqs, const std::vector
   LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_end, st));
   for (size_t i = 0; i < reqs.size(); ++i) {
     reqs[i]->prefilled += take[i];
-    if (reqs[i]->prefilled == reqs[i]->prompt.size()) reqs[i]->launched = 1;
+    if (reqs[i]->prefilled == reqs[i]->prompt.size()) reqs[i]->launched = reqs[i]->harvested + 1;
   }
   steps_prefill++;
   tokens_prefill += T;
@@ -1041,6 +1055,23 @@ int llmlb_engine::run_decode(const std::vector<ReqPtr>& batch) {
     memcpy(stg, slots.data(), nb * 4);
     LLMLB_CUDA_CHECK(cudaMemcpyAsync(B.slots, stg, nb * 4, cudaMemcpyHostToDevice, st));
     cur_batch_slots = slots;
+  }
+  {   // pages taken since the last step (a sequence crossing a 64-token boundary): patch the device block table
+    uint32_t n_new = 0;
+    for (auto& r : batch) n_new += uint32_t(r->pages.size()) - r->pages_published;
+    if (n_new) {
+      int32_t* stg = reinterpret_cast<int32_t*>(next_stage());
+      uint32_t off = 0;
+      for (auto& r : batch) {
+        const uint32_t have = r->pages_published, now = uint32_t(r->pages.size());
+        if (now == have) continue;
+        memcpy(stg + off, r->pages.data() + have, size_t(now - have) * 4);
+        LLMLB_CUDA_CHECK(cudaMemcpyAsync(d_block_tables + size_t(r->slot) * pages_per_seq + have, stg + off, size_t(now - have) * 4,
+                                         cudaMemcpyHostToDevice, st));
+        off += now - have;
+        r->pages_published = now;
+      }
+    }
   }
   InflightStep step;
   step.n_tokens = nb;
@@ -1066,7 +1097,22 @@ void llmlb_engine::release_resources(const ReqPtr& r) {  // mu held
   }
   for (int32_t p : r->pages) free_pages.push_back(p);
   r->pages.clear();
+  r->pages_published = 0;
   running.erase(std::remove(running.begin(), running.end(), r), running.end());
+}
+
+// Evict a running sequence: its pages and slot go back to the pools and it returns to the HEAD of the
+// queue with its context extended by what it generated (recomputed at re-admission).  Only called
+// with nothing in flight, so every launched token has been harvested.  mu held.
+void llmlb_engine::preempt(const ReqPtr& r) {
+  r->prompt.insert(r->prompt.end(), r->gen.begin() + r->gen_in_prompt, r->gen.end());
+  r->gen_in_prompt = uint32_t(r->gen.size());
+  r->prefilled = 0;
+  r->launched = r->harvested;
+  r->preempted++;
+  release_resources(r);
+  waiting.push_front(r);
+  preemptions++;
 }
 
 void llmlb_engine::finish_request(const ReqPtr& r, uint32_t reason) {  // mu held
@@ -1074,14 +1120,14 @@ void llmlb_engine::finish_request(const ReqPtr& r, uint32_t reason) {  // mu hel
   r->finished = true;
   r->finish_reason = reason;
   if (r->events.empty() || r->events.back().finish_reason == LLMLB_FINISH_NONE) {
-    if (!r->events.empty() && reason != LLMLB_FINISH_CANCELLED && reason != LLMLB_FINISH_ERROR) {
+    if (!r->events.empty() && (reason == LLMLB_FINISH_STOP || reason == LLMLB_FINISH_LENGTH)) {
       r->events.back().finish_reason = reason;
     } else {
       llmlb_token_event ev{};
       ev.token_id = -1;
       ev.index = r->harvested;
       ev.finish_reason = reason;
-      ev.prompt_tokens = (uint32_t)r->prompt.size();
+      ev.prompt_tokens = r->n_prompt0;
       ev.completion_tokens = r->harvested;
       ev.t_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - r->t_submit).count();
       r->events.push_back(ev);
@@ -1111,7 +1157,8 @@ void llmlb_engine::harvest_one() {
     llmlb_token_event ev{};
     ev.token_id = tok;
     ev.index = r->harvested++;
-    ev.prompt_tokens = (uint32_t)r->prompt.size();
+    r->gen.push_back(tok);
+    ev.prompt_tokens = r->n_prompt0;
     ev.completion_tokens = r->harvested;
     ev.t_ms = std::chrono::duration<double, std::milli>(now - r->t_submit).count();
     r->events.push_back(ev);
@@ -1132,13 +1179,13 @@ bool llmlb_engine::sched_iteration(std::unique_lock<std::mutex>& lk) {
   std::vector<ReqPtr> pf_reqs;
   std::vector<uint32_t> pf_take;
   std::vector<ReqPtr> dec;
-  // cancellations
+  // cancellations (client cancel / release, queue timeout, deadline: cancel_reason says which)
   for (auto it = waiting.begin(); it != waiting.end();) {
-    if ((*it)->cancel) { ReqPtr r = *it; it = waiting.erase(it); finish_request(r, LLMLB_FINISH_CANCELLED); }
+    if ((*it)->cancel) { ReqPtr r = *it; it = waiting.erase(it); finish_request(r, r->cancel_reason); }
     else ++it;
   }
   for (size_t i = 0; i < running.size();) {
-    if (running[i]->cancel && !running[i]->finished) finish_request(running[i], LLMLB_FINISH_CANCELLED);
+    if (running[i]->cancel && !running[i]->finished) finish_request(running[i], running[i]->cancel_reason);
     else ++i;
   }
   if (!paused) {
@@ -1151,14 +1198,21 @@ bool llmlb_engine::sched_iteration(std::unique_lock<std::mutex>& lk) {
         pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
       }
     }
-    // admit in FIFO order while a slot, the pages for prompt+max_tokens and token budget exist
+    // admit in FIFO order while a slot, the pages of the CONTEXT (prompt, plus what a preempted
+    // sequence had generated) and token budget exist.  Pages for generated tokens are taken one at a
+    // time as a sequence crosses a page boundary; when the pool runs dry the most recently admitted
+    // sequence is evicted and recomputed later (below).
     while (!waiting.empty() && budget > 0 && !free_slots.empty()) {
       ReqPtr r = waiting.front();
-      uint32_t need = ceil_div((uint32_t)r->prompt.size() + r->s.max_tokens, kPageTokens);
-      if (need > free_pages.size()) break;
+      uint32_t need = ceil_div((uint32_t)r->prompt.size(), kPageTokens);
+      // first admission keeps one page per running sequence in reserve, so that admitting does not
+      // immediately force an eviction
+      const size_t reserve = r->admitted_once ? 0 : running.size();
+      if (need + reserve > free_pages.size() && !(running.empty() && need <= free_pages.size())) break;
       waiting.pop_front();
       r->slot = free_slots.back(); free_slots.pop_back();
       for (uint32_t i = 0; i < need; ++i) { r->pages.push_back(free_pages.back()); free_pages.pop_back(); }
+      r->admitted_once = true;
       running.push_back(r);
       uint32_t t = std::min<uint32_t>(budget, (uint32_t)r->prompt.size());
       pf_reqs.push_back(r); pf_take.push_back(t); budget -= t;
@@ -1167,6 +1221,30 @@ bool llmlb_engine::sched_iteration(std::unique_lock<std::mutex>& lk) {
       for (auto& r : running)
         if (!r->finished && r->prefilled == r->prompt.size() && r->launched < r->s.max_tokens)
           dec.push_back(r);
+      // every sequence of the step needs the page that holds position n_prompt0 + launched - 1
+      bool shortage = false;
+      for (auto& r : dec) {
+        const uint32_t need = ceil_div(r->n_prompt0 + r->launched, kPageTokens);
+        while (r->pages.size() < need) {
+          if (free_pages.empty()) { shortage = true; break; }
+          r->pages.push_back(free_pages.back()); free_pages.pop_back();
+        }
+        if (shortage) break;
+      }
+      if (shortage) {
+        dec.clear();
+        if (inflight.empty()) {
+          // nothing in flight: every launched token is known, so a sequence can be evicted.  Victim:
+          // the most recently admitted one (the oldest always makes progress).
+          ReqPtr victim;
+          for (auto it = running.rbegin(); it != running.rend(); ++it) if (!(*it)->finished) { victim = *it; break; }
+          if (victim && running.size() > 1) preempt(victim);
+          else if (victim) finish_request(victim, LLMLB_FINISH_ERROR);   // a lone sequence the pool cannot hold
+          lk.unlock();
+          return true;    // state changed: schedule again at once
+        }
+        // steps in flight: the loop harvests them first, then comes back here
+      }
     }
   }
   lk.unlock();
@@ -1183,6 +1261,33 @@ bool llmlb_engine::sched_iteration(std::unique_lock<std::mutex>& lk) {
   return true;
 }
 
+// Time-based decisions belong to ONE clock: the single rank's, or rank 0's under a plan channel
+// (followers replay kPlanExpire).  Lock-step tensor parallelism without a plan channel has no
+// timeouts.  mu held.
+void llmlb_engine::expire_requests() {
+  if (tp > 1 && !(plan_on && plan.leader)) return;
+  if (!cfg.queue_timeout_ms && !cfg.request_timeout_ms) return;
+  const auto now = std::chrono::steady_clock::now();
+  auto mark = [&](const ReqPtr& r, uint32_t reason) {
+    r->cancel = true;
+    r->cancel_reason = reason;
+    uint8_t rec[12];
+    memcpy(rec, &r->id, 8); memcpy(rec + 8, &reason, 4);
+    plan_log(kPlanExpire, rec, 12);
+  };
+  for (auto& r : waiting) {
+    if (r->cancel) continue;
+    const double ms = std::chrono::duration<double, std::milli>(now - r->t_submit).count();
+    if (cfg.request_timeout_ms && ms > cfg.request_timeout_ms) mark(r, LLMLB_FINISH_DEADLINE);
+    else if (cfg.queue_timeout_ms && !r->admitted_once && ms > cfg.queue_timeout_ms) mark(r, LLMLB_FINISH_QUEUE_TIMEOUT);
+  }
+  if (cfg.request_timeout_ms)
+    for (auto& r : running) {
+      if (r->cancel || r->finished) continue;
+      if (std::chrono::duration<double, std::milli>(now - r->t_submit).count() > cfg.request_timeout_ms) mark(r, LLMLB_FINISH_DEADLINE);
+    }
+}
+
 void llmlb_engine::loop() {
   cudaSetDevice(cfg.device);
   for (;;) {
@@ -1194,6 +1299,7 @@ void llmlb_engine::loop() {
       });
       if (stop) break;
       if (plan_on && !plan.leader) { lk.unlock(); loop_follower(); return; }
+      expire_requests();               // logged as kPlanExpire before the iteration that applies them
       plan_log(kPlanSched);            // followers run the same iteration, concurrently with ours
       launched = sched_iteration(lk);
     }
@@ -1225,6 +1331,7 @@ void llmlb_engine::loop_follower() {
         uint32_t n_prompt = 0, n_stop = 0;
         memcpy(&n_prompt, p, 4); memcpy(&n_stop, p + 4, 4); p += 8;
         r->prompt.assign(reinterpret_cast<const int32_t*>(p), reinterpret_cast<const int32_t*>(p) + n_prompt);
+        r->n_prompt0 = n_prompt;
         p += size_t(n_prompt) * 4;
         r->stop_ids.assign(reinterpret_cast<const int32_t*>(p), reinterpret_cast<const int32_t*>(p) + n_stop);
         r->s.stop_ids = nullptr;
@@ -1247,6 +1354,14 @@ void llmlb_engine::loop_follower() {
       case kPlanPause: {
         std::lock_guard<std::mutex> lk(mu);
         paused = !buf.empty() && buf[0] != 0;
+        break;
+      }
+      case kPlanExpire: {
+        uint64_t id = 0; uint32_t reason = LLMLB_FINISH_CANCELLED;
+        if (buf.size() >= 12) { memcpy(&id, buf.data(), 8); memcpy(&reason, buf.data() + 8, 4); }
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = requests.find(id);
+        if (it != requests.end()) { it->second->cancel = true; it->second->cancel_reason = reason; }
         break;
       }
       case kPlanSched: {
@@ -1355,6 +1470,7 @@ extern "C" int llmlb_engine_health(const llmlb_engine* ce, llmlb_health* out) {
   out->tokens_prefill = e->tokens_prefill; out->tokens_decode = e->tokens_decode;
   out->gpu_ms_prefill = e->gpu_ms_prefill; out->gpu_ms_decode = e->gpu_ms_decode;
   out->kernel_launches = g_kernel_launches.load();
+  out->preemptions = e->preemptions.load();
   return LLMLB_OK;
 }
 
@@ -1372,6 +1488,7 @@ extern "C" int llmlb_request_submit(llmlb_engine* e, const int32_t* prompt_ids, 
   if (s->temperature < 0.f || s->top_p < 0.f) { set_error("negative temperature/top_p"); return LLMLB_E_INVALID_ARG; }
   auto r = std::make_shared<Request>();
   r->prompt.assign(prompt_ids, prompt_ids + n_prompt);
+  r->n_prompt0 = n_prompt;
   r->s = *s;
   if (s->stop_ids && s->n_stop_ids) r->stop_ids.assign(s->stop_ids, s->stop_ids + s->n_stop_ids);
   r->s.stop_ids = nullptr;
@@ -1380,7 +1497,7 @@ extern "C" int llmlb_request_submit(llmlb_engine* e, const int32_t* prompt_ids, 
     std::lock_guard<std::mutex> lk(e->mu);
     if (e->plan_on && !e->plan.leader) { set_error("follower rank of a plan channel: requests enter through rank 0"); return LLMLB_E_UNSUPPORTED; }
     if (!e->fatal_error.empty()) { set_error("engine failed: " + e->fatal_error); return LLMLB_E_DEVICE; }
-    if (e->waiting.size() >= 4096) { set_error("queue full"); return LLMLB_E_QUEUE_FULL; }
+    if (e->waiting.size() >= (e->cfg.queue_max ? e->cfg.queue_max : 4096u)) { set_error("Request queue is full"); return LLMLB_E_QUEUE_FULL; }
     r->id = e->next_id++;
     e->requests[r->id] = r;
     e->waiting.push_back(r);
@@ -1678,7 +1795,7 @@ extern "C" int llmlb_debug_prefill_logits(llmlb_engine* e, const int32_t* prompt
   LLMLB_CUDA_CHECK(cudaMemcpy(e->d_pos, pos.data(), n * 4, cudaMemcpyHostToDevice));
   LLMLB_CUDA_CHECK(cudaMemcpy(e->d_page_of_tok, page.data(), n * 4, cudaMemcpyHostToDevice));
   LLMLB_CUDA_CHECK(cudaMemcpy(e->d_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice));
-  slot_init_kernel<<<1, 1, 0, st>>>(e->S, slot, 0.f, 1.f, 0, 0);
+  slot_init_kernel<<<1, 1, 0, st>>>(e->S, slot, 0.f, 1.f, 0, 0, 0);
   LLMLB_LAUNCH_CHECK();
   RC(llmlb_op_embed(e->embed, e->d_ids, e->x, n, e->M.hidden, e->M.vocab, st));
   llmlb_engine::FwdState fs;

@@ -13,7 +13,7 @@ OK = 0
 E_INVALID_ARG, E_MODEL_NOT_FOUND, E_QUEUE_FULL, E_TIMEOUT = -1, -2, -3, -4
 E_DEVICE, E_INTERNAL, E_NOT_FOUND, E_UNSUPPORTED = -5, -6, -7, -8
 EPI_STORE_BF16, EPI_RESID_F32, EPI_SILU_MUL, EPI_STORE_F32 = 0, 1, 2, 3
-FINISH_NONE, FINISH_STOP, FINISH_LENGTH, FINISH_CANCELLED, FINISH_ERROR = 0, 1, 2, 3, 4
+FINISH_NONE, FINISH_STOP, FINISH_LENGTH, FINISH_CANCELLED, FINISH_ERROR, FINISH_QUEUE_TIMEOUT, FINISH_DEADLINE = 0, 1, 2, 3, 4, 5, 6
 ABI_VERSION = 1
 
 
@@ -29,7 +29,8 @@ class EngineConfig(C.Structure):
                 ("max_seqs", C.c_uint32), ("max_ctx", C.c_uint32), ("kv_block_tokens", C.c_uint32),
                 ("kv_pages", C.c_uint32), ("max_step_tokens", C.c_uint32),
                 ("synthetic_seed", C.c_uint64), ("use_cuda_graphs", C.c_uint32),
-                ("gemm_impl", C.c_uint32), ("lookahead", C.c_uint32), ("reserved", C.c_uint32 * 8)]
+                ("gemm_impl", C.c_uint32), ("lookahead", C.c_uint32), ("queue_max", C.c_uint32),
+                ("queue_timeout_ms", C.c_uint32), ("request_timeout_ms", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class ModelInfo(C.Structure):
@@ -44,7 +45,7 @@ class Health(C.Structure):
                 ("total_kv_pages", C.c_uint32), ("steps_prefill", C.c_uint64),
                 ("steps_decode", C.c_uint64), ("tokens_prefill", C.c_uint64),
                 ("tokens_decode", C.c_uint64), ("gpu_ms_prefill", C.c_double),
-                ("gpu_ms_decode", C.c_double), ("kernel_launches", C.c_uint64)]
+                ("gpu_ms_decode", C.c_double), ("kernel_launches", C.c_uint64), ("preemptions", C.c_uint64)]
 
 
 class Sampling(C.Structure):
@@ -154,7 +155,7 @@ class Engine:
 
     def __init__(self, model, model_id="llama-3-8b-synthetic", device=0, tp_rank=0, tp_size=1,
                  max_seqs=8, max_ctx=1024, kv_pages=0, max_step_tokens=0, seed=0,
-                 use_cuda_graphs=True, gemm_impl=0, lookahead=0):
+                 use_cuda_graphs=True, gemm_impl=0, lookahead=0, queue_max=0, queue_timeout_ms=0, request_timeout_ms=0):
         cfg = EngineConfig()
         cfg.abi_version = ABI_VERSION
         for k, v in model.items():
@@ -166,6 +167,7 @@ class Engine:
         cfg.synthetic_seed = seed
         cfg.use_cuda_graphs = 1 if use_cuda_graphs else 0
         cfg.gemm_impl, cfg.lookahead = gemm_impl, lookahead
+        cfg.queue_max, cfg.queue_timeout_ms, cfg.request_timeout_ms = queue_max, queue_timeout_ms, request_timeout_ms
         self.model = dict(model)
         self.cfg = cfg
         self._h = vp()

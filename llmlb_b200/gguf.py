@@ -269,8 +269,11 @@ def geometry(meta, tensors):
     hidden, heads = int(g("embedding_length")), int(g("attention.head_count"))
     emb = [t for t in tensors if t["name"] == "token_embd.weight"]
     vocab = emb[0]["shape"][0] if emb else int(g("vocab_size", len(meta.get("tokenizer.ggml.tokens", []))))
+    # head width: metadata when present, else the q projection's own shape (rows / heads)
+    q = [t for t in tensors if t["name"].endswith("attn_q.weight")]
+    hd_default = q[0]["shape"][0] // heads if q and q[0]["shape"][1] == hidden else hidden // heads
     return {"hidden": hidden, "n_layers": int(g("block_count")), "n_heads": heads, "n_kv_heads": int(g("attention.head_count_kv", heads)),
-            "head_dim": int(g("attention.key_length", hidden // heads)), "ffn": int(g("feed_forward_length")), "vocab": int(vocab),
+            "head_dim": int(g("attention.key_length", hd_default)), "ffn": int(g("feed_forward_length")), "vocab": int(vocab),
             "rope_theta": float(g("rope.freq_base", 10000.0)), "rms_eps": float(g("attention.layer_norm_rms_epsilon", 1e-5))}
 
 

@@ -362,7 +362,12 @@ bool Checkpoint::open_gguf(std::string* err) {
   geo_.n_layers = uint32_t(g("block_count", 0));
   geo_.n_heads = n_head;
   geo_.n_kv_heads = n_kv_head;
-  geo_.head_dim = uint32_t(g("attention.key_length", geo_.n_heads ? geo_.hidden / geo_.n_heads : 0));
+  // head width: metadata when present, else the q projection's own shape (rows / heads) — a model
+  // whose head_dim is not hidden / heads (e.g. hidden 512, 8 heads of 128) must not be guessed wrong
+  uint32_t hd_from_q = 0;
+  for (const CkptTensor& t : tensors_)
+    if (n_head && t.name.size() > 23 && t.name.compare(t.name.size() - 23, 23, "self_attn.q_proj.weight") == 0 && t.cols == geo_.hidden) { hd_from_q = uint32_t(t.rows / n_head); break; }
+  geo_.head_dim = uint32_t(g("attention.key_length", hd_from_q ? hd_from_q : (geo_.n_heads ? geo_.hidden / geo_.n_heads : 0)));
   geo_.ffn = uint32_t(g("feed_forward_length", 0));
   if (!geo_.vocab) geo_.vocab = uint32_t(g("vocab_size", double(tok_tokens_.size())));
   geo_.rope_theta = float(g("rope.freq_base", 10000.0));

@@ -406,6 +406,22 @@ Json completion_body(const std::string& id, const std::string& model, int64_t cr
   root.set("choices", choices); root.set("usage", chat_usage(p, c));
   return root;
 }
+Json completion_chunk(const std::string& id, const std::string& model, int64_t created, const std::string* text, const char* finish_reason) {
+  Json choice = Json::object();
+  choice.set("index", 0); choice.set("text", text ? *text : std::string()); choice.set("logprobs", Json());
+  choice.set("finish_reason", finish_reason ? Json(finish_reason) : Json());
+  Json choices = Json::array(); choices.push(choice);
+  Json root = Json::object();
+  root.set("id", id); root.set("object", "text_completion"); root.set("created", created); root.set("model", model);
+  root.set("choices", choices);
+  return root;
+}
+Json completion_usage_chunk(const std::string& id, const std::string& model, int64_t created, uint32_t p, uint32_t c) {
+  Json root = Json::object();
+  root.set("id", id); root.set("object", "text_completion"); root.set("created", created);
+  root.set("model", model); root.set("choices", Json::array()); root.set("usage", chat_usage(p, c));
+  return root;
+}
 static Json resp_usage(uint32_t i, uint32_t o) {
   Json u = Json::object();
   u.set("input_tokens", i); u.set("output_tokens", o); u.set("total_tokens", i + o);

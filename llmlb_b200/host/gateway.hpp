@@ -201,6 +201,9 @@ Json chat_usage_chunk(const std::string& id, const std::string& model, int64_t c
 Json chat_completion_body(const std::string& id, const std::string& model, int64_t created,
                           const std::string& content, const char* finish_reason,
                           uint32_t prompt_tokens, uint32_t completion_tokens);
+// legacy /v1/completions stream: {"object":"text_completion","choices":[{"index":0,"text":...,"finish_reason":...}]}
+Json completion_chunk(const std::string& id, const std::string& model, int64_t created, const std::string* text, const char* finish_reason);
+Json completion_usage_chunk(const std::string& id, const std::string& model, int64_t created, uint32_t prompt_tokens, uint32_t completion_tokens);
 Json completion_body(const std::string& id, const std::string& model, int64_t created,
                      const std::string& text, const char* finish_reason, uint32_t prompt_tokens,
                      uint32_t completion_tokens);

@@ -43,6 +43,7 @@ struct Server {
   std::atomic<uint64_t> seq{0};
   std::unique_ptr<BpeTokenizer> tok;   // null: byte-level placeholder
   std::vector<int32_t> stop_ids;       // <|eot_id|>, <|end_of_text|>, <|eom_id|> when a tokenizer is loaded
+  uint32_t queue_timeout_ms = 60000, request_timeout_ms = 120000;
 };
 static Server G;
 
@@ -110,7 +111,7 @@ static bool send_all(int fd, const std::string& s) {
 }
 static const char* reason(int st) {
   switch (st) { case 200: return "OK"; case 400: return "Bad Request"; case 401: return "Unauthorized";
-    case 404: return "Not Found"; case 405: return "Method Not Allowed"; case 502: return "Bad Gateway";
+    case 404: return "Not Found"; case 405: return "Method Not Allowed"; case 429: return "Too Many Requests"; case 502: return "Bad Gateway";
     case 503: return "Service Unavailable"; case 504: return "Gateway Timeout"; default: return "Error"; }
 }
 static bool send_json(int fd, int status, const std::string& body, const char* extra = "") {
@@ -230,13 +231,18 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   }
   StopMatcher stopper(stop_strings);
   const bool stream = req.get("stream") && req.get("stream")->as_bool();
-  bool include_usage = kind != 0;
+  bool include_usage = kind == 1;
   if (const Json* so = req.get("stream_options")) if (const Json* iu = so->get("include_usage")) include_usage = iu->as_bool();
   if (ids.size() + s.max_tokens > G.max_ctx) s.max_tokens = ids.size() < G.max_ctx ? uint32_t(G.max_ctx - ids.size()) : 0;
 
   const auto t0 = std::chrono::steady_clock::now();
   uint64_t rid = 0;
   int rc = s.max_tokens ? llmlb_request_submit(G.eng, ids.data(), uint32_t(ids.size()), &s, &rid) : LLMLB_E_INVALID_ARG;
+  if (rc == LLMLB_E_QUEUE_FULL) {   // openai.rs:841-861: 429 rate_limit_exceeded + Retry-After = queue timeout
+    const std::string ra = "Retry-After: " + std::to_string(std::max<uint32_t>(1, G.queue_timeout_ms / 1000)) + "\r\n";
+    send_err(429, "Request queue is full", "rate_limit_exceeded", ra.c_str());
+    return;
+  }
   if (rc != LLMLB_OK) {
     int st = map_error(rc);
     send_err(st, s.max_tokens ? llmlb_last_error() : "prompt exceeds the context length", st == 400 ? "invalid_request_error" : "endpoint_request_error");
@@ -279,6 +285,7 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
         const std::string piece = stopper.feed(raw_piece);
         text += piece;
         if (stream && !piece.empty()) out += kind == 1 ? sse_event(responses_event_delta(piece))
+                                     : kind == 2 ? sse_event(completion_chunk(id, jm->str(), created, &piece, nullptr))
                                      : sse_event(chat_chunk(id, jm->str(), created, nullptr, &piece, nullptr));
       }
       prompt_tokens = ev[i].prompt_tokens; completion_tokens = ev[i].completion_tokens;
@@ -296,7 +303,9 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     if (!stopper.hit()) rest += stopper.flush();
     if (!rest.empty()) {
       text += rest;
-      if (stream && ok) send_sse(kind == 1 ? sse_event(responses_event_delta(rest)) : sse_event(chat_chunk(id, jm->str(), created, nullptr, &rest, nullptr)));
+      if (stream && ok) send_sse(kind == 1 ? sse_event(responses_event_delta(rest))
+                                 : kind == 2 ? sse_event(completion_chunk(id, jm->str(), created, &rest, nullptr))
+                                 : sse_event(chat_chunk(id, jm->str(), created, nullptr, &rest, nullptr)));
     }
   }
   llmlb_request_release(G.eng, rid);
@@ -306,15 +315,30 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   G.lm.finish_request(ep, success, ms, completion_tokens);
   if (success && completion_tokens) G.lm.update_tps(ep, pm.base, api, completion_tokens, ms);
   const char* fr = finish == LLMLB_FINISH_STOP ? "stop" : "length";
-  if (finish == LLMLB_FINISH_ERROR && !stream) { send_err(502, "engine failure", "endpoint_request_error"); return; }
+  // failures map like the gateway maps an upstream's (openai.rs:862-882, openai_util.rs:86-134)
+  const bool failed = finish != LLMLB_FINISH_STOP && finish != LLMLB_FINISH_LENGTH && !(client_gone && completion_tokens > 0);
+  int fail_status = 502; std::string fail_msg = "Failed to proxy request to upstream endpoint", fail_type = "endpoint_request_error";
+  if (finish == LLMLB_FINISH_QUEUE_TIMEOUT) { fail_status = 504; fail_msg = "Queue wait timeout"; fail_type = "timeout"; }
+  else if (finish == LLMLB_FINISH_DEADLINE) { fail_status = 504; fail_msg = "Upstream endpoint request timed out after " + std::to_string(G.request_timeout_ms / 1000) + " seconds"; fail_type = "timeout"; }
+  if (failed && !stream) { send_err(fail_status, fail_msg, fail_type.c_str()); return; }
   if (stream) {
     if (!ok) return;
+    if (failed) {   // headers are gone: say so in-band and end the stream WITHOUT a finish chunk or [DONE]
+      Json err = Json::object(); err.set("message", fail_msg); err.set("type", fail_type); err.set("code", fail_status);
+      Json root = Json::object(); root.set("error", err);
+      send_chunk(fd, sse_event(root));
+      send_all(fd, "0\r\n\r\n");
+      return;
+    }
     std::string tail;
     if (kind == 0) {
       tail += sse_event(chat_chunk(id, jm->str(), created, nullptr, nullptr, fr));
       if (include_usage) tail += sse_event(chat_usage_chunk(id, jm->str(), created, prompt_tokens, completion_tokens));
     } else if (kind == 1) {
       tail += sse_event(responses_event_text_done(text)) + sse_event(responses_event_done(id, prompt_tokens, completion_tokens));
+    } else {   // legacy completions: text_completion chunks, a finish chunk, optional usage
+      tail += sse_event(completion_chunk(id, jm->str(), created, nullptr, fr));
+      if (include_usage) tail += sse_event(completion_usage_chunk(id, jm->str(), created, prompt_tokens, completion_tokens));
     }
     tail += sse_done();
     if (anthropic) {  // usage always travels to the transformer (message_delta carries output_tokens)
@@ -407,12 +431,90 @@ static void serve_conn(int fd) {
   close(fd);
 }
 
+// ---- checkpoint planning (no GPU involved; `--dry-run` stops after it) ----
+// geometry of a sharded checkpoint: every file contributes what it knows; the layer count is the
+// maximum (safetensors shards only see their own layers), everything else must agree
+static bool merge_geometry(CkptGeometry* g, const CkptGeometry& f, std::string* err) {
+  auto take = [&](uint32_t* dst, uint32_t v, const char* what) {
+    if (!v) return true;
+    if (*dst && *dst != v) { *err = std::string("the weight files disagree about ") + what; return false; }
+    *dst = v;
+    return true;
+  };
+  g->n_layers = std::max(g->n_layers, f.n_layers);
+  if (f.known || f.hidden) { g->rope_theta = f.rope_theta; g->rms_eps = f.rms_eps; }
+  return take(&g->hidden, f.hidden, "hidden") && take(&g->n_heads, f.n_heads, "n_heads") && take(&g->n_kv_heads, f.n_kv_heads, "n_kv_heads") &&
+         take(&g->head_dim, f.head_dim, "head_dim") && take(&g->ffn, f.ffn, "ffn") && take(&g->vocab, f.vocab, "vocab");
+}
+
+struct WeightPlan {
+  struct Load { size_t ckpt, index; std::string as; };   // tensor `index` of file `ckpt`, loaded under engine name `as`
+  std::vector<Load> loads;
+  bool lm_head_tied = false;
+};
+
+// buffers that ship inside checkpoints but are not model weights
+static bool is_ignorable_tensor(const std::string& n) {
+  auto ends = [&](const char* suf) { const size_t l = strlen(suf); return n.size() >= l && n.compare(n.size() - l, l, suf) == 0; };
+  return ends("rotary_emb.inv_freq") || ends("rope_freqs.weight") || ends(".attn.bias") || ends(".masked_bias");
+}
+
+static bool plan_weights(const llmlb_model_config& m, const std::vector<std::unique_ptr<Checkpoint>>& ckpts, WeightPlan* plan, std::string* err) {
+  std::map<std::string, std::pair<uint64_t, uint64_t>> want;   // name -> full (rows, cols)
+  const uint64_t H = m.hidden, q = uint64_t(m.n_heads) * m.head_dim, kv = uint64_t(m.n_kv_heads) * m.head_dim, F = m.ffn, V = m.vocab;
+  want["model.embed_tokens.weight"] = {V, H}; want["model.norm.weight"] = {1, H}; want["lm_head.weight"] = {V, H};
+  for (uint32_t l = 0; l < m.n_layers; ++l) {
+    const std::string p = "model.layers." + std::to_string(l) + ".";
+    want[p + "self_attn.q_proj.weight"] = {q, H}; want[p + "self_attn.k_proj.weight"] = {kv, H}; want[p + "self_attn.v_proj.weight"] = {kv, H};
+    want[p + "self_attn.o_proj.weight"] = {H, q}; want[p + "mlp.gate_proj.weight"] = {F, H}; want[p + "mlp.up_proj.weight"] = {F, H};
+    want[p + "mlp.down_proj.weight"] = {H, F}; want[p + "input_layernorm.weight"] = {1, H}; want[p + "post_attention_layernorm.weight"] = {1, H};
+  }
+  std::map<std::string, WeightPlan::Load> found;
+  for (size_t ci = 0; ci < ckpts.size(); ++ci) {
+    const auto& ts = ckpts[ci]->tensors();
+    for (size_t i = 0; i < ts.size(); ++i) {
+      const CkptTensor& t = ts[i];
+      auto w = want.find(t.name);
+      if (w == want.end()) {
+        if (is_ignorable_tensor(t.name)) continue;
+        *err = "unexpected tensor " + t.name + " (not part of a Llama decoder of this geometry)";
+        return false;
+      }
+      if (t.rows != w->second.first || t.cols != w->second.second) {
+        *err = t.name + " is " + std::to_string(t.rows) + "x" + std::to_string(t.cols) + ", the model needs " + std::to_string(w->second.first) + "x" + std::to_string(w->second.second);
+        return false;
+      }
+      if (found.count(t.name)) { *err = t.name + " appears in more than one file"; return false; }
+      found[t.name] = WeightPlan::Load{ci, i, t.name};
+    }
+  }
+  // a tied output head (no lm_head.weight in the files): serve it from the embedding
+  if (!found.count("lm_head.weight") && found.count("model.embed_tokens.weight")) {
+    WeightPlan::Load ld = found["model.embed_tokens.weight"];
+    ld.as = "lm_head.weight";
+    found["lm_head.weight"] = ld;
+    plan->lm_head_tied = true;
+  }
+  std::string missing;
+  size_t n_missing = 0;
+  for (const auto& w : want)
+    if (!found.count(w.first)) { if (n_missing++ < 4) missing += (missing.empty() ? "" : ", ") + w.first; }
+  if (n_missing) { *err = std::to_string(n_missing) + " weights of the model are in none of the files: " + missing + (n_missing > 4 ? ", ..." : ""); return false; }
+  for (const auto& f : found) plan->loads.push_back(f.second);
+  return true;
+}
+
 int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
   int port = 8011; std::string geometry = "8b", tokenizer_path;
   std::vector<std::string> weight_files;   // --weights x.gguf | shard.safetensors (repeatable)
   uint32_t max_seqs = 64, max_ctx = 2048, vocab_override = 0;
+  // queue limits of the gateway (llmlb/src/config.rs:80-99: LLMLB_QUEUE_MAX 100, LLMLB_QUEUE_TIMEOUT_SECS 60)
+  // and its per-request inference timeout (types/endpoint.rs:389: 120 s)
+  uint32_t queue_max = 100, queue_timeout_ms = 60000, request_timeout_ms = 120000;
+  bool dry_run = false;
   G.model_id = "llama-3-8b";
+  for (int i = 1; i < argc; ++i) if (std::string(argv[i]) == "--dry-run") { dry_run = true; for (int j = i; j + 1 < argc; ++j) argv[j] = argv[j + 1]; --argc; --i; }
   for (int i = 1; i + 1 < argc; i += 2) {
     std::string k = argv[i], v = argv[i + 1];
     if (k == "--port") port = atoi(v.c_str()); else if (k == "--model") geometry = v;
@@ -421,12 +523,17 @@ int main(int argc, char** argv) {
     else if (k == "--tokenizer") tokenizer_path = v;
     else if (k == "--weights") weight_files.push_back(v);
     else if (k == "--vocab") vocab_override = uint32_t(atoi(v.c_str()));
+    else if (k == "--queue-max") queue_max = uint32_t(atoi(v.c_str()));
+    else if (k == "--queue-timeout-ms") queue_timeout_ms = uint32_t(atoi(v.c_str()));
+    else if (k == "--request-timeout-ms") request_timeout_ms = uint32_t(atoi(v.c_str()));
   }
   llmlb_engine_config cfg; memset(&cfg, 0, sizeof cfg);
   cfg.abi_version = LLMLB_ABI_VERSION;
   if (geometry == "tiny") cfg.model = {512, 2, 8, 2, 128, 1024, 2048, 500000.f, 1e-5f};
   else cfg.model = {4096, 32, 32, 8, 128, 14336, 128256, 500000.f, 1e-5f};
-  // real checkpoints: geometry from the first file (--model auto), tensors loaded after create
+  // real checkpoints: geometry merged over ALL files (--model auto; a sharded safetensors checkpoint
+  // spreads the layers over its shards), every tensor validated BEFORE the engine exists, and
+  // start-up fails unless every weight of the model was found (no silently synthetic layers)
   std::vector<std::unique_ptr<Checkpoint>> ckpts;
   for (const auto& wf : weight_files) {
     std::string err;
@@ -434,49 +541,61 @@ int main(int argc, char** argv) {
     if (!ckpts.back()->open(wf, &err)) { fprintf(stderr, "weights %s: %s\n", wf.c_str(), err.c_str()); return 2; }
   }
   if (geometry == "auto") {
-    if (ckpts.empty() || !ckpts[0]->geometry().known) { fprintf(stderr, "--model auto needs --weights with a file that describes the model\n"); return 2; }
-    const CkptGeometry& g = ckpts[0]->geometry();
-    cfg.model = {g.hidden, g.n_layers, g.n_heads, g.n_kv_heads, g.head_dim, g.ffn, g.vocab, g.rope_theta, g.rms_eps};
+    if (ckpts.empty()) { fprintf(stderr, "--model auto needs --weights with a file that describes the model\n"); return 2; }
+    CkptGeometry g{};
+    std::string err;
+    for (const auto& c : ckpts) if (!merge_geometry(&g, c->geometry(), &err)) { fprintf(stderr, "weights: %s\n", err.c_str()); return 2; }
+    if (!(g.hidden && g.n_layers && g.n_heads && g.n_kv_heads && g.ffn && g.vocab)) { fprintf(stderr, "--model auto: the weight files do not describe the whole model (hidden %u, layers %u, heads %u/%u, ffn %u, vocab %u)\n", g.hidden, g.n_layers, g.n_heads, g.n_kv_heads, g.ffn, g.vocab); return 2; }
+    cfg.model = {g.hidden, g.n_layers, g.n_heads, g.n_kv_heads, g.head_dim ? g.head_dim : 128, g.ffn, g.vocab, g.rope_theta, g.rms_eps};
   }
   if (vocab_override) cfg.model.vocab = vocab_override;   // synthetic weights: any vocabulary size works
+  WeightPlan plan;
+  if (!ckpts.empty()) {
+    std::string err;
+    if (!plan_weights(cfg.model, ckpts, &plan, &err)) { fprintf(stderr, "weights: %s\n", err.c_str()); return 2; }
+  }
   strncpy(cfg.model_id, G.model_id.c_str(), sizeof cfg.model_id - 1);
   cfg.tp_size = 1; cfg.max_seqs = max_seqs; cfg.max_ctx = max_ctx; cfg.kv_block_tokens = 64; cfg.use_cuda_graphs = 1;
-  if (llmlb_engine_create(&cfg, &G.eng) != LLMLB_OK) { fprintf(stderr, "engine: %s\n", llmlb_last_error()); return 2; }
-  G.vocab = cfg.model.vocab; G.max_ctx = max_ctx;
-  for (size_t ci = 0; ci < ckpts.size(); ++ci) {
-    size_t loaded = 0;
-    std::vector<uint16_t> bits;
-    for (size_t i = 0; i < ckpts[ci]->tensors().size(); ++i) {
-      const CkptTensor& t = ckpts[ci]->tensors()[i];
-      std::string err;
-      if (!ckpts[ci]->read_bf16(i, &bits, &err)) { fprintf(stderr, "weights: %s\n", err.c_str()); return 2; }
-      const int rc = llmlb_engine_load_tensor(G.eng, t.name.c_str(), bits.data(), t.rows, t.cols);
-      if (rc == LLMLB_OK) ++loaded;
-      else if (rc != LLMLB_E_NOT_FOUND) { fprintf(stderr, "weights: %s: %s\n", t.name.c_str(), llmlb_last_error()); return 2; }
-    }
-    fprintf(stderr, "weights: %s: %zu tensors loaded\n", weight_files[ci].c_str(), loaded);
-    if (tokenizer_path.empty() && !G.tok) {   // a .gguf carries its tokenizer
-      const std::string tj = ckpts[ci]->tokenizer_json();
-      if (!tj.empty()) {
-        std::string err;
-        G.tok.reset(new BpeTokenizer());
-        if (!G.tok->load_json(tj, &err)) { fprintf(stderr, "tokenizer embedded in %s: %s\n", weight_files[ci].c_str(), err.c_str()); return 2; }
-      }
-    }
-  }
-  ckpts.clear();
+  cfg.queue_max = queue_max; cfg.queue_timeout_ms = queue_timeout_ms; cfg.request_timeout_ms = request_timeout_ms;
+  G.vocab = cfg.model.vocab; G.max_ctx = max_ctx; G.queue_timeout_ms = queue_timeout_ms; G.request_timeout_ms = request_timeout_ms;
+  // tokenizer: --tokenizer file, else the one a .gguf carries
+  std::string tok_json, tok_src = tokenizer_path;
   if (!tokenizer_path.empty()) {
     std::ifstream f(tokenizer_path, std::ios::binary);
     std::stringstream ss; ss << f.rdbuf();
+    if (!f) { fprintf(stderr, "tokenizer %s: cannot read\n", tokenizer_path.c_str()); return 2; }
+    tok_json = ss.str();
+  } else {
+    for (size_t ci = 0; ci < ckpts.size() && tok_json.empty(); ++ci) { tok_json = ckpts[ci]->tokenizer_json(); tok_src = "embedded in " + weight_files[ci]; }
+  }
+  if (!tok_json.empty()) {
     std::string err;
     G.tok.reset(new BpeTokenizer());
-    if (!f || !G.tok->load_json(ss.str(), &err)) { fprintf(stderr, "tokenizer %s: %s\n", tokenizer_path.c_str(), f ? err.c_str() : "cannot read"); return 2; }
-  }
-  if (G.tok) {
+    if (!G.tok->load_json(tok_json, &err)) { fprintf(stderr, "tokenizer %s: %s\n", tok_src.c_str(), err.c_str()); return 2; }
     if (G.tok->vocab_size() > G.vocab) { fprintf(stderr, "tokenizer has %u entries, the model only %u\n", G.tok->vocab_size(), G.vocab); return 2; }
     for (const char* name : {"<|eot_id|>", "<|end_of_text|>", "<|eom_id|>"}) { const int32_t id = G.tok->special_id(name); if (id >= 0) G.stop_ids.push_back(id); }
     fprintf(stderr, "tokenizer: %u entries, %zu stop ids\n", G.tok->vocab_size(), G.stop_ids.size());
   }
+  if (dry_run) {   // everything that does not need the GPU has been checked: report and leave
+    const llmlb_model_config& m = cfg.model;
+    printf("{\"dry_run\":true,\"model\":{\"hidden\":%u,\"n_layers\":%u,\"n_heads\":%u,\"n_kv_heads\":%u,\"head_dim\":%u,\"ffn\":%u,\"vocab\":%u},"
+           "\"tensors_to_load\":%zu,\"lm_head_tied\":%s,\"tokenizer_entries\":%u,\"stop_ids\":%zu}\n",
+           m.hidden, m.n_layers, m.n_heads, m.n_kv_heads, m.head_dim, m.ffn, m.vocab, plan.loads.size(), plan.lm_head_tied ? "true" : "false",
+           G.tok ? G.tok->vocab_size() : 0u, G.stop_ids.size());
+    return 0;
+  }
+  if (llmlb_engine_create(&cfg, &G.eng) != LLMLB_OK) { fprintf(stderr, "engine: %s\n", llmlb_last_error()); return 2; }
+  {
+    std::vector<uint16_t> bits;
+    for (const WeightPlan::Load& ld : plan.loads) {
+      const CkptTensor& t = ckpts[ld.ckpt]->tensors()[ld.index];
+      std::string err;
+      if (!ckpts[ld.ckpt]->read_bf16(ld.index, &bits, &err)) { fprintf(stderr, "weights: %s\n", err.c_str()); return 2; }
+      if (llmlb_engine_load_tensor(G.eng, ld.as.c_str(), bits.data(), t.rows, t.cols) != LLMLB_OK) { fprintf(stderr, "weights: %s: %s\n", ld.as.c_str(), llmlb_last_error()); return 2; }
+    }
+    if (!plan.loads.empty()) fprintf(stderr, "weights: %zu tensors loaded from %zu file(s)%s\n", plan.loads.size(), ckpts.size(), plan.lm_head_tied ? " (lm_head tied to the embedding)" : "");
+  }
+  ckpts.clear();
   G.lm.add_endpoint("local", true, false);
   G.lm.add_model("local", G.model_id, "");
   int ls = socket(AF_INET, SOCK_STREAM, 0), one = 1;
