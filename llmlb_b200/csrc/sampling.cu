@@ -11,12 +11,18 @@
 // Thresholds are found by an 8-bit radix select over the (monotone) bit pattern of e_i: each
 // pass histograms count and mass per bin in shared memory and a single warp suffix-scans the
 // 256 bins with shuffles to pick the bin where the cumulative crosses the target.
+// The per-bin masses are accumulated in 2^-40 FIXED POINT with integer atomics: integer addition is
+// associative, so the threshold — and with it the sampled token — does not depend on the order in
+// which threads reach the atomics.  Tensor-parallel ranks sample the same all-gathered logits
+// independently and must agree bit for bit (their schedulers replay each other's finishes).
 #include "../../include/llmlb_b200.h"
 #include "common.cuh"
 
 namespace llmlb {
 
 constexpr int kSampThreads = 1024;
+typedef unsigned long long u64q;   // probability mass in units of 2^-40 (e <= 1, vocab < 2^17: sums stay below 2^58)
+__device__ __forceinline__ u64q mass_q(float e) { return (u64q)__float2ull_rd(e * 1099511627776.f); }
 
 __device__ __forceinline__ float block_reduce_max(float v, float* red) {
   v = warp_max(v);
@@ -42,15 +48,15 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 // mode 1: largest key v such that mass(e >= v)  >= target_mass
 __device__ uint32_t radix_select(const float* __restrict__ logits, uint32_t vocab, float inv_t,
                                  float zmax, uint32_t floor_key, int mode, uint32_t target_count,
-                                 float target_mass, int* s_cnt, float* s_mass, uint32_t* s_sel,
-                                 float* s_above) {
+                                 u64q target_mass, int* s_cnt, u64q* s_mass, uint32_t* s_sel,
+                                 u64q* s_above) {
   uint32_t prefix = 0, prefix_mask = 0;
   uint32_t cnt_above = 0;
-  float mass_above = 0.f;
+  u64q mass_above = 0;
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += kSampThreads) {
       s_cnt[i] = 0;
-      s_mass[i] = 0.f;
+      s_mass[i] = 0;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < vocab; i += kSampThreads) {
@@ -59,7 +65,7 @@ __device__ uint32_t radix_select(const float* __restrict__ logits, uint32_t voca
       if (key >= floor_key && (key & prefix_mask) == prefix) {
         uint32_t b = (key >> shift) & 255u;
         atomicAdd(&s_cnt[b], 1);
-        if (mode == 1) atomicAdd(&s_mass[b], e);
+        if (mode == 1) atomicAdd(&s_mass[b], mass_q(e));
       }
     }
     __syncthreads();
@@ -67,9 +73,9 @@ __device__ uint32_t radix_select(const float* __restrict__ logits, uint32_t voca
       // suffix scan from bin 255 down: lane l owns bins [255-8l-7, 255-8l]
       const int lane = threadIdx.x;
       int c_loc[8];
-      float m_loc[8];
+      u64q m_loc[8];
       int c_sum = 0;
-      float m_sum = 0.f;
+      u64q m_sum = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int b = 255 - (lane * 8 + j);
@@ -79,18 +85,18 @@ __device__ uint32_t radix_select(const float* __restrict__ logits, uint32_t voca
         m_sum += m_loc[j];
       }
       int c_inc = c_sum;
-      float m_inc = m_sum;
+      u64q m_inc = m_sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         int c2 = __shfl_up_sync(0xffffffffu, c_inc, o);
-        float m2 = __shfl_up_sync(0xffffffffu, m_inc, o);
+        u64q m2 = __shfl_up_sync(0xffffffffu, m_inc, o);
         if (lane >= o) { c_inc += c2; m_inc += m2; }
       }
       int c_run = c_inc - c_sum + int(cnt_above);   // mass/count strictly above this lane's bins
-      float m_run = m_inc - m_sum + mass_above;
+      u64q m_run = m_inc - m_sum + mass_above;
       int found_bin = -1;
       int c_at = 0;
-      float m_at = 0.f;
+      u64q m_at = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         bool hit = (mode == 0) ? (uint32_t(c_run + c_loc[j]) >= target_count)
@@ -125,7 +131,7 @@ __device__ uint32_t radix_select(const float* __restrict__ logits, uint32_t voca
         int src = __ffs(ballot) - 1;
         int fb = __shfl_sync(0xffffffffu, found_bin, src);
         int ca = __shfl_sync(0xffffffffu, c_at, src);
-        float ma = __shfl_sync(0xffffffffu, m_at, src);
+        u64q ma = __shfl_sync(0xffffffffu, m_at, src);
         if (lane == 0) {
           s_sel[0] = uint32_t(fb);
           s_sel[1] = uint32_t(ca);
@@ -152,9 +158,10 @@ sample_kernel(const float* __restrict__ logits_all, uint32_t vocab,
   __shared__ float red[32];
   __shared__ int red_i[32];
   __shared__ int s_cnt[256];
-  __shared__ float s_mass[256];
+  __shared__ u64q s_mass[256];
   __shared__ uint32_t s_sel[4];
-  __shared__ float s_above[2];
+  __shared__ u64q s_above[2];
+  __shared__ u64q red_q[32];
   __shared__ float s_warp_tot[32];
   __shared__ int s_result;
 
@@ -200,17 +207,24 @@ sample_kernel(const float* __restrict__ logits_all, uint32_t vocab,
   uint32_t floor_key = 0;
   const int32_t k = top_k ? top_k[row] : 0;
   if (k > 0 && uint32_t(k) < vocab)
-    floor_key = radix_select(logits, vocab, inv_t, zm, 0u, 0, uint32_t(k), 0.f, s_cnt, s_mass,
+    floor_key = radix_select(logits, vocab, inv_t, zm, 0u, 0, uint32_t(k), 0ull, s_cnt, s_mass,
                              s_sel, s_above);
   const float p = top_p ? top_p[row] : 1.f;
   if (p > 0.f && p < 1.f) {
-    float mass = 0.f;
+    u64q mass = 0;   // kept mass, same fixed point as the bins (integer sums: order-free)
     for (uint32_t i = threadIdx.x; i < vocab; i += kSampThreads) {
       float e = __expf(logits[i] * inv_t - zm);
-      if (__float_as_uint(e) >= floor_key) mass += e;
+      if (__float_as_uint(e) >= floor_key) mass += mass_q(e);
     }
-    mass = block_reduce_sum(mass, red);
-    floor_key = radix_select(logits, vocab, inv_t, zm, floor_key, 1, 0u, p * mass, s_cnt, s_mass,
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mass += __shfl_xor_sync(0xffffffffu, mass, o);
+    if (lane == 0) red_q[warp] = mass;
+    __syncthreads();
+    mass = 0;
+    for (int w = 0; w < 32; ++w) mass += red_q[w];
+    __syncthreads();
+    const u64q target_q = (u64q)__double2ull_rd(double(p) * double(mass));
+    floor_key = radix_select(logits, vocab, inv_t, zm, floor_key, 1, 0u, target_q, s_cnt, s_mass,
                              s_sel, s_above);
   }
 

@@ -189,6 +189,68 @@ bool LoadManager::finish_request(const std::string& eid, bool success, uint64_t 
   e->output_tokens += output_tokens;
   return true;
 }
+bool LoadManager::begin_request_lease(const std::string& eid, RequestLease* out) {
+  if (!begin_request(eid)) return false;   // EndpointNotFound (balancer/mod.rs:2274-2276)
+  *out = RequestLease(this, eid);
+  return true;
+}
+bool LoadManager::finish_request_outcome(const std::string& eid, RequestOutcome outcome, uint64_t duration_ms,
+                                         const TokenUsage* usage) {
+  std::lock_guard<std::mutex> lk(mu_);
+  Endpoint* e = find(eid);
+  if (!e) return false;
+  if (outcome == RequestOutcome::Queued) return true;   // mod.rs:2300-2301: nothing moves
+  if (e->active_requests) e->active_requests -= 1;
+  (outcome == RequestOutcome::Success ? e->success : e->errors) += 1;
+  e->latency_ms_sum += duration_ms;
+  if (usage) {   // mod.rs:2376-2396
+    if (usage->has_in) e->input_tokens += usage->in;
+    if (usage->has_out) e->output_tokens += usage->out;
+    if (usage->has_total) e->total_tokens += usage->total;
+    else if (usage->has_in || usage->has_out) e->total_tokens += uint64_t(usage->has_in ? usage->in : 0) + (usage->has_out ? usage->out : 0);
+  }
+  return true;
+}
+bool LoadManager::endpoint_stats(const std::string& eid, Endpoint* out) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  const Endpoint* e = find(eid);
+  if (!e) return false;
+  *out = *e;
+  return true;
+}
+double LoadManager::average_latency_ms(const std::string& eid) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  const Endpoint* e = find(eid);
+  const uint64_t completed = e ? e->success + e->errors : 0;
+  return completed ? double(e->latency_ms_sum) / double(completed) : -1.0;
+}
+
+RequestLease::RequestLease(LoadManager* lm, std::string endpoint_id)
+    : lm_(lm), endpoint_id_(std::move(endpoint_id)), started_(std::chrono::steady_clock::now()) {}
+RequestLease::RequestLease(RequestLease&& o) noexcept : lm_(o.lm_), endpoint_id_(std::move(o.endpoint_id_)), started_(o.started_) { o.lm_ = nullptr; }
+RequestLease& RequestLease::operator=(RequestLease&& o) noexcept {
+  if (this != &o) {
+    if (lm_) lm_->finish_request_outcome(endpoint_id_, RequestOutcome::Error, elapsed_ms(), nullptr);   // the lease being overwritten leaks
+    lm_ = o.lm_; endpoint_id_ = std::move(o.endpoint_id_); started_ = o.started_;
+    o.lm_ = nullptr;
+  }
+  return *this;
+}
+RequestLease::~RequestLease() {   // lease.rs:71-100: dropped without complete => Error, elapsed time
+  if (lm_) lm_->finish_request_outcome(endpoint_id_, RequestOutcome::Error, elapsed_ms(), nullptr);
+  lm_ = nullptr;
+}
+uint64_t RequestLease::elapsed_ms() const {
+  return uint64_t(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - started_).count());
+}
+bool RequestLease::complete(RequestOutcome outcome, uint64_t duration_ms) { return complete_with_tokens(outcome, duration_ms, nullptr); }
+bool RequestLease::complete_with_tokens(RequestOutcome outcome, uint64_t duration_ms, const TokenUsage* usage) {
+  LoadManager* lm = lm_;
+  lm_ = nullptr;                       // take(): a second complete, or the destructor, is a no-op
+  if (!lm) return true;
+  return lm->finish_request_outcome(endpoint_id_, outcome, duration_ms, usage);
+}
+
 uint32_t LoadManager::active_requests(const std::string& eid) const {
   std::lock_guard<std::mutex> lk(mu_);
   const Endpoint* e = find(eid);
@@ -196,6 +258,22 @@ uint32_t LoadManager::active_requests(const std::string& eid) const {
 }
 
 // ---------------------------------------------------------------- usage / accumulator --------
+TokenUsage extract_or_estimate_tokens(const Json& body, const std::string* request_text, const std::string* response_text,
+                                      TokenCountFn count, void* ctx) {
+  TokenUsage u;
+  if (extract_usage_from_response(body, &u)) return u;     // the usage field wins (token/mod.rs:241-244)
+  u = TokenUsage{};
+  auto est = [&](const std::string* t, bool* has, uint32_t* v) {
+    if (!t || !count) return;
+    const int64_t n = count(*t, ctx);
+    if (n >= 0) { *has = true; *v = uint32_t(n); }
+  };
+  est(request_text, &u.has_in, &u.in);
+  est(response_text, &u.has_out, &u.out);
+  if (u.has_in || u.has_out) { u.has_total = true; u.total = (u.has_in ? u.in : 0) + (u.has_out ? u.out : 0); }
+  return u;
+}
+
 bool extract_usage_from_response(const Json& body, TokenUsage* u) {
   const Json* usage = body.get("usage");
   if (!usage) {
@@ -673,6 +751,41 @@ size_t llmlb_lm_lookup_keys(void* p, const char* model, char* out, size_t cap) {
 int llmlb_lm_begin_request(void* p, const char* eid) { return static_cast<LoadManager*>(p)->begin_request(eid) ? 0 : -1; }
 int llmlb_lm_finish_request(void* p, const char* eid, int success, uint64_t ms, uint64_t tokens) { return static_cast<LoadManager*>(p)->finish_request(eid, success != 0, ms, tokens) ? 0 : -1; }
 uint32_t llmlb_lm_active(void* p, const char* eid) { return static_cast<LoadManager*>(p)->active_requests(eid); }
+// leases: begin -> handle; complete (usage fields < 0 = absent) or drop (leak: the destructor finishes it as Error)
+void* llmlb_lm_lease_begin(void* p, const char* eid) {
+  RequestLease* l = new RequestLease();
+  if (!static_cast<LoadManager*>(p)->begin_request_lease(eid, l)) { delete l; return nullptr; }
+  return l;
+}
+int llmlb_lm_lease_complete(void* lease, int outcome, uint64_t ms, int with_usage, int64_t in, int64_t out, int64_t total) {
+  RequestLease* l = static_cast<RequestLease*>(lease);
+  TokenUsage u;
+  if (in >= 0) { u.has_in = true; u.in = uint32_t(in); }
+  if (out >= 0) { u.has_out = true; u.out = uint32_t(out); }
+  if (total >= 0) { u.has_total = true; u.total = uint32_t(total); }
+  return l->complete_with_tokens(RequestOutcome(outcome), ms, with_usage ? &u : nullptr) ? 0 : -1;
+}
+void llmlb_lm_lease_drop(void* lease) { delete static_cast<RequestLease*>(lease); }
+// out[8]: active, total_assigned, success, errors, latency_ms_sum, input_tokens, output_tokens, total_tokens
+int llmlb_lm_stats(void* p, const char* eid, uint64_t* out8) {
+  Endpoint e;
+  if (!static_cast<LoadManager*>(p)->endpoint_stats(eid, &e)) return -1;
+  const uint64_t v[8] = {e.active_requests, e.total_requests, e.success, e.errors, e.latency_ms_sum, e.input_tokens, e.output_tokens, e.total_tokens};
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  return 0;
+}
+double llmlb_lm_average_latency(void* p, const char* eid) { return static_cast<LoadManager*>(p)->average_latency_ms(eid); }
+// extract_or_estimate_tokens with a whitespace-word counter standing in for the tokenizer (tests);
+// returns has-bits (1 in, 2 out, 4 total), values in out3
+static int64_t count_words(const std::string& t, void*) { int64_t n = 0; bool in = false; for (char c : t) { const bool w = c != ' ' && c != '\n' && c != '\t'; if (w && !in) ++n; in = w; } return n; }
+int llmlb_extract_or_estimate(const char* body_json, const char* req_text, const char* resp_text, int with_counter, uint32_t* out3) {
+  Json body;
+  if (!Json::parse(body_json ? body_json : "null", &body)) body = Json();
+  std::string rq = req_text ? req_text : "", rs = resp_text ? resp_text : "";
+  TokenUsage u = extract_or_estimate_tokens(body, req_text ? &rq : nullptr, resp_text ? &rs : nullptr, with_counter ? count_words : nullptr, nullptr);
+  out3[0] = u.in; out3[1] = u.out; out3[2] = u.total;
+  return (u.has_in ? 1 : 0) | (u.has_out ? 2 : 0) | (u.has_total ? 4 : 0);
+}
 
 static void usage_out(const TokenUsage& u, int64_t out[3]) {
   out[0] = u.has_in ? int64_t(u.in) : -1; out[1] = u.has_out ? int64_t(u.out) : -1; out[2] = u.has_total ? int64_t(u.total) : -1;

@@ -17,6 +17,7 @@
 //   stream_options.include_usage injection  llmlb/src/api/openai.rs:977-992
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -46,9 +47,38 @@ struct Endpoint {
   // LoadManager state (balancer/types.rs:157-173)
   uint32_t active_requests = 0;
   uint64_t total_requests = 0, success = 0, errors = 0, latency_ms_sum = 0, output_tokens = 0;
+  uint64_t input_tokens = 0, total_tokens = 0;   // finish_request_with_tokens (balancer/mod.rs:2346-2425)
 };
 
 enum SelectError { kSelectOk = 0, kNoCapableEndpoints = 1, kNoEndpointsAvailable = 2 };
+enum class RequestOutcome { Success = 0, Error = 1, Queued = 2 };
+struct TokenUsage { bool has_in = false, has_out = false, has_total = false; uint32_t in = 0, out = 0, total = 0; };
+class LoadManager;
+
+// RAII request lease (llmlb/src/balancer/lease.rs:16-100): a request that is neither completed
+// explicitly nor survives to its normal end (early return, exception, client gone) still gives
+// its active slot back — the destructor finishes it as Error with the elapsed time.
+class RequestLease {
+ public:
+  RequestLease() = default;
+  RequestLease(LoadManager* lm, std::string endpoint_id);
+  RequestLease(RequestLease&& o) noexcept;
+  RequestLease& operator=(RequestLease&& o) noexcept;
+  RequestLease(const RequestLease&) = delete;
+  RequestLease& operator=(const RequestLease&) = delete;
+  ~RequestLease();
+  const std::string& endpoint_id() const { return endpoint_id_; }
+  uint64_t elapsed_ms() const;
+  bool armed() const { return lm_ != nullptr; }
+  // both return true when there is nothing to do (already completed / never armed), like the
+  // reference's Ok(()) for a lease without a load manager (lease.rs:47-49)
+  bool complete(RequestOutcome outcome, uint64_t duration_ms);
+  bool complete_with_tokens(RequestOutcome outcome, uint64_t duration_ms, const TokenUsage* usage);
+ private:
+  LoadManager* lm_ = nullptr;
+  std::string endpoint_id_;
+  std::chrono::steady_clock::time_point started_{};
+};
 
 class LoadManager {
  public:
@@ -68,6 +98,13 @@ class LoadManager {
   bool begin_request(const std::string& endpoint_id);
   bool finish_request(const std::string& endpoint_id, bool success, uint64_t duration_ms,
                       uint64_t output_tokens);
+  // balancer/mod.rs:2273-2425.  Queued leaves every counter alone; usage == nullptr = finish_request
+  bool begin_request_lease(const std::string& endpoint_id, RequestLease* out);
+  bool finish_request_outcome(const std::string& endpoint_id, RequestOutcome outcome, uint64_t duration_ms,
+                              const TokenUsage* usage);
+  bool endpoint_stats(const std::string& endpoint_id, Endpoint* out) const;   // copy of the counters
+  // mean latency over completed requests, < 0 when none completed (balancer/types.rs:188-195)
+  double average_latency_ms(const std::string& endpoint_id) const;
   uint32_t active_requests(const std::string& endpoint_id) const;
 
  private:
@@ -99,7 +136,6 @@ struct InferenceLatency {
 // 60-minute request history (balancer/mod.rs:2643-2658, 2973-3060): per-minute success / error
 // counts, newest minute incremented in place, points older than the window dropped on insert;
 // window(now) = exactly 60 points, oldest first, zero-filled.  Timestamps are unix seconds.
-enum class RequestOutcome { Success = 0, Error = 1, Queued = 2 };
 struct RequestHistoryPoint { int64_t minute = 0; uint64_t success = 0, error = 0; };
 class RequestHistory {
  public:
@@ -113,8 +149,14 @@ class RequestHistory {
   std::vector<RequestHistoryPoint> points_;
 };
 
-struct TokenUsage { bool has_in = false, has_out = false, has_total = false; uint32_t in = 0, out = 0, total = 0; };
 bool extract_usage_from_response(const Json& body, TokenUsage* usage);
+// token/mod.rs:235-259: usage when the body carries one, else an estimate of the request / response
+// texts.  The reference estimates with tiktoken's cl100k_base ranks (token/mod.rs:217-223), a
+// third-party table; an in-process endpoint has the MODEL's tokenizer instead, so `count` is
+// that tokenizer's encode-with-specials length (nullptr or a negative return = cannot estimate).
+typedef int64_t (*TokenCountFn)(const std::string& text, void* ctx);
+TokenUsage extract_or_estimate_tokens(const Json& body, const std::string* request_text, const std::string* response_text,
+                                      TokenCountFn count, void* ctx);
 
 class StreamingTokenAccumulator {
  public:

@@ -248,7 +248,10 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     send_err(st, s.max_tokens ? llmlb_last_error() : "prompt exceeds the context length", st == 400 ? "invalid_request_error" : "endpoint_request_error");
     return;
   }
-  G.lm.begin_request(ep);
+  // every exit path below gives the endpoint's active slot back: a path that forgets to complete
+  // the lease finishes it as Error when the lease goes out of scope (balancer/lease.rs:71-100)
+  RequestLease lease;
+  if (!G.lm.begin_request_lease(ep, &lease)) { llmlb_request_cancel(G.eng, rid); llmlb_request_release(G.eng, rid); send_err(502, "endpoint disappeared", "endpoint_request_error"); return; }
   const uint64_t n = G.seq.fetch_add(1);
   const std::string id = std::string(kind == 0 ? "chatcmpl-" : kind == 1 ? "resp_" : "cmpl-") + std::to_string(n);
   const int64_t created = int64_t(std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch()).count());
@@ -312,7 +315,10 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   const uint64_t ms = uint64_t(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count());
   // streaming drop still counts as success when tokens flowed (openai.rs:2556-2648)
   const bool success = finish == LLMLB_FINISH_STOP || finish == LLMLB_FINISH_LENGTH || (client_gone && completion_tokens > 0);
-  G.lm.finish_request(ep, success, ms, completion_tokens);
+  {
+    TokenUsage tu; tu.has_in = tu.has_out = tu.has_total = true; tu.in = prompt_tokens; tu.out = completion_tokens; tu.total = prompt_tokens + completion_tokens;
+    lease.complete_with_tokens(success ? RequestOutcome::Success : RequestOutcome::Error, ms, &tu);
+  }
   if (success && completion_tokens) G.lm.update_tps(ep, pm.base, api, completion_tokens, ms);
   const char* fr = finish == LLMLB_FINISH_STOP ? "stop" : "length";
   // failures map like the gateway maps an upstream's (openai.rs:862-882, openai_util.rs:86-134)

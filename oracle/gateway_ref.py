@@ -133,6 +133,108 @@ class LoadManager:
 
 
 # --- llmlb/src/token/mod.rs:182-206  extract_usage_from_response ------------------------------
+# ---- request leases and completion counters -------------------------------------------------------
+# llmlb/src/balancer/mod.rs:2273-2425 (begin_request / finish_request / finish_request_with_tokens),
+# llmlb/src/balancer/lease.rs:16-100 (RequestLease: complete* consume the lease; a lease DROPPED
+# without complete finishes as Error with the elapsed time), balancer/types.rs:188-195 (average latency).
+class EndpointLoadState:
+    def __init__(self):
+        self.assigned_active = 0
+        self.total_assigned = 0
+        self.success_count = 0
+        self.error_count = 0
+        self.total_latency_ms = 0
+        self.total_input_tokens = 0
+        self.total_output_tokens = 0
+        self.total_tokens = 0
+
+    def average_latency_ms(self):
+        done = self.success_count + self.error_count
+        return None if done == 0 else self.total_latency_ms / done
+
+    def as_list(self):
+        return [self.assigned_active, self.total_assigned, self.success_count, self.error_count, self.total_latency_ms,
+                self.total_input_tokens, self.total_output_tokens, self.total_tokens]
+
+
+class LeaseBook:
+    """The lease side of LoadManager, keyed by endpoint id."""
+
+    def __init__(self, endpoint_ids):
+        self.state = {e: EndpointLoadState() for e in endpoint_ids}
+
+    def begin_request(self, endpoint_id):
+        if endpoint_id not in self.state:
+            return None                                  # LbError::EndpointNotFound
+        st = self.state[endpoint_id]
+        st.assigned_active += 1
+        st.total_assigned += 1
+        return RequestLease(self, endpoint_id)
+
+    def finish_request(self, endpoint_id, outcome, duration_ms, usage=None):
+        """outcome: "success" | "error" | "queued"; usage: dict with optional input/output/total or None"""
+        if endpoint_id not in self.state:
+            return False
+        st = self.state[endpoint_id]
+        if outcome == "queued":
+            return True
+        if st.assigned_active > 0:
+            st.assigned_active -= 1
+        if outcome == "success":
+            st.success_count += 1
+        else:
+            st.error_count += 1
+        st.total_latency_ms += int(duration_ms)
+        if usage is not None:
+            i, o, t = usage.get("input"), usage.get("output"), usage.get("total")
+            if i is not None:
+                st.total_input_tokens += i
+            if o is not None:
+                st.total_output_tokens += o
+            if t is None and (i is not None or o is not None):
+                t = (i or 0) + (o or 0)
+            if t is not None:
+                st.total_tokens += t
+        return True
+
+
+class RequestLease:
+    def __init__(self, book, endpoint_id):
+        self.book, self.endpoint_id = book, endpoint_id
+
+    def complete(self, outcome, duration_ms, usage=None):
+        book, self.book = self.book, None                # take(): later complete / drop is a no-op
+        if book is None:
+            return True
+        return book.finish_request(self.endpoint_id, outcome, duration_ms, usage)
+
+    def drop(self, elapsed_ms=0):
+        """Rust's Drop: a lease that was never completed finishes as Error."""
+        book, self.book = self.book, None
+        if book is not None:
+            book.finish_request(self.endpoint_id, "error", elapsed_ms)
+
+
+def extract_or_estimate_tokens(body, request_text, response_text, count):
+    """llmlb/src/token/mod.rs:235-259.  `count(text) -> int | None` stands for estimate_tokens
+    (:217-223; tiktoken cl100k_base in the reference — a third-party rank table that is not in this image;
+    the in-process endpoint counts with the model's own tokenizer instead).  Returns dict(input, output, total)."""
+    u = extract_usage_from_response(body)
+    if u is not None:
+        return u
+    i = count(request_text) if (request_text is not None and count) else None
+    o = count(response_text) if (response_text is not None and count) else None
+    if i is not None and o is not None:
+        t = i + o
+    elif i is not None:
+        t = i
+    elif o is not None:
+        t = o
+    else:
+        t = None
+    return {"input_tokens": i, "output_tokens": o, "total_tokens": t}
+
+
 def extract_usage_from_response(body):
     if not isinstance(body, dict):
         return None

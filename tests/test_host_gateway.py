@@ -727,3 +727,123 @@ def test_stop_matcher(H):
             pieces.append(raw[pos:pos + step])
             pos += step
         assert run(stops, pieces) == _stop_ref(stops, text), (stops, text)
+
+
+# ---- request leases (a1.9) and the usage-or-estimate fallback (a1.13) ------------------------------
+def _lease_api(H):
+    vp, cp, u64, i64 = C.c_void_p, C.c_char_p, C.c_uint64, C.c_int64
+    H.llmlb_lm_lease_begin.restype, H.llmlb_lm_lease_begin.argtypes = vp, [vp, cp]
+    H.llmlb_lm_lease_complete.restype, H.llmlb_lm_lease_complete.argtypes = C.c_int, [vp, C.c_int, u64, C.c_int, i64, i64, i64]
+    H.llmlb_lm_lease_drop.restype, H.llmlb_lm_lease_drop.argtypes = None, [vp]
+    H.llmlb_lm_stats.restype, H.llmlb_lm_stats.argtypes = C.c_int, [vp, cp, C.POINTER(u64)]
+    H.llmlb_lm_average_latency.restype, H.llmlb_lm_average_latency.argtypes = C.c_double, [vp, cp]
+    H.llmlb_extract_or_estimate.restype, H.llmlb_extract_or_estimate.argtypes = C.c_int, [cp, cp, cp, C.c_int, C.POINTER(C.c_uint32)]
+
+
+def _stats(H, lm, eid):
+    out = (C.c_uint64 * 8)()
+    assert H.llmlb_lm_stats(lm, b(eid), out) == 0
+    return [int(v) for v in out]
+
+
+OUTCOME = {"success": 0, "error": 1, "queued": 2}
+
+
+def test_lease_known_answers_from_the_reference_tests(H):
+    """llmlb/src/balancer/mod.rs:222-283: complete() releases the active counter and counts a success;
+    a lease dropped without complete releases it too and counts a failure.  types.rs:487-497: mean latency."""
+    _lease_api(H)
+    lm = H.llmlb_lm_create()
+    H.llmlb_lm_add_endpoint(lm, b"ep", 1, 0)
+    lease = H.llmlb_lm_lease_begin(lm, b"ep")
+    assert lease and _stats(H, lm, "ep")[0] == 1                        # active_before == 1
+    assert H.llmlb_lm_lease_complete(lease, OUTCOME["success"], 3, 0, -1, -1, -1) == 0
+    st = _stats(H, lm, "ep")
+    assert st[0] == 0 and st[2] == 1                                    # active 0, successful_requests 1
+    assert H.llmlb_lm_lease_complete(lease, OUTCOME["error"], 9, 0, -1, -1, -1) == 0   # consumed: Ok(()) and nothing moves
+    assert _stats(H, lm, "ep") == st
+    H.llmlb_lm_lease_drop(lease)                                        # dropping a completed lease: nothing
+    assert _stats(H, lm, "ep") == st
+    leaked = H.llmlb_lm_lease_begin(lm, b"ep")
+    assert _stats(H, lm, "ep")[0] == 1
+    H.llmlb_lm_lease_drop(leaked)                                       # never completed -> Error
+    st = _stats(H, lm, "ep")
+    assert st[0] == 0 and st[3] == 1                                    # active 0, failed_requests 1
+    assert H.llmlb_lm_lease_begin(lm, b"nope") is None                  # EndpointNotFound
+    # 3 successes + 1 error, 800 ms in total -> 200 ms mean
+    lm2 = H.llmlb_lm_create()
+    H.llmlb_lm_add_endpoint(lm2, b"e", 1, 0)
+    assert H.llmlb_lm_average_latency(lm2, b"e") < 0                    # none completed -> None
+    for outcome, ms in (("success", 100), ("success", 300), ("error", 150), ("success", 250)):
+        l2 = H.llmlb_lm_lease_begin(lm2, b"e")
+        H.llmlb_lm_lease_complete(l2, OUTCOME[outcome], ms, 0, -1, -1, -1)
+        H.llmlb_lm_lease_drop(l2)
+    assert abs(H.llmlb_lm_average_latency(lm2, b"e") - 200.0) < 0.01
+    H.llmlb_lm_destroy(lm); H.llmlb_lm_destroy(lm2)
+
+
+def test_lease_sequences_match_the_oracle(H):
+    _lease_api(H)
+    rnd = random.Random(5)
+    for trial in range(60):
+        eps = ["a", "b", "c"][: rnd.randint(1, 3)]
+        lm = H.llmlb_lm_create()
+        for e in eps:
+            H.llmlb_lm_add_endpoint(lm, b(e), 1, 0)
+        book = G.LeaseBook(eps)
+        live = []
+        for _ in range(rnd.randint(5, 60)):
+            op = rnd.random()
+            if op < 0.45 or not live:
+                e = rnd.choice(eps)
+                live.append((H.llmlb_lm_lease_begin(lm, b(e)), book.begin_request(e)))
+            else:
+                h, o = live.pop(rnd.randrange(len(live)))
+                if op < 0.6:
+                    H.llmlb_lm_lease_drop(h); o.drop(0)                       # leaked
+                else:
+                    outcome = rnd.choice(["success", "error", "queued"])
+                    ms = rnd.randint(0, 5000)
+                    usage = None
+                    if rnd.random() < 0.7:
+                        usage = {k: (rnd.randint(0, 4000) if rnd.random() < 0.7 else None) for k in ("input", "output", "total")}
+                    f = lambda v: -1 if v is None else v
+                    assert H.llmlb_lm_lease_complete(h, OUTCOME[outcome], ms, 1 if usage is not None else 0,
+                                                     f(usage and usage["input"]), f(usage and usage["output"]), f(usage and usage["total"])) == 0
+                    assert o.complete(outcome, ms, usage)
+                    H.llmlb_lm_lease_drop(h); o.drop(0)                       # a completed lease going out of scope: nothing more
+            for e in eps:
+                st = _stats(H, lm, e)
+                assert st == book.state[e].as_list(), (trial, e)
+                # the mean ignores elapsed time of leaked leases only through duration 0 here
+                want = book.state[e].average_latency_ms()
+                got = H.llmlb_lm_average_latency(lm, b(e))
+                assert (want is None and got < 0) or abs(got - want) < 1e-9
+        for h, o in live:
+            H.llmlb_lm_lease_drop(h); o.drop(0)
+        for e in eps:   # ("queued" completions leave the active counter alone, like the reference: mod.rs:2300-2301)
+            assert _stats(H, lm, e) == book.state[e].as_list()
+        H.llmlb_lm_destroy(lm)
+
+
+def test_extract_or_estimate_tokens(H):
+    """llmlb/src/token/mod.rs:418-460: usage wins; without it both texts are estimated and total is
+    their sum; nothing to go on -> empty.  The counter here is a word counter (the reference's is
+    tiktoken cl100k_base, the shim's the model tokenizer): the structure is what is pinned."""
+    _lease_api(H)
+    out = (C.c_uint32 * 3)()
+    words = lambda t: len(t.split())
+    cases = [({"usage": {"prompt_tokens": 100, "completion_tokens": 50, "total_tokens": 150}}, "What is 2+2?", "2+2=4"),
+             ({"choices": [{"message": {"content": "The answer is 4."}}]}, "What is 2+2?", "The answer is 4."),
+             ({}, None, None), ({}, "only a request text", None), ({}, None, "only the response"),
+             ({"response": {"usage": {"input_tokens": 7, "output_tokens": 9}}}, "x", "y")]
+    for body, rq, rs in cases:
+        bits = H.llmlb_extract_or_estimate(json.dumps(body).encode(), b(rq), b(rs), 1, out)
+        want = G.extract_or_estimate_tokens(body, rq, rs, words)
+        got = {"input_tokens": out[0] if bits & 1 else None, "output_tokens": out[1] if bits & 2 else None, "total_tokens": out[2] if bits & 4 else None}
+        assert got == want, (body, got, want)
+    assert H.llmlb_extract_or_estimate(b"{}", b"some text", b"more", 0, out) == 0      # no counter: cannot estimate
+    bits = H.llmlb_extract_or_estimate(json.dumps(cases[0][0]).encode(), b"q", b"a", 1, out)
+    assert bits == 7 and list(out) == [100, 50, 150]
+    bits = H.llmlb_extract_or_estimate(json.dumps(cases[1][0]).encode(), b"What is 2+2?", b"The answer is 4.", 1, out)
+    assert bits == 7 and out[2] == out[0] + out[1] and out[0] > 0 and out[1] > 0

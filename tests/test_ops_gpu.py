@@ -312,3 +312,55 @@ def test_sample_topk_topp_vs_oracle(L, V):
             assert margin < 1e-4, (r, got[r], tok, margin)
             bad += 1
     assert bad <= 2
+
+
+# ---- sampler against an INDEPENDENT definition (not oracle/sampling_ref.py, which restates the kernel) ----
+@pytest.mark.parametrize("temperature,top_k,top_p", [(0.7, 40, 0.9), (1.0, 0, 1.0), (1.3, 0, 0.6), (0.5, 7, 1.0)])
+def test_sample_distribution_chi_square(L, temperature, top_k, top_p):
+    """10^5 draws of one logits row (distinct RNG counters) against the textbook distribution computed
+    in fp64: softmax(logits / T), keep the k most probable, keep the smallest prefix of those (by
+    descending probability) whose mass reaches top_p, renormalise.  Every draw must fall inside the kept
+    set and the counts must pass a chi-square goodness-of-fit test."""
+    from scipy import stats
+    V, N = 512, 100_000
+    rs = np.random.RandomState(11)
+    row = (rs.randn(V) * 2.0).astype(np.float32)
+    z = row.astype(np.float64) / temperature
+    pr = np.exp(z - z.max()); pr /= pr.sum()
+    order = np.argsort(-pr, kind="stable")
+    keep = np.zeros(V, dtype=bool)
+    kk = top_k if 0 < top_k < V else V
+    keep[order[:kk]] = True
+    if 0.0 < top_p < 1.0:
+        pk = pr[order[:kk]]
+        cs = np.cumsum(pk)
+        n_keep = int(np.searchsorted(cs, top_p * cs[-1], side="left")) + 1
+        keep[:] = False
+        keep[order[:n_keep]] = True
+    want = np.where(keep, pr, 0.0); want /= want.sum()
+    logits = torch.from_numpy(row).to(dev()).repeat(N, 1).contiguous()
+    t = torch.full((N,), temperature, device=dev())
+    tp = torch.full((N,), top_p, device=dev())
+    tk = torch.full((N,), top_k, dtype=torch.int32, device=dev())
+    seed = torch.full((N,), 1234, dtype=torch.int64, device=dev())
+    step = torch.arange(N, dtype=torch.int64, device=dev())
+    out = torch.empty(N, dtype=torch.int32, device=dev())
+    ok(L.llmlb_op_sample(p(logits), N, V, p(t), p(tp), p(tk), p(seed), p(step), p(out), stream_ptr()))
+    sync()
+    got = np.bincount(out.cpu().numpy(), minlength=V).astype(np.float64)
+    assert got[~keep].sum() == 0, "draws outside the kept set: %s" % np.nonzero(got * ~keep)[0][:8]
+    # pool the tail so that every expected count is >= 5
+    idx = np.argsort(-want)
+    exp, obs = want[idx] * N, got[idx]
+    cut = int(np.searchsorted(-exp, -5.0))          # first index with expected < 5
+    if cut < len(exp):
+        exp = np.append(exp[:cut], exp[cut:].sum()); obs = np.append(obs[:cut], obs[cut:].sum())
+    nz = exp > 0
+    exp, obs = exp[nz], obs[nz]
+    chi2, pval = stats.chisquare(obs, exp * (obs.sum() / exp.sum()))
+    assert pval > 1e-4, (chi2, pval, len(exp))
+    # and the same call twice gives the same tokens (fixed-point masses: no order dependence)
+    out2 = torch.empty_like(out)
+    ok(L.llmlb_op_sample(p(logits), N, V, p(t), p(tp), p(tk), p(seed), p(step), p(out2), stream_ptr()))
+    sync()
+    assert torch.equal(out, out2)
