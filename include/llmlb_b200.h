@@ -82,7 +82,8 @@ typedef struct llmlb_engine_config {
   uint32_t queue_max;          /* waiting requests beyond this: submit returns LLMLB_E_QUEUE_FULL (gateway: 429) */
   uint32_t queue_timeout_ms;   /* a request still waiting for admission after this finishes QUEUE_TIMEOUT (504) */
   uint32_t request_timeout_ms; /* a request not finished this long after submit finishes DEADLINE (504 timeout) */
-  uint32_t reserved[5];
+  uint32_t attn_impl;          /* prefill attention: 0 = tcgen05 + TMEM + TMA (default), 1 = mma.sync baseline */
+  uint32_t reserved[4];
 } llmlb_engine_config;
 
 int llmlb_engine_create(const llmlb_engine_config* cfg, llmlb_engine** out);
@@ -238,6 +239,13 @@ int llmlb_op_prefill_attention(const void* qkv_bf16, const void* k_pages, const 
                                const int32_t* block_tables, uint32_t bt_stride,
                                const int32_t* tiles, uint32_t n_tiles, void* out_bf16,
                                uint32_t n_heads, uint32_t n_kv_heads, void* stream);
+/* a2.6 on the 5th-generation tensor cores (tcgen05.mma, S and PV in TMEM, Q/K/V staged by TMA; V is
+ * consumed MN-major straight from its [token][d] pages).  Same contract as above with q tiles of up to
+ * 128 rows; k_pages / v_pages are ONE layer's pool [n_pages][n_kv][64][128]; n_tokens = rows of qkv. */
+int llmlb_op_prefill_attention_tc(const void* qkv_bf16, uint32_t n_tokens, const void* k_pages,
+                                  const void* v_pages, uint32_t n_pages, const int32_t* block_tables,
+                                  uint32_t bt_stride, const int32_t* tiles, uint32_t n_tiles,
+                                  void* out_bf16, uint32_t n_heads, uint32_t n_kv_heads, void* stream);
 /* a2.4+a2.5+a2.7 decode: per sequence rotate the new q,k, append k,v, attend over the pages.
  * seq_lens[b] = tokens INCLUDING the new one; bt_rows[b] = block-table row of sequence b (NULL =
  * identity).  workspace: llmlb_op_decode_attention_ws(ws_seqs, n_heads, n_splits) bytes, zeroed

@@ -31,7 +31,11 @@ __global__ void __launch_bounds__(256)
 rope_append_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ positions,
                    const int32_t* __restrict__ page_of_token, const float2* __restrict__ rope,
                    __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
-                   uint32_t n_heads, uint32_t n_kv) {
+                   uint32_t n_heads, uint32_t n_kv, uint32_t pdl) {
+  // programmatic dependent launch: the attention kernel behind may set itself up now; this grid
+  // may itself have been scheduled before the QKV projection finished
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t t = blockIdx.x;
   const uint32_t width = (n_heads + 2 * n_kv) * kHeadDim;
   __nv_bfloat16* row = qkv + size_t(t) * width;
@@ -601,6 +605,28 @@ extern "C" int llmlb_op_rope_table(float* table, uint32_t max_pos, float theta, 
   return LLMLB_OK;
 }
 
+namespace llmlb {
+int rope_append_launch(void* qkv, const int32_t* positions, const int32_t* page_of_token, const float* rope_table,
+                       void* k_pages, void* v_pages, uint32_t n_tokens, uint32_t n_heads, uint32_t n_kv, bool pdl,
+                       cudaStream_t st) {
+  if (n_tokens == 0) return LLMLB_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_tokens);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rope_append_kernel, (__nv_bfloat16*)qkv, positions, page_of_token,
+                                      (const float2*)rope_table, (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages, n_heads, n_kv,
+                                      pdl ? 1u : 0u));
+  LLMLB_LAUNCH_CHECK();
+  return LLMLB_OK;
+}
+}  // namespace llmlb
+
 extern "C" int llmlb_op_rope_append(void* qkv, const int32_t* positions,
                                     const int32_t* page_of_token, const float* rope_table,
                                     void* k_pages, void* v_pages, uint32_t n_tokens,
@@ -609,12 +635,8 @@ extern "C" int llmlb_op_rope_append(void* qkv, const int32_t* positions,
     set_error("llmlb_op_rope_append: null argument");
     return LLMLB_E_INVALID_ARG;
   }
-  if (n_tokens == 0) return LLMLB_OK;
-  rope_append_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)qkv, positions, page_of_token, (const float2*)rope_table,
-      (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages, n_heads, n_kv);
-  LLMLB_LAUNCH_CHECK();
-  return LLMLB_OK;
+  return rope_append_launch(qkv, positions, page_of_token, rope_table, k_pages, v_pages, n_tokens, n_heads, n_kv, false,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int llmlb_op_prefill_attention(const void* qkv, const void* k_pages,

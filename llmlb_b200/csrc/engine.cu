@@ -54,6 +54,8 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
 void ks_set_trace(const TraceBuf& tb);
 void tc_set_trace(const TraceBuf& tb);
 void attn_set_trace(const TraceBuf& tb);
+void tp_set_trace(const TraceBuf& tb);
+void tc2_set_trace(const TraceBuf& tb);
 
 // tensor parallel (tp_common.cuh): fused GEMV consumer / producer of protocol A, pull kernels
 int gemv_tp_consume(const TpCtx& ctx, uint32_t coll_in, const void* w, const float* x_in, float* x_out,
@@ -64,6 +66,15 @@ int gemv_tp_push(const TpCtx& ctx, uint32_t coll_out, const void* w, const void*
 int ar_allreduce_add(const TpCtx& P, uint64_t off, float* x, uint64_t n, cudaStream_t st);
 int ar_allgather_cols(const TpCtx& P, uint64_t off, float* out, uint32_t rows, uint32_t cols_local, cudaStream_t st);
 constexpr uint32_t kTpMaxSplit = 4;   // K-split parts a push-RS GEMM may use (slot capacity)
+// prefill attention on tcgen05 (attention_tc.cu)
+int make_tmap_attn_q(CUtensorMap* m, const void* qkv, uint64_t n_tokens, uint64_t width);
+int make_tmap_attn_kv(CUtensorMap* m, const void* pool, uint64_t n_layers, uint64_t n_pages, uint64_t n_kv);
+int prefill_attention_tc_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, uint32_t layer,
+                                const int32_t* block_tables, uint32_t bt_stride, const int32_t* tiles, uint32_t n_tiles,
+                                void* out, uint32_t n_heads, uint32_t n_kv, bool pdl, cudaStream_t st);
+int rope_append_launch(void* qkv, const int32_t* positions, const int32_t* page_of_token, const float* rope_table,
+                       void* k_pages, void* v_pages, uint32_t n_tokens, uint32_t n_heads, uint32_t n_kv, bool pdl,
+                       cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
@@ -345,6 +356,8 @@ struct llmlb_engine {
   float* x_last = nullptr;       // [max_seqs][hidden]
   void* attn_ws = nullptr;
   CUtensorMap m_y[5]{}, m_attn[5]{}, m_h[5]{};  // box rows 16,32,64,128,256
+  CUtensorMap m_attn_q{}, m_kpool{}, m_vpool{};  // tcgen05 prefill attention: q rows of qkv, the K / V pools (5-D)
+  uint32_t pf_tile = 128;                         // q rows per prefill-attention tile (64 for the mma.sync baseline)
 
   // per-step metadata (device) + pinned staging ring
   int32_t *d_ids = nullptr, *d_pos = nullptr, *d_page_of_tok = nullptr, *d_tiles = nullptr,
@@ -486,6 +499,7 @@ int llmlb_engine::init() {
   }
   if (!(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank >= tp) { set_error("bad tp_size/tp_rank"); return LLMLB_E_INVALID_ARG; }
   if (cfg.gemm_impl != 0) { set_error("gemm_impl: only 0 (tcgen05 tiles) is built into the library"); return LLMLB_E_INVALID_ARG; }
+  if (cfg.attn_impl > 1) { set_error("attn_impl: 0 (tcgen05) or 1 (mma.sync baseline)"); return LLMLB_E_INVALID_ARG; }
   if (M.n_kv_heads == 0 || M.n_heads % M.n_kv_heads || M.n_kv_heads % tp || M.ffn % tp || M.vocab % tp ||
       ((M.n_heads / M.n_kv_heads) % 4) || M.hidden % 8 || (M.ffn / tp) % 8 || (M.vocab / tp) % 4 ||
       M.n_layers == 0 || M.vocab == 0) {
@@ -557,6 +571,9 @@ int llmlb_engine::alloc_all() {
   layer_pool_elems = size_t(n_pages) * nkv_l * kPageTokens * kHeadDim;
   RC(dmalloc(&k_pool, layer_pool_elems * M.n_layers));
   RC(dmalloc(&v_pool, layer_pool_elems * M.n_layers));
+  pf_tile = cfg.attn_impl == 0 ? 128 : 64;
+  RC(make_tmap_attn_kv(&m_kpool, k_pool, M.n_layers, n_pages, nkv_l));
+  RC(make_tmap_attn_kv(&m_vpool, v_pool, M.n_layers, n_pages, nkv_l));
   RC(dmalloc(&rope, size_t(cfg.max_ctx) * 64 * 2));
   RC(llmlb_op_rope_table(rope, cfg.max_ctx, M.rope_theta, st));
   RC(dmalloc(&d_block_tables, size_t(cfg.max_seqs) * pages_per_seq));
@@ -590,6 +607,7 @@ int llmlb_engine::alloc_all() {
     RC(dmalloc(&y, size_t(t_cap) * H));
   }
   RC(dmalloc(&qkv, size_t(t_cap) * qkv_w));
+  RC(make_tmap_attn_q(&m_attn_q, qkv, t_cap, qkv_w));
   RC(dmalloc(&attn, size_t(t_cap) * nq_l * kHeadDim));
   RC(dmalloc(&h, size_t(t_cap) * ffn_l));
   RC(dmalloc(&logits, size_t(cfg.max_seqs) * M.vocab));
@@ -686,7 +704,11 @@ int llmlb_engine::attention_block(uint32_t l, uint32_t T, bool decode, uint32_t 
   if (decode)
     return decode_attention_launch(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, B.slots, B.seq_lens, nb,
                                    attn, nq_l, nkv_l, rope, decode_splits(nb), pdl, st);
-  RC(llmlb_op_rope_append(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, st));
+  // both kernels are programmatic dependents: their set-up overlaps the tail of the kernel before
+  RC(rope_append_launch(qkv, d_pos, d_page_of_tok, rope, kpool(l), vpool(l), T, nq_l, nkv_l, true, st));
+  if (cfg.attn_impl == 0)
+    return prefill_attention_tc_launch(m_attn_q, m_kpool, m_vpool, l, d_block_tables, pages_per_seq, d_tiles, n_tiles, attn,
+                                       nq_l, nkv_l, true, st);
   return llmlb_op_prefill_attention(qkv, kpool(l), vpool(l), d_block_tables, pages_per_seq, d_tiles, n_tiles, attn,
                                     nq_l, nkv_l, st);
 }
@@ -983,9 +1005,9 @@ int llmlb_engine::run_prefill(const std::vector<ReqPtr>& reqs, const std::vector
       s_pos[row + j] = int32_t(pos);
       s_page[row + j] = r.pages[pos / kPageTokens];
     }
-    for (uint32_t j = 0; j < take[i]; j += 64) {
+    for (uint32_t j = 0; j < take[i]; j += pf_tile) {
       s_tiles[n_tiles * 4 + 0] = int32_t(row + j);
-      s_tiles[n_tiles * 4 + 1] = int32_t(std::min<uint32_t>(64, take[i] - j));
+      s_tiles[n_tiles * 4 + 1] = int32_t(std::min<uint32_t>(pf_tile, take[i] - j));
       s_tiles[n_tiles * 4 + 2] = int32_t(p0 + j);
       s_tiles[n_tiles * 4 + 3] = r.slot;
       ++n_tiles;
@@ -1789,7 +1811,7 @@ extern "C" int llmlb_debug_prefill_logits(llmlb_engine* e, const int32_t* prompt
   const int slot = e->debug_slot;
   std::vector<int32_t> pos(n), page(n), tiles;
   for (uint32_t i = 0; i < n; ++i) { pos[i] = int32_t(i); page[i] = e->debug_pages[i / kPageTokens]; }
-  for (uint32_t j = 0; j < n; j += 64) { tiles.push_back(int32_t(j)); tiles.push_back(int32_t(std::min<uint32_t>(64, n - j))); tiles.push_back(int32_t(j)); tiles.push_back(slot); }
+  for (uint32_t j = 0; j < n; j += e->pf_tile) { tiles.push_back(int32_t(j)); tiles.push_back(int32_t(std::min<uint32_t>(e->pf_tile, n - j))); tiles.push_back(int32_t(j)); tiles.push_back(slot); }
   LLMLB_CUDA_CHECK(cudaMemcpy(e->d_block_tables + size_t(slot) * e->pages_per_seq, e->debug_pages.data(), e->debug_pages.size() * 4, cudaMemcpyHostToDevice));
   LLMLB_CUDA_CHECK(cudaMemcpy(e->d_ids, prompt, n * 4, cudaMemcpyHostToDevice));
   LLMLB_CUDA_CHECK(cudaMemcpy(e->d_pos, pos.data(), n * 4, cudaMemcpyHostToDevice));
@@ -1861,6 +1883,8 @@ extern "C" int llmlb_debug_trace_enable(uint32_t cap) {
   ks_set_trace(g_tb);
   attn_set_trace(g_tb);
   tc_set_trace(g_tb);
+  tp_set_trace(g_tb);
+  tc2_set_trace(g_tb);
   return LLMLB_OK;
 }
 extern "C" int llmlb_debug_trace_dump(unsigned long long* out, uint32_t cap_records, uint32_t* n) {

@@ -85,6 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   __shared__ long long stall[4];
   const long long c_begin = clock64();
   long long c_wait = 0;
+  const unsigned long long g_begin = tb.data ? gtime_ns() : 0ull;
 
   // tile -> (m_tile, t_tile, split): t fastest so consecutive CTAs share the W slab in L2
   auto decode_tile = [&](uint32_t tile, uint32_t& mt, uint32_t& tt, uint32_t& ks) {
@@ -262,6 +263,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (tb.data && threadIdx.x == 0)
+    trace_emit(tb, (6ull << 60) | ((unsigned long long)EPI << 56) | ((unsigned long long)n_out << 32) | K, g_begin, g_begin, gtime_ns(), n_tokens);
+  if (tb.data && threadIdx.x == 0)
     trace_emit(tb, (2ull << 60) | ((unsigned long long)n_out << 32) | ((unsigned long long)EPI << 28) | K,
                (unsigned long long)(clock64() - c_begin), (unsigned long long)stall[0], (unsigned long long)stall[1],
                (unsigned long long)stall[2]);
@@ -316,6 +319,28 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return LLMLB_E_DEVICE;
+  }
+  return LLMLB_OK;
+}
+
+// general tiled map, bf16, 128B swizzle: dims / box innermost first, strides (bytes) of dims 1..rank-1
+int make_tmap_nd(CUtensorMap* m, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return LLMLB_E_DEVICE;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (uint32_t i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (uint32_t i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (rank " + std::to_string(rank) + ") failed: " + std::to_string((int)r));
     return LLMLB_E_DEVICE;
   }
   return LLMLB_OK;

@@ -20,6 +20,8 @@
 
 namespace llmlb {
 
+static __device__ TraceBuf d_trace_tc2;
+void tc2_set_trace(const TraceBuf& tb) { cudaMemcpyToSymbol(d_trace_tc2, &tb, sizeof(tb)); }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -76,6 +78,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 void* __restrict__ out, uint32_t n_tokens, uint32_t n_out, uint32_t K, uint32_t out_stride,
                 uint32_t m_tiles /*256-row slabs*/, uint32_t t_tiles, uint32_t split_k, const TpPushRS tp) {
   using Cfg = Tc2Cfg<BN>;
+  const TraceBuf tb = d_trace_tc2;
+  unsigned long long tr0 = 0, tr1 = 0;
+  if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may set itself up on freed SMs
   __shared__ uint8_t* s_peer_slot[kTpMaxRanks];   // kEpiPushRS: slot base of every rank
   if constexpr (EPI == kEpiPushRS) {
     if (threadIdx.x < tp.ctx.size) s_peer_slot[threadIdx.x] = tp.ctx.base[threadIdx.x] + tp.ctx.slot_off[tp.coll & 1];
@@ -122,6 +128,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   cluster_sync_all();  // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: barrier init, TMEM allocation and the tensor-map fetch above
+  // overlapped the previous kernel's tail; its outputs (our activations) are needed from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tb.data && threadIdx.x == 0) tr1 = gtime_ns();
 
   auto decode_tile = [&](uint32_t tile, uint32_t& mt, uint32_t& tt, uint32_t& ks) {
     tt = tile % t_tiles;
@@ -241,6 +251,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 
   tc_fence_before();
   cluster_sync_all();  // nobody frees TMEM / exits while the peer may still signal or read
+  if (tb.data && threadIdx.x == 0)
+    trace_emit(tb, (4ull << 60) | ((unsigned long long)EPI << 56) | ((unsigned long long)n_out << 32) | K, tr0, tr1, gtime_ns(), n_tokens);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(Cfg::kTmemCols))
@@ -271,13 +283,15 @@ static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* o
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   TpPushRS tp{};
   if (tpp) tp = *tpp;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx_half, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, tp));

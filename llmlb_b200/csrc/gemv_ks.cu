@@ -81,7 +81,7 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
     }
   };
   const TraceBuf tb = d_trace_ks;
-  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr_flag = 0;
   if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
   // PDL: let the next kernel in the stream start its own weight prefetch right away ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -105,6 +105,7 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
       const uint32_t slot = tp.coll_in & 1;
       TpFlags* mine = tp_flags(tp.ctx, tp.ctx.rank);
       tp_wait_flags(mine, mine->push_flag[slot], tp.ctx.size, tp_epoch(tp.ctx, tp.coll_in));
+      if (tb.data && threadIdx.x == 0) tr_flag = gtime_ns();
       const float4* sb = reinterpret_cast<const float4*>(tp.ctx.base[tp.ctx.rank] + tp.ctx.slot_off[slot]);
       for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
 #pragma unroll
@@ -260,7 +261,10 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
     tp_signal_when_grid_done(tp.ctx, &tp_flags(tp.ctx, tp.ctx.rank)->done[slot], gridDim.x, tp_epoch(tp.ctx, tp.coll_out),
                              [&](TpFlags* f) { return &f->push_flag[slot][tp.ctx.rank]; });
   }
-  if (tb.data && threadIdx.x == 0) trace_emit(tb, (unsigned long long)n_out << 32 | K, tr0, tr1, tr2, gtime_ns());
+  if (tb.data && threadIdx.x == 0) {
+    trace_emit(tb, ((unsigned long long)TPM << 58) | ((unsigned long long)n_out << 32) | K, tr0, tr1, tr2, gtime_ns());
+    if (TPM == 1) trace_emit(tb, (5ull << 60) | ((unsigned long long)n_out << 32) | K, tr1, tr_flag, tr2, 0);   // dependency wait -> flags in -> fold + norm done
+  }
 }
 
 // picks (TW, CW): TW*CW*256 == K, TW <= 16, CW in {1,2,4}, B*CW <= 4.  Returns false if none.

@@ -14,6 +14,8 @@
 namespace llmlb {
 
 constexpr int kArMaxBlocks = 148;
+static __device__ TraceBuf d_trace_tp;
+void tp_set_trace(const TraceBuf& tb) { cudaMemcpyToSymbol(d_trace_tp, &tb, sizeof(tb)); }
 
 struct ArSignals {  // start of every rank's exchange region: barrier flags of the pull kernels
   uint32_t flag[kArMaxBlocks][kTpMaxRanks];  // flag[block][src_rank]: epoch written by src_rank's block
@@ -69,6 +71,9 @@ __global__ void __launch_bounds__(256)
 tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_bfloat16* __restrict__ gain,
                       uint32_t n_tokens, uint32_t rpr, uint32_t n_own, uint32_t hidden, float eps, uint32_t n_parts) {
   __shared__ float red[8];
+  const TraceBuf tb = d_trace_tp;
+  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+  if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
   // the projection GEMM that follows may start pulling its weights now (it waits for this grid
   // before it touches y)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -76,6 +81,7 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
   TpFlags* mine = tp_flags(c, c.rank);
   const unsigned long long epoch = tp_epoch(c, coll);
   tp_wait_flags(mine, mine->push_flag[slot], c.size, epoch);
+  if (tb.data && threadIdx.x == 0) tr1 = gtime_ns();
   if (blockIdx.x < n_own) {
     const uint32_t t = c.rank * rpr + blockIdx.x;
     float4* xr = reinterpret_cast<float4*>(x + size_t(t) * hidden);
@@ -109,11 +115,13 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
         st_peer_u2(reinterpret_cast<uint2*>(c.base[r] + c.y_off) + size_t(t) * (hidden / 4) + i, o);
     }
   }
+  if (tb.data && threadIdx.x == 0) tr2 = gtime_ns();
   tp_signal_when_grid_done(c, &mine->done[2 + slot], gridDim.x, epoch,
                            [&](TpFlags* f) { return &f->ag_flag[slot][c.rank]; });
   // the grid (hence the kernel boundary the next GEMM waits on) outlives the arrival of every
   // owner's rows in MY y buffer
   if (blockIdx.x == 0) tp_wait_flags(mine, mine->ag_flag[slot], c.size, epoch);
+  if (tb.data && threadIdx.x == 0) trace_emit(tb, (3ull << 60) | n_tokens, tr0, tr1, tr2, gtime_ns());   // start, partials in, rows pushed, end
 }
 
 // ---------------------------------------------------------------- protocol A, unfused -------

@@ -30,7 +30,8 @@ class EngineConfig(C.Structure):
                 ("kv_pages", C.c_uint32), ("max_step_tokens", C.c_uint32),
                 ("synthetic_seed", C.c_uint64), ("use_cuda_graphs", C.c_uint32),
                 ("gemm_impl", C.c_uint32), ("lookahead", C.c_uint32), ("queue_max", C.c_uint32),
-                ("queue_timeout_ms", C.c_uint32), ("request_timeout_ms", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("queue_timeout_ms", C.c_uint32), ("request_timeout_ms", C.c_uint32), ("attn_impl", C.c_uint32),
+                ("reserved", C.c_uint32 * 4)]
 
 
 class ModelInfo(C.Structure):
@@ -91,6 +92,7 @@ PROTOTYPES = {
     "llmlb_op_rope_table": (C.c_int, [vp, u32, f32, vp]),
     "llmlb_op_rope_append": (C.c_int, [vp, vp, vp, vp, vp, vp, u32, u32, u32, vp]),
     "llmlb_op_prefill_attention": (C.c_int, [vp, vp, vp, vp, u32, vp, u32, vp, u32, u32, vp]),
+    "llmlb_op_prefill_attention_tc": (C.c_int, [vp, u32, vp, vp, u32, vp, u32, vp, u32, vp, u32, u32, vp]),
     "llmlb_op_decode_attention_ws": (C.c_size_t, [u32, u32, u32]),
     "llmlb_op_decode_attention": (C.c_int, [vp, vp, vp, vp, u32, vp, vp, u32, vp, u32, u32, vp,
                                             u32, u32, vp, vp]),
@@ -155,7 +157,7 @@ class Engine:
 
     def __init__(self, model, model_id="llama-3-8b-synthetic", device=0, tp_rank=0, tp_size=1,
                  max_seqs=8, max_ctx=1024, kv_pages=0, max_step_tokens=0, seed=0,
-                 use_cuda_graphs=True, gemm_impl=0, lookahead=0, queue_max=0, queue_timeout_ms=0, request_timeout_ms=0):
+                 use_cuda_graphs=True, gemm_impl=0, lookahead=0, queue_max=0, queue_timeout_ms=0, request_timeout_ms=0, attn_impl=0):
         cfg = EngineConfig()
         cfg.abi_version = ABI_VERSION
         for k, v in model.items():
@@ -168,6 +170,7 @@ class Engine:
         cfg.use_cuda_graphs = 1 if use_cuda_graphs else 0
         cfg.gemm_impl, cfg.lookahead = gemm_impl, lookahead
         cfg.queue_max, cfg.queue_timeout_ms, cfg.request_timeout_ms = queue_max, queue_timeout_ms, request_timeout_ms
+        cfg.attn_impl = attn_impl
         self.model = dict(model)
         self.cfg = cfg
         self._h = vp()

@@ -391,9 +391,9 @@ def test_queue_limit_queue_timeout_and_deadline(built_lib):
     a full queue refuses (429 upstream), a request that waits too long for admission ends QUEUE_TIMEOUT,
     a request that runs past its deadline ends DEADLINE with the tokens it had."""
     p = list(range(1, 40))
-    with ffi.Engine(TINY, max_seqs=1, max_ctx=1024, seed=0, queue_max=2, queue_timeout_ms=30) as e:
-        long_rid = e.submit(p, 900, ignore_eos=True)           # occupies the only slot for a while
-        time.sleep(0.05)
+    with ffi.Engine(TINY, max_seqs=1, max_ctx=16384, seed=0, queue_max=2, queue_timeout_ms=30) as e:
+        long_rid = e.submit(p, 16000, ignore_eos=True)         # occupies the only slot for about a second
+        time.sleep(0.02)
         w1 = e.submit(p, 4, ignore_eos=True)
         w2 = e.submit(p, 4, ignore_eos=True)
         with pytest.raises(RuntimeError) as ei:

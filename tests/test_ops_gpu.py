@@ -156,70 +156,102 @@ def test_rope_table(L):
     assert torch.allclose(tab[..., 1].cpu().double(), torch.sin(ang), atol=1e-6)
 
 
-@pytest.mark.parametrize("nh,nkv", [(32, 8), (8, 2), (8, 1)])
-def test_rope_append_and_prefill_attention(L, nh, nkv):
-    """Two sequences packed in one step (ragged: 150 and 37 tokens, the 2nd with 70 tokens of
-    earlier context) against dense fp32 attention."""
+def _prefill_attention_case(L, nh, nkv, seqs, impl):
+    """Sequences packed in one step (ragged; some with earlier context already in the cache) against
+    dense fp32 attention.  seqs: list of (context tokens already cached, new tokens).
+    impl "mma": llmlb_op_prefill_attention, 64-row tiles; "tc": the tcgen05 kernel, 128-row tiles."""
     torch.manual_seed(0)
-    rope = _mk_rope(L, 1024)
+    max_len = max(c + n for c, n in seqs)
+    rope = _mk_rope(L, 2048)
     W = (nh + 2 * nkv) * 128
-    n_pages, bt_stride = 16, 4
+    bt_stride = (max_len + 63) // 64 + 1
+    n_pages = len(seqs) * bt_stride + 3
     kp = torch.zeros(n_pages, nkv, 64, 128, dtype=torch.bfloat16, device=dev())
     vp = torch.zeros_like(kp)
-    bt = torch.tensor([[3, 7, 1, 0], [9, 2, 5, 0]], dtype=torch.int32, device=dev())
-    seqs = [(0, 150), (70, 37)]  # (context already cached, new tokens)
-    # pre-existing context for sequence 1: run a first rope_append step for its 70 tokens
-    ctx = bf16_randn((70, W), seed=11)
-    pos_c = torch.arange(70, dtype=torch.int32, device=dev())
-    page_c = bt[1][(pos_c // 64).long()].contiguous()
-    ok(L.llmlb_op_rope_append(p(ctx), p(pos_c), p(page_c), p(rope), p(kp), p(vp), 70, nh, nkv, stream_ptr()))
-    qkv = bf16_randn((187, W), seed=12)
+    perm = torch.randperm(n_pages, generator=torch.Generator().manual_seed(5))[: len(seqs) * bt_stride]
+    bt = perm.view(len(seqs), bt_stride).to(torch.int32).to(dev())
+    ctx_raw = []
+    for i, (c, n) in enumerate(seqs):   # earlier context: its own rope_append step
+        if c == 0:
+            ctx_raw.append(None)
+            continue
+        ctx = bf16_randn((c, W), seed=100 + i)
+        ctx_raw.append(ctx.clone())
+        pos_c = torch.arange(c, dtype=torch.int32, device=dev())
+        page_c = bt[i][(pos_c // 64).long()].contiguous()
+        ok(L.llmlb_op_rope_append(p(ctx), p(pos_c), p(page_c), p(rope), p(kp), p(vp), c, nh, nkv, stream_ptr()))
+    T = sum(n for _, n in seqs)
+    qkv = bf16_randn((T, W), seed=12)
     raw = qkv.clone()
-    pos = torch.cat([torch.arange(0, 150), torch.arange(70, 107)]).to(torch.int32).to(dev())
-    page = torch.cat([bt[0][(pos[:150] // 64).long()], bt[1][(pos[150:] // 64).long()]]).contiguous()
-    ok(L.llmlb_op_rope_append(p(qkv), p(pos), p(page), p(rope), p(kp), p(vp), 187, nh, nkv, stream_ptr()))
-    tiles = []
-    for (row0, n, p0, r) in [(0, 150, 0, 0), (150, 37, 70, 1)]:
-        for j in range(0, n, 64):
-            tiles.append([row0 + j, min(64, n - j), p0 + j, r])
+    pos = torch.cat([torch.arange(c, c + n) for c, n in seqs]).to(torch.int32).to(dev())
+    page = torch.cat([bt[i][(torch.arange(c, c + n) // 64).long().to(dev())] for i, (c, n) in enumerate(seqs)]).contiguous()
+    ok(L.llmlb_op_rope_append(p(qkv), p(pos), p(page), p(rope), p(kp), p(vp), T, nh, nkv, stream_ptr()))
+    tile = 64 if impl == "mma" else 128
+    tiles, row0 = [], 0
+    for i, (c, n) in enumerate(seqs):
+        for j in range(0, n, tile):
+            tiles.append([row0 + j, min(tile, n - j), c + j, i])
+        row0 += n
     tiles_t = torch.tensor(tiles, dtype=torch.int32, device=dev())
-    out = torch.zeros(187, nh * 128, dtype=torch.bfloat16, device=dev())
-    ok(L.llmlb_op_prefill_attention(p(qkv), p(kp), p(vp), p(bt), bt_stride, p(tiles_t), len(tiles),
-                                    p(out), nh, nkv, stream_ptr()))
+    out = torch.zeros(T, nh * 128, dtype=torch.bfloat16, device=dev())
+    if impl == "mma":
+        ok(L.llmlb_op_prefill_attention(p(qkv), p(kp), p(vp), p(bt), bt_stride, p(tiles_t), len(tiles), p(out), nh, nkv, stream_ptr()))
+    else:
+        ok(L.llmlb_op_prefill_attention_tc(p(qkv), T, p(kp), p(vp), n_pages, p(bt), bt_stride, p(tiles_t), len(tiles), p(out), nh, nkv,
+                                           stream_ptr()))
     sync()
-    # reference
+
     def split(t):
         t = t.float()
         return (t[:, : nh * 128].view(-1, nh, 128), t[:, nh * 128:(nh + nkv) * 128].view(-1, nkv, 128),
                 t[:, (nh + nkv) * 128:].view(-1, nkv, 128))
-    q0, k0, v0 = split(raw[:150]); q1, k1, v1 = split(raw[150:]); _, kc, vc = split(ctx.clone())
-    # ctx was rotated in place by the first call; rebuild from its own raw copy
-    ctx_raw = bf16_randn((70, W), seed=11)
-    _, kc, vc = split(ctx_raw)
-    def rt(x, ps): return _rope_ref(x, ps).to(torch.bfloat16).float()
+
+    def rt(x, ps):
+        return _rope_ref(x, ps).to(torch.bfloat16).float()
     g = nh // nkv
-    refs = []
-    for (q, k, v, kpre, vpre, p0) in [(q0, k0, v0, None, None, 0), (q1, k1, v1, kc, vc, 70)]:
-        n = q.shape[0]
-        qp = torch.arange(p0, p0 + n, device=dev())
-        qr = rt(q, qp)
-        kr = rt(k, qp)
-        if kpre is not None:
-            kr = torch.cat([rt(kpre, torch.arange(0, p0, device=dev())), kr]); v = torch.cat([vpre, v])
+    refs, row0 = [], 0
+    for i, (c, n) in enumerate(seqs):
+        q, k, v = split(raw[row0:row0 + n])
+        qp = torch.arange(c, c + n, device=dev())
+        qr, kr = rt(q, qp), rt(k, qp)
+        if c:
+            _, kc, vc = split(ctx_raw[i])
+            kr = torch.cat([rt(kc, torch.arange(0, c, device=dev())), kr]); v = torch.cat([vc, v])
         S = kr.shape[0]
         sc = torch.einsum("thd,shd->hts", qr, kr.repeat_interleave(g, 1)) / math.sqrt(128)
         mask = torch.arange(S, device=dev())[None, :] > qp[:, None]
         pr = torch.softmax(sc.masked_fill(mask[None], float("-inf")), -1)
         refs.append(torch.einsum("hts,shd->thd", pr, v.repeat_interleave(g, 1)).reshape(n, nh * 128))
+        row0 += n
     ref = torch.cat(refs)
+    # attention: P is rounded to bf16 before P·V (2^-9 relative per term), outputs stored as bf16
+    err = (out.float() - ref).abs()
+    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=2 ** -6), "max err %g at row %d" % (err.max().item(), int(err.max(dim=1).values.argmax()))
+    return raw, qkv, kp, vp, bt, rt, split
+
+
+@pytest.mark.parametrize("nh,nkv", [(32, 8), (8, 2), (8, 1)])
+def test_rope_append_and_prefill_attention(L, nh, nkv):
+    """Two sequences packed in one step (ragged: 150 and 37 tokens, the 2nd with 70 tokens of
+    earlier context); also checks the rotated q / appended K,V bit patterns."""
+    raw, qkv, kp, vp, bt, rt, split = _prefill_attention_case(L, nh, nkv, [(0, 150), (70, 37)], "mma")
+    q0, k0, _ = split(raw[:150])
     # q,k rotated values in the activation buffer are bit-identical to the bf16-rounded reference
     assert torch.allclose(qkv[:, : nh * 128].float().view(-1, nh, 128)[:150], rt(q0, torch.arange(150, device=dev())), atol=1e-2, rtol=2 ** -7)
-    # attention: P is rounded to bf16 before P·V (2^-9 relative per term), outputs stored as bf16
-    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=2 ** -6)
-    # appended K/V land in the right page slots
-    tok = 100
+    tok = 100   # appended K/V land in the right page slots
     assert torch.equal(kp[bt[0, tok // 64], :, tok % 64].float(), rt(k0, torch.arange(150, device=dev()))[tok].to(torch.bfloat16).float())
     assert torch.equal(vp[bt[0, tok // 64], :, tok % 64], raw[tok, (nh + nkv) * 128:].view(nkv, 128))
+
+
+@pytest.mark.parametrize("nh,nkv", [(32, 8), (8, 2), (8, 1), (4, 1)])
+@pytest.mark.parametrize("seqs", [[(0, 150), (70, 37)], [(0, 512)], [(0, 1), (0, 64), (0, 65), (3, 128), (200, 129)], [(640, 300), (0, 257)]],
+                         ids=["ragged", "baseline512", "edges", "long_ctx"])
+def test_prefill_attention_tcgen05(L, nh, nkv, seqs):
+    """The tcgen05 / TMEM / TMA kernel (attention_tc.cu): 128-row q tiles, 128-token KV blocks, V
+    consumed MN-major from its pages.  Edge cases: a 1-token prompt, exact page and block boundaries,
+    a tile that starts in the middle of a page, contexts of several blocks, a block whose second
+    page does not exist."""
+    _prefill_attention_case(L, nh, nkv, seqs, "tc")
 
 
 @pytest.mark.parametrize("nh,nkv", [(32, 8), (8, 2), (8, 1)])
