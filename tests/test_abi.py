@@ -95,3 +95,13 @@ def test_host_library_exports_every_declared_symbol():
         c = os.path.join(d, "h.c")
         open(c, "w").write('#include "llmlb_host.h"\nvoid* (*probe)(void) = llmlb_tok_stream_create;\nint main(void){return 0;}\n')
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "h.o")])
+
+
+def test_rust_ffi_crate_matches_the_header():
+    """ffi/llmlb-b200-sys (source only: no cargo here): #[repr(C)] layouts, constants and the extern
+    block against include/llmlb_b200.h, via gcc offsetof (tools/check_rust_layout.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("check_rust_layout", os.path.join(ROOT, "tools", "check_rust_layout.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check() == []
