@@ -267,7 +267,7 @@ def run_ours(args):
     n_streams = args.streams if args.streams >= 0 else (128 if world >= 8 else 64)
     max_seqs = max(4, args.batch, n_streams)
     eng = ffi.Engine(model, model_id="llama-3-8b-synthetic", device=local, tp_rank=rank, tp_size=tp,
-                     max_seqs=max_seqs, max_ctx=1024, seed=0, use_cuda_graphs=not args.no_graphs)
+                     max_seqs=max_seqs, max_ctx=1024, seed=0, use_cuda_graphs=not args.no_graphs, tp_proto=args.tp_proto)
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, eng.tp_export())
@@ -487,6 +487,7 @@ def main():
     ap.add_argument("--streams", type=int, default=-1, help="streams leg width (-1: 64, or 128 at 8 GPUs; 0: skip)")
     ap.add_argument("--stream-steps", type=int, default=2)
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--tp-proto", type=int, default=0, help="tensor-parallel decode exchange: 0 = value+epoch pairs, 1 = flags")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-ref-shape", action="store_true")

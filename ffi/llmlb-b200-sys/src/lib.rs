@@ -70,7 +70,8 @@ pub struct llmlb_engine_config {
     pub queue_timeout_ms: u32,
     pub request_timeout_ms: u32,
     pub attn_impl: u32,
-    pub reserved: [u32; 4],
+    pub tp_proto: u32,
+    pub reserved: [u32; 3],
 }
 
 #[repr(C)]
@@ -247,7 +248,8 @@ impl Engine {
             queue_timeout_ms: 60_000,
             request_timeout_ms: 120_000,
             attn_impl: 0,
-            reserved: [0; 4],
+            tp_proto: 0,
+            reserved: [0; 3],
         }
     }
 

@@ -60,9 +60,9 @@ void tc2_set_trace(const TraceBuf& tb);
 // tensor parallel (tp_common.cuh): fused GEMV consumer / producer of protocol A, pull kernels
 int gemv_tp_consume(const TpCtx& ctx, uint32_t coll_in, const void* w, const float* x_in, float* x_out,
                     const void* gain, float eps, void* out, uint32_t n_tokens, uint32_t n_out, uint32_t k,
-                    uint32_t epi, uint32_t out_stride, cudaStream_t st);
+                    uint32_t epi, uint32_t out_stride, bool ll, cudaStream_t st);
 int gemv_tp_push(const TpCtx& ctx, uint32_t coll_out, const void* w, const void* x_bf16, uint32_t n_tokens,
-                 uint32_t n_out, uint32_t k, cudaStream_t st);
+                 uint32_t n_out, uint32_t k, bool ll, cudaStream_t st);
 int ar_allreduce_add(const TpCtx& P, uint64_t off, float* x, uint64_t n, cudaStream_t st);
 int ar_allgather_cols(const TpCtx& P, uint64_t off, float* out, uint32_t rows, uint32_t cols_local, cudaStream_t st);
 constexpr uint32_t kTpMaxSplit = 4;   // K-split parts a push-RS GEMM may use (slot capacity)
@@ -379,6 +379,7 @@ struct llmlb_engine {
   uint64_t logits_slot_off = 0, pull_slot_off = 0, pull_slot_bytes = 0;
   bool tp_ready = false;
   uint32_t tp_coll = 0;              // collectives issued so far in the current forward pass
+  bool tp_ll = true;                 // protocol A variant: {value, epoch} pairs (default) or values + end-of-grid flags
   float* xb = nullptr;               // second residual buffer (protocol A ping-pong)
   float* tp_stage = nullptr;         // [4][hidden] fp32: partial rows of projections the fused GEMV does not take
   __nv_bfloat16* ylast = nullptr;    // [max_seqs][hidden] normalised rows that need logits (protocol B)
@@ -431,7 +432,7 @@ struct llmlb_engine {
     bool y_final = false;      // tp, protocol B: y holds RMSNorm(x) * final_norm for all rows (bf16)
   };
   int proj(const CUtensorMap& mw, const void* w, const void* xin, const CUtensorMap* mx, void* out, uint32_t T,
-           uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride);
+           uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, int wait_coll = -1);
   int layer_stack_decode(uint32_t nb);
   int launch_decode_step(uint32_t nb);
   int forward_tokens(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs);
@@ -499,6 +500,7 @@ int llmlb_engine::init() {
   }
   if (!(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank >= tp) { set_error("bad tp_size/tp_rank"); return LLMLB_E_INVALID_ARG; }
   if (cfg.gemm_impl != 0) { set_error("gemm_impl: only 0 (tcgen05 tiles) is built into the library"); return LLMLB_E_INVALID_ARG; }
+  if (cfg.tp_proto > 1) { set_error("tp_proto: 0 (value+epoch pairs) or 1 (flags)"); return LLMLB_E_INVALID_ARG; }
   if (cfg.attn_impl > 1) { set_error("attn_impl: 0 (tcgen05) or 1 (mma.sync baseline)"); return LLMLB_E_INVALID_ARG; }
   if (M.n_kv_heads == 0 || M.n_heads % M.n_kv_heads || M.n_kv_heads % tp || M.ffn % tp || M.vocab % tp ||
       ((M.n_heads / M.n_kv_heads) % 4) || M.hidden % 8 || (M.ffn / tp) % 8 || (M.vocab / tp) % 4 ||
@@ -572,6 +574,7 @@ int llmlb_engine::alloc_all() {
   RC(dmalloc(&k_pool, layer_pool_elems * M.n_layers));
   RC(dmalloc(&v_pool, layer_pool_elems * M.n_layers));
   pf_tile = cfg.attn_impl == 0 ? 128 : 64;
+  tp_ll = cfg.tp_proto == 0;
   RC(make_tmap_attn_kv(&m_kpool, k_pool, M.n_layers, n_pages, nkv_l));
   RC(make_tmap_attn_kv(&m_vpool, v_pool, M.n_layers, n_pages, nkv_l));
   RC(dmalloc(&rope, size_t(cfg.max_ctx) * 64 * 2));
@@ -590,6 +593,9 @@ int llmlb_engine::alloc_all() {
     tpc.slot_off[0] = off; off += slot;
     tpc.slot_off[1] = off; off += slot;
     tpc.slot_bytes = slot;
+    const size_t llslot = up(size_t(kTpMaxRanks) * kTpSmallRows * H * 8);
+    tpc.ll_off[0] = off; off += llslot;
+    tpc.ll_off[1] = off; off += llslot;
     logits_slot_off = off; off += lslot;
     tpc.y_off = off; off += up(size_t(t_cap) * H * 2);
     xchg_bytes = off;
@@ -695,7 +701,12 @@ __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, c
 
 // One tensor-core projection of bf16 activations (T > 4).
 int llmlb_engine::proj(const CUtensorMap& mw, const void*, const void*, const CUtensorMap* mx, void* out, uint32_t T,
-                       uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride) {
+                       uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, int wait_coll) {
+  if (wait_coll >= 0) {   // tensor parallel: the activation operand is y of that collective (its all-gather flags gate the loads)
+    TpPushRS tpp{};
+    tpp.ctx = tpc; tpp.wait_coll_plus1 = uint32_t(wait_coll) + 1;
+    return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &tpp);
+  }
   return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)]);
 }
 
@@ -776,9 +787,9 @@ int llmlb_engine::forward_small_tp(uint32_t T, bool decode, uint32_t nb, uint32_
   int pending = -1;   // collective pushed but not yet folded into `cur`
   auto consume = [&](const void* w, const __nv_bfloat16* gain, void* out, uint32_t n_out, uint32_t epi, uint32_t out_stride) -> int {
     if (pending >= 0) {
-      int rc = gemv_tp_consume(tpc, uint32_t(pending), w, cur, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, st);
+      int rc = gemv_tp_consume(tpc, uint32_t(pending), w, cur, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, tp_ll, st);
       if (rc == LLMLB_E_UNSUPPORTED) {   // odd shape: fold with its own kernel, then the plain projection
-        RC(tp_fold_rows(tpc, uint32_t(pending), cur, oth, T, H, st));
+        RC(tp_fold_rows(tpc, uint32_t(pending), cur, oth, T, H, tp_ll, st));
         rc = gemv_decode(w, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, st);
       }
       RC(rc);
@@ -790,10 +801,10 @@ int llmlb_engine::forward_small_tp(uint32_t T, bool decode, uint32_t nb, uint32_
   };
   auto push = [&](const void* w, const void* xin_bf16, uint32_t k) -> int {
     const uint32_t c = tp_coll++;
-    int rc = gemv_tp_push(tpc, c, w, xin_bf16, T, H, k, st);
+    int rc = gemv_tp_push(tpc, c, w, xin_bf16, T, H, k, tp_ll, st);
     if (rc == LLMLB_E_UNSUPPORTED) {
       RC(llmlb_op_gemv(w, xin_bf16, nullptr, M.rms_eps, tp_stage, T, H, k, LLMLB_EPI_STORE_F32, H, st));
-      rc = tp_push_rows(tpc, c, tp_stage, T, H, st);
+      rc = tp_push_rows(tpc, c, tp_stage, T, H, tp_ll, st);
     }
     RC(rc);
     pending = int(c);
@@ -814,7 +825,7 @@ int llmlb_engine::forward_small_tp(uint32_t T, bool decode, uint32_t nb, uint32_
 
 int llmlb_engine::finish_small_tp(FwdState* fs, uint32_t T) {
   if (!fs->pending) return LLMLB_OK;
-  RC(tp_fold_rows(tpc, fs->pending_coll, fs->xres, fs->xother, T, M.hidden, st));
+  RC(tp_fold_rows(tpc, fs->pending_coll, fs->xres, fs->xother, T, M.hidden, tp_ll, st));
   std::swap(fs->xres, fs->xother);
   fs->pending = false;
   return LLMLB_OK;
@@ -826,23 +837,28 @@ int llmlb_engine::finish_small_tp(FwdState* fs, uint32_t T) {
 int llmlb_engine::forward_big_tp(uint32_t T, bool decode, uint32_t nb, uint32_t n_tiles, FwdState* fs) {
   const uint32_t H = M.hidden, ko = nq_l * kHeadDim;
   const uint32_t rpr = ceil_div(T, tp);
-  auto push_rs = [&](const CUtensorMap& mw, const CUtensorMap* mx, uint32_t k, const __nv_bfloat16* next_gain) -> int {
+  // returns the collective's index; last: the consumers of y behind it are not tensor-core GEMMs of
+  // this loop, so the reduce kernel itself waits for the all-gather
+  auto push_rs = [&](const CUtensorMap& mw, const CUtensorMap* mx, uint32_t k, const __nv_bfloat16* next_gain, bool last, int* coll) -> int {
     TpPushRS tpp{};
     tpp.ctx = tpc; tpp.coll = tp_coll++; tpp.rpr = rpr;
+    *coll = int(tpp.coll);
     uint32_t n_parts = 1;
     RC(gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], nullptr, T, H, k, kEpiPushRS, H, st, &mx[bn_index(128)], &n_parts,
                       &tpp, kTpMaxSplit));
-    return tp_reduce_norm(tpc, tpp.coll, x, next_gain, T, H, M.rms_eps, n_parts, st);
+    return tp_reduce_norm(tpc, tpp.coll, x, next_gain, T, H, M.rms_eps, n_parts, last, st);
   };
   // layer 0: the embedding rows are complete on every rank
   RC(llmlb_op_rmsnorm(x, layers[0].attn_norm, y, T, H, M.rms_eps, st));
+  int c_prev = -1;   // collective whose all-gathered y the next projection consumes
   for (uint32_t l = 0; l < M.n_layers; ++l) {
     LayerW& L = layers[l];
-    RC(proj(L.m_wqkv, L.wqkv, y, m_y, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w));
+    RC(proj(L.m_wqkv, L.wqkv, y, m_y, qkv, T, qkv_w, H, LLMLB_EPI_STORE_BF16, qkv_w, c_prev));
     RC(attention_block(l, T, decode, nb, n_tiles, false));
-    RC(push_rs(L.m_wo, m_attn, ko, L.ffn_norm));
-    RC(proj(L.m_wgu, L.wgu, y, m_y, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l));
-    RC(push_rs(L.m_wdown, m_h, ffn_l, l + 1 < M.n_layers ? layers[l + 1].attn_norm : final_norm));
+    RC(push_rs(L.m_wo, m_attn, ko, L.ffn_norm, false, &c_prev));
+    RC(proj(L.m_wgu, L.wgu, y, m_y, h, T, 2 * ffn_l, H, LLMLB_EPI_SILU_MUL, ffn_l, c_prev));
+    const bool last = l + 1 == M.n_layers;
+    RC(push_rs(L.m_wdown, m_h, ffn_l, last ? final_norm : layers[l + 1].attn_norm, last, &c_prev));
   }
   fs->y_final = true;
   return LLMLB_OK;
@@ -876,7 +892,7 @@ int llmlb_engine::logits_from_y(const __nv_bfloat16* src, const CUtensorMap* map
 // protocol A, decode: the lm_head GEMV's prologue consumes the last down projection's collective
 int llmlb_engine::logits_tp_consume(FwdState* fs, uint32_t R) {
   int rc = gemv_tp_consume(tpc, fs->pending_coll, lm_head, fs->xres, fs->xother, final_norm, M.rms_eps, logits_dst(), R,
-                           vocab_l, M.hidden, LLMLB_EPI_STORE_F32, vocab_l, st);
+                           vocab_l, M.hidden, LLMLB_EPI_STORE_F32, vocab_l, tp_ll, st);
   if (rc == LLMLB_E_UNSUPPORTED) {
     RC(finish_small_tp(fs, R));
     return logits_from_x(fs->xres, R);

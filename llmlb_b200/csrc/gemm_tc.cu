@@ -124,10 +124,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       // the activation halves of those stages follow after griddepcontrol.wait (same full barrier,
       // its expect_tx already counts both)
       bool dep_ready = pdl == 0;
+      if (dep_ready && tp.wait_coll_plus1) tp_wait_ag_single(tp.ctx, tp.wait_coll_plus1 - 1);
       uint32_t n_deferred = 0;
       uint32_t d_stage[Cfg::kStages], d_kb[Cfg::kStages], d_tt[Cfg::kStages];
       auto release_deferred = [&]() {
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (tp.wait_coll_plus1) tp_wait_ag_single(tp.ctx, tp.wait_coll_plus1 - 1);
         for (uint32_t i = 0; i < n_deferred; ++i)
           tma_load_2d(smem + d_stage[i] * Cfg::kStageBytes + kBM * kBK * 2, &tmap_x, full_bar + d_stage[i],
                       int32_t(d_kb[i] * kBK), int32_t(d_tt[i] * BN));
@@ -237,8 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                   reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
                 else if constexpr (EPI == kEpiPushRS) {    // reduce-scatter by address into the row owner's slot
                   const uint32_t owner = t / tp.rpr, tl = t - owner * tp.rpr;
-                  st_peer_f32(reinterpret_cast<float*>(s_peer_slot[owner]) +
-                                  (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * out_stride + n, v);
+                  st_peer_bf16(reinterpret_cast<__nv_bfloat16*>(s_peer_slot[owner]) +
+                                   (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * out_stride + n, v);
                 } else {
                   if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
                   else reinterpret_cast<float*>(out)[idx] += v;

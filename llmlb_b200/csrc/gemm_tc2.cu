@@ -142,6 +142,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer (both CTAs) ----
+      if (tp.wait_coll_plus1) tp_wait_ag_single(tp.ctx, tp.wait_coll_plus1 - 1);
       uint32_t stage = 0, phase = 0;
       for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs) {
         uint32_t mt, tt, ks;
@@ -232,8 +233,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               else if constexpr (EPI == kEpiPartialF32) reinterpret_cast<float*>(out)[size_t(ks) * n_tokens * out_stride + idx] = v;
               else if constexpr (EPI == kEpiPushRS) {    // reduce-scatter by address into the row owner's slot
                 const uint32_t owner = t / tp.rpr, tl = t - owner * tp.rpr;
-                st_peer_f32(reinterpret_cast<float*>(s_peer_slot[owner]) +
-                                (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * out_stride + n, v);
+                st_peer_bf16(reinterpret_cast<__nv_bfloat16*>(s_peer_slot[owner]) +
+                                 (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * out_stride + n, v);
               } else {
                 if (split_k > 1) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
                 else reinterpret_cast<float*>(out)[idx] += v;

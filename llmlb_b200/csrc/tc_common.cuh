@@ -16,8 +16,10 @@ constexpr int kEpiPartialF32 = 4;
 constexpr int kEpiPushRS = 5;
 struct TpPushRS {
   TpCtx ctx;
-  uint32_t coll;      // collective index within the step (slot = coll & 1)
-  uint32_t rpr;       // token rows per owner rank = ceil(n_tokens / size)
+  uint32_t coll;      // kEpiPushRS: collective index within the step (slot = coll & 1)
+  uint32_t rpr;       // kEpiPushRS: token rows per owner rank = ceil(n_tokens / size)
+  uint32_t wait_coll_plus1;   // any epilogue: the activation operand is y of collective (this - 1): the TMA
+                              // producer waits for its all-gather flags before the first activation load (0 = none)
 };
 constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
 constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row

@@ -56,6 +56,8 @@ struct TpCtx {                      // kernel parameter, by value
   uint32_t rank, size;
   uint64_t flags_off;               // TpFlags
   uint64_t slot_off[kTpSlots];      // fp32 partial slots
+  uint64_t ll_off[kTpSlots];        // {value, epoch} pair slots of the LL variant (never written by anything else,
+                                    // so a stale word can only be an older epoch)
   uint64_t y_off;                   // bf16 [t_cap, hidden] normalised activations
   uint64_t slot_bytes;
 };
@@ -86,8 +88,29 @@ __device__ __forceinline__ float4 ld_pushed_f4(const float4* p) {
 __device__ __forceinline__ void st_peer_f32(float* p, float v) {
   asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void st_peer_bf16(__nv_bfloat16* p, float v) {   // reduce-scatter partials travel as bf16
+  const unsigned short b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  asm volatile("st.relaxed.sys.global.u16 [%0], %1;" ::"l"(p), "h"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_pushed_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_peer_u2(void* p, uint2 v) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+// ---- "LL" variant of protocol A: every pushed value travels with its epoch in ONE 8-byte store
+// {value bits, epoch32}.  8-byte stores are single-copy atomic, so a consumer that reads the pair and
+// finds its epoch has the value: no fence, no ticket, no flag, no last-CTA — the push is visible one
+// NVLink flight after the producing lane computed it.  Costs 2x the (tiny) bytes on the wire.
+__device__ __forceinline__ void st_peer_pair(void* p, float v, uint32_t epoch) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ld_pairs(const uint4* p) {   // two {value, epoch} pairs
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ TpFlags* tp_flags(const TpCtx& c, uint32_t r) {
   return reinterpret_cast<TpFlags*>(c.base[r] + c.flags_off);
@@ -95,6 +118,27 @@ __device__ __forceinline__ TpFlags* tp_flags(const TpCtx& c, uint32_t r) {
 // read AFTER the kernel's dependency wait: tp_step_begin_kernel of this step has completed
 __device__ __forceinline__ unsigned long long tp_epoch(const TpCtx& c, uint32_t coll) {
   return (ld_relaxed_sys_u64(&tp_flags(c, c.rank)->step) << 12) | (unsigned long long)(coll + 1);
+}
+// never 0 (slots start zeroed); equality is the test, so wrap-around after 2^24 steps is harmless:
+// a slot is rewritten every second collective
+__device__ __forceinline__ uint32_t tp_epoch32(const TpCtx& c, uint32_t coll) {
+  return (uint32_t(ld_relaxed_sys_u64(&tp_flags(c, c.rank)->step)) << 8) | (coll + 1);
+}
+// four values of one source row whose pairs sit at p[0], p[1]: spin until all four carry `epoch`
+__device__ __forceinline__ float4 tp_take_pairs(TpFlags* mine, const uint4* p, uint4 a, uint4 b, uint32_t epoch) {
+  if (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
+    const unsigned long long t0 = gtime_ns();
+    unsigned int spins = 0;
+    do {
+      a = ld_pairs(p); b = ld_pairs(p + 1);
+      if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) {
+        mine->timed_out = 1;
+        __threadfence_system();
+        __trap();
+      }
+    } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 // Threads 0..size-1 of the CTA each wait for one flag; then the CTA barriers.  A peer that never
 // arrives (crashed process) must not hang the GPU forever: after ~20 s the kernel records the
@@ -116,6 +160,25 @@ __device__ __forceinline__ void tp_wait_flags(TpFlags* mine, const unsigned long
     }
   }
   __syncthreads();
+}
+// ONE thread (the TMA producer of a GEMM that consumes y) waits until every owner's rows of
+// collective `coll` have landed in this rank's y, then orders the tensor-map (async proxy) reads
+// behind what it observed.
+__device__ __forceinline__ void tp_wait_ag_single(const TpCtx& c, uint32_t coll) {
+  TpFlags* mine = tp_flags(c, c.rank);
+  const unsigned long long epoch = tp_epoch(c, coll);
+  const unsigned long long t0 = gtime_ns();
+  for (uint32_t r = 0; r < c.size; ++r) {
+    unsigned int spins = 0;
+    while (ld_acquire_sys_u64(&mine->ag_flag[coll & 1][r]) < epoch) {
+      if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) {
+        mine->timed_out = 1;
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 // Every thread of every CTA of the grid calls this after its last push.  When the whole grid is
 // through, threads 0..size-1 of the last CTA raise `flag_of(peer)` = epoch on every rank.
@@ -143,10 +206,12 @@ __device__ __forceinline__ void tp_signal_when_grid_done(const TpCtx& c, unsigne
 size_t tp_region_prefix_bytes();      // ArSignals + TpFlags
 int tp_step_begin(const TpCtx& c, cudaStream_t st);
 // fallbacks of protocol A for projection shapes the fused GEMV does not take
-int tp_push_rows(const TpCtx& c, uint32_t coll, const float* partial, uint32_t rows, uint32_t hidden, cudaStream_t st);
-int tp_fold_rows(const TpCtx& c, uint32_t coll, const float* x_in, float* x_out, uint32_t rows, uint32_t hidden, cudaStream_t st);
+int tp_push_rows(const TpCtx& c, uint32_t coll, const float* partial, uint32_t rows, uint32_t hidden, bool ll, cudaStream_t st);
+int tp_fold_rows(const TpCtx& c, uint32_t coll, const float* x_in, float* x_out, uint32_t rows, uint32_t hidden, bool ll, cudaStream_t st);
 // protocol B consumer
+// wait_ag: the grid does not end before every owner's rows arrived here (for consumers of y that are
+// not tensor-core GEMMs; those wait for the flags themselves: TpPushRS::wait_coll_plus1)
 int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, uint32_t n_tokens, uint32_t hidden,
-                   float eps, uint32_t split_k, cudaStream_t st);
+                   float eps, uint32_t split_k, bool wait_ag, cudaStream_t st);
 
 }  // namespace llmlb

@@ -69,7 +69,8 @@ __global__ void tp_step_begin_kernel(TpCtx c) {
 // grid = max(1, owned rows); CTA b owns token row rank*rpr + b.
 __global__ void __launch_bounds__(256)
 tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_bfloat16* __restrict__ gain,
-                      uint32_t n_tokens, uint32_t rpr, uint32_t n_own, uint32_t hidden, float eps, uint32_t n_parts) {
+                      uint32_t n_tokens, uint32_t rpr, uint32_t n_own, uint32_t hidden, float eps, uint32_t n_parts,
+                      uint32_t wait_ag) {
   __shared__ float red[8];
   const TraceBuf tb = d_trace_tp;
   unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
@@ -89,10 +90,9 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
     float ss = 0.f;
     for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
       float4 v = xr[i];
-      for (uint32_t r = 0; r < n_parts; ++r) {   // part = rank * split_k + ks, ascending: a fixed order
-        const float4 a = ld_pushed_f4(reinterpret_cast<const float4*>(slot_base) +
-                                      (size_t(r) * rpr + blockIdx.x) * (hidden / 4) + i);
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      for (uint32_t r = 0; r < n_parts; ++r) {   // part = rank * split_k + ks, ascending: a fixed order; bf16 on the wire
+        const uint2 a = ld_pushed_u2(reinterpret_cast<const uint2*>(slot_base) + (size_t(r) * rpr + blockIdx.x) * (hidden / 4) + i);
+        v.x += bf16_lo(a.x); v.y += bf16_hi(a.x); v.z += bf16_lo(a.y); v.w += bf16_hi(a.y);
       }
       xr[i] = v;
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
@@ -120,26 +120,36 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
                            [&](TpFlags* f) { return &f->ag_flag[slot][c.rank]; });
   // the grid (hence the kernel boundary the next GEMM waits on) outlives the arrival of every
   // owner's rows in MY y buffer
-  if (blockIdx.x == 0) tp_wait_flags(mine, mine->ag_flag[slot], c.size, epoch);
+  if (wait_ag && blockIdx.x == 0) tp_wait_flags(mine, mine->ag_flag[slot], c.size, epoch);
   if (tb.data && threadIdx.x == 0) trace_emit(tb, (3ull << 60) | n_tokens, tr0, tr1, tr2, gtime_ns());   // start, partials in, rows pushed, end
 }
 
 // ---------------------------------------------------------------- protocol A, unfused -------
 // partial [rows <= 4][hidden] fp32 (local) -> slot[coll & 1][src = me] of every rank, then flag
 __global__ void __launch_bounds__(256)
-tp_push_rows_kernel(TpCtx c, uint32_t coll, const float* __restrict__ partial, uint32_t rows, uint32_t hidden) {
+tp_push_rows_kernel(TpCtx c, uint32_t coll, const float* __restrict__ partial, uint32_t rows, uint32_t hidden, uint32_t ll) {
   const uint32_t slot = coll & 1;
   const uint32_t n4 = rows * hidden / 4;
   const uint32_t h4 = hidden / 4;
+  const uint32_t ep32 = tp_epoch32(c, coll);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(partial)[i];
     const uint32_t row = i / h4, col = i - row * h4;
+    if (ll) {   // {value, epoch} pairs, two 16-byte stores per float4
+      for (uint32_t r = 0; r < c.size; ++r) {
+        uint4* dst = reinterpret_cast<uint4*>(c.base[r] + c.ll_off[slot]) + ((size_t(c.rank) * kTpSmallRows + row) * hidden + 4 * size_t(col)) / 2;
+        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(__float_as_uint(v.x)), "r"(ep32), "r"(__float_as_uint(v.y)), "r"(ep32) : "memory");
+        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 1), "r"(__float_as_uint(v.z)), "r"(ep32), "r"(__float_as_uint(v.w)), "r"(ep32) : "memory");
+      }
+      continue;
+    }
     for (uint32_t r = 0; r < c.size; ++r) {
       float4* dst = reinterpret_cast<float4*>(c.base[r] + c.slot_off[slot]) +
                     (size_t(c.rank) * kTpSmallRows + row) * h4 + col;
       asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     }
   }
+  if (ll) return;   // a 16-byte store of two pairs is not one atomic unit, but each 8-byte pair is: enough
   TpFlags* mine = tp_flags(c, c.rank);
   tp_signal_when_grid_done(c, &mine->done[slot], gridDim.x, tp_epoch(c, coll),
                            [&](TpFlags* f) { return &f->push_flag[slot][c.rank]; });
@@ -147,15 +157,25 @@ tp_push_rows_kernel(TpCtx c, uint32_t coll, const float* __restrict__ partial, u
 // x_out = x_in + sum over src of slot[src]   (rows <= 4)
 __global__ void __launch_bounds__(256)
 tp_fold_rows_kernel(TpCtx c, uint32_t coll, const float* __restrict__ x_in, float* __restrict__ x_out,
-                    uint32_t rows, uint32_t hidden) {
+                    uint32_t rows, uint32_t hidden, uint32_t ll) {
   const uint32_t slot = coll & 1;
   TpFlags* mine = tp_flags(c, c.rank);
-  tp_wait_flags(mine, mine->push_flag[slot], c.size, tp_epoch(c, coll));
+  if (!ll) tp_wait_flags(mine, mine->push_flag[slot], c.size, tp_epoch(c, coll));
+  const uint32_t ep32 = tp_epoch32(c, coll);
   const uint32_t n4 = rows * hidden / 4, h4 = hidden / 4;
-  const float4* sb = reinterpret_cast<const float4*>(c.base[c.rank] + c.slot_off[slot]);
+  const float4* sb = reinterpret_cast<const float4*>(c.base[c.rank] + (ll ? c.ll_off[slot] : c.slot_off[slot]));
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const uint32_t row = i / h4, col = i - row * h4;
     float4 v = reinterpret_cast<const float4*>(x_in)[i];
+    if (ll) {
+      for (uint32_t r = 0; r < c.size; ++r) {
+        const uint4* pp = reinterpret_cast<const uint4*>(sb) + ((size_t(r) * kTpSmallRows + row) * hidden + 4 * size_t(col)) / 2;
+        const float4 a = tp_take_pairs(mine, pp, ld_pairs(pp), ld_pairs(pp + 1), ep32);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      reinterpret_cast<float4*>(x_out)[i] = v;
+      continue;
+    }
     for (uint32_t r = 0; r < c.size; ++r) {
       const float4 a = ld_pushed_f4(sb + (size_t(r) * kTpSmallRows + row) * h4 + col);
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
@@ -211,27 +231,39 @@ int tp_step_begin(const TpCtx& c, cudaStream_t st) {
 }
 
 int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, uint32_t n_tokens, uint32_t hidden,
-                   float eps, uint32_t split_k, cudaStream_t st) {
+                   float eps, uint32_t split_k, bool wait_ag, cudaStream_t st) {
   const uint32_t rpr = (n_tokens + c.size - 1) / c.size;
   const uint32_t lo = c.rank * rpr;
   const uint32_t n_own = lo >= n_tokens ? 0u : (n_tokens - lo < rpr ? n_tokens - lo : rpr);
-  tp_reduce_norm_kernel<<<n_own ? n_own : 1u, 256, 0, st>>>(c, coll, x, (const __nv_bfloat16*)gain, n_tokens, rpr, n_own,
-                                                            hidden, eps, c.size * split_k);
+  // programmatic dependent launch WITHOUT a dependency wait in the kernel: everything it reads arrives by
+  // flag (the local rank's partials included), it writes nothing the producer GEMM or anything before it
+  // still reads, and its done[] counters are its own — so it may sit on the SMs, polling, while the GEMM drains
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_own ? n_own : 1u);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tp_reduce_norm_kernel, c, coll, x, (const __nv_bfloat16*)gain, n_tokens, rpr, n_own,
+                                      hidden, eps, c.size * split_k, wait_ag ? 1u : 0u));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
 
-int tp_push_rows(const TpCtx& c, uint32_t coll, const float* partial, uint32_t rows, uint32_t hidden, cudaStream_t st) {
+int tp_push_rows(const TpCtx& c, uint32_t coll, const float* partial, uint32_t rows, uint32_t hidden, bool ll, cudaStream_t st) {
   uint32_t blocks = (rows * hidden / 4 + 255) / 256;
   if (blocks > 32) blocks = 32;
-  tp_push_rows_kernel<<<blocks, 256, 0, st>>>(c, coll, partial, rows, hidden);
+  tp_push_rows_kernel<<<blocks, 256, 0, st>>>(c, coll, partial, rows, hidden, ll ? 1u : 0u);
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
-int tp_fold_rows(const TpCtx& c, uint32_t coll, const float* x_in, float* x_out, uint32_t rows, uint32_t hidden, cudaStream_t st) {
+int tp_fold_rows(const TpCtx& c, uint32_t coll, const float* x_in, float* x_out, uint32_t rows, uint32_t hidden, bool ll, cudaStream_t st) {
   uint32_t blocks = (rows * hidden / 4 + 255) / 256;
   if (blocks > 32) blocks = 32;
-  tp_fold_rows_kernel<<<blocks, 256, 0, st>>>(c, coll, x_in, x_out, rows, hidden);
+  tp_fold_rows_kernel<<<blocks, 256, 0, st>>>(c, coll, x_in, x_out, rows, hidden, ll ? 1u : 0u);
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }

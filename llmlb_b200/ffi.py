@@ -31,7 +31,7 @@ class EngineConfig(C.Structure):
                 ("synthetic_seed", C.c_uint64), ("use_cuda_graphs", C.c_uint32),
                 ("gemm_impl", C.c_uint32), ("lookahead", C.c_uint32), ("queue_max", C.c_uint32),
                 ("queue_timeout_ms", C.c_uint32), ("request_timeout_ms", C.c_uint32), ("attn_impl", C.c_uint32),
-                ("reserved", C.c_uint32 * 4)]
+                ("tp_proto", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class ModelInfo(C.Structure):
@@ -157,7 +157,7 @@ class Engine:
 
     def __init__(self, model, model_id="llama-3-8b-synthetic", device=0, tp_rank=0, tp_size=1,
                  max_seqs=8, max_ctx=1024, kv_pages=0, max_step_tokens=0, seed=0,
-                 use_cuda_graphs=True, gemm_impl=0, lookahead=0, queue_max=0, queue_timeout_ms=0, request_timeout_ms=0, attn_impl=0):
+                 use_cuda_graphs=True, gemm_impl=0, lookahead=0, queue_max=0, queue_timeout_ms=0, request_timeout_ms=0, attn_impl=0, tp_proto=0):
         cfg = EngineConfig()
         cfg.abi_version = ABI_VERSION
         for k, v in model.items():
@@ -170,7 +170,7 @@ class Engine:
         cfg.use_cuda_graphs = 1 if use_cuda_graphs else 0
         cfg.gemm_impl, cfg.lookahead = gemm_impl, lookahead
         cfg.queue_max, cfg.queue_timeout_ms, cfg.request_timeout_ms = queue_max, queue_timeout_ms, request_timeout_ms
-        cfg.attn_impl = attn_impl
+        cfg.attn_impl, cfg.tp_proto = attn_impl, tp_proto
         self.model = dict(model)
         self.cfg = cfg
         self._h = vp()

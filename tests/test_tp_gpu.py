@@ -30,14 +30,15 @@ def _free_port():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("proto", [0, 1], ids=["pairs", "flags"])
 @pytest.mark.parametrize("geom", ["tiny", "odd"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_tensor_parallel_matches_oracle_and_single_gpu(built_lib, world, geom):
+def test_tensor_parallel_matches_oracle_and_single_gpu(built_lib, world, geom, proto):
     if _n_gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tools", "tp_check.py"), "--geom", geom]
+           os.path.join(ROOT, "tools", "tp_check.py"), "--geom", geom, "--proto", str(proto)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-3000:]
     assert "ranks identical: True" in r.stdout

@@ -42,12 +42,13 @@ def geometry(world, kind):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--geom", default="tiny", choices=["tiny", "odd"])
+    ap.add_argument("--proto", type=int, default=0, help="decode exchange: 0 = {value, epoch} pairs, 1 = values + flags")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = geometry(world, args.geom)
-    eng = ffi.Engine(cfg, device=local, tp_rank=rank, tp_size=world, max_seqs=8, max_ctx=512, seed=0)
+    eng = ffi.Engine(cfg, device=local, tp_rank=rank, tp_size=world, max_seqs=8, max_ctx=512, seed=0, tp_proto=args.proto)
     handles = [None] * world
     dist.all_gather_object(handles, eng.tp_export())
     eng.tp_import(handles)
@@ -117,9 +118,9 @@ def main():
             s1 = [one.debug_decode_logits(7), one.debug_decode_logits(99)]
         d0 = float(np.abs(lg - l1).max())
         d1 = max(float(np.abs(a - b).max()) for a, b in zip(step, s1))
-        print("tp=%d geom=%s max|dlogit| vs oracle: prefill150 %.4g decode %.4g %.4g prefill3 %.4g decode %.4g; vs tp=1 engine: prefill %.4g decode %.4g; "
+        print("tp=%d geom=%s proto=%d max|dlogit| vs oracle: prefill150 %.4g decode %.4g %.4g prefill3 %.4g decode %.4g; vs tp=1 engine: prefill %.4g decode %.4g; "
               "ranks identical: %s; top-1 agreement %d/%d, all near-argmax: %s, lengths ok: %s"
-              % (world, args.geom, e0, e1, e2, e3, e4, d0, d1, same, agree, total, near, lens_ok))
+              % (world, args.geom, args.proto, e0, e1, e2, e3, e4, d0, d1, same, agree, total, near, lens_ok))
         ok = max(e0, e1, e2, e3, e4) < TOL and max(d0, d1) < TOL and same and near and lens_ok and agree >= int(0.9 * total)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

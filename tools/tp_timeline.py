@@ -96,6 +96,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--gen", type=int, default=6)
+    ap.add_argument("--proto", type=int, default=0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dist = None
@@ -108,7 +109,7 @@ def main():
     L.llmlb_debug_trace_enable.argtypes = [C.c_uint32]
     L.llmlb_debug_trace_dump.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     model = ffi.LLAMA3_8B
-    eng = ffi.Engine(model, device=local, tp_rank=rank, tp_size=world, max_seqs=max(4, args.streams), max_ctx=1024, seed=0)
+    eng = ffi.Engine(model, device=local, tp_rank=rank, tp_size=world, max_seqs=max(4, args.streams), max_ctx=1024, seed=0, tp_proto=args.proto)
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, eng.tp_export())
