@@ -190,14 +190,15 @@ __device__ __forceinline__ void tp_signal_when_grid_done(const TpCtx& c, unsigne
   __shared__ unsigned int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence_system();         // this CTA's pushes are performed system-wide before its ticket is taken
     const unsigned int old = atomicAdd(done, 1u);
     const unsigned int last = (old == n_ctas - 1) ? 1u : 0u;
     if (last) *done = 0;            // the next user of this counter is ordered after this kernel
-    __threadfence_system();
     s_last = last;
   }
   __syncthreads();
+  // the release stores below are themselves fences for what the last CTA observed (the other CTAs'
+  // tickets, each taken after that CTA's own system fence): no second full fence on every CTA
   if (s_last && threadIdx.x < c.size) st_release_sys_u64(flag_of(tp_flags(c, threadIdx.x)), epoch);
 }
 #endif
