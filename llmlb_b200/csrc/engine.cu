@@ -391,6 +391,8 @@ struct llmlb_engine {
   bool paused = false;
   std::string fatal_error;
   float* part_ws = nullptr;         // [8 splits][t_cap][hidden] fp32: K-split partials of O / down (tp == 1)
+  float* sk_ws = nullptr;           // in-kernel K-split of the store-epilogue GEMMs: parked fp32 tiles (tc_common.cuh)
+  unsigned int* sk_cnt = nullptr;   //   and one arrival counter per output tile
   int warmup();
   std::vector<int32_t> cur_batch_slots;  // what d B.slots currently holds
 
@@ -582,6 +584,8 @@ int llmlb_engine::alloc_all() {
   RC(dmalloc(&d_block_tables, size_t(cfg.max_seqs) * pages_per_seq));
 
   RC(dmalloc(&x, size_t(t_cap) * H));
+  RC(dmalloc(&sk_ws, kSkWsBytes / 4, false));
+  RC(dmalloc(&sk_cnt, kSkCounters));
   if (tp > 1) {
     // the exchange region (tp_common.cuh): [pull barrier flags | TpFlags | slot 0 | slot 1 | logits | y]
     const size_t al = 1024;
@@ -596,6 +600,9 @@ int llmlb_engine::alloc_all() {
     const size_t llslot = up(size_t(kTpMaxRanks) * kTpSmallRows * H * 8);
     tpc.ll_off[0] = off; off += llslot;
     tpc.ll_off[1] = off; off += llslot;
+    const size_t gslot = up(size_t(kTpSmallRows) * H * 8);   // the consumer grid's own all-gather of the folded residual
+    tpc.gather_off[0] = off; off += gslot;
+    tpc.gather_off[1] = off; off += gslot;
     logits_slot_off = off; off += lslot;
     tpc.y_off = off; off += up(size_t(t_cap) * H * 2);
     xchg_bytes = off;
@@ -702,12 +709,12 @@ __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, c
 // One tensor-core projection of bf16 activations (T > 4).
 int llmlb_engine::proj(const CUtensorMap& mw, const void*, const void*, const CUtensorMap* mx, void* out, uint32_t T,
                        uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, int wait_coll) {
+  TpPushRS tpp{};
+  tpp.sk_ws = sk_ws; tpp.sk_cnt = sk_cnt;   // narrow projections K-split inside the kernel
   if (wait_coll >= 0) {   // tensor parallel: the activation operand is y of that collective (its all-gather flags gate the loads)
-    TpPushRS tpp{};
     tpp.ctx = tpc; tpp.wait_coll_plus1 = uint32_t(wait_coll) + 1;
-    return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &tpp);
   }
-  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)]);
+  return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &tpp);
 }
 
 // RoPE + KV append + attention of layer l over the rows in qkv -> attn
@@ -1471,7 +1478,7 @@ extern "C" void llmlb_engine_destroy(llmlb_engine* e) {
   if (e->tp_ready)
     for (uint32_t r = 0; r < e->tp; ++r)
       if (r != e->rank && e->tpc.base[r]) cudaIpcCloseMemHandle(e->tpc.base[r]);
-  F(e->xchg); F(e->part_ws);
+  F(e->xchg); F(e->part_ws); F(e->sk_ws); F(e->sk_cnt);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;

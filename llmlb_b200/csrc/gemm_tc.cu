@@ -204,6 +204,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       // two warps share a TMEM lane quarter: each takes half of the token columns
       constexpr uint32_t kColsPerWarp = (BN / 2 >= 16) ? BN / 2 : 16;
       const uint32_t c_begin = ((warp - 4) >> 2) * kColsPerWarp;
+      if constexpr (EPI == LLMLB_EPI_STORE_BF16 || EPI == LLMLB_EPI_SILU_MUL || EPI == LLMLB_EPI_STORE_F32) {
+        if (split_k > 1) {
+          // ---- in-kernel K-split: the split_k CTAs of an output tile each park their fp32 partial in the
+          // workspace, meet at the tile's counter, and then each finishes every split_k-th 16-token column
+          // group (sum over the parts in part order: deterministic), so the reduction itself is spread
+          // over the CTAs that did the products.  All CTAs of the grid are co-resident (one tile per CTA,
+          // grid <= SM count) and nobody waits before it has parked its own part.
+          const uint32_t otile = mt * t_tiles + tt;
+          float* wtile = tp.sk_ws + size_t(otile) * split_k * (BN * kBM);
+          float* wmine = wtile + size_t(ks) * (BN * kBM);
+#pragma unroll 1
+          for (uint32_t c = c_begin; c < c_begin + kColsPerWarp && c < BN; c += 16) {
+            if (t0 + c >= n_tokens) break;
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
+            tc_wait_ld();
+            float4* dst = reinterpret_cast<float4*>(wmine + (c >> 4) * (16 * kBM) + (q * 32 + lane) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + acc);
+          epi_bar();
+          if (threadIdx.x == 128) {
+            __threadfence();                        // the CTA's parked part is performed device-wide before its arrival
+            atomicAdd(tp.sk_cnt + otile, 1u);
+            const unsigned long long w0 = gtime_ns();
+            unsigned int spins = 0;
+            while (ld_acquire_gpu_u32(tp.sk_cnt + otile) < split_k) {
+              if ((++spins & 0xFFFu) == 0 && gtime_ns() - w0 > 2000000000ull) __trap();   // a part never arrived: fail, do not hang
+            }
+          }
+          epi_bar();
+          const uint32_t et = threadIdx.x - 128;    // 0..255
+          const uint32_t n_groups = (min(uint32_t(BN), n_tokens - t0) + 15) >> 4;
+          for (uint32_t grp = ks; grp < n_groups; grp += split_k) {
+            const float* src = wtile + grp * (16 * kBM);
+            if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
+              const uint32_t pr = et & 63, qt = et >> 6;           // rows (2pr, 2pr+1) = (gate, up); 4 tokens
+              float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
+              for (uint32_t s2 = 0; s2 < split_k; ++s2) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(src + size_t(s2) * (BN * kBM) + (2 * pr) * 16 + qt * 4));
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + size_t(s2) * (BN * kBM) + (2 * pr + 1) * 16 + qt * 4));
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+                u.x += b.x; u.y += b.y; u.z += b.z; u.w += b.w;
+              }
+              const uint32_t nn = mt * kBM + 2 * pr;
+              if (nn + 1 < n_out) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+                const float gv[4] = {g.x, g.y, g.z, g.w}, uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t t = t0 + grp * 16 + qt * 4 + j;
+                  if (t < n_tokens) o[size_t(t) * out_stride + (nn >> 1)] = __float2bfloat16_rn(__fdividef(gv[j], 1.f + __expf(-gv[j])) * uv[j]);
+                }
+              }
+            } else {
+              const uint32_t row = et & 127, hf = et >> 7;         // one weight row, 8 tokens
+              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+              for (uint32_t s2 = 0; s2 < split_k; ++s2) {
+                const float4* p4 = reinterpret_cast<const float4*>(src + size_t(s2) * (BN * kBM) + row * 16 + hf * 8);
+                const float4 a = __ldcg(p4), b = __ldcg(p4 + 1);
+                a0.x += a.x; a0.y += a.y; a0.z += a.z; a0.w += a.w;
+                a1.x += b.x; a1.y += b.y; a1.z += b.z; a1.w += b.w;
+              }
+              const uint32_t nn = mt * kBM + row;
+              if (nn < n_out) {
+                const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint32_t t = t0 + grp * 16 + hf * 8 + j;
+                  if (t < n_tokens) {
+                    const size_t idx = size_t(t) * out_stride + nn;
+                    if constexpr (EPI == LLMLB_EPI_STORE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v[j]);
+                    else reinterpret_cast<float*>(out)[idx] = v[j];
+                  }
+                }
+              }
+            }
+          }
+          // second pass over the counter: the CTA that sees every part gone through the meeting point zeroes it
+          if (threadIdx.x == 128 && atomicAdd(tp.sk_cnt + otile, 1u) == 2 * split_k - 1) atomicExch(tp.sk_cnt + otile, 0u);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (uint32_t c = c_begin; c < c_begin + kColsPerWarp && c < BN; c += 16) {
         if (t0 + c >= n_tokens) break;                  // warp-uniform
@@ -348,6 +436,9 @@ int make_tmap_nd(CUtensorMap* m, const void* base, uint32_t rank, const uint64_t
   return LLMLB_OK;
 }
 
+uint32_t tc_pick_bn(uint32_t n_tokens);
+uint32_t tc_store_split(uint32_t n_tokens, uint32_t n_out, uint32_t k, const TpPushRS* tpp);
+
 template <int BN, int EPI>
 static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint32_t n_tokens,
                      uint32_t n_out, uint32_t k, uint32_t out_stride, uint32_t split_k,
@@ -394,14 +485,14 @@ static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMa
                            uint32_t split_k, cudaStream_t st, const TpPushRS* tpp) {
   switch (epi) {
     case LLMLB_EPI_STORE_BF16:
-      return launch_tc<BN, LLMLB_EPI_STORE_BF16>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+      return launch_tc<BN, LLMLB_EPI_STORE_BF16>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
     case LLMLB_EPI_RESID_F32:
       return launch_tc<BN, LLMLB_EPI_RESID_F32>(tw, tx, out, n_tokens, n_out, k, out_stride,
                                                 split_k, st);
     case LLMLB_EPI_SILU_MUL:
-      return launch_tc<BN, LLMLB_EPI_SILU_MUL>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+      return launch_tc<BN, LLMLB_EPI_SILU_MUL>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
     case LLMLB_EPI_STORE_F32:
-      return launch_tc<BN, LLMLB_EPI_STORE_F32>(tw, tx, out, n_tokens, n_out, k, out_stride, 1, st);
+      return launch_tc<BN, LLMLB_EPI_STORE_F32>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
     case kEpiPartialF32:
       return launch_tc<BN, kEpiPartialF32>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
     case kEpiPushRS:
@@ -409,6 +500,22 @@ static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMa
   }
   set_error("gemm_tc: unknown epilogue");
   return LLMLB_E_INVALID_ARG;
+}
+
+// K-split of a store-epilogue GEMM (one 128 x BN tile per CTA, all co-resident): as many parts as keep the grid
+// within the SM count, at least 4 K blocks each, every part non-empty.  1 = no split (no workspace, or enough tiles).
+uint32_t tc_store_split(uint32_t n_tokens, uint32_t n_out, uint32_t k, const TpPushRS* tpp) {
+  if (!tpp || !tpp->sk_ws || !tpp->sk_cnt) return 1;
+  const uint32_t bn = tc_pick_bn(n_tokens);
+  const uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
+  const uint32_t kblocks = (k + kBK - 1) / kBK;
+  if (tiles * 2 > (uint32_t)kNumSMs || tiles > kSkCounters) return 1;
+  uint32_t s = (uint32_t)kNumSMs / tiles;
+  if (s > 16) s = 16;
+  if (s > kblocks / 4) s = kblocks / 4;
+  if (s < 2) return 1;
+  const uint32_t per = (kblocks + s - 1) / s;
+  return (kblocks + per - 1) / per;
 }
 
 uint32_t tc_pick_bn(uint32_t n_tokens) {
@@ -436,7 +543,12 @@ int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint
                    const TpPushRS* tpp, uint32_t max_split) {
   const uint32_t bn = tc_pick_bn(n_tokens);
   if (n_parts) *n_parts = 1;
-  if (tx_half && bn == 256 && n_out >= 256)
+  // CTA pairs when there are enough 256 x 256 tiles to occupy most of the GPU; a narrow projection (tensor-
+  // parallel shards: QKV at tp = 8 has 6 pair tiles) runs 128-row tiles with an in-kernel K-split instead
+  const bool store_epi = epi == LLMLB_EPI_STORE_BF16 || epi == LLMLB_EPI_SILU_MUL || epi == LLMLB_EPI_STORE_F32;
+  const uint32_t pair_ctas = 2 * ((n_out + 255) / 256) * ((n_tokens + 255) / 256);
+  const bool narrow = store_epi && pair_ctas < 96 && tc_store_split(n_tokens, n_out, k, tpp) > 1;
+  if (tx_half && bn == 256 && n_out >= 256 && !narrow)
     return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts, tpp, max_split);
   // split K for the residual epilogues when the tile count cannot fill the GPU
   uint32_t split_k = 1;
@@ -444,6 +556,8 @@ int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint
     uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
     uint32_t kblocks = (k + kBK - 1) / kBK;
     while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8 && split_k * 2 <= max_split) split_k *= 2;
+  } else {
+    split_k = tc_store_split(n_tokens, n_out, k, tpp);   // store epilogues: K-split reduced inside the kernel
   }
   if (n_parts) *n_parts = split_k;
   switch (bn) {
@@ -490,5 +604,15 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   if (rc) return rc;
   rc = make_tmap_bf16(&txh, x, n_tokens, k, 128);
   if (rc) return rc;
-  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, nullptr, 8);
+  // the kernel-level entry point owns one K-split workspace per process (callers are serialised tests / benches)
+  static float* op_ws = nullptr;
+  static unsigned int* op_cnt = nullptr;
+  if (!op_ws) {
+    LLMLB_CUDA_CHECK(cudaMalloc((void**)&op_ws, kSkWsBytes));
+    LLMLB_CUDA_CHECK(cudaMalloc((void**)&op_cnt, kSkCounters * sizeof(unsigned int)));
+    LLMLB_CUDA_CHECK(cudaMemset(op_cnt, 0, kSkCounters * sizeof(unsigned int)));
+  }
+  TpPushRS tpp{};
+  tpp.sk_ws = op_ws; tpp.sk_cnt = op_cnt;
+  return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, &tpp, 8);
 }

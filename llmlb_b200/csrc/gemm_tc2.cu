@@ -312,10 +312,10 @@ int gemm_tc2_launch(const CUtensorMap& tw, const CUtensorMap& tx_half, void* out
   }
   if (n_parts) *n_parts = split_k;
   switch (epi) {
-    case LLMLB_EPI_STORE_BF16: return launch_tc2<256, LLMLB_EPI_STORE_BF16>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
+    case LLMLB_EPI_STORE_BF16: return launch_tc2<256, LLMLB_EPI_STORE_BF16>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st, tpp);
     case LLMLB_EPI_RESID_F32: return launch_tc2<256, LLMLB_EPI_RESID_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
-    case LLMLB_EPI_SILU_MUL: return launch_tc2<256, LLMLB_EPI_SILU_MUL>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
-    case LLMLB_EPI_STORE_F32: return launch_tc2<256, LLMLB_EPI_STORE_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st);
+    case LLMLB_EPI_SILU_MUL: return launch_tc2<256, LLMLB_EPI_SILU_MUL>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st, tpp);
+    case LLMLB_EPI_STORE_F32: return launch_tc2<256, LLMLB_EPI_STORE_F32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, 1, st, tpp);
     case kEpiPartialF32: return launch_tc2<256, kEpiPartialF32>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st);
     case kEpiPushRS: return launch_tc2<256, kEpiPushRS>(tw, tx_half, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
   }

@@ -113,12 +113,17 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
         if (tb.data && threadIdx.x == 0) tr_flag = gtime_ns();
       }
       const uint8_t* slot_base = tp.ctx.base[tp.ctx.rank] + (tp.ll ? tp.ctx.ll_off[slot] : tp.ctx.slot_off[slot]);
-      for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+      uint4* gat = reinterpret_cast<uint4*>(tp.ctx.base[tp.ctx.rank] + tp.ctx.gather_off[slot]);
+      // (1) OWNER FOLD.  float4 i of every row belongs to CTA i % gridDim.x: only that CTA reads the N pushed
+      // partials (148 CTAs each folding the whole residual cost 148 x N x K x 8 B of L2 reads per launch —
+      // 39 MB at N = 8, ~5 us; measured in profiles/r2_tp8_decode_timeline.txt), sums them onto the residual
+      // in rank order (identical sums on every rank), writes the new residual and publishes it to the rest
+      // of the grid as {value, epoch} pairs.
+      for (uint32_t i = blockIdx.x + gridDim.x * threadIdx.x; i < K / 4; i += gridDim.x * kKsThreads) {
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           float4 v = reinterpret_cast<const float4*>(xf + size_t(b) * K)[i];
-          // the loads of up to four sources are issued together, then summed in rank order
-          // (identical sums on every rank)
+          // the loads of up to four sources are issued together
           for (uint32_t r0 = 0; r0 < tp.ctx.size; r0 += 4) {
             if (tp.ll) {
               const uint4* pp[4];
@@ -146,8 +151,21 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
                 if (r0 + q < tp.ctx.size) { v.x += a[q].x; v.y += a[q].y; v.z += a[q].z; v.w += a[q].w; }
             }
           }
+          reinterpret_cast<float4*>(tp.x_out + size_t(b) * K)[i] = v;
+          uint4* g = gat + (size_t(b) * K + 4 * size_t(i)) / 2;
+          st_pairs_gpu(g, v.x, v.y, ep32);
+          st_pairs_gpu(g + 1, v.z, v.w, ep32);
+        }
+      }
+      // (2) GATHER.  Every CTA reads the whole folded residual back from L2 (K x 8 B per row), spinning on
+      // the epochs of pieces whose owner CTA is not through yet.  All CTAs of the grid are co-resident
+      // (grid <= SM count, one CTA per SM) and every owner publishes BEFORE it spins: no circular wait.
+      for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const uint4* g = gat + (size_t(b) * K + 4 * size_t(i)) / 2;
+          const float4 v = tp_take_pairs_gpu(mine, g, ld_pairs_gpu(g), ld_pairs_gpu(g + 1), ep32);
           reinterpret_cast<float4*>(ks_dyn + size_t(b) * K)[i] = v;
-          if (i % gridDim.x == blockIdx.x) reinterpret_cast<float4*>(tp.x_out + size_t(b) * K)[i] = v;
           ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         }
       }

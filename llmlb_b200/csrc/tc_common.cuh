@@ -20,7 +20,13 @@ struct TpPushRS {
   uint32_t rpr;       // kEpiPushRS: token rows per owner rank = ceil(n_tokens / size)
   uint32_t wait_coll_plus1;   // any epilogue: the activation operand is y of collective (this - 1): the TMA
                               // producer waits for its all-gather flags before the first activation load (0 = none)
+  // in-kernel K-split of the store epilogues (bf16 / SiLU*up / fp32): fp32 partial tiles parked in sk_ws,
+  // one arrival counter per output tile in sk_cnt (zero between launches); nullptr = no K-split
+  float* sk_ws;
+  unsigned int* sk_cnt;
 };
+constexpr size_t kSkWsBytes = size_t(148) * 128 * 256 * 4;   // every CTA of a full grid parks one 128 x 256 fp32 tile
+constexpr uint32_t kSkCounters = 256;
 constexpr int kBM = 128;          // weight rows per tile  (UMMA M)
 constexpr int kBK = 64;           // bf16 per K slab = 128 B = one swizzle row
 constexpr int kTcThreads = 384;    // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps

@@ -58,6 +58,8 @@ struct TpCtx {                      // kernel parameter, by value
   uint64_t slot_off[kTpSlots];      // fp32 partial slots
   uint64_t ll_off[kTpSlots];        // {value, epoch} pair slots of the LL variant (never written by anything else,
                                     // so a stale word can only be an older epoch)
+  uint64_t gather_off[kTpSlots];    // protocol A consumer: the folded residual as {value, epoch} pairs, written by the
+                                    // owner CTAs of THIS rank's consumer grid and read back by all of its CTAs
   uint64_t y_off;                   // bf16 [t_cap, hidden] normalised activations
   uint64_t slot_bytes;
 };
@@ -112,6 +114,15 @@ __device__ __forceinline__ uint4 ld_pairs(const uint4* p) {   // two {value, epo
   asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+// the same pairs inside ONE GPU (the consumer grid's own all-gather of the folded residual): gpu scope
+__device__ __forceinline__ void st_pairs_gpu(uint4* p, float a, float b, uint32_t epoch) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(epoch), "r"(__float_as_uint(b)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ld_pairs_gpu(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ TpFlags* tp_flags(const TpCtx& c, uint32_t r) {
   return reinterpret_cast<TpFlags*>(c.base[r] + c.flags_off);
 }
@@ -131,6 +142,22 @@ __device__ __forceinline__ float4 tp_take_pairs(TpFlags* mine, const uint4* p, u
     unsigned int spins = 0;
     do {
       a = ld_pairs(p); b = ld_pairs(p + 1);
+      if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) {
+        mine->timed_out = 1;
+        __threadfence_system();
+        __trap();
+      }
+    } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+// same, for pairs written by other CTAs of this GPU
+__device__ __forceinline__ float4 tp_take_pairs_gpu(TpFlags* mine, const uint4* p, uint4 a, uint4 b, uint32_t epoch) {
+  if (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
+    const unsigned long long t0 = gtime_ns();
+    unsigned int spins = 0;
+    do {
+      a = ld_pairs_gpu(p); b = ld_pairs_gpu(p + 1);
       if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) {
         mine->timed_out = 1;
         __threadfence_system();
@@ -168,16 +195,22 @@ __device__ __forceinline__ void tp_wait_ag_single(const TpCtx& c, uint32_t coll)
   TpFlags* mine = tp_flags(c, c.rank);
   const unsigned long long epoch = tp_epoch(c, coll);
   const unsigned long long t0 = gtime_ns();
-  for (uint32_t r = 0; r < c.size; ++r) {
-    unsigned int spins = 0;
-    while (ld_acquire_sys_u64(&mine->ag_flag[coll & 1][r]) < epoch) {
-      if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) {
-        mine->timed_out = 1;
-        __threadfence_system();
-        __trap();
-      }
+  unsigned int spins = 0;
+  // the N flag loads of one round are independent (relaxed) and in flight together: one L2 round trip per
+  // round instead of N; the acquire is the fence after the last round
+  for (;;) {
+    bool all = true;
+#pragma unroll
+    for (uint32_t r = 0; r < uint32_t(kTpMaxRanks); ++r)
+      if (r < c.size) all &= ld_relaxed_sys_u64(&mine->ag_flag[coll & 1][r]) >= epoch;
+    if (all) break;
+    if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) {
+      mine->timed_out = 1;
+      __threadfence_system();
+      __trap();
     }
   }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 // Every thread of every CTA of the grid calls this after its last push.  When the whole grid is

@@ -102,7 +102,9 @@ GEMM_SHAPES = [(512, 6144, 4096), (512, 4096, 14336), (64, 4096, 4096), (16, 102
 
 
 @pytest.mark.parametrize("impl", [0], ids=["tc"])
-@pytest.mark.parametrize("T,N,K", GEMM_SHAPES + [(128, 6144, 4096), (100, 1002, 520), (64, 4096, 14336), (7, 128, 4096)])
+@pytest.mark.parametrize("T,N,K", GEMM_SHAPES + [(128, 6144, 4096), (100, 1002, 520), (64, 4096, 14336), (7, 128, 4096),
+                                                 # tensor-parallel shard shapes: few tiles -> in-kernel K-split (gemm_tc.cu), up to 16 parts
+                                                 (512, 768, 4096), (128, 768, 4096), (512, 7168, 4096), (128, 3584, 4096), (64, 1536, 4096)])
 @pytest.mark.parametrize("epi", [ffi.EPI_STORE_BF16, ffi.EPI_RESID_F32, ffi.EPI_SILU_MUL, ffi.EPI_STORE_F32])
 def test_gemm(L, impl, T, N, K, epi):
     if epi == ffi.EPI_SILU_MUL and N % 2:
@@ -120,6 +122,30 @@ def test_gemm(L, impl, T, N, K, epi):
     err = (out.float() - ref).abs()
     lim = tol * ref.abs() + 2e-3 * math.sqrt(K / 4096)
     assert bool((err <= lim).all()), "max err %g at %s" % (err.max().item(), (err - lim).argmax().item())
+
+
+def test_gemm_ksplit_back_to_back_is_bit_reproducible(L):
+    """The in-kernel K-split meets at per-tile counters that the last part zeroes: 40 launches back to back
+    (alternating shapes and epilogues that share the workspace) must give bit-identical results."""
+    cases = [(128, 768, 4096, ffi.EPI_STORE_BF16), (64, 3584, 4096, ffi.EPI_SILU_MUL), (7, 128, 4096, ffi.EPI_STORE_F32)]
+    data = []
+    for T, N, K, epi in cases:
+        w = bf16_randn((N, K), std=0.02, seed=11 + N)
+        x = bf16_randn((T, K), seed=12 + T)
+        n_cols = N // 2 if epi == ffi.EPI_SILU_MUL else N
+        dt = torch.float32 if epi == ffi.EPI_STORE_F32 else torch.bfloat16
+        data.append((w, x, n_cols, dt, []))
+    for rep in range(40):
+        for (T, N, K, epi), (w, x, n_cols, dt, outs) in zip(cases, data):
+            out = torch.zeros(T, n_cols, dtype=dt, device=dev())
+            ok(L.llmlb_op_gemm(p(w), p(x), p(out), T, N, K, epi, n_cols, 0, stream_ptr()))
+            outs.append(out)
+    sync()
+    for (T, N, K, epi), (w, x, n_cols, dt, outs) in zip(cases, data):
+        ref = _gemm_ref(w, x, epi, torch.zeros(T, n_cols, device=dev()))
+        assert (outs[0].float() - ref).abs().max().item() < 2e-2
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
 
 
 def test_gemm_other_impls_are_not_in_the_library(L):

@@ -146,6 +146,8 @@ def main():
         ls = launches_of(r)
         vl = model["vocab"] // world
         heads = [i for i, l in enumerate(ls) if (l["tag"] >> 60) in (0, 4, 6) and ((l["tag"] >> 32) & 0xFFFFFF) == vl]
+        # one lm_head grid whose CTAs start more than 3 us apart (PDL early starters) shows up as adjacent pieces: keep the last
+        heads = [h for j, h in enumerate(heads) if j + 1 == len(heads) or heads[j + 1] - h > 4]
         print("tp=%d streams=%d: %d trace records, %d launches, %d lm_head launches" % (world, args.streams, len(r), len(ls), len(heads)))
         det = r[(r[:, 0] >> np.uint64(60)) == np.uint64(5)]
         if heads:
