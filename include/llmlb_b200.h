@@ -83,7 +83,8 @@ typedef struct llmlb_engine_config {
   uint32_t queue_timeout_ms;   /* a request still waiting for admission after this finishes QUEUE_TIMEOUT (504) */
   uint32_t request_timeout_ms; /* a request not finished this long after submit finishes DEADLINE (504 timeout) */
   uint32_t attn_impl;          /* prefill attention: 0 = tcgen05 + TMEM + TMA (default), 1 = mma.sync baseline */
-  uint32_t tp_proto;           /* tensor-parallel decode exchange: 0 = {value, epoch} pairs (default), 1 = values + flags */
+  uint32_t tp_proto;           /* tensor-parallel decode exchange: bit 0: 0 = {value, epoch} pairs (default), 1 = values + flags;
+                                  bit 1: 1 = owner CTAs fold the partials and the consumer grid gathers the result through L2 */
   uint32_t reserved[3];
 } llmlb_engine_config;
 

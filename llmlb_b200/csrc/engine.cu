@@ -60,7 +60,7 @@ void tc2_set_trace(const TraceBuf& tb);
 // tensor parallel (tp_common.cuh): fused GEMV consumer / producer of protocol A, pull kernels
 int gemv_tp_consume(const TpCtx& ctx, uint32_t coll_in, const void* w, const float* x_in, float* x_out,
                     const void* gain, float eps, void* out, uint32_t n_tokens, uint32_t n_out, uint32_t k,
-                    uint32_t epi, uint32_t out_stride, bool ll, cudaStream_t st);
+                    uint32_t epi, uint32_t out_stride, bool ll, bool gather, cudaStream_t st);
 int gemv_tp_push(const TpCtx& ctx, uint32_t coll_out, const void* w, const void* x_bf16, uint32_t n_tokens,
                  uint32_t n_out, uint32_t k, bool ll, cudaStream_t st);
 int ar_allreduce_add(const TpCtx& P, uint64_t off, float* x, uint64_t n, cudaStream_t st);
@@ -380,6 +380,8 @@ struct llmlb_engine {
   bool tp_ready = false;
   uint32_t tp_coll = 0;              // collectives issued so far in the current forward pass
   bool tp_ll = true;                 // protocol A variant: {value, epoch} pairs (default) or values + end-of-grid flags
+  bool tp_gather = false;            // protocol A consumer: owner CTAs fold + in-GPU gather (tp_proto bit 1) instead of every CTA folding
+  bool dbg_no_ksplit = false, dbg_no_agwait = false;
   float* xb = nullptr;               // second residual buffer (protocol A ping-pong)
   float* tp_stage = nullptr;         // [4][hidden] fp32: partial rows of projections the fused GEMV does not take
   __nv_bfloat16* ylast = nullptr;    // [max_seqs][hidden] normalised rows that need logits (protocol B)
@@ -466,6 +468,9 @@ struct llmlb_engine {
   uint8_t* next_stage() { return h_stage[(stage_seq++) % kRing]; }
   uint32_t decode_splits(uint32_t nb) const {
     uint32_t ctas = nb * (nq_l / 4);
+    // batched steps with enough (sequence, head group) pairs: the tensor-core kernel, one warp per pair, no KV split
+    // (tp = 2, 64 streams: the 2-way split SIMT kernel took 45 us per layer for 75 MB of K/V)
+    if (nb > 4 && ctas >= 96) return 1;
     uint32_t sp = (2 * kNumSMs + ctas - 1) / ctas;
     if (sp > 16) sp = 16;
     if (sp < 1) sp = 1;
@@ -502,7 +507,7 @@ int llmlb_engine::init() {
   }
   if (!(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank >= tp) { set_error("bad tp_size/tp_rank"); return LLMLB_E_INVALID_ARG; }
   if (cfg.gemm_impl != 0) { set_error("gemm_impl: only 0 (tcgen05 tiles) is built into the library"); return LLMLB_E_INVALID_ARG; }
-  if (cfg.tp_proto > 1) { set_error("tp_proto: 0 (value+epoch pairs) or 1 (flags)"); return LLMLB_E_INVALID_ARG; }
+  if (cfg.tp_proto > 3) { set_error("tp_proto: bit 0 = flags instead of value+epoch pairs, bit 1 = owner-fold + gather consumer"); return LLMLB_E_INVALID_ARG; }
   if (cfg.attn_impl > 1) { set_error("attn_impl: 0 (tcgen05) or 1 (mma.sync baseline)"); return LLMLB_E_INVALID_ARG; }
   if (M.n_kv_heads == 0 || M.n_heads % M.n_kv_heads || M.n_kv_heads % tp || M.ffn % tp || M.vocab % tp ||
       ((M.n_heads / M.n_kv_heads) % 4) || M.hidden % 8 || (M.ffn / tp) % 8 || (M.vocab / tp) % 4 ||
@@ -576,7 +581,11 @@ int llmlb_engine::alloc_all() {
   RC(dmalloc(&k_pool, layer_pool_elems * M.n_layers));
   RC(dmalloc(&v_pool, layer_pool_elems * M.n_layers));
   pf_tile = cfg.attn_impl == 0 ? 128 : 64;
-  tp_ll = cfg.tp_proto == 0;
+  tp_ll = (cfg.tp_proto & 1) == 0;
+  tp_gather = (cfg.tp_proto & 2) != 0;
+  // diagnostics, resolved once here (never read on the launch path)
+  dbg_no_ksplit = getenv("LLMLB_DEBUG_NO_KSPLIT") != nullptr;
+  dbg_no_agwait = getenv("LLMLB_DEBUG_NO_AGWAIT") != nullptr;
   RC(make_tmap_attn_kv(&m_kpool, k_pool, M.n_layers, n_pages, nkv_l));
   RC(make_tmap_attn_kv(&m_vpool, v_pool, M.n_layers, n_pages, nkv_l));
   RC(dmalloc(&rope, size_t(cfg.max_ctx) * 64 * 2));
@@ -710,8 +719,8 @@ __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, c
 int llmlb_engine::proj(const CUtensorMap& mw, const void*, const void*, const CUtensorMap* mx, void* out, uint32_t T,
                        uint32_t n_out, uint32_t k, uint32_t epi, uint32_t out_stride, int wait_coll) {
   TpPushRS tpp{};
-  tpp.sk_ws = sk_ws; tpp.sk_cnt = sk_cnt;   // narrow projections K-split inside the kernel
-  if (wait_coll >= 0) {   // tensor parallel: the activation operand is y of that collective (its all-gather flags gate the loads)
+  if (!dbg_no_ksplit) { tpp.sk_ws = sk_ws; tpp.sk_cnt = sk_cnt; }   // narrow projections K-split inside the kernel
+  if (wait_coll >= 0 && !dbg_no_agwait) {   // tensor parallel: the activation operand is y of that collective (its all-gather flags gate the loads)
     tpp.ctx = tpc; tpp.wait_coll_plus1 = uint32_t(wait_coll) + 1;
   }
   return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &tpp);
@@ -794,7 +803,7 @@ int llmlb_engine::forward_small_tp(uint32_t T, bool decode, uint32_t nb, uint32_
   int pending = -1;   // collective pushed but not yet folded into `cur`
   auto consume = [&](const void* w, const __nv_bfloat16* gain, void* out, uint32_t n_out, uint32_t epi, uint32_t out_stride) -> int {
     if (pending >= 0) {
-      int rc = gemv_tp_consume(tpc, uint32_t(pending), w, cur, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, tp_ll, st);
+      int rc = gemv_tp_consume(tpc, uint32_t(pending), w, cur, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, tp_ll, tp_gather, st);
       if (rc == LLMLB_E_UNSUPPORTED) {   // odd shape: fold with its own kernel, then the plain projection
         RC(tp_fold_rows(tpc, uint32_t(pending), cur, oth, T, H, tp_ll, st));
         rc = gemv_decode(w, oth, gain, M.rms_eps, out, T, n_out, H, epi, out_stride, st);
@@ -899,7 +908,7 @@ int llmlb_engine::logits_from_y(const __nv_bfloat16* src, const CUtensorMap* map
 // protocol A, decode: the lm_head GEMV's prologue consumes the last down projection's collective
 int llmlb_engine::logits_tp_consume(FwdState* fs, uint32_t R) {
   int rc = gemv_tp_consume(tpc, fs->pending_coll, lm_head, fs->xres, fs->xother, final_norm, M.rms_eps, logits_dst(), R,
-                           vocab_l, M.hidden, LLMLB_EPI_STORE_F32, vocab_l, tp_ll, st);
+                           vocab_l, M.hidden, LLMLB_EPI_STORE_F32, vocab_l, tp_ll, tp_gather, st);
   if (rc == LLMLB_E_UNSUPPORTED) {
     RC(finish_small_tp(fs, R));
     return logits_from_x(fs->xres, R);

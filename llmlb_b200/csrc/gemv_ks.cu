@@ -33,6 +33,7 @@ struct TpGemv {
   uint32_t coll_in, coll_out;   // collective consumed by the prologue / produced by the epilogue
   float* x_out;                 // TPM == 1: residual after the fold
   uint32_t ll;                  // 1: {value, epoch} pairs (no flags), 0: values + end-of-grid flags
+  uint32_t gather;              // TPM == 1: 1 = owner CTAs fold, the grid gathers the result through L2; 0 = every CTA folds
 };
 
 constexpr int kKsThreads = 512;
@@ -114,59 +115,75 @@ gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin
       }
       const uint8_t* slot_base = tp.ctx.base[tp.ctx.rank] + (tp.ll ? tp.ctx.ll_off[slot] : tp.ctx.slot_off[slot]);
       uint4* gat = reinterpret_cast<uint4*>(tp.ctx.base[tp.ctx.rank] + tp.ctx.gather_off[slot]);
-      // (1) OWNER FOLD.  float4 i of every row belongs to CTA i % gridDim.x: only that CTA reads the N pushed
-      // partials (148 CTAs each folding the whole residual cost 148 x N x K x 8 B of L2 reads per launch —
-      // 39 MB at N = 8, ~5 us; measured in profiles/r2_tp8_decode_timeline.txt), sums them onto the residual
-      // in rank order (identical sums on every rank), writes the new residual and publishes it to the rest
-      // of the grid as {value, epoch} pairs.
-      for (uint32_t i = blockIdx.x + gridDim.x * threadIdx.x; i < K / 4; i += gridDim.x * kKsThreads) {
+      // x_in[b][4i..4i+3] + the N pushed partials, summed in rank order (identical sums on every rank); the loads
+      // of up to four sources are issued together
+      auto fold_one = [&](int b, uint32_t i) -> float4 {
+        float4 v = reinterpret_cast<const float4*>(xf + size_t(b) * K)[i];
+        for (uint32_t r0 = 0; r0 < tp.ctx.size; r0 += 4) {
+          if (tp.ll) {
+            const uint4* pp[4];
+            uint4 pa[4], pb[4];
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          float4 v = reinterpret_cast<const float4*>(xf + size_t(b) * K)[i];
-          // the loads of up to four sources are issued together
-          for (uint32_t r0 = 0; r0 < tp.ctx.size; r0 += 4) {
-            if (tp.ll) {
-              const uint4* pp[4];
-              uint4 pa[4], pb[4];
+            for (int q = 0; q < 4; ++q)
+              if (r0 + q < tp.ctx.size) {
+                pp[q] = reinterpret_cast<const uint4*>(slot_base) + ((size_t(r0 + q) * kTpSmallRows + b) * K + 4 * size_t(i)) / 2;
+                pa[q] = ld_pairs(pp[q]); pb[q] = ld_pairs(pp[q] + 1);
+              }
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (r0 + q < tp.ctx.size) {
-                  pp[q] = reinterpret_cast<const uint4*>(slot_base) + ((size_t(r0 + q) * kTpSmallRows + b) * K + 4 * size_t(i)) / 2;
-                  pa[q] = ld_pairs(pp[q]); pb[q] = ld_pairs(pp[q] + 1);
-                }
+            for (int q = 0; q < 4; ++q)
+              if (r0 + q < tp.ctx.size) {
+                const float4 a = tp_take_pairs(mine, pp[q], pa[q], pb[q], ep32);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+              }
+          } else {
+            float4 a[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (r0 + q < tp.ctx.size) {
-                  const float4 a = tp_take_pairs(mine, pp[q], pa[q], pb[q], ep32);
-                  v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                }
-            } else {
-              float4 a[4];
+            for (int q = 0; q < 4; ++q)
+              if (r0 + q < tp.ctx.size)
+                a[q] = ld_pushed_f4(reinterpret_cast<const float4*>(slot_base) + (size_t(r0 + q) * kTpSmallRows + b) * (K / 4) + i);
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (r0 + q < tp.ctx.size)
-                  a[q] = ld_pushed_f4(reinterpret_cast<const float4*>(slot_base) + (size_t(r0 + q) * kTpSmallRows + b) * (K / 4) + i);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (r0 + q < tp.ctx.size) { v.x += a[q].x; v.y += a[q].y; v.z += a[q].z; v.w += a[q].w; }
-            }
+            for (int q = 0; q < 4; ++q)
+              if (r0 + q < tp.ctx.size) { v.x += a[q].x; v.y += a[q].y; v.z += a[q].z; v.w += a[q].w; }
           }
-          reinterpret_cast<float4*>(tp.x_out + size_t(b) * K)[i] = v;
-          uint4* g = gat + (size_t(b) * K + 4 * size_t(i)) / 2;
-          st_pairs_gpu(g, v.x, v.y, ep32);
-          st_pairs_gpu(g + 1, v.z, v.w, ep32);
         }
-      }
-      // (2) GATHER.  Every CTA reads the whole folded residual back from L2 (K x 8 B per row), spinning on
-      // the epochs of pieces whose owner CTA is not through yet.  All CTAs of the grid are co-resident
-      // (grid <= SM count, one CTA per SM) and every owner publishes BEFORE it spins: no circular wait.
-      for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+        return v;
+      };
+      if (tp.gather) {
+        // (1) OWNER FOLD.  float4 i of every row belongs to CTA i % gridDim.x: only that CTA reads the N pushed
+        // partials (every CTA folding the whole residual costs 148 x N x K x 8 B of L2 reads per launch: 39 MB at
+        // N = 8), writes the new residual and publishes it to the rest of the grid as {value, epoch} pairs.
+        for (uint32_t i = blockIdx.x + gridDim.x * threadIdx.x; i < K / 4; i += gridDim.x * kKsThreads) {
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          const uint4* g = gat + (size_t(b) * K + 4 * size_t(i)) / 2;
-          const float4 v = tp_take_pairs_gpu(mine, g, ld_pairs_gpu(g), ld_pairs_gpu(g + 1), ep32);
-          reinterpret_cast<float4*>(ks_dyn + size_t(b) * K)[i] = v;
-          ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          for (int b = 0; b < B; ++b) {
+            const float4 v = fold_one(b, i);
+            reinterpret_cast<float4*>(tp.x_out + size_t(b) * K)[i] = v;
+            uint4* g = gat + (size_t(b) * K + 4 * size_t(i)) / 2;
+            st_pairs_gpu(g, v.x, v.y, ep32);
+            st_pairs_gpu(g + 1, v.z, v.w, ep32);
+          }
+        }
+        // (2) GATHER.  Every CTA reads the whole folded residual back from L2 (K x 8 B per row), spinning on
+        // the epochs of pieces whose owner CTA is not through yet.  All CTAs of the grid are co-resident
+        // (grid <= SM count, one CTA per SM) and every owner publishes BEFORE it spins: no circular wait.
+        for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const uint4* g = gat + (size_t(b) * K + 4 * size_t(i)) / 2;
+            const float4 v = tp_take_pairs_gpu(mine, g, ld_pairs_gpu(g), ld_pairs_gpu(g + 1), ep32);
+            reinterpret_cast<float4*>(ks_dyn + size_t(b) * K)[i] = v;
+            ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          }
+        }
+      } else {
+        // every CTA folds the whole residual itself (one L2 hop after the push lands)
+        for (uint32_t i = threadIdx.x; i < K / 4; i += kKsThreads) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const float4 v = fold_one(b, i);
+            reinterpret_cast<float4*>(ks_dyn + size_t(b) * K)[i] = v;
+            if (i % gridDim.x == blockIdx.x) reinterpret_cast<float4*>(tp.x_out + size_t(b) * K)[i] = v;
+            ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          }
         }
       }
       if (tp.ll && tb.data && threadIdx.x == 0) tr_flag = gtime_ns();
@@ -412,11 +429,11 @@ bool gemv_tp_shape_ok(uint32_t n_tokens, uint32_t k) {
 // consumer: x_out = x_in + sum of the pushed partials of collective coll_in; out = epi(W . RMSNorm(x_out))
 int gemv_tp_consume(const TpCtx& ctx, uint32_t coll_in, const void* w, const float* x_in, float* x_out,
                     const void* gain, float eps, void* out, uint32_t n_tokens, uint32_t n_out, uint32_t k,
-                    uint32_t epi, uint32_t out_stride, bool ll, cudaStream_t st) {
+                    uint32_t epi, uint32_t out_stride, bool ll, bool gather, cudaStream_t st) {
   uint32_t tw = 0, cw = 0;
   if (n_tokens == 0 || n_tokens > 4 || !gain || !ks_pick(n_tokens, k, &tw, &cw)) return LLMLB_E_UNSUPPORTED;
   TpGemv tp{};
-  tp.ctx = ctx; tp.coll_in = coll_in; tp.x_out = x_out; tp.ll = ll ? 1u : 0u;
+  tp.ctx = ctx; tp.coll_in = coll_in; tp.x_out = x_out; tp.ll = ll ? 1u : 0u; tp.gather = gather ? 1u : 0u;
 #define KS_TC(BB, CC)                                                                                                          \
   switch (epi) {                                                                                                               \
     case LLMLB_EPI_STORE_BF16: return ks_launch<BB, LLMLB_EPI_STORE_BF16, true, CC, 1>(w, x_in, gain, eps, out, n_out, k, out_stride, tw, st, nullptr, 0, &tp); \

@@ -67,11 +67,11 @@ __global__ void tp_step_begin_kernel(TpCtx c) {
 
 // ---------------------------------------------------------------- protocol B consumer -------
 // grid = max(1, owned rows); CTA b owns token row rank*rpr + b.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_bfloat16* __restrict__ gain,
                       uint32_t n_tokens, uint32_t rpr, uint32_t n_own, uint32_t hidden, float eps, uint32_t n_parts,
                       uint32_t wait_ag) {
-  __shared__ float red[8];
+  __shared__ float red[32];
   const TraceBuf tb = d_trace_tp;
   unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
   if (tb.data && threadIdx.x == 0) tr0 = gtime_ns();
@@ -86,33 +86,46 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
   if (blockIdx.x < n_own) {
     const uint32_t t = c.rank * rpr + blockIdx.x;
     float4* xr = reinterpret_cast<float4*>(x + size_t(t) * hidden);
-    const uint8_t* slot_base = c.base[c.rank] + c.slot_off[slot];
+    const uint2* slot_row = reinterpret_cast<const uint2*>(c.base[c.rank] + c.slot_off[slot]) + size_t(blockIdx.x) * (hidden / 4);
+    const size_t part_stride = size_t(rpr) * (hidden / 4);
     float ss = 0.f;
-    for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
+    // a thread's elements stay in registers between the two passes (hidden <= 2 * 4 * blockDim; more: re-read)
+    float4 keep[2];
+    uint32_t it = 0;
+    for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x, ++it) {
       float4 v = xr[i];
-      for (uint32_t r = 0; r < n_parts; ++r) {   // part = rank * split_k + ks, ascending: a fixed order; bf16 on the wire
-        const uint2 a = ld_pushed_u2(reinterpret_cast<const uint2*>(slot_base) + (size_t(r) * rpr + blockIdx.x) * (hidden / 4) + i);
-        v.x += bf16_lo(a.x); v.y += bf16_hi(a.x); v.z += bf16_lo(a.y); v.w += bf16_hi(a.y);
+      // part = rank * split_k + ks, ascending: a fixed order; bf16 on the wire.  Eight loads are in flight
+      // together (one dependent L2 round trip per eight parts instead of one per part)
+      for (uint32_t r0 = 0; r0 < n_parts; r0 += 8) {
+        uint2 a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (r0 + q < n_parts) a[q] = ld_pushed_u2(slot_row + size_t(r0 + q) * part_stride + i);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (r0 + q < n_parts) { v.x += bf16_lo(a[q].x); v.y += bf16_hi(a[q].x); v.z += bf16_lo(a[q].y); v.w += bf16_hi(a[q].y); }
       }
       xr[i] = v;
+      if (it < 2) keep[it] = v;
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
     const float rs = rsqrtf(tot / float(hidden) + eps);
     const uint2* g2 = reinterpret_cast<const uint2*>(gain);
-    for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x) {
-      const float4 v = xr[i];  // own writes, same thread
+    it = 0;
+    for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x, ++it) {
+      const float4 v = it < 2 ? keep[it] : xr[i];  // own writes, same thread
       const uint2 g = __ldg(g2 + i);
       uint2 o;
       o.x = pack_bf16(v.x * rs * bf16_lo(g.x), v.y * rs * bf16_hi(g.x));
       o.y = pack_bf16(v.z * rs * bf16_lo(g.y), v.w * rs * bf16_hi(g.y));
-      for (uint32_t r = 0; r < c.size; ++r)
-        st_peer_u2(reinterpret_cast<uint2*>(c.base[r] + c.y_off) + size_t(t) * (hidden / 4) + i, o);
+#pragma unroll
+      for (uint32_t r = 0; r < uint32_t(kTpMaxRanks); ++r)
+        if (r < c.size) st_peer_u2(reinterpret_cast<uint2*>(c.base[r] + c.y_off) + size_t(t) * (hidden / 4) + i, o);
     }
   }
   if (tb.data && threadIdx.x == 0) tr2 = gtime_ns();
@@ -240,7 +253,11 @@ int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, ui
   // still reads, and its done[] counters are its own — so it may sit on the SMs, polling, while the GEMM drains
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_own ? n_own : 1u);
-  cfg.blockDim = dim3(256);
+  // one element group (4 values) per thread where the row allows it: every load of a row is in flight at once
+  uint32_t threads = ((hidden / 4 + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  if (threads < 64) threads = 64;
+  cfg.blockDim = dim3(threads);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -143,7 +143,7 @@ def test_gemm_ksplit_back_to_back_is_bit_reproducible(L):
     sync()
     for (T, N, K, epi), (w, x, n_cols, dt, outs) in zip(cases, data):
         ref = _gemm_ref(w, x, epi, torch.zeros(T, n_cols, device=dev()))
-        assert (outs[0].float() - ref).abs().max().item() < 2e-2
+        assert bool(((outs[0].float() - ref).abs() <= 2 ** -7 * ref.abs() + 4e-3).all())
         for o in outs[1:]:
             assert torch.equal(o, outs[0])
 

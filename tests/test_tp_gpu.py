@@ -30,8 +30,8 @@ def _free_port():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("proto", [0, 1], ids=["pairs", "flags"])
-@pytest.mark.parametrize("geom", ["tiny", "odd"])
+@pytest.mark.parametrize("proto", [0, 1, 2], ids=["pairs", "flags", "gather"])
+@pytest.mark.parametrize("geom", ["tiny", "odd", "8b4"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_tensor_parallel_matches_oracle_and_single_gpu(built_lib, world, geom, proto):
     if _n_gpus() < world:

@@ -30,6 +30,10 @@ NEAR = 0.06       # teacher-forced tokens must be within this of the oracle's ar
 
 
 def geometry(world, kind):
+    if kind == "8b4":                         # full Llama-3-8B widths, 4 layers: the shard shapes of the benchmark
+        cfg = dict(ffi.LLAMA3_8B)
+        cfg["n_layers"] = 4
+        return cfg
     cfg = dict(ffi.LLAMA_TINY)
     cfg["n_kv_heads"] = max(2, world)         # kv heads must divide by tp
     cfg["n_heads"] = 4 * cfg["n_kv_heads"]
@@ -41,19 +45,20 @@ def geometry(world, kind):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--geom", default="tiny", choices=["tiny", "odd"])
-    ap.add_argument("--proto", type=int, default=0, help="decode exchange: 0 = {value, epoch} pairs, 1 = values + flags")
+    ap.add_argument("--geom", default="tiny", choices=["tiny", "odd", "8b4"])
+    ap.add_argument("--proto", type=int, default=0, help="decode exchange: bit 0: 0 = {value, epoch} pairs, 1 = values + flags; bit 1: owner-fold + gather consumer")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = geometry(world, args.geom)
-    eng = ffi.Engine(cfg, device=local, tp_rank=rank, tp_size=world, max_seqs=8, max_ctx=512, seed=0, tp_proto=args.proto)
+    eng = ffi.Engine(cfg, device=local, tp_rank=rank, tp_size=world, max_seqs=8, max_ctx=1024, seed=0, tp_proto=args.proto)
     handles = [None] * world
     dist.all_gather_object(handles, eng.tp_export())
     eng.tp_import(handles)
     dist.barrier()
-    prompt = np.random.RandomState(3).randint(0, cfg["vocab"], 150).tolist()
+    big = args.geom == "8b4"
+    prompt = np.random.RandomState(3).randint(0, cfg["vocab"], 512 if big else 150).tolist()
     lg = eng.debug_prefill_logits(prompt)
     step = [eng.debug_decode_logits(7), eng.debug_decode_logits(99)]
     eng.debug_reset()
@@ -87,7 +92,26 @@ def main():
     dist.all_gather_object(gathered, (lg[:64].tolist(), toks3, toks7))
     eng.close()
     ok = True
-    if rank == 0:
+    if rank == 0 and big:
+        # 8B widths: the tp = 1 engine (itself pinned to the oracle by tests/test_parity_8b_gpu.py) is the checker
+        with ffi.Engine(cfg, device=local, max_seqs=8, max_ctx=1024, seed=0) as one:
+            l1 = one.debug_prefill_logits(prompt)
+            s1 = [one.debug_decode_logits(7), one.debug_decode_logits(99)]
+            one.debug_reset()
+            l3 = one.debug_prefill_logits(prompt[:3])
+            s3 = one.debug_decode_logits(11)
+            one.debug_reset()
+            ref3 = [one.generate(p, 24, ignore_eos=True)[0] for p in p3]
+        d = [float(np.abs(lg - l1).max()), float(np.abs(step[0] - s1[0]).max()), float(np.abs(step[1] - s1[1]).max()),
+             float(np.abs(lg3 - l3).max()), float(np.abs(step3 - s3).max())]
+        same = all(g == gathered[0] for g in gathered)
+        eq3 = sum(int(a == b) for a, b in zip(toks3, ref3))
+        lens_ok = all(len(t) == 24 for t in toks3) and all(len(t) == 10 for t in toks7)
+        print("tp=%d geom=8b4 proto=%d max|dlogit| vs tp=1 engine: prefill512 %.4g decode %.4g %.4g prefill3 %.4g decode %.4g (logit std %.3f); "
+              "ranks identical: %s; staggered requests token-identical to tp=1: %d/3; lengths ok: %s"
+              % (world, args.proto, d[0], d[1], d[2], d[3], d[4], float(l1.std()), same, eq3, lens_ok))
+        ok = max(d) < 0.08 and same and lens_ok
+    elif rank == 0:
         from oracle.llama_ref import LlamaRef
         from oracle.synth import synth_state_dict
         sd = synth_state_dict(cfg, 0)
