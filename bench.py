@@ -331,6 +331,15 @@ def run_ours(args):
                           "ranks_identical": all(a == got for a in allt),
                           "ok": bool(max(margins) <= PARITY_TOL_TP and all(a == got for a in allt) and len(got) == GEN)}
             barrier()
+    if args.parity_only:
+        if rank == 0:
+            print(json.dumps({"parity_only": True, "n_gpus": world, "max_seqs": max_seqs, "parity": parity}))
+            sys.stdout.flush()
+        eng.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---------------- main leg: batch-1 requests ----------------
     for i in range(args.warmup):
@@ -490,6 +499,7 @@ def main():
     ap.add_argument("--tp-proto", type=int, default=0, help="tensor-parallel decode exchange: 0 = value+epoch pairs, 1 = flags")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-only", action="store_true", help="diagnostic: print the tp parity record and stop")
     ap.add_argument("--no-ref-shape", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-prompt", type=int, default=32)

@@ -344,7 +344,12 @@ struct DecPartial {               // per-CTA result, read by the cluster leader
 };
 
 __global__ void __launch_bounds__(kDecThreads)
-decode_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* k_pages,
+decode_attention_kernel(const __nv_bfloat16* qkv /* NOT __restrict__: written by the predecessor grid while this one may
+                                                           already be resident (programmatic launch) — with restrict + const
+                                                           the compiler hoisted four q loads above griddepcontrol.wait as
+                                                           LDG.CONSTANT (SASS, round 2) and the kernel read the previous
+                                                           layer's rows */,
+                        __nv_bfloat16* k_pages,
                         __nv_bfloat16* v_pages, const int32_t* __restrict__ block_tables,
                         uint32_t bt_stride, const int32_t* __restrict__ bt_rows,
                         const int32_t* __restrict__ seq_lens,
@@ -618,7 +623,7 @@ int rope_append_launch(void* qkv, const int32_t* positions, const int32_t* page_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = (pdl && !(g_dbg_no_pdl & 16u)) ? 1 : 0;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rope_append_kernel, (__nv_bfloat16*)qkv, positions, page_of_token,
                                       (const float2*)rope_table, (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages, n_heads, n_kv,
                                       pdl ? 1u : 0u));
@@ -912,7 +917,7 @@ int decode_attention_launch(const void* qkv, void* k_pages, void* v_pages, const
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
+  cfg.numAttrs = (pdl && !(g_dbg_no_pdl & 8u)) ? 2 : 1;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(
       &cfg, decode_attention_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_pages,
       (__nv_bfloat16*)v_pages, block_tables, bt_stride, bt_rows, seq_lens,

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 // This is where the K-split partial products of the O / down projections are folded into the
 // residual stream — a fixed-order replacement for fp32 atomics (and the hook for TP partials).
 __global__ void __launch_bounds__(256) rmsnorm_parts_kernel(float* __restrict__ x,
-                                                            const float* __restrict__ parts,
+                                                            const float* parts /* predecessor output: no restrict (PDL) */,
                                                             uint32_t n_parts, size_t part_stride,
                                                             const __nv_bfloat16* __restrict__ gain,
                                                             __nv_bfloat16* __restrict__ y,

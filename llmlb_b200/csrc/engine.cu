@@ -79,6 +79,7 @@ int rope_append_launch(void* qkv, const int32_t* positions, const int32_t* page_
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
 std::atomic<uint64_t> g_kernel_launches{0};
+unsigned int g_dbg_no_pdl = 0;
 
 #define RC(expr)                 \
   do {                           \
@@ -584,6 +585,7 @@ int llmlb_engine::alloc_all() {
   tp_ll = (cfg.tp_proto & 1) == 0;
   tp_gather = (cfg.tp_proto & 2) != 0;
   // diagnostics, resolved once here (never read on the launch path)
+  g_dbg_no_pdl = getenv("LLMLB_DEBUG_NO_PDL") ? (unsigned int)atoi(getenv("LLMLB_DEBUG_NO_PDL")) : 0u;
   dbg_no_ksplit = getenv("LLMLB_DEBUG_NO_KSPLIT") != nullptr;
   dbg_no_agwait = getenv("LLMLB_DEBUG_NO_AGWAIT") != nullptr;
   RC(make_tmap_attn_kv(&m_kpool, k_pool, M.n_layers, n_pages, nkv_l));

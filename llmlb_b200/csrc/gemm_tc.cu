@@ -472,7 +472,7 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& tx, void* out, ui
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (g_dbg_no_pdl & 16u) ? 0 : 1;
     LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, 1u, tp));
   }
   LLMLB_LAUNCH_CHECK();

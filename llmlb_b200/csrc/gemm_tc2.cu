@@ -292,7 +292,7 @@ static int launch_tc2(const CUtensorMap& tw, const CUtensorMap& tx_half, void* o
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = (g_dbg_no_pdl & 16u) ? 1 : 2;
   TpPushRS tp{};
   if (tpp) tp = *tpp;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tw, tx_half, out, n_tokens, n_out, k, out_stride, m_tiles, t_tiles, split_k, tp));

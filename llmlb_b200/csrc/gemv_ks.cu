@@ -47,7 +47,7 @@ __device__ __forceinline__ void team_barrier(int id, int threads) {
 
 template <int B, int EPI, bool NORM, int CW, int TPM>
 __global__ void __launch_bounds__(kKsThreads)
-gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* __restrict__ xin,
+gemv_ks_kernel(const __nv_bfloat16* __restrict__ W, const void* xin /* predecessor output: no restrict (PDL) */,
                const __nv_bfloat16* __restrict__ gain, float eps, void* __restrict__ out,
                uint32_t n_out, uint32_t K, uint32_t out_stride, uint32_t TW,
                const uint8_t* __restrict__ pf_ptr, uint32_t pf_bytes, const TpGemv tp) {
@@ -376,7 +376,7 @@ static int ks_launch(const void* w, const void* x, const void* gain, float eps, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // programmatic dependent launch
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_dbg_no_pdl & (TPM == 0 ? 1u : TPM == 1 ? 2u : 4u)) ? 0 : 1;
   TpGemv tpv{};
   if (tp) tpv = *tp;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)w, x,

@@ -263,7 +263,7 @@ int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, ui
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_dbg_no_pdl & 16u) ? 0 : 1;
   LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tp_reduce_norm_kernel, c, coll, x, (const __nv_bfloat16*)gain, n_tokens, rpr, n_own,
                                       hidden, eps, c.size * split_k, wait_ag ? 1u : 0u));
   LLMLB_LAUNCH_CHECK();
