@@ -382,7 +382,7 @@ struct llmlb_engine {
   uint32_t tp_coll = 0;              // collectives issued so far in the current forward pass
   bool tp_ll = true;                 // protocol A variant: {value, epoch} pairs (default) or values + end-of-grid flags
   bool tp_gather = false;            // protocol A consumer: owner CTAs fold + in-GPU gather (tp_proto bit 1) instead of every CTA folding
-  bool dbg_no_ksplit = false, dbg_no_agwait = false;
+  bool dbg_no_ksplit = false, dbg_no_agwait = false, dbg_no_rsll = false;
   float* xb = nullptr;               // second residual buffer (protocol A ping-pong)
   float* tp_stage = nullptr;         // [4][hidden] fp32: partial rows of projections the fused GEMV does not take
   __nv_bfloat16* ylast = nullptr;    // [max_seqs][hidden] normalised rows that need logits (protocol B)
@@ -587,6 +587,7 @@ int llmlb_engine::alloc_all() {
   // diagnostics, resolved once here (never read on the launch path)
   g_dbg_no_pdl = getenv("LLMLB_DEBUG_NO_PDL") ? (unsigned int)atoi(getenv("LLMLB_DEBUG_NO_PDL")) : 0u;
   dbg_no_ksplit = getenv("LLMLB_DEBUG_NO_KSPLIT") != nullptr;
+  dbg_no_rsll = getenv("LLMLB_DEBUG_NO_RSLL") != nullptr;
   dbg_no_agwait = getenv("LLMLB_DEBUG_NO_AGWAIT") != nullptr;
   RC(make_tmap_attn_kv(&m_kpool, k_pool, M.n_layers, n_pages, nkv_l));
   RC(make_tmap_attn_kv(&m_vpool, v_pool, M.n_layers, n_pages, nkv_l));
@@ -611,6 +612,9 @@ int llmlb_engine::alloc_all() {
     const size_t llslot = up(size_t(kTpMaxRanks) * kTpSmallRows * H * 8);
     tpc.ll_off[0] = off; off += llslot;
     tpc.ll_off[1] = off; off += llslot;
+    const size_t rsslot = up(size_t(kTpMaxSplit) * (kTpLLTokens + kTpMaxRanks) * H * 4);   // parts x rows-per-owner <= split x (T + N)
+    tpc.rsll_off[0] = off; off += rsslot;
+    tpc.rsll_off[1] = off; off += rsslot;
     const size_t gslot = up(size_t(kTpSmallRows) * H * 8);   // the consumer grid's own all-gather of the folded residual
     tpc.gather_off[0] = off; off += gslot;
     tpc.gather_off[1] = off; off += gslot;
@@ -862,9 +866,10 @@ int llmlb_engine::forward_big_tp(uint32_t T, bool decode, uint32_t nb, uint32_t 
     tpp.ctx = tpc; tpp.coll = tp_coll++; tpp.rpr = rpr;
     *coll = int(tpp.coll);
     uint32_t n_parts = 1;
-    RC(gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], nullptr, T, H, k, kEpiPushRS, H, st, &mx[bn_index(128)], &n_parts,
+    const bool ll = T <= kTpLLTokens && !dbg_no_rsll;   // narrow steps: {value, epoch} words, no flag round
+    RC(gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], nullptr, T, H, k, ll ? kEpiPushRSLL : kEpiPushRS, H, st, &mx[bn_index(128)], &n_parts,
                       &tpp, kTpMaxSplit));
-    return tp_reduce_norm(tpc, tpp.coll, x, next_gain, T, H, M.rms_eps, n_parts, last, st);
+    return tp_reduce_norm(tpc, tpp.coll, x, next_gain, T, H, M.rms_eps, n_parts, last, ll, st);
   };
   // layer 0: the embedding rows are complete on every rank
   RC(llmlb_op_rmsnorm(x, layers[0].attn_norm, y, T, H, M.rms_eps, st));

@@ -34,6 +34,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   if constexpr (EPI == kEpiPushRS) {
     if (threadIdx.x < tp.ctx.size) s_peer_slot[threadIdx.x] = tp.ctx.base[threadIdx.x] + tp.ctx.slot_off[tp.coll & 1];
   }
+  if constexpr (EPI == kEpiPushRSLL) {
+    if (threadIdx.x < tp.ctx.size) s_peer_slot[threadIdx.x] = tp.ctx.base[threadIdx.x] + tp.ctx.rsll_off[tp.coll & 1];
+  }
   // Programmatic dependent launch: the next kernel of the stream may be
   // scheduled as soon as SMs free up, and THIS kernel may have been scheduled before its
   // predecessor finished: until griddepcontrol.wait it touches nothing but weights.
@@ -194,6 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t acc = 0, acc_phase = 0;
     if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs may alias what earlier kernels read
+    uint32_t ep_ll = 0;
+    if constexpr (EPI == kEpiPushRSLL) ep_ll = tp_epoch32(tp.ctx, tp.coll);   // the step counter is final after the wait
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       uint32_t mt, tt, ks;
       decode_tile(tile, mt, tt, ks);
@@ -298,7 +303,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         uint32_t r[16];
         tc_ld16(tmem_base + ((q * 32) << 16) + acc * BN + c, r);
         tc_wait_ld();
-        if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
+        if constexpr (EPI == kEpiPushRSLL) {
+          // lanes (2i, 2i+1) hold output features (n, n+1) of the same tokens: one 8-byte word {bf16 n, bf16 n+1, epoch}
+          // per token; even lanes send the even token columns, odd lanes the odd ones
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = __uint_as_float(r[j]);
+            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            const uint32_t t = t0 + c + j;
+            if (((j ^ lane) & 1) == 0 && (n | 1) < n_out && t < n_tokens) {
+              const float lo = (lane & 1) ? other : v, hi = (lane & 1) ? v : other;
+              const uint32_t owner = t / tp.rpr, tl = t - owner * tp.rpr;
+              uint2 w;
+              w.x = pack_bf16(lo, hi);
+              w.y = ep_ll;
+              st_peer_u2(reinterpret_cast<uint2*>(s_peer_slot[owner]) +
+                             (size_t(tp.ctx.rank * split_k + ks) * tp.rpr + tl) * (out_stride / 2) + (n >> 1), w);
+            }
+          }
+        } else if constexpr (EPI == LLMLB_EPI_SILU_MUL) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -497,6 +520,9 @@ static int dispatch_tc_epi(uint32_t epi, const CUtensorMap& tw, const CUtensorMa
       return launch_tc<BN, kEpiPartialF32>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st);
     case kEpiPushRS:
       return launch_tc<BN, kEpiPushRS>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
+    case kEpiPushRSLL:
+      if constexpr (BN <= 128) return launch_tc<BN, kEpiPushRSLL>(tw, tx, out, n_tokens, n_out, k, out_stride, split_k, st, tpp);
+      break;
   }
   set_error("gemm_tc: unknown epilogue");
   return LLMLB_E_INVALID_ARG;
@@ -552,7 +578,7 @@ int gemm_tc_launch(const CUtensorMap& tw, const CUtensorMap& tx, void* out, uint
     return gemm_tc2_launch(tw, *tx_half, out, n_tokens, n_out, k, epi, out_stride, st, n_parts, tpp, max_split);
   // split K for the residual epilogues when the tile count cannot fill the GPU
   uint32_t split_k = 1;
-  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32 || epi == (uint32_t)kEpiPushRS) {
+  if (epi == LLMLB_EPI_RESID_F32 || epi == (uint32_t)kEpiPartialF32 || epi == (uint32_t)kEpiPushRS || epi == (uint32_t)kEpiPushRSLL) {
     uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
     uint32_t kblocks = (k + kBK - 1) / kBK;
     while (tiles * split_k * 2 <= (uint32_t)kNumSMs && kblocks / (split_k * 2) >= 8 && split_k * 2 <= max_split) split_k *= 2;

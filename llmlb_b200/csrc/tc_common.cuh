@@ -14,6 +14,11 @@ constexpr int kEpiPartialF32 = 4;
 // tensor parallel, protocol B (tp_common.cuh): the fp32 partial of token row t, K-split ks, goes
 // straight into the slot of the rank that OWNS the row: part (rank * split_k + ks), row t % rpr
 constexpr int kEpiPushRS = 5;
+// the same for narrow steps (batched decode, T <= kTpLLTokens): every pushed 8-byte word carries two bf16 values of
+// adjacent output features AND the collective's epoch, so the owner's reduce kernel spins on the data itself —
+// no system fence per CTA, no ticket, no flag round at the end of the GEMM grid (tp_common.cuh, "LL" variant)
+constexpr int kEpiPushRSLL = 6;
+constexpr uint32_t kTpLLTokens = 128;
 struct TpPushRS {
   TpCtx ctx;
   uint32_t coll;      // kEpiPushRS: collective index within the step (slot = coll & 1)

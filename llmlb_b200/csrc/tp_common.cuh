@@ -58,6 +58,8 @@ struct TpCtx {                      // kernel parameter, by value
   uint64_t slot_off[kTpSlots];      // fp32 partial slots
   uint64_t ll_off[kTpSlots];        // {value, epoch} pair slots of the LL variant (never written by anything else,
                                     // so a stale word can only be an older epoch)
+  uint64_t rsll_off[kTpSlots];      // protocol B, narrow steps: {bf16 x 2, epoch} words of the reduce-scatter
+                                    // [part][row of the owner][hidden / 2] (never written by anything else)
   uint64_t gather_off[kTpSlots];    // protocol A consumer: the folded residual as {value, epoch} pairs, written by the
                                     // owner CTAs of THIS rank's consumer grid and read back by all of its CTAs
   uint64_t y_off;                   // bf16 [t_cap, hidden] normalised activations
@@ -246,6 +248,6 @@ int tp_fold_rows(const TpCtx& c, uint32_t coll, const float* x_in, float* x_out,
 // wait_ag: the grid does not end before every owner's rows arrived here (for consumers of y that are
 // not tensor-core GEMMs; those wait for the flags themselves: TpPushRS::wait_coll_plus1)
 int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, uint32_t n_tokens, uint32_t hidden,
-                   float eps, uint32_t split_k, bool wait_ag, cudaStream_t st);
+                   float eps, uint32_t split_k, bool wait_ag, bool ll, cudaStream_t st);
 
 }  // namespace llmlb

@@ -67,6 +67,7 @@ __global__ void tp_step_begin_kernel(TpCtx c) {
 
 // ---------------------------------------------------------------- protocol B consumer -------
 // grid = max(1, owned rows); CTA b owns token row rank*rpr + b.
+template <bool LL>
 __global__ void __launch_bounds__(1024)
 tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_bfloat16* __restrict__ gain,
                       uint32_t n_tokens, uint32_t rpr, uint32_t n_own, uint32_t hidden, float eps, uint32_t n_parts,
@@ -81,7 +82,8 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
   const uint32_t slot = coll & 1;
   TpFlags* mine = tp_flags(c, c.rank);
   const unsigned long long epoch = tp_epoch(c, coll);
-  tp_wait_flags(mine, mine->push_flag[slot], c.size, epoch);
+  const uint32_t ep32 = tp_epoch32(c, coll);
+  if constexpr (!LL) tp_wait_flags(mine, mine->push_flag[slot], c.size, epoch);
   if (tb.data && threadIdx.x == 0) tr1 = gtime_ns();
   if (blockIdx.x < n_own) {
     const uint32_t t = c.rank * rpr + blockIdx.x;
@@ -96,6 +98,29 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
       float4 v = xr[i];
       // part = rank * split_k + ks, ascending: a fixed order; bf16 on the wire.  Eight loads are in flight
       // together (one dependent L2 round trip per eight parts instead of one per part)
+      if constexpr (LL) {
+        // narrow steps: every 8-byte word is {bf16 x 2, epoch}: spin on the words themselves (no flag round)
+        const uint4* ll_row = reinterpret_cast<const uint4*>(c.base[c.rank] + c.rsll_off[slot]) + size_t(blockIdx.x) * (hidden / 4);
+        for (uint32_t r0 = 0; r0 < n_parts; r0 += 8) {
+          uint4 a[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (r0 + q < n_parts) a[q] = ld_pairs(ll_row + size_t(r0 + q) * part_stride + i);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (r0 + q < n_parts) {
+              if (a[q].y != ep32 || a[q].w != ep32) {
+                const unsigned long long t0 = gtime_ns();
+                unsigned int spins = 0;
+                do {
+                  a[q] = ld_pairs(ll_row + size_t(r0 + q) * part_stride + i);
+                  if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) { mine->timed_out = 1; __threadfence_system(); __trap(); }
+                } while (a[q].y != ep32 || a[q].w != ep32);
+              }
+              v.x += bf16_lo(a[q].x); v.y += bf16_hi(a[q].x); v.z += bf16_lo(a[q].z); v.w += bf16_hi(a[q].z);
+            }
+        }
+      } else {
       for (uint32_t r0 = 0; r0 < n_parts; r0 += 8) {
         uint2 a[8];
 #pragma unroll
@@ -104,6 +129,7 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (r0 + q < n_parts) { v.x += bf16_lo(a[q].x); v.y += bf16_hi(a[q].x); v.z += bf16_lo(a[q].y); v.w += bf16_hi(a[q].y); }
+      }
       }
       xr[i] = v;
       if (it < 2) keep[it] = v;
@@ -244,7 +270,7 @@ int tp_step_begin(const TpCtx& c, cudaStream_t st) {
 }
 
 int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, uint32_t n_tokens, uint32_t hidden,
-                   float eps, uint32_t split_k, bool wait_ag, cudaStream_t st) {
+                   float eps, uint32_t split_k, bool wait_ag, bool ll, cudaStream_t st) {
   const uint32_t rpr = (n_tokens + c.size - 1) / c.size;
   const uint32_t lo = c.rank * rpr;
   const uint32_t n_own = lo >= n_tokens ? 0u : (n_tokens - lo < rpr ? n_tokens - lo : rpr);
@@ -264,8 +290,12 @@ int tp_reduce_norm(const TpCtx& c, uint32_t coll, float* x, const void* gain, ui
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (g_dbg_no_pdl & 16u) ? 0 : 1;
-  LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tp_reduce_norm_kernel, c, coll, x, (const __nv_bfloat16*)gain, n_tokens, rpr, n_own,
-                                      hidden, eps, c.size * split_k, wait_ag ? 1u : 0u));
+  if (ll)
+    LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tp_reduce_norm_kernel<true>, c, coll, x, (const __nv_bfloat16*)gain, n_tokens, rpr, n_own,
+                                        hidden, eps, c.size * split_k, wait_ag ? 1u : 0u));
+  else
+    LLMLB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tp_reduce_norm_kernel<false>, c, coll, x, (const __nv_bfloat16*)gain, n_tokens, rpr, n_own,
+                                        hidden, eps, c.size * split_k, wait_ag ? 1u : 0u));
   LLMLB_LAUNCH_CHECK();
   return LLMLB_OK;
 }
