@@ -95,12 +95,35 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
     float4 keep[2];
     uint32_t it = 0;
     for (uint32_t i = threadIdx.x; i < hidden / 4; i += blockDim.x, ++it) {
-      float4 v = xr[i];
+      float4 v;
+      if constexpr (!LL) v = xr[i];
       // part = rank * split_k + ks, ascending: a fixed order; bf16 on the wire.  Eight loads are in flight
       // together (one dependent L2 round trip per eight parts instead of one per part)
       if constexpr (LL) {
         // narrow steps: every 8-byte word is {bf16 x 2, epoch}: spin on the words themselves (no flag round)
         const uint4* ll_row = reinterpret_cast<const uint4*>(c.base[c.rank] + c.rsll_off[slot]) + size_t(blockIdx.x) * (hidden / 4);
+        // The residual row is read only after THIS rank's own words of the collective arrived.  This kernel has no
+        // dependency wait and may be resident while the previous collective's reduce kernel (which writes x) is
+        // still running (programmatic launches overlap whole kernels when grids are small); the local projection
+        // GEMM's words prove it finished: words <- this rank's GEMM <- (its dependency wait) the GEMM before <-
+        // that reduce kernel.  (Reading x first gave wrong tokens on 7-wide decode steps: tools/tp_check.py.)
+        {
+          const uint32_t split_k = n_parts / c.size;
+          for (uint32_t ks = 0; ks < split_k; ++ks) {
+            const uint4* w = ll_row + size_t(c.rank * split_k + ks) * part_stride + i;
+            uint4 a0 = ld_pairs(w);
+            if (a0.y != ep32 || a0.w != ep32) {
+              const unsigned long long t0 = gtime_ns();
+              unsigned int spins = 0;
+              do {
+                a0 = ld_pairs(w);
+                if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) { mine->timed_out = 1; __threadfence_system(); __trap(); }
+              } while (a0.y != ep32 || a0.w != ep32);
+            }
+          }
+          __threadfence();
+          v = __ldcg(xr + i);
+        }
         for (uint32_t r0 = 0; r0 < n_parts; r0 += 8) {
           uint4 a[8];
 #pragma unroll
@@ -117,8 +140,10 @@ tp_reduce_norm_kernel(TpCtx c, uint32_t coll, float* __restrict__ x, const __nv_
                   if ((++spins & 0xFFFu) == 0 && gtime_ns() - t0 > 20000000000ull) { mine->timed_out = 1; __threadfence_system(); __trap(); }
                 } while (a[q].y != ep32 || a[q].w != ep32);
               }
-              v.x += bf16_lo(a[q].x); v.y += bf16_hi(a[q].x); v.z += bf16_lo(a[q].z); v.w += bf16_hi(a[q].z);
             }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (r0 + q < n_parts) { v.x += bf16_lo(a[q].x); v.y += bf16_hi(a[q].x); v.z += bf16_lo(a[q].z); v.w += bf16_hi(a[q].z); }
         }
       } else {
       for (uint32_t r0 = 0; r0 < n_parts; r0 += 8) {

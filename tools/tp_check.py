@@ -102,15 +102,25 @@ def main():
             s3 = one.debug_decode_logits(11)
             one.debug_reset()
             ref3 = [one.generate(p, 24, ignore_eos=True)[0] for p in p3]
+            # batched steps (3-wide protocol A, 7-wide protocol B): every token the sharded engine picked must be a
+            # near-arg-max of the tp=1 engine's logits when teacher-forced along the sharded engine's own tokens
+            worst = 0.0
+            for pr, ts in list(zip(p3, toks3)) + list(zip(p7, toks7)):
+                cur = one.debug_prefill_logits(pr)
+                for j, tok in enumerate(ts):
+                    worst = max(worst, float(cur.max() - cur[tok]))
+                    if j + 1 < len(ts):
+                        cur = one.debug_decode_logits(tok)
+                one.debug_reset()
         d = [float(np.abs(lg - l1).max()), float(np.abs(step[0] - s1[0]).max()), float(np.abs(step[1] - s1[1]).max()),
              float(np.abs(lg3 - l3).max()), float(np.abs(step3 - s3).max())]
         same = all(g == gathered[0] for g in gathered)
         eq3 = sum(int(a == b) for a, b in zip(toks3, ref3))
         lens_ok = all(len(t) == 24 for t in toks3) and all(len(t) == 10 for t in toks7)
         print("tp=%d geom=8b4 proto=%d max|dlogit| vs tp=1 engine: prefill512 %.4g decode %.4g %.4g prefill3 %.4g decode %.4g (logit std %.3f); "
-              "ranks identical: %s; staggered requests token-identical to tp=1: %d/3; lengths ok: %s"
-              % (world, args.proto, d[0], d[1], d[2], d[3], d[4], float(l1.std()), same, eq3, lens_ok))
-        ok = max(d) < 0.08 and same and lens_ok
+              "ranks identical: %s; staggered requests token-identical to tp=1: %d/3; worst margin of a batched-step token to the tp=1 arg-max %.4f; lengths ok: %s"
+              % (world, args.proto, d[0], d[1], d[2], d[3], d[4], float(l1.std()), same, eq3, worst, lens_ok))
+        ok = max(d) < 0.08 and same and lens_ok and worst < 0.2
     elif rank == 0:
         from oracle.llama_ref import LlamaRef
         from oracle.synth import synth_state_dict
@@ -126,15 +136,19 @@ def main():
         same = all(g == gathered[0] for g in gathered)
         # teacher-forced: every engine token must be a (near-)arg-max of the oracle's logits
         agree, total, near = 0, 0, True
+        detail = []
         for ps, ts in ((p3, toks3), (p7, toks7)):
             for pr, t in zip(ps, ts):
                 r2 = LlamaRef(cfg, sd)
                 cur = r2.forward(pr).numpy()[-1]
+                a = 0
                 for tok in t:
                     near &= bool(cur[tok] >= cur.max() - NEAR)
-                    agree += int(tok == int(np.argmax(cur)))
+                    a += int(tok == int(np.argmax(cur)))
                     total += 1
                     cur = r2.forward([tok]).numpy()[-1]
+                agree += a
+                detail.append("%d/%d" % (a, len(t)))
         lens_ok = all(len(t) == 24 for t in toks3) and all(len(t) == 10 for t in toks7)
         # the same model on ONE GPU: tensor parallelism only changes the summation order
         with ffi.Engine(cfg, device=local, max_seqs=8, max_ctx=512, seed=0) as one:
@@ -143,8 +157,8 @@ def main():
         d0 = float(np.abs(lg - l1).max())
         d1 = max(float(np.abs(a - b).max()) for a, b in zip(step, s1))
         print("tp=%d geom=%s proto=%d max|dlogit| vs oracle: prefill150 %.4g decode %.4g %.4g prefill3 %.4g decode %.4g; vs tp=1 engine: prefill %.4g decode %.4g; "
-              "ranks identical: %s; top-1 agreement %d/%d, all near-argmax: %s, lengths ok: %s"
-              % (world, args.geom, args.proto, e0, e1, e2, e3, e4, d0, d1, same, agree, total, near, lens_ok))
+              "ranks identical: %s; top-1 agreement %d/%d (per request %s), all near-argmax: %s, lengths ok: %s"
+              % (world, args.geom, args.proto, e0, e1, e2, e3, e4, d0, d1, same, agree, total, " ".join(detail), near, lens_ok))
         ok = max(e0, e1, e2, e3, e4) < TOL and max(d0, d1) < TOL and same and near and lens_ok and agree >= int(0.9 * total)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
