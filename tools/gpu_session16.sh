@@ -15,7 +15,7 @@ timeout 200 $TR --master-port 29902 tools/tp_timeline.py --proto 2 > gpurun_out/
 timeout 200 $TR --master-port 29903 tools/tp_timeline.py --streams 128 --gen 3 > gpurun_out/s16_timeline_tp8_s128.log 2>&1
 timeout 400 $TR --master-port 29904 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/s16_bench_n8.json 2> gpurun_out/s16_bench_n8.err
 timeout 300 $TR --master-port 29905 bench.py --gpus 8 --steps 5 --warmup 3 --tp-proto 2 --streams 0 --no-parity > gpurun_out/s16_bench_n8_gather.json 2> gpurun_out/s16_bench_n8_gather.err
-timeout 400 $TR --master-port 29906 tools/bench_70b_mixed.py > gpurun_out/s16_70b_mixed.json 2> gpurun_out/s16_70b_mixed.err
+timeout 400 $TR --master-port 29906 tools/bench_70b_mixed.py --rate 8 > gpurun_out/s16_70b_mixed.json 2> gpurun_out/s16_70b_mixed.err
 timeout 300 $TR --master-port 29907 tools/bench_70b_mixed.py --kv-frac 0.35 --rate 0 > gpurun_out/s16_70b_mixed_oversub.json 2> gpurun_out/s16_70b_mixed_oversub.err
 grep -h "consumers" gpurun_out/s16_timeline_tp8.log gpurun_out/s16_timeline_tp8_gather.log | cut -c1-200
 tail -c 600 gpurun_out/s16_bench_n8.json; tail -c 400 gpurun_out/s16_70b_mixed.json
