@@ -382,7 +382,7 @@ struct llmlb_engine {
   uint32_t tp_coll = 0;              // collectives issued so far in the current forward pass
   bool tp_ll = true;                 // protocol A variant: {value, epoch} pairs (default) or values + end-of-grid flags
   bool tp_gather = false;            // protocol A consumer: owner CTAs fold + in-GPU gather (tp_proto bit 1) instead of every CTA folding
-  bool dbg_no_ksplit = false, dbg_no_agwait = false, dbg_no_rsll = false;
+  bool dbg_no_ksplit = false, dbg_no_agwait = false, dbg_no_rsll = false, dbg_no_wave_tail = false;
   float* xb = nullptr;               // second residual buffer (protocol A ping-pong)
   float* tp_stage = nullptr;         // [4][hidden] fp32: partial rows of projections the fused GEMV does not take
   __nv_bfloat16* ylast = nullptr;    // [max_seqs][hidden] normalised rows that need logits (protocol B)
@@ -588,6 +588,7 @@ int llmlb_engine::alloc_all() {
   g_dbg_no_pdl = getenv("LLMLB_DEBUG_NO_PDL") ? (unsigned int)atoi(getenv("LLMLB_DEBUG_NO_PDL")) : 0u;
   dbg_no_ksplit = getenv("LLMLB_DEBUG_NO_KSPLIT") != nullptr;
   dbg_no_rsll = getenv("LLMLB_DEBUG_NO_RSLL") != nullptr;
+  dbg_no_wave_tail = getenv("LLMLB_DEBUG_NO_WAVE_TAIL") != nullptr;
   dbg_no_agwait = getenv("LLMLB_DEBUG_NO_AGWAIT") != nullptr;
   RC(make_tmap_attn_kv(&m_kpool, k_pool, M.n_layers, n_pages, nkv_l));
   RC(make_tmap_attn_kv(&m_vpool, v_pool, M.n_layers, n_pages, nkv_l));
@@ -728,6 +729,22 @@ int llmlb_engine::proj(const CUtensorMap& mw, const void*, const void*, const CU
   if (!dbg_no_ksplit) { tpp.sk_ws = sk_ws; tpp.sk_cnt = sk_cnt; }   // narrow projections K-split inside the kernel
   if (wait_coll >= 0 && !dbg_no_agwait) {   // tensor parallel: the activation operand is y of that collective (its all-gather flags gate the loads)
     tpp.ctx = tpc; tpp.wait_coll_plus1 = uint32_t(wait_coll) + 1;
+  }
+  // A projection whose CTA-pair tiles fill whole waves plus a short ragged one (gate/up at 512 tokens: 224 tiles on
+  // 74 pairs = 3.03 waves, run as 4): the rows of the ragged wave go to a second launch of 128-row tiles with the
+  // in-kernel K-split (all SMs, a fraction of a tile time) and the pair kernel runs exact waves.
+  const bool store_epi = epi == LLMLB_EPI_STORE_BF16 || epi == LLMLB_EPI_SILU_MUL || epi == LLMLB_EPI_STORE_F32;
+  if (store_epi && T > 128 && n_out % 256 == 0 && tpp.sk_ws && !dbg_no_wave_tail) {
+    const uint32_t t_tiles = ceil_div(T, 256u), m_pairs = n_out / 256, pairs = uint32_t(kNumSMs / 2);
+    const uint32_t pair_tiles = m_pairs * t_tiles, waves = pair_tiles / pairs, rem = pair_tiles % pairs;
+    if (waves >= 2 && rem > 0 && rem % t_tiles == 0 && rem / t_tiles <= 2) {
+      const uint32_t rem_m = rem / t_tiles;
+      TpPushRS main = tpp, tail = tpp;
+      main.row0 = 0; main.n_rows = (m_pairs - rem_m) * 256;
+      tail.row0 = main.n_rows; tail.n_rows = rem_m * 256;
+      RC(gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &main));
+      return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &tail);
+    }
   }
   return gemm_tc_launch(mw, mx[bn_index(tc_pick_bn(T))], out, T, n_out, k, epi, out_stride, st, &mx[bn_index(128)], nullptr, &tpp);
 }
