@@ -48,6 +48,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # arrivals are announced over a CPU-side group: a NCCL broadcast is a kernel that sits on an SM of every
+        # rank until rank 0 reaches it, and the engine's narrow GEMMs need all SMs co-resident (the first 8-GPU run
+        # of this tool broadcast over NCCL while serving and tripped the 2 s spin guard of the in-kernel K-split)
+        cpu_group = dist.new_group(backend="gloo")
     model = dict(ffi.LLAMA3_70B if args.model == "70b" else ffi.LLAMA3_8B)
     if args.layers:
         model["n_layers"] = args.layers
@@ -85,8 +89,8 @@ def main():
                 while due < len(idx) and (not clocked or arrive[idx[due]] - arrive[idx[0]] <= now):
                     due += 1
                 if world > 1:
-                    t = torch.tensor([due], device="cuda")
-                    dist.broadcast(t, 0)
+                    t = torch.tensor([due])
+                    dist.broadcast(t, 0, group=cpu_group)
                     due = int(t.item())
             if due > nxt:
                 if world > 1:
@@ -98,7 +102,7 @@ def main():
                     evs[i] = []
                     pending.add(i)
                 if world > 1:
-                    dist.barrier()
+                    dist.barrier(group=cpu_group)
                     eng.pause(False)
                 nxt = due
             for i in list(pending):
