@@ -222,6 +222,7 @@ enum PlanEvent : uint32_t { kPlanSubmit = 1, kPlanCancel = 2, kPlanRelease = 3, 
                             kPlanExpire = 8 /* id + finish reason: a time-based decision of rank 0's clock */ };
 constexpr uint32_t kPlanMagic = 0x4C4C5031u;   // "LLP1"
 constexpr size_t kPlanHeaderBytes = 4096, kPlanRingBytes = size_t(8) << 20;
+constexpr long long kPlanStallMs = 30000;   // a follower that has not drained an 8 MiB ring for this long is gone
 
 struct PlanChannel {
   PlanHeader* h = nullptr;
@@ -282,20 +283,26 @@ struct PlanChannel {
     if (n > first) memcpy(static_cast<uint8_t*>(dst) + first, ring, n - first);
   }
   // leader: record = [u32 payload bytes][u32 type][payload, padded to 8]
-  void write(uint32_t type, const void* payload, uint32_t len) {
+  // false: a follower stopped reading (ring full for kPlanStallMs) — the caller holds the scheduler mutex, so the wait is
+  // bounded and the engine is failed instead of wedging submit / poll / health behind a dead rank
+  bool write(uint32_t type, const void* payload, uint32_t len) {
     const uint32_t padded = (len + 7u) & ~7u;
     const uint64_t need = 8 + padded;
     uint64_t head = h->head.load(std::memory_order_relaxed);
-    for (;;) {   // back-pressure: never overwrite what the slowest follower has not read
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t spins = 0;; ++spins) {   // back-pressure: never overwrite what the slowest follower has not read
       uint64_t lo = head;
       for (uint32_t r = 1; r < h->n_ranks; ++r) lo = std::min(lo, h->tail[r].load(std::memory_order_acquire));
       if (head + need - lo <= kPlanRingBytes) break;
+      if ((spins & 0x3FFu) == 0x3FFu &&
+          std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > kPlanStallMs) return false;
       usleep(50);
     }
     const uint32_t hdr[2] = {len, type};
     copy_in(head, hdr, 8);
     if (len) copy_in(head + 8, payload, len);
     h->head.store(head + need, std::memory_order_release);
+    return true;
   }
   // follower: blocks until the next record is there (0 = aborted by engine destroy)
   uint32_t read(std::vector<uint8_t>* payload, const std::atomic<bool>& abort) {
@@ -458,8 +465,13 @@ struct llmlb_engine {
   void loop_follower();
   bool sched_iteration(std::unique_lock<std::mutex>& lk);   // one scheduling decision + launch; lk held on entry, released inside
   // the log has ONE writer at a time: every append happens with mu held
-  void plan_log(uint32_t type, const void* payload = nullptr, uint32_t len = 0) { if (plan_on && plan.leader) plan.write(type, payload, len); }
-  void plan_log_locked(uint32_t type) { if (plan_on && plan.leader) { std::lock_guard<std::mutex> lk(mu); plan.write(type, nullptr, 0); } }
+  void plan_log(uint32_t type, const void* payload = nullptr, uint32_t len = 0) {
+    if (plan_on && plan.leader && !plan.write(type, payload, len)) {
+      plan_on = false;   // no further appends; submits are refused from here on (fatal_error), running requests end with an error
+      if (fatal_error.empty()) fatal_error = "tensor-parallel follower stopped reading the plan channel";
+    }
+  }
+  void plan_log_locked(uint32_t type) { if (plan_on && plan.leader) { std::lock_guard<std::mutex> lk(mu); plan_log(type); } }
   void finish_request(const ReqPtr& r, uint32_t reason);
   void release_resources(const ReqPtr& r);
   void preempt(const ReqPtr& r);
@@ -1259,6 +1271,13 @@ bool llmlb_engine::sched_iteration(std::unique_lock<std::mutex>& lk) {
   std::vector<ReqPtr> pf_reqs;
   std::vector<uint32_t> pf_take;
   std::vector<ReqPtr> dec;
+  if (!fatal_error.empty()) {   // failed engine (device error, dead follower): everything in flight ends with an error event
+    for (auto& r : std::vector<ReqPtr>(running)) finish_request(r, LLMLB_FINISH_ERROR);
+    while (!waiting.empty()) { ReqPtr r = waiting.front(); waiting.pop_front(); finish_request(r, LLMLB_FINISH_ERROR); }
+    cv_events.notify_all();
+    lk.unlock();
+    return false;
+  }
   // cancellations (client cancel / release, queue timeout, deadline: cancel_reason says which)
   for (auto it = waiting.begin(); it != waiting.end();) {
     if ((*it)->cancel) { ReqPtr r = *it; it = waiting.erase(it); finish_request(r, r->cancel_reason); }
