@@ -381,6 +381,84 @@ std::string model_unavailable_body(const std::string& message, const std::string
   return root.dump();
 }
 
+// ---- error conventions -------------------------------------------------------------------------
+ClientError classify_upstream_request_error(UpstreamFailure kind, uint32_t timeout_secs, const std::string* ollama_loading_model) {
+  ClientError e;
+  if (kind == UpstreamFailure::Timeout) {
+    e.status = 504;
+    if (ollama_loading_model) {
+      e.type = "model_loading";
+      e.message = "Ollama model '" + *ollama_loading_model + "' is still loading. Retry after the initial load finishes or increase endpoint inference timeout above " +
+                  std::to_string(timeout_secs) + " seconds.";
+    } else {
+      e.type = "timeout";
+      e.message = "Upstream endpoint request timed out after " + std::to_string(timeout_secs) + " seconds";
+    }
+    return e;
+  }
+  e.status = 502;
+  if (kind == UpstreamFailure::Connect) { e.type = "connection_error"; e.message = "Failed to connect to upstream endpoint"; }
+  else { e.type = "endpoint_request_error"; e.message = "Failed to proxy request to upstream endpoint"; }
+  return e;
+}
+ClientError queue_capacity_exceeded(uint64_t queue_timeout_secs) {
+  ClientError e;
+  e.status = 429; e.type = "rate_limit_exceeded"; e.message = "Request queue is full";
+  e.retry_after = (long long)(queue_timeout_secs < 1 ? 1 : queue_timeout_secs);
+  return e;
+}
+ClientError queue_wait_timeout() {
+  ClientError e;
+  e.status = 504; e.type = "timeout"; e.message = "Queue wait timeout";
+  return e;
+}
+
+namespace {
+struct LbRow { const char* name; int status; const char* type; const char* external; bool expose_detail; };
+// common/error.rs:124-204 (external_message, error_type, status_code) and api/error.rs:162-195 (which text reaches the client)
+const LbRow kLbRows[] = {
+    {"common_validation", 400, "invalid_request_error", "Request error", true},
+    {"common_other", 400, "invalid_request_error", "Request error", false},
+    {"endpoint_not_found", 404, "not_found_error", "Endpoint not found", false},
+    {"not_found", 404, "not_found_error", "Not found", true},
+    {"no_endpoints_available", 503, "service_unavailable", "No available endpoints", false},
+    {"no_capable_endpoints", 404, "not_found_error", "No capable endpoints", false},
+    {"database", 500, "server_error", "Database error", false},
+    {"http", 502, "service_unavailable", "Backend service unavailable", false},
+    {"timeout", 504, "server_error", "Request timeout", false},
+    {"service_unavailable", 503, "service_unavailable", "Service temporarily unavailable", false},
+    {"internal", 500, "server_error", "Internal server error", false},
+    {"endpoint_offline", 503, "service_unavailable", "Endpoint offline", false},
+    {"invalid_model_name", 400, "invalid_request_error", "Invalid model name", true},
+    {"insufficient_storage", 507, "server_error", "Insufficient storage", true},
+    {"password_hash", 401, "authentication_error", "Authentication error", false},
+    {"jwt", 401, "authentication_error", "Authentication error", false},
+    {"authentication", 401, "authentication_error", "Authentication failed", true},
+    {"authorization", 403, "permission_error", "Access denied", true},
+    {"conflict", 409, "invalid_request_error", "Resource conflict", true},
+};
+static_assert(sizeof(kLbRows) / sizeof(kLbRows[0]) == size_t(LbErrorKind::kCount), "one row per LbError variant");
+const LbRow& lb_row(LbErrorKind k) { return kLbRows[size_t(k) < size_t(LbErrorKind::kCount) ? size_t(k) : size_t(LbErrorKind::Internal)]; }
+}  // namespace
+int lb_error_status(LbErrorKind k) { return lb_row(k).status; }
+const char* lb_error_type(LbErrorKind k) { return lb_row(k).type; }
+const char* lb_error_external_message(LbErrorKind k) { return lb_row(k).external; }
+const char* lb_error_name(LbErrorKind k) { return lb_row(k).name; }
+std::string lb_error_openai_body(LbErrorKind k) {
+  Json err = Json::object();
+  err.set("message", std::string(lb_row(k).external)); err.set("type", std::string(lb_row(k).type)); err.set("code", std::to_string(lb_row(k).status));
+  Json root = Json::object(); root.set("error", err);
+  return root.dump();
+}
+std::string app_error_body(LbErrorKind k, const std::string& detail) {
+  bool expose = lb_row(k).expose_detail;
+  if (k == LbErrorKind::CommonOther)   // only the GPU-requirement text of a non-validation CommonError is passed through
+    expose = detail.find("GPU is required") != std::string::npos || detail.find("GPU hardware is required") != std::string::npos;
+  Json root = Json::object();
+  root.set("error", expose ? detail : std::string(lb_row(k).external));
+  return root.dump();
+}
+
 int extract_api_key(const char* x_api_key, const char* authorization, std::string* key, std::string* err) {
   if (x_api_key) { *key = x_api_key; return 0; }
   if (authorization) {
@@ -813,6 +891,29 @@ int llmlb_parse_model_name(const char* model, char* base, char* quant, size_t ca
 }
 size_t llmlb_error_body(const char* message, const char* type, int status, char* out, size_t cap) { return copy_out(openai_error_body(message, type, status), out, cap); }
 size_t llmlb_gate_rejection_body(char* out, size_t cap) { return copy_out(InferenceGate::rejection_body(), out, cap); }
+// error conventions: JSON {"status","type","message","retry_after"(-1 = none),"body"} of the classified failure
+static std::string client_error_json(const ClientError& e) {
+  Json j = Json::object();
+  j.set("status", e.status); j.set("type", e.type); j.set("message", e.message); j.set("retry_after", int64_t(e.retry_after)); j.set("body", e.body());
+  return j.dump();
+}
+size_t llmlb_classify_upstream_error(int kind, uint32_t timeout_secs, const char* ollama_loading_model, char* out, size_t cap) {
+  std::string m = ollama_loading_model ? ollama_loading_model : "";
+  return copy_out(client_error_json(classify_upstream_request_error(UpstreamFailure(kind < 0 || kind > 2 ? 2 : kind), timeout_secs, ollama_loading_model ? &m : nullptr)), out, cap);
+}
+size_t llmlb_queue_error(int which, uint64_t queue_timeout_secs, char* out, size_t cap) {   // 0 capacity exceeded, 1 wait timeout
+  return copy_out(client_error_json(which == 0 ? queue_capacity_exceeded(queue_timeout_secs) : queue_wait_timeout()), out, cap);
+}
+int llmlb_lb_error_count(void) { return int(LbErrorKind::kCount); }
+// JSON {"name","status","type","external","openai_body","app_body"} of LbError variant `kind` carrying `detail`
+size_t llmlb_lb_error(int kind, const char* detail, char* out, size_t cap) {
+  if (kind < 0 || kind >= int(LbErrorKind::kCount)) return 0;
+  const LbErrorKind k = LbErrorKind(kind);
+  Json j = Json::object();
+  j.set("name", std::string(lb_error_name(k))); j.set("status", lb_error_status(k)); j.set("type", std::string(lb_error_type(k)));
+  j.set("external", std::string(lb_error_external_message(k))); j.set("openai_body", lb_error_openai_body(k)); j.set("app_body", app_error_body(k, detail ? detail : ""));
+  return copy_out(j.dump(), out, cap);
+}
 int llmlb_extract_api_key(const char* x_api_key, const char* authorization, char* out, size_t cap) {
   std::string key, err;
   int rc = extract_api_key(x_api_key, authorization, &key, &err);

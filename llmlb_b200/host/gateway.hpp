@@ -184,6 +184,26 @@ bool parse_quantized_model_name(const std::string& model, ParsedModelName* out);
 std::string openai_error_body(const std::string& message, const std::string& type, int status);
 std::string model_unavailable_body(const std::string& message, const std::string& code);
 
+// ---- error conventions ----
+// What a client sees for a failed request: status, OpenAI error type, message, optional Retry-After seconds (-1 = no header).
+struct ClientError { int status = 502; std::string type, message; long long retry_after = -1; std::string body() const { return openai_error_body(message, type, status); } };
+// reqwest failure classes of the upstream call (is_timeout / is_connect / anything else): api/openai_util.rs:86-134.  For the in-process
+// engine: Timeout = the request deadline (types/endpoint.rs:389), Other = the engine failed the request.
+enum class UpstreamFailure { Timeout = 0, Connect = 1, Other = 2 };
+ClientError classify_upstream_request_error(UpstreamFailure kind, uint32_t timeout_secs, const std::string* ollama_loading_model = nullptr);
+ClientError queue_capacity_exceeded(uint64_t queue_timeout_secs);   // api/openai.rs:841-861: 429 rate_limit_exceeded, Retry-After max(1, secs)
+ClientError queue_wait_timeout();                                   // api/openai.rs:863-882: 504 timeout
+// LbError (common/error.rs:41-214): one row per variant; order = the reference's declaration order, Common split in two
+enum class LbErrorKind { CommonValidation = 0, CommonOther, EndpointNotFound, NotFound, NoEndpointsAvailable, NoCapableEndpoints, Database, Http, Timeout,
+                         ServiceUnavailable, Internal, EndpointOffline, InvalidModelName, InsufficientStorage, PasswordHash, Jwt, Authentication,
+                         Authorization, Conflict, kCount };
+int lb_error_status(LbErrorKind k);
+const char* lb_error_type(LbErrorKind k);
+const char* lb_error_external_message(LbErrorKind k);
+const char* lb_error_name(LbErrorKind k);                             // snake_case name used by the tests / oracle
+std::string lb_error_openai_body(LbErrorKind k);                      // to_openai_error: {"error":{"message","type","code":"<status>"}}
+std::string app_error_body(LbErrorKind k, const std::string& detail); // api/error.rs:154-203: {"error": detail or the generic message}
+
 // 0 ok; 1 invalid Authorization format; 2 missing  (messages as auth/middleware.rs:292-321)
 int extract_api_key(const char* x_api_key, const char* authorization, std::string* key, std::string* err);
 std::string sha256_hex(const std::string& data);

@@ -239,8 +239,9 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   uint64_t rid = 0;
   int rc = s.max_tokens ? llmlb_request_submit(G.eng, ids.data(), uint32_t(ids.size()), &s, &rid) : LLMLB_E_INVALID_ARG;
   if (rc == LLMLB_E_QUEUE_FULL) {   // openai.rs:841-861: 429 rate_limit_exceeded + Retry-After = queue timeout
-    const std::string ra = "Retry-After: " + std::to_string(std::max<uint32_t>(1, G.queue_timeout_ms / 1000)) + "\r\n";
-    send_err(429, "Request queue is full", "rate_limit_exceeded", ra.c_str());
+    const ClientError qe = queue_capacity_exceeded(G.queue_timeout_ms / 1000);
+    const std::string ra = "Retry-After: " + std::to_string(qe.retry_after) + "\r\n";
+    send_err(qe.status, qe.message, qe.type.c_str(), ra.c_str());
     return;
   }
   if (rc != LLMLB_OK) {
@@ -323,9 +324,11 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   const char* fr = finish == LLMLB_FINISH_STOP ? "stop" : "length";
   // failures map like the gateway maps an upstream's (openai.rs:862-882, openai_util.rs:86-134)
   const bool failed = finish != LLMLB_FINISH_STOP && finish != LLMLB_FINISH_LENGTH && !(client_gone && completion_tokens > 0);
-  int fail_status = 502; std::string fail_msg = "Failed to proxy request to upstream endpoint", fail_type = "endpoint_request_error";
-  if (finish == LLMLB_FINISH_QUEUE_TIMEOUT) { fail_status = 504; fail_msg = "Queue wait timeout"; fail_type = "timeout"; }
-  else if (finish == LLMLB_FINISH_DEADLINE) { fail_status = 504; fail_msg = "Upstream endpoint request timed out after " + std::to_string(G.request_timeout_ms / 1000) + " seconds"; fail_type = "timeout"; }
+  ClientError fe = classify_upstream_request_error(UpstreamFailure::Other, 0);                 // the engine failed the request
+  if (finish == LLMLB_FINISH_QUEUE_TIMEOUT) fe = queue_wait_timeout();
+  else if (finish == LLMLB_FINISH_DEADLINE) fe = classify_upstream_request_error(UpstreamFailure::Timeout, G.request_timeout_ms / 1000);
+  const int fail_status = fe.status;
+  const std::string fail_msg = fe.message, fail_type = fe.type;
   if (failed && !stream) { send_err(fail_status, fail_msg, fail_type.c_str()); return; }
   if (stream) {
     if (!ok) return;

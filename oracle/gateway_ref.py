@@ -331,6 +331,77 @@ def gate_rejection():
     return 503, {"retry-after": "30"}, openai_error_body("Server is updating. Please retry.", "service_unavailable", 503)
 
 
+# --- llmlb/src/common/error.rs:41-214 LbError: status_code / error_type / external_message / to_openai_error;
+#     llmlb/src/api/error.rs:154-203 AppError::into_response (which message reaches the client) --------------------
+# kind -> (status, OpenAI error type, external message, AppError exposes the detail text?)
+LB_ERRORS = {
+    "common_validation":    (400, "invalid_request_error", "Request error", True),
+    "common_other":         (400, "invalid_request_error", "Request error", False),
+    "endpoint_not_found":   (404, "not_found_error", "Endpoint not found", False),
+    "not_found":            (404, "not_found_error", "Not found", True),
+    "no_endpoints_available": (503, "service_unavailable", "No available endpoints", False),
+    "no_capable_endpoints": (404, "not_found_error", "No capable endpoints", False),
+    "database":             (500, "server_error", "Database error", False),
+    "http":                 (502, "service_unavailable", "Backend service unavailable", False),
+    "timeout":              (504, "server_error", "Request timeout", False),
+    "service_unavailable":  (503, "service_unavailable", "Service temporarily unavailable", False),
+    "internal":             (500, "server_error", "Internal server error", False),
+    "endpoint_offline":     (503, "service_unavailable", "Endpoint offline", False),
+    "invalid_model_name":   (400, "invalid_request_error", "Invalid model name", True),
+    "insufficient_storage": (507, "server_error", "Insufficient storage", True),
+    "password_hash":        (401, "authentication_error", "Authentication error", False),
+    "jwt":                  (401, "authentication_error", "Authentication error", False),
+    "authentication":       (401, "authentication_error", "Authentication failed", True),
+    "authorization":        (403, "permission_error", "Access denied", True),
+    "conflict":             (409, "invalid_request_error", "Resource conflict", True),
+}
+
+
+def lb_error_openai(kind):
+    """LbError::to_openai_error (common/error.rs:206-214): the code is the status AS A STRING."""
+    status, etype, ext, _ = LB_ERRORS[kind]
+    return status, {"error": {"message": ext, "type": etype, "code": str(status)}}
+
+
+def app_error_response(kind, detail=""):
+    """AppError::into_response (api/error.rs:154-203): errors that may carry internal details (addresses, ports, DB text)
+    answer with the generic external message; developer-crafted ones pass their text through.  A non-validation
+    CommonError passes through only when it is the GPU-requirement message."""
+    status, _, ext, expose = LB_ERRORS[kind]
+    if kind == "common_other":
+        expose = "GPU is required" in detail or "GPU hardware is required" in detail
+    return status, {"error": detail if expose else ext}
+
+
+# --- llmlb/src/api/openai_util.rs:86-134 classify_upstream_request_error ---------------------------------------------
+def classify_upstream_request_error(kind, timeout_secs, ollama_loading_model=None):
+    """kind: "timeout" | "connect" | anything else (reqwest's is_timeout / is_connect).  -> (status, type, client message)"""
+    if kind == "timeout":
+        if ollama_loading_model is not None:
+            return 504, "model_loading", ("Ollama model '%s' is still loading. Retry after the initial load finishes or increase endpoint "
+                                          "inference timeout above %d seconds." % (ollama_loading_model, timeout_secs))
+        return 504, "timeout", "Upstream endpoint request timed out after %d seconds" % timeout_secs
+    if kind == "connect":
+        return 502, "connection_error", "Failed to connect to upstream endpoint"
+    return 502, "endpoint_request_error", "Failed to proxy request to upstream endpoint"
+
+
+# --- llmlb/src/api/openai_util.rs:264-292 queue_error_response; call sites openai.rs:841-882 ------------------------
+def queue_error_response(status, message, error_type, retry_after=None):
+    headers = {} if retry_after is None else {"retry-after": str(retry_after)}
+    return status, headers, {"error": {"message": message, "type": error_type, "code": status}}
+
+
+def queue_capacity_exceeded(queue_timeout_secs):
+    """QueueSelection::CapacityExceeded (openai.rs:841-861): 429 rate_limit_exceeded, Retry-After = max(1, queue timeout)."""
+    return queue_error_response(429, "Request queue is full", "rate_limit_exceeded", max(1, int(queue_timeout_secs)))
+
+
+def queue_wait_timeout():
+    """QueueSelection::Timeout (openai.rs:863-882): 504 timeout, no Retry-After."""
+    return queue_error_response(504, "Queue wait timeout", "timeout", None)
+
+
 # --- llmlb/src/auth/middleware.rs:292-321 extract_api_key; :254-289 SHA-256 lookup -------------
 def extract_api_key(headers):
     h = {k.lower(): v for k, v in headers.items()}

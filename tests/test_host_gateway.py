@@ -43,6 +43,10 @@ def H():
         "llmlb_gate_end": (None, [vp]), "llmlb_gate_set_rejecting": (None, [vp, C.c_int]), "llmlb_gate_in_flight": (C.c_uint32, [vp]),
         "llmlb_frame": (C.c_size_t, [C.c_int, cp, cp, i64, C.POINTER(cp), C.c_uint32, C.c_uint32, cp, C.c_char_p, C.c_size_t]),
         "llmlb_json_roundtrip": (C.c_size_t, [cp, C.c_char_p, C.c_size_t]),
+        "llmlb_classify_upstream_error": (C.c_size_t, [C.c_int, C.c_uint32, cp, C.c_char_p, C.c_size_t]),
+        "llmlb_queue_error": (C.c_size_t, [C.c_int, u64, C.c_char_p, C.c_size_t]),
+        "llmlb_lb_error_count": (C.c_int, []),
+        "llmlb_lb_error": (C.c_size_t, [C.c_int, cp, C.c_char_p, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -847,3 +851,57 @@ def test_extract_or_estimate_tokens(H):
     assert bits == 7 and list(out) == [100, 50, 150]
     bits = H.llmlb_extract_or_estimate(json.dumps(cases[1][0]).encode(), b"What is 2+2?", b"The answer is 4.", 1, out)
     assert bits == 7 and out[2] == out[0] + out[1] and out[0] > 0 and out[1] > 0
+
+
+# ---- error conventions (row a1.16) -----------------------------------------------------------------------------------
+def _out_json(fn, *args):
+    buf = C.create_string_buffer(4096)
+    n = fn(*args, buf, 4096)
+    assert 0 < n < 4096
+    return json.loads(buf.value.decode())
+
+
+def test_lb_error_table_cpp_vs_reference_and_oracle(H):
+    kinds = {}
+    for k in range(H.llmlb_lb_error_count()):
+        r = _out_json(H.llmlb_lb_error, k, b("detail text 10.0.0.1:8080"))
+        kinds[r["name"]] = k
+        status, etype, ext, _ = G.LB_ERRORS[r["name"]]
+        assert (r["status"], r["type"], r["external"]) == (status, etype, ext)
+        assert json.loads(r["openai_body"]) == G.lb_error_openai(r["name"])[1]
+        assert json.loads(r["app_body"]) == G.app_error_response(r["name"], "detail text 10.0.0.1:8080")[1]
+    assert set(kinds) == set(G.LB_ERRORS)          # one C++ row per variant of the reference enum
+    L = V["lb_errors"]
+    for kind, status in L["status"]["cases"]:
+        assert _out_json(H.llmlb_lb_error, kinds[kind], b(""))["status"] == status
+    for kind, etype in L["types"]["cases"]:
+        assert _out_json(H.llmlb_lb_error, kinds[kind], b(""))["type"] == etype
+    for kind, msg, etype, code in L["openai"]["cases"]:
+        assert json.loads(_out_json(H.llmlb_lb_error, kinds[kind], b("x"))["openai_body"]) == {"error": {"message": msg, "type": etype, "code": code}}
+    for kind, detail, status, shown in L["app"]["cases"]:
+        r = _out_json(H.llmlb_lb_error, kinds[kind], b(detail))
+        assert (r["status"], json.loads(r["app_body"])) == (status, {"error": shown}), (kind, detail)
+    for text, shown in (("Configuration error: GPU hardware is required", "Configuration error: GPU hardware is required"), ("Configuration error: bad port", "Request error")):
+        assert json.loads(_out_json(H.llmlb_lb_error, kinds["common_other"], b(text))["app_body"]) == {"error": shown}
+
+
+def test_queue_and_upstream_errors_cpp_vs_reference_and_oracle(H):
+    for c in V["queue_errors"]["call_sites"]:
+        r = _out_json(H.llmlb_queue_error, 0 if c["fn"] == "capacity" else 1, c.get("queue_timeout_secs", 0))
+        assert (r["status"], r["type"], r["message"]) == (c["status"], c["type"], c["message"])
+        assert (None if r["retry_after"] < 0 else str(r["retry_after"])) == c["header"]
+        assert json.loads(r["body"]) == {"error": {"message": c["message"], "type": c["type"], "code": c["status"]}}
+    for secs in (0, 1, 59, 60, 3600):
+        status, headers, body = G.queue_capacity_exceeded(secs)
+        r = _out_json(H.llmlb_queue_error, 0, secs)
+        assert (r["status"], str(r["retry_after"]), json.loads(r["body"])) == (status, headers["retry-after"], body)
+    KINDS = {"timeout": 0, "connect": 1, "other": 2}
+    for c in V["upstream_errors"]:
+        r = _out_json(H.llmlb_classify_upstream_error, KINDS[c["kind"]], c["timeout_secs"], b(c["ollama_loading_model"]))
+        assert (r["status"], r["type"], r["message"], r["retry_after"]) == (c["status"], c["type"], c["message"], -1)
+        assert json.loads(r["body"]) == G.openai_error_body(c["message"], c["type"], c["status"])
+    for kind, k in KINDS.items():
+        for secs in (1, 30, 120):
+            for model in (None, "qwen2.5:7b"):
+                r = _out_json(H.llmlb_classify_upstream_error, k, secs, b(model))
+                assert (r["status"], r["type"], r["message"]) == G.classify_upstream_request_error(kind, secs, model)

@@ -287,3 +287,36 @@ def test_inference_latency_ema(v):
     if v["ms"] == "inf":
         l.update(50.0)                       # first sample after a reset replaces the infinity
         assert l.ms == 50.0
+
+
+# ---- error conventions (row a1.16): LbError table, upstream failure classes, queue errors -----------------------------
+def test_lb_error_table_matches_the_reference_tests():
+    L = V["lb_errors"]
+    for kind, status in L["status"]["cases"]:
+        assert G.LB_ERRORS[kind][0] == status, kind
+    for kind, etype in L["types"]["cases"]:
+        assert G.LB_ERRORS[kind][1] == etype, kind
+    for kind, msg, etype, code in L["openai"]["cases"]:
+        status, body = G.lb_error_openai(kind)
+        assert body == {"error": {"message": msg, "type": etype, "code": code}} and str(status) == code
+    nl = L["external_no_leak"]
+    assert G.LB_ERRORS[nl["kind"]][2] == nl["external"] and "192.168" not in G.app_error_response(nl["kind"], nl["detail"])[1]["error"]
+    for kind, detail, status, shown in L["app"]["cases"]:
+        assert G.app_error_response(kind, detail) == (status, {"error": shown}), (kind, detail)
+    # a non-validation CommonError passes its text through only when it is the GPU-requirement message (api/error.rs:178-188)
+    assert G.app_error_response("common_other", "Configuration error: GPU is required")[1]["error"].endswith("GPU is required")
+    assert G.app_error_response("common_other", "Configuration error: bad port 70000")[1]["error"] == "Request error"
+
+
+def test_queue_and_upstream_error_responses_match_the_reference():
+    Q = V["queue_errors"]
+    for c in Q["cases"]:
+        status, headers, body = G.queue_error_response(c["status"], c["message"], c["type"], c["retry_after"])
+        assert status == c["status"] and headers.get("retry-after") == c["header"]
+        assert body == {"error": {"message": c["message"], "type": c["type"], "code": c["status"]}}
+    for c in Q["call_sites"]:
+        status, headers, body = G.queue_capacity_exceeded(c["queue_timeout_secs"]) if c["fn"] == "capacity" else G.queue_wait_timeout()
+        assert (status, headers.get("retry-after")) == (c["status"], c["header"])
+        assert body["error"] == {"message": c["message"], "type": c["type"], "code": c["status"]}
+    for c in V["upstream_errors"]:
+        assert G.classify_upstream_request_error(c["kind"], c["timeout_secs"], c["ollama_loading_model"]) == (c["status"], c["type"], c["message"])
