@@ -81,16 +81,19 @@ def build_host():
     """Gateway-side C++ (no CUDA): libllmlb_host.so, plus the HTTP shim linked to the engine."""
     hd = os.path.join(HERE, "host")
     deps = [os.path.join(hd, f) for f in ("gateway.cpp", "gateway.hpp", "json.hpp", "tokenizer.cpp", "tokenizer.hpp",
-                                          "unicode_tables.inc", "anthropic.cpp", "anthropic.hpp", "checkpoint.cpp", "checkpoint.hpp")]
+                                          "unicode_tables.inc", "anthropic.cpp", "anthropic.hpp", "checkpoint.cpp", "checkpoint.hpp",
+                                          "download.cpp", "download.hpp")]
     if _newer(HOST_LIB, deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread",
                                os.path.join(hd, "gateway.cpp"), os.path.join(hd, "tokenizer.cpp"),
-                               os.path.join(hd, "anthropic.cpp"), os.path.join(hd, "checkpoint.cpp"), "-o", HOST_LIB])
+                               os.path.join(hd, "anthropic.cpp"), os.path.join(hd, "checkpoint.cpp"), os.path.join(hd, "download.cpp"),
+                               "-o", HOST_LIB])
     sdeps = deps + [os.path.join(hd, "server.cpp"), LIB, os.path.join(HERE, "..", "include", "llmlb_b200.h")]
     if os.path.exists(LIB) and _newer(SERVER, sdeps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", os.path.join(hd, "server.cpp"),
                                os.path.join(hd, "gateway.cpp"), os.path.join(hd, "tokenizer.cpp"),
-                               os.path.join(hd, "anthropic.cpp"), os.path.join(hd, "checkpoint.cpp"), "-o", SERVER,
+                               os.path.join(hd, "anthropic.cpp"), os.path.join(hd, "checkpoint.cpp"), os.path.join(hd, "download.cpp"),
+                               "-o", SERVER,
                                "-L" + HERE, "-lllmlb_b200",
                                "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + "/usr/local/cuda/lib64"])
     return HOST_LIB

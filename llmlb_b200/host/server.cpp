@@ -29,6 +29,7 @@
 #include "../../include/llmlb_b200.h"
 #include "anthropic.hpp"
 #include "checkpoint.hpp"
+#include "download.hpp"
 #include "gateway.hpp"
 #include "tokenizer.hpp"
 
@@ -44,6 +45,7 @@ struct Server {
   std::unique_ptr<BpeTokenizer> tok;   // null: byte-level placeholder
   std::vector<int32_t> stop_ids;       // <|eot_id|>, <|end_of_text|>, <|eom_id|> when a tokenizer is loaded
   uint32_t queue_timeout_ms = 60000, request_timeout_ms = 120000;
+  std::unique_ptr<DownloadManager> downloads;   // POST /api/models/download, GET /api/download/progress (xllm/download.rs:97,147)
 };
 static Server G;
 
@@ -423,6 +425,19 @@ static void handle(int fd, const Request& rq) {
   else if (rq.method == "POST" && path == "/v1/responses") handle_generate(fd, rq, 1);
   else if (rq.method == "POST" && path == "/v1/completions") handle_generate(fd, rq, 2);
   else if (rq.method == "POST" && path == "/v1/messages") handle_messages(fd, rq);
+  else if (rq.method == "POST" && path == "/api/models/download") {        // llmlb/src/xllm/download.rs:97-139 is the client of this route
+    Json body, resp;
+    if (!Json::parse(rq.body, &body)) { send_json(fd, 400, "{\"error\":\"invalid JSON body\"}"); return; }
+    const int st = G.downloads->start(body, &resp);
+    send_json(fd, st, resp.dump());
+  } else if (rq.method == "GET" && path == "/api/download/progress") {       // download.rs:147-190
+    std::string task_id;
+    const size_t q = rq.path.find("task_id=");
+    if (q != std::string::npos) { task_id = rq.path.substr(q + 8); task_id = task_id.substr(0, task_id.find('&')); }
+    Json resp;
+    const int st = G.downloads->progress(task_id, &resp);
+    send_json(fd, st, resp.dump());
+  }
   else if (rq.method == "POST" && path == "/admin/drain") { G.gate.set_rejecting(rq.body.find("true") != std::string::npos); send_json(fd, 200, "{\"ok\":true}"); }
   else send_json(fd, 404, openai_error_body("not found", "invalid_request_error", 404));
 }
@@ -515,7 +530,7 @@ static bool plan_weights(const llmlb_model_config& m, const std::vector<std::uni
 
 int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
-  int port = 8011; std::string geometry = "8b", tokenizer_path;
+  int port = 8011; std::string geometry = "8b", tokenizer_path, mirror_root, models_dir;
   std::vector<std::string> weight_files;   // --weights x.gguf | shard.safetensors (repeatable)
   uint32_t max_seqs = 64, max_ctx = 2048, vocab_override = 0;
   // queue limits of the gateway (llmlb/src/config.rs:80-99: LLMLB_QUEUE_MAX 100, LLMLB_QUEUE_TIMEOUT_SECS 60)
@@ -535,6 +550,8 @@ int main(int argc, char** argv) {
     else if (k == "--queue-max") queue_max = uint32_t(atoi(v.c_str()));
     else if (k == "--queue-timeout-ms") queue_timeout_ms = uint32_t(atoi(v.c_str()));
     else if (k == "--request-timeout-ms") request_timeout_ms = uint32_t(atoi(v.c_str()));
+    else if (k == "--mirror-root") mirror_root = v;      // local mirror of the model hub (the box has no network)
+    else if (k == "--models-dir") models_dir = v;        // where downloaded files land
   }
   llmlb_engine_config cfg; memset(&cfg, 0, sizeof cfg);
   cfg.abi_version = LLMLB_ABI_VERSION;
@@ -605,6 +622,7 @@ int main(int argc, char** argv) {
     if (!plan.loads.empty()) fprintf(stderr, "weights: %zu tensors loaded from %zu file(s)%s\n", plan.loads.size(), ckpts.size(), plan.lm_head_tied ? " (lm_head tied to the embedding)" : "");
   }
   ckpts.clear();
+  G.downloads.reset(new DownloadManager(mirror_root, models_dir));   // unconfigured: the routes answer 503
   G.lm.add_endpoint("local", true, false);
   G.lm.add_model("local", G.model_id, "");
   int ls = socket(AF_INET, SOCK_STREAM, 0), one = 1;

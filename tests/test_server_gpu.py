@@ -311,3 +311,48 @@ def test_stop_strings_end_the_text_before_the_match(server):
     acc = G.StreamingTokenAccumulator("tiny-llama")
     assert G.process_sse_lines(d.decode("utf-8"), acc) == "" and acc.done
     assert acc.accumulated_content == cfull[:cfull.find(cstop)]
+
+
+def test_model_download_routes(server, built_lib, tmp_path):
+    """POST /api/models/download + GET /api/download/progress (the gateway is the client: llmlb/src/xllm/download.rs:97,147).
+    The default server has no mirror configured: the route answers 503 and queues nothing.  A server started with
+    --mirror-root / --models-dir copies the file and reports DownloadProgressResponse-shaped documents (the manager
+    itself is tested on CPU: tests/test_host_download.py)."""
+    st, _, d = call(server, "POST", "/api/models/download", {"repo": "org/model-GGUF"})
+    assert st == 503 and "not configured" in json.loads(d)["error"]
+    st, _, d = call(server, "GET", "/api/download/progress?task_id=task-1")
+    assert st == 404 and "error" in json.loads(d)
+    root, models = tmp_path / "mirror", tmp_path / "models"
+    (root / "org" / "model-GGUF").mkdir(parents=True)
+    blob = os.urandom(1 << 20)
+    (root / "org" / "model-GGUF" / "model-Q4_K_M.gguf").write_bytes(blob)
+    (root / "org" / "model-GGUF" / "model-Q8_0.gguf").write_bytes(b"x" * 10)
+    port = _free_port()
+    proc = subprocess.Popen([BIN, "--port", str(port), "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "4", "--max-ctx", "256",
+                             "--mirror-root", str(root), "--models-dir", str(models)], stderr=subprocess.PIPE)
+    try:
+        deadline = time.time() + 120
+        while time.time() < deadline:
+            try:
+                c = http.client.HTTPConnection("127.0.0.1", port, timeout=2); c.request("GET", "/v1/models"); c.getresponse().read(); c.close()
+                break
+            except OSError:
+                assert proc.poll() is None, proc.stderr.read().decode()
+                time.sleep(0.2)
+        st, _, d = call(port, "POST", "/api/models/download", {"repo": "org/model-GGUF"})
+        init = json.loads(d)
+        assert st == 200 and set(init) == {"task_id", "model", "status"}
+        for _ in range(400):
+            st, _, d = call(port, "GET", "/api/download/progress?task_id=" + init["task_id"])
+            p = json.loads(d)
+            assert st == 200 and p["status"] in ("pending", "downloading", "completed") and 0.0 <= p["progress"] <= 100.0
+            if p["status"] == "completed":
+                break
+            time.sleep(0.01)
+        assert p["status"] == "completed" and p["filename"] == "model-Q4_K_M.gguf" and p["progress"] == 100.0
+        assert (models / "org--model-GGUF" / "model-Q4_K_M.gguf").read_bytes() == blob
+        st, _, d = call(port, "POST", "/api/models/download", {"repo": "../outside"})
+        assert st == 400
+    finally:
+        proc.terminate()
+        proc.wait(timeout=20)
