@@ -137,13 +137,16 @@ def main():
         # teacher-forced: every engine token must be a (near-)arg-max of the oracle's logits
         agree, total, near = 0, 0, True
         detail = []
+        # the near-arg-max margin follows the rounding noise of the widest dot product: the "odd" geometry's FFN grows with
+        # the world size (5120 per rank), and bf16 activation rounding accumulates ~ sqrt(K)
+        near_tol = NEAR * max(1.0, (cfg["ffn"] / 10240.0) ** 0.5)
         for ps, ts in ((p3, toks3), (p7, toks7)):
             for pr, t in zip(ps, ts):
                 r2 = LlamaRef(cfg, sd)
                 cur = r2.forward(pr).numpy()[-1]
                 a = 0
                 for tok in t:
-                    near &= bool(cur[tok] >= cur.max() - NEAR)
+                    near &= bool(cur[tok] >= cur.max() - near_tol)
                     a += int(tok == int(np.argmax(cur)))
                     total += 1
                     cur = r2.forward([tok]).numpy()[-1]
