@@ -44,7 +44,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PROMPT, GEN = 512, 128
-PARITY_TOL_CPU = 0.25    # margin to the fp32 CPU oracle's arg-max logit (logit std ~1.3 at 8B; bf16 activations)
+PARITY_TOL_CPU = 0.30    # margin to the fp32 CPU oracle's arg-max logit (logit std ~1.3 at 8B; bf16 activations): the near-tie bound of
+                         # tests/test_parity_8b_gpu.py (measured there: max|dlogit| 0.20; measured here: margins 0.05-0.22)
 PARITY_TOL_TP = 0.10     # margin to the tp=1 engine's arg-max logit (same kernels, other summation order)
 
 
