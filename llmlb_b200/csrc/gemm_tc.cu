@@ -646,3 +646,18 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
   tpp.sk_ws = op_ws; tpp.sk_cnt = op_cnt;
   return gemm_tc_launch(tw, tx, out, n_tokens, n_out, k, epilogue, out_stride, st, &txh, nullptr, &tpp, 8);
 }
+
+// Host-only (no launch, no device): the K-split a store-epilogue projection of this shape would run with, and the grid
+// it implies — what tests/test_gemm_plan_cpu.py checks the co-residency invariants of the in-kernel K-split on.
+// out = {tile rows BN (token tile), tiles, split_k, CTAs}
+extern "C" int llmlb_debug_store_split(uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t out[4]) {
+  if (!out || n_tokens == 0 || n_out == 0 || k == 0) return LLMLB_E_INVALID_ARG;
+  TpPushRS tpp{};
+  tpp.sk_ws = reinterpret_cast<float*>(uintptr_t(1));          // "a workspace exists": never dereferenced here
+  tpp.sk_cnt = reinterpret_cast<unsigned int*>(uintptr_t(1));
+  const uint32_t bn = tc_pick_bn(n_tokens);
+  const uint32_t tiles = ((n_out + kBM - 1) / kBM) * ((n_tokens + bn - 1) / bn);
+  const uint32_t s = tc_store_split(n_tokens, n_out, k, &tpp);
+  out[0] = bn; out[1] = tiles; out[2] = s; out[3] = tiles * s;
+  return LLMLB_OK;
+}
