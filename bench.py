@@ -121,7 +121,7 @@ def make_prompt(i, vocab, n=PROMPT):
 
 
 # ------------------------------------------------------------------------------ CPU arms ----
-def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forced=None):
+def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forced=None, weights="bf16"):
     """Oracle port on the host cores: synthetic bf16 weights (C generator), C/OpenMP matmuls.
     Bounded sample of the 512/128 workload: `sample_prompt` prompt tokens + `sample_gen` decoded
     tokens per step, full 8B geometry (nothing skipped).
@@ -137,16 +137,25 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forc
     torch.set_num_threads(cores)
     synth_native.set_threads(cores)
     t0 = time.time()
-    sd = synth_native.synth_state_dict_bits(model, seed=0)
+    # weights="q4_0": every matmul weight as ggml Q4_0 blocks (4.5 bits/weight) — the weight width of the reference path's own
+    # CPU configuration (BASELINE.json configs[0]: llama.cpp, Llama-3-8B q4); same model, same sample, same formula
+    sd = synth_native.synth_state_dict_q4(model, seed=0) if weights == "q4_0" else synth_native.synth_state_dict_bits(model, seed=0)
     ref = LlamaRef(model, sd)
     t_load = time.time() - t0
     # probe one lm_head-sized GEMV and shrink the sample if this host is slow, so the run stays
     # inside its time box (~30 s of CPU work per step) whatever the core quota is
-    probe_w = sd["lm_head.weight"].bits
-    px = np.zeros((1, probe_w.shape[1]), dtype=np.float32)
-    synth_native.linear_bf16(probe_w, px)
-    tp0 = time.time(); synth_native.linear_bf16(probe_w, px); probe = time.time() - tp0
-    est_token_s = probe * (algorithmic_bytes_per_decode_step(model, 0, 0) / (probe_w.size * 2.0))
+    if weights == "q4_0":
+        pw = sd["lm_head.weight"]
+        px = np.zeros((1, pw.k), dtype=np.float32)
+        synth_native.linear_q4_0(pw.blocks, pw.k, px)
+        tp0 = time.time(); synth_native.linear_q4_0(pw.blocks, pw.k, px); probe = time.time() - tp0
+        est_token_s = probe * (algorithmic_bytes_per_decode_step(model, 0, 0) / (pw.blocks.shape[0] * pw.k * 2.0))
+    else:
+        probe_w = sd["lm_head.weight"].bits
+        px = np.zeros((1, probe_w.shape[1]), dtype=np.float32)
+        synth_native.linear_bf16(probe_w, px)
+        tp0 = time.time(); synth_native.linear_bf16(probe_w, px); probe = time.time() - tp0
+        est_token_s = probe * (algorithmic_bytes_per_decode_step(model, 0, 0) / (probe_w.size * 2.0))
     if forced is None and est_token_s * (sample_prompt / 4.0 + sample_gen) > 30.0:
         sample_gen = max(1, min(sample_gen, int(10.0 / max(est_token_s, 1e-3))))
         sample_prompt = max(4, min(sample_prompt, int(4 * 15.0 / max(est_token_s, 1e-3))))
@@ -180,7 +189,8 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forc
             dec_tok += n_gen; dec_s += c - b
     return {"decode_tok_s": dec_tok / dec_s, "prefill_tok_s": pre_tok / pre_s, "cores": cores,
             "weights_s": t_load, "ms_per_step": 1e3 * (pre_s + dec_s) / max(1, steps), "parity": parity,
-            "sample": "%d prompt + %d decoded tokens per step, full Llama-3-8B geometry, bf16 weights, C/OpenMP fp32-accumulate linears (oracle/llama_cpu.c), %d threads" % (sample_prompt, sample_gen, cores)}
+            "sample": "%d prompt + %d decoded tokens per step, full Llama-3-8B geometry, %s weights, C/OpenMP fp32-accumulate linears (oracle/llama_cpu.c), %d threads"
+                      % (sample_prompt, sample_gen, "ggml Q4_0 (4.5 bits/weight)" if weights == "q4_0" else "bf16", cores)}
 
 
 def run_reference(args):
@@ -477,6 +487,18 @@ def run_ours(args):
                                     "sample": r["sample"], "prefill_tok_s": r["prefill_tok_s"]}
             if r["parity"]:
                 line["parity"] = r["parity"]
+            if args.cpu_q4:
+                # opt-in context, not the reference arm: the same port with ggml Q4_0 weights — the weight width BASELINE.json
+                # configs[0] quotes the reference path on (llama.cpp q4).  The port's Q4_0 GEMV is scalar-unpack C (3 GB/s of
+                # weight bytes on 8 cores: compute-bound, 2x SLOWER than its bf16 GEMV), nothing like llama.cpp's integer kernels,
+                # so it is off by default and the bf16 figure stays the baseline
+                try:
+                    del r
+                    rq = cpu_reference_run(model, 1, 0, args.cpu_prompt, args.cpu_gen, weights="q4_0")
+                    line["cpu_baseline"]["q4_0"] = {"value": rq["decode_tok_s"], "unit": "tok/s", "prefill_tok_s": rq["prefill_tok_s"],
+                                                   "weights_s": rq["weights_s"], "sample": rq["sample"]}
+                except Exception as ex:   # never lose the line over the context figure
+                    line["cpu_baseline"]["q4_0"] = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
         line["parity_ok"] = None if line["parity"] is None else line["parity"]["ok"]
         print(json.dumps(line))
         sys.stdout.flush()
@@ -503,6 +525,7 @@ def main():
     ap.add_argument("--parity-only", action="store_true", help="diagnostic: print the tp parity record and stop")
     ap.add_argument("--no-ref-shape", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-q4", action="store_true", help="also time the CPU port with ggml Q4_0 weights (about a minute more; see the comment in run_ours)")
     ap.add_argument("--cpu-prompt", type=int, default=32)
     ap.add_argument("--cpu-gen", type=int, default=8)
     args = ap.parse_args()

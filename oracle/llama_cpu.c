@@ -47,3 +47,112 @@ void oracle_linear_bf16(const uint16_t* W, const float* X, float* Y, int64_t n_o
     }
   }
 }
+
+
+/* ---- Q4_0: the weight format of the reference path's CPU endpoint in BASELINE.json configs[0] ("llama.cpp ... Llama-3-8B q4").
+ * Restates ggml's published block format and reference quantiser (ggml-quants.c quantize_row_q4_0_ref /
+ * dequantize_row_q4_0; llama.cpp is an external, un-vendored dependency of the reference: SURVEY.md §8c): a block is 32
+ * weights = one fp16 scale d followed by 16 bytes of nibbles; w[j] = d * (q[j] - 8), low nibbles are elements 0..15, high
+ * nibbles 16..31; d = (the value of largest magnitude, sign kept) / -8.  Pinned bit for bit to llama.cpp's own `gguf`
+ * Python package in tests/test_oracle_q4.py.  The product engine computes in bf16; this exists only so that the CPU
+ * baseline can also be quoted at the reference configuration's weight width (4.5 bits/weight streamed per token). */
+static inline uint16_t f32_to_f16(float f) {          /* round to nearest even, like GGML_FP32_TO_FP16 (F16C) */
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  int32_t e = (int32_t)((x >> 23) & 0xFF) - 127 + 15;
+  uint32_t m = x & 0x7FFFFFu;
+  if (((x >> 23) & 0xFF) == 0xFF) return (uint16_t)(sign | 0x7C00u | (m ? 0x200u : 0));
+  if (e >= 31) return (uint16_t)(sign | 0x7C00u);
+  if (e <= 0) {
+    if (e < -10) return (uint16_t)sign;
+    m |= 0x800000u;
+    const int shift = 14 - e;
+    uint32_t h = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;   /* may carry into the exponent: still correct */
+  return (uint16_t)(sign | h);
+}
+static inline float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t e = (h >> 10) & 0x1F, m = h & 0x3FFu, x;
+  if (e == 0) {
+    if (m == 0) x = sign;
+    else { e = 127 - 15 + 1; while (!(m & 0x400u)) { m <<= 1; --e; } x = sign | (e << 23) | ((m & 0x3FFu) << 13); }
+  } else if (e == 31) x = sign | 0x7F800000u | (m << 13);
+  else x = sign | ((e - 15 + 127) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+
+#define QK4_0 32
+#define Q4_0_BLOCK_BYTES 18
+
+/* W: bf16 bits [n_out, k] (k % 32 == 0) -> out: [n_out, k / 32] blocks of 18 bytes.
+ * No FMA contraction here: x*id and +8.5 are two roundings in the reference quantiser (and in gguf-py, the pin). */
+__attribute__((optimize("-ffp-contract=off")))
+void oracle_quantize_q4_0(const uint16_t* W, uint8_t* out, int64_t n_out, int64_t k) {
+  const int64_t nb = k / QK4_0;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_out; ++n) {
+    for (int64_t b = 0; b < nb; ++b) {
+      float x[QK4_0];
+      float amax = 0.f, max = 0.f;
+      for (int j = 0; j < QK4_0; ++j) {
+        x[j] = bf16_to_f32(W[n * k + b * QK4_0 + j]);
+        const float a = x[j] < 0 ? -x[j] : x[j];
+        if (amax < a) { amax = a; max = x[j]; }
+      }
+      const float d = max / -8.f;
+      const float id = d ? 1.0f / d : 0.0f;
+      uint8_t* blk = out + (n * nb + b) * Q4_0_BLOCK_BYTES;
+      const uint16_t dh = f32_to_f16(d);
+      memcpy(blk, &dh, 2);
+      for (int j = 0; j < QK4_0 / 2; ++j) {
+        const float x0 = x[j] * id, x1 = x[QK4_0 / 2 + j] * id;
+        int q0 = (int)(int8_t)(x0 + 8.5f), q1 = (int)(int8_t)(x1 + 8.5f);
+        if (q0 > 15) q0 = 15;
+        if (q1 > 15) q1 = 15;
+        blk[2 + j] = (uint8_t)(q0 | (q1 << 4));
+      }
+    }
+  }
+}
+
+/* y[t, n] = sum over blocks of d * sum_j (q_j - 8) * x[t, j]   (fp32 activations; llama.cpp itself quantises the
+ * activations to Q8_0 and runs integer dot products — same bytes per token, different arithmetic: a port, not llama.cpp) */
+void oracle_linear_q4_0(const uint8_t* Wq, const float* X, float* Y, int64_t n_out, int64_t k, int64_t T) {
+  const int64_t nb = k / QK4_0;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_out; ++n) {
+    const uint8_t* row = Wq + n * nb * Q4_0_BLOCK_BYTES;
+    for (int64_t t = 0; t < T; ++t) {
+      const float* x = X + t * k;
+      float acc = 0.f;
+      for (int64_t b = 0; b < nb; ++b) {
+        const uint8_t* blk = row + b * Q4_0_BLOCK_BYTES;
+        uint16_t dh;
+        memcpy(&dh, blk, 2);
+        const float d = f16_to_f32(dh);
+        const float* xb = x + b * QK4_0;
+        float w[QK4_0];
+#pragma omp simd
+        for (int j = 0; j < QK4_0 / 2; ++j) {
+          w[j] = (float)((int)(blk[2 + j] & 0x0F) - 8);
+          w[QK4_0 / 2 + j] = (float)((int)(blk[2 + j] >> 4) - 8);
+        }
+        float s = 0.f;
+#pragma omp simd reduction(+ : s)
+        for (int j = 0; j < QK4_0; ++j) s += w[j] * xb[j];
+        acc += d * s;
+      }
+      Y[t * n_out + n] = acc;
+    }
+  }
+}

@@ -37,7 +37,7 @@ class LlamaRef:
             torch.set_num_threads(threads)
         self.w = {}
         for k, v in state_dict.items():
-            if getattr(v, "dtype", None) == "bf16_bits":   # oracle.synth_native.Bf16Weight: C kernel path
+            if getattr(v, "dtype", None) in ("bf16_bits", "q4_0"):   # oracle.synth_native.Bf16Weight / Q4Weight: C kernel path
                 self.w[k] = v
             else:
                 t = torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v
@@ -62,6 +62,9 @@ class LlamaRef:
         if getattr(w, "dtype", None) == "bf16_bits":  # CPU-baseline mode: bf16 weights, C/OpenMP GEMV
             from .synth_native import linear_bf16
             return torch.from_numpy(linear_bf16(w.bits, x.numpy()))
+        if getattr(w, "dtype", None) == "q4_0":       # CPU baseline at the reference configuration's weight width (ggml Q4_0)
+            from .synth_native import linear_q4_0
+            return torch.from_numpy(linear_q4_0(w.blocks, w.k, x.numpy()))
         if w.dtype == torch.float32:
             return x @ w.t()
         return (x.to(w.dtype) @ w.t()).to(torch.float32)

@@ -71,6 +71,55 @@ def linear_bf16(w_bits, x):
     return y
 
 
+def _cpu_lib():
+    global _cpu
+    if _cpu is None:
+        linear_bf16(np.zeros((1, 32), dtype=np.uint16), np.zeros((1, 32), dtype=np.float32))   # loads + prototypes the bf16 entry
+    if not getattr(_cpu, "_q4_ready", False):
+        _cpu.oracle_quantize_q4_0.restype = None
+        _cpu.oracle_quantize_q4_0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        _cpu.oracle_linear_q4_0.restype = None
+        _cpu.oracle_linear_q4_0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+        _cpu._q4_ready = True
+    return _cpu
+
+
+def quantize_q4_0(w_bits):
+    """bf16 bit pattern [n, k] -> ggml Q4_0 blocks, uint8 [n, k // 32 * 18] (oracle/llama_cpu.c)."""
+    n, k = w_bits.shape
+    assert k % 32 == 0
+    out = np.empty((n, k // 32 * 18), dtype=np.uint8)
+    _cpu_lib().oracle_quantize_q4_0(np.ascontiguousarray(w_bits).ctypes.data, out.ctypes.data, n, k)
+    return out
+
+
+def linear_q4_0(wq, k, x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = wq.shape[0]
+    y = np.empty((x.shape[0], n), dtype=np.float32)
+    _cpu_lib().oracle_linear_q4_0(wq.ctypes.data, x.ctypes.data, y.ctypes.data, n, k, x.shape[0])
+    return y
+
+
+class Q4Weight:
+    """ggml Q4_0 blocks of a [n, k] weight; llama_ref._mm dispatches to the C kernel for it."""
+
+    def __init__(self, blocks, k):
+        self.blocks, self.k = blocks, k
+        self.dtype = "q4_0"
+
+
+def synth_state_dict_q4(cfg, seed=0):
+    """The synthetic model with every matmul weight (lm_head included) quantised to Q4_0; embedding rows and norm gains as in
+    synth_state_dict_bits.  4.5 bits per weight: 4.2 GB for Llama-3-8B."""
+    sd = synth_state_dict_bits(cfg, seed)
+    for name in list(sd):
+        w = sd[name]
+        if getattr(w, "dtype", None) == "bf16_bits" and name != "model.embed_tokens.weight":
+            sd[name] = Q4Weight(quantize_q4_0(w.bits), w.bits.shape[1])
+    return sd
+
+
 _lib = None
 
 
