@@ -121,7 +121,7 @@ def make_prompt(i, vocab, n=PROMPT):
 
 
 # ------------------------------------------------------------------------------ CPU arms ----
-def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forced=None, weights="bf16"):
+def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forced=None, weights="bf16", sd_bits=None):
     """Oracle port on the host cores: synthetic bf16 weights (C generator), C/OpenMP matmuls.
     Bounded sample of the 512/128 workload: `sample_prompt` prompt tokens + `sample_gen` decoded
     tokens per step, full 8B geometry (nothing skipped).
@@ -139,7 +139,9 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forc
     t0 = time.time()
     # weights="q4_0": every matmul weight as ggml Q4_0 blocks (4.5 bits/weight) — the weight width of the reference path's own
     # CPU configuration (BASELINE.json configs[0]: llama.cpp, Llama-3-8B q4); same model, same sample, same formula
-    sd = synth_native.synth_state_dict_q4(model, seed=0) if weights == "q4_0" else synth_native.synth_state_dict_bits(model, seed=0)
+    if sd_bits is None:
+        sd_bits = synth_native.synth_state_dict_bits(model, seed=0)     # pass it in to share the 16 GB between the two legs
+    sd = synth_native.q4_from_bits(sd_bits) if weights == "q4_0" else sd_bits
     ref = LlamaRef(model, sd)
     t_load = time.time() - t0
     # probe one lm_head-sized GEMV and shrink the sample if this host is slow, so the run stays
@@ -189,8 +191,9 @@ def cpu_reference_run(model, steps, warmup, sample_prompt=32, sample_gen=4, forc
             dec_tok += n_gen; dec_s += c - b
     return {"decode_tok_s": dec_tok / dec_s, "prefill_tok_s": pre_tok / pre_s, "cores": cores,
             "weights_s": t_load, "ms_per_step": 1e3 * (pre_s + dec_s) / max(1, steps), "parity": parity,
-            "sample": "%d prompt + %d decoded tokens per step, full Llama-3-8B geometry, %s weights, C/OpenMP fp32-accumulate linears (oracle/llama_cpu.c), %d threads"
-                      % (sample_prompt, sample_gen, "ggml Q4_0 (4.5 bits/weight)" if weights == "q4_0" else "bf16", cores)}
+            "sample": "%d prompt + %d decoded tokens per step, full Llama-3-8B geometry, %s (oracle/llama_cpu.c), %d threads"
+                      % (sample_prompt, sample_gen, "ggml Q4_0 weights (4.5 bits/weight) x Q8_0 activations, integer block dot products (AVX2), C/OpenMP" if weights == "q4_0"
+                         else "bf16 weights, C/OpenMP fp32-accumulate linears", cores)}
 
 
 def run_reference(args):
@@ -482,19 +485,21 @@ def run_ours(args):
         }
         if args.cpu_baseline and world == 1:
             eng.close()
-            r = cpu_reference_run(model, 1, 0, args.cpu_prompt, args.cpu_gen, forced=forced_for_cpu)
+            from oracle import synth_native as _sn
+            _sn.set_threads(_sn.effective_cpus())
+            sd_bits = _sn.synth_state_dict_bits(model, seed=0)
+            r = cpu_reference_run(model, 1, 0, args.cpu_prompt, args.cpu_gen, forced=forced_for_cpu, sd_bits=sd_bits)
             line["cpu_baseline"] = {"value": r["decode_tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"], "prefill_tok_s": r["prefill_tok_s"]}
             if r["parity"]:
                 line["parity"] = r["parity"]
-            if args.cpu_q4:
-                # opt-in context, not the reference arm: the same port with ggml Q4_0 weights — the weight width BASELINE.json
-                # configs[0] quotes the reference path on (llama.cpp q4).  The port's Q4_0 GEMV is scalar-unpack C (3 GB/s of
-                # weight bytes on 8 cores: compute-bound, 2x SLOWER than its bf16 GEMV), nothing like llama.cpp's integer kernels,
-                # so it is off by default and the bf16 figure stays the baseline
+            if not args.no_cpu_q4:
+                # context, not the reference arm: the same port at the weight width BASELINE.json configs[0] quotes the reference
+                # path on (llama.cpp, Llama-3-8B q4): ggml Q4_0 weights, activations quantised to Q8_0, integer block dot products
+                # (llama.cpp's CPU scheme restated in oracle/llama_cpu.c, quantisers pinned bit for bit to the gguf package).
+                # The bf16 figure above stays the like-for-like baseline of the bf16 engine.
                 try:
-                    del r
-                    rq = cpu_reference_run(model, 1, 0, args.cpu_prompt, args.cpu_gen, weights="q4_0")
+                    rq = cpu_reference_run(model, 1, 0, args.cpu_prompt, args.cpu_gen, weights="q4_0", sd_bits=sd_bits)
                     line["cpu_baseline"]["q4_0"] = {"value": rq["decode_tok_s"], "unit": "tok/s", "prefill_tok_s": rq["prefill_tok_s"],
                                                    "weights_s": rq["weights_s"], "sample": rq["sample"]}
                 except Exception as ex:   # never lose the line over the context figure
@@ -525,7 +530,7 @@ def main():
     ap.add_argument("--parity-only", action="store_true", help="diagnostic: print the tp parity record and stop")
     ap.add_argument("--no-ref-shape", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--cpu-q4", action="store_true", help="also time the CPU port with ggml Q4_0 weights (about a minute more; see the comment in run_ours)")
+    ap.add_argument("--no-cpu-q4", action="store_true", help="skip the Q4_0-weights context figure of the CPU baseline (about 20 s)")
     ap.add_argument("--cpu-prompt", type=int, default=32)
     ap.add_argument("--cpu-gen", type=int, default=8)
     args = ap.parse_args()

@@ -5,6 +5,8 @@
  *   gcc -O3 -march=native -fopenmp -shared -fPIC oracle/llama_cpu.c -o oracle/liboracle_cpu.so
  *
  *   y[t, n] = sum_k x[t, k] * W[n, k]      W bf16 [n_out, k] row-major, x/y fp32, T <= 64     */
+#include <immintrin.h>
+#include <math.h>
 #include <omp.h>
 #include <stdint.h>
 #include <string.h>
@@ -102,25 +104,31 @@ void oracle_quantize_q4_0(const uint16_t* W, uint8_t* out, int64_t n_out, int64_
 #pragma omp parallel for schedule(static)
   for (int64_t n = 0; n < n_out; ++n) {
     for (int64_t b = 0; b < nb; ++b) {
-      float x[QK4_0];
-      float amax = 0.f, max = 0.f;
+      float x[QK4_0], ax[QK4_0];
+#pragma omp simd
       for (int j = 0; j < QK4_0; ++j) {
         x[j] = bf16_to_f32(W[n * k + b * QK4_0 + j]);
-        const float a = x[j] < 0 ? -x[j] : x[j];
-        if (amax < a) { amax = a; max = x[j]; }
+        ax[j] = fabsf(x[j]);
       }
+      float amax = 0.f;
+#pragma omp simd reduction(max : amax)
+      for (int j = 0; j < QK4_0; ++j) amax = ax[j] > amax ? ax[j] : amax;
+      float max = 0.f;                                  /* the FIRST element of largest magnitude, sign kept */
+      for (int j = 0; j < QK4_0; ++j) if (ax[j] == amax) { max = x[j]; break; }
       const float d = max / -8.f;
       const float id = d ? 1.0f / d : 0.0f;
       uint8_t* blk = out + (n * nb + b) * Q4_0_BLOCK_BYTES;
       const uint16_t dh = f32_to_f16(d);
       memcpy(blk, &dh, 2);
-      for (int j = 0; j < QK4_0 / 2; ++j) {
-        const float x0 = x[j] * id, x1 = x[QK4_0 / 2 + j] * id;
-        int q0 = (int)(int8_t)(x0 + 8.5f), q1 = (int)(int8_t)(x1 + 8.5f);
-        if (q0 > 15) q0 = 15;
-        if (q1 > 15) q1 = 15;
-        blk[2 + j] = (uint8_t)(q0 | (q1 << 4));
+      int32_t q[QK4_0];
+#pragma omp simd
+      for (int j = 0; j < QK4_0; ++j) {
+        const float v = x[j] * id;                      /* two roundings (no FMA): as the reference quantiser */
+        const float u = v + 8.5f;
+        int32_t qi = (int32_t)u;                        /* u >= 0.5 by construction: truncation = the (int8_t) cast */
+        q[j] = qi > 15 ? 15 : qi;
       }
+      for (int j = 0; j < QK4_0 / 2; ++j) blk[2 + j] = (uint8_t)(q[j] | (q[QK4_0 / 2 + j] << 4));
     }
   }
 }
@@ -153,6 +161,94 @@ void oracle_linear_q4_0(const uint8_t* Wq, const float* X, float* Y, int64_t n_o
         acc += d * s;
       }
       Y[t * n_out + n] = acc;
+    }
+  }
+}
+
+
+/* ---- Q4_0 x Q8_0: how llama.cpp's CPU backend actually multiplies a Q4_0 weight: the ACTIVATIONS are quantised to Q8_0
+ * (block of 32 = fp16 scale + 32 int8, d = amax / 127, q = roundf(x / d); ggml-quants.c quantize_row_q8_0_ref) and the dot
+ * product runs on integers, one (d4 * d8) scaling per block (ggml_vec_dot_q4_0_q8_0).  The AVX2 body below is that
+ * published scheme (unsigned x signed bytes through abs/sign + maddubs + madd), restated; the quantiser is pinned bit for
+ * bit to gguf-py, the product to a numpy evaluation of the same integers (tests/test_oracle_q4.py). */
+#define Q8_0_BLOCK_BYTES 34
+
+__attribute__((optimize("-ffp-contract=off")))
+void oracle_quantize_q8_0(const float* X, uint8_t* out, int64_t T, int64_t k) {
+  const int64_t nb = k / QK4_0;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < T * nb; ++i) {
+    const float* x = X + i * QK4_0;
+    float amax = 0.f;
+    for (int j = 0; j < QK4_0; ++j) { const float a = fabsf(x[j]); if (a > amax) amax = a; }
+    const float d = amax / 127.f;
+    const float id = d ? 1.0f / d : 0.0f;
+    uint8_t* blk = out + i * Q8_0_BLOCK_BYTES;
+    const uint16_t dh = f32_to_f16(d);
+    memcpy(blk, &dh, 2);
+    for (int j = 0; j < QK4_0; ++j) ((int8_t*)(blk + 2))[j] = (int8_t)roundf(x[j] * id);
+  }
+}
+
+#if defined(__AVX2__)
+static inline float hsum8(__m256 v) {
+  __m128 lo = _mm256_castps256_ps128(v), hi = _mm256_extractf128_ps(v, 1);
+  lo = _mm_add_ps(lo, hi);
+  lo = _mm_add_ps(lo, _mm_movehl_ps(lo, lo));
+  lo = _mm_add_ss(lo, _mm_movehdup_ps(lo));
+  return _mm_cvtss_f32(lo);
+}
+#endif
+
+/* y[t, n] = sum_b d4[n,b] * d8[t,b] * sum_j (q4[n,b,j] - 8) * q8[t,b,j]      Xq: [T, k/32] Q8_0 blocks */
+void oracle_linear_q4_0_q8_0(const uint8_t* Wq, const uint8_t* Xq, float* Y, int64_t n_out, int64_t k, int64_t T) {
+  const int64_t nb = k / QK4_0;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_out; ++n) {
+    const uint8_t* row = Wq + n * nb * Q4_0_BLOCK_BYTES;
+    for (int64_t t = 0; t < T; ++t) {
+      const uint8_t* xr = Xq + t * nb * Q8_0_BLOCK_BYTES;
+#if defined(__AVX2__)
+      __m256 acc = _mm256_setzero_ps();
+      const __m256i m4 = _mm256_set1_epi8(0x0F), off = _mm256_set1_epi8(8), ones = _mm256_set1_epi16(1);
+      for (int64_t b = 0; b < nb; ++b) {
+        const uint8_t* wb = row + b * Q4_0_BLOCK_BYTES;
+        const uint8_t* xb = xr + b * Q8_0_BLOCK_BYTES;
+        uint16_t dw, dx;
+        memcpy(&dw, wb, 2);
+        memcpy(&dx, xb, 2);
+#if defined(__F16C__)
+        const __m256 d = _mm256_set1_ps(_cvtsh_ss(dw) * _cvtsh_ss(dx));
+#else
+        const __m256 d = _mm256_set1_ps(f16_to_f32(dw) * f16_to_f32(dx));
+#endif
+        const __m128i nib = _mm_loadu_si128((const __m128i*)(wb + 2));
+        __m256i q4 = _mm256_set_m128i(_mm_srli_epi16(nib, 4), nib);          /* low nibbles = elements 0..15, high = 16..31 */
+        q4 = _mm256_sub_epi8(_mm256_and_si256(q4, m4), off);                   /* -8 .. 7 */
+        const __m256i q8 = _mm256_loadu_si256((const __m256i*)(xb + 2));
+        const __m256i ax = _mm256_sign_epi8(q4, q4), sy = _mm256_sign_epi8(q8, q4);
+        const __m256i p16 = _mm256_maddubs_epi16(ax, sy);
+        const __m256i p32 = _mm256_madd_epi16(p16, ones);
+        acc = _mm256_fmadd_ps(d, _mm256_cvtepi32_ps(p32), acc);
+      }
+      Y[t * n_out + n] = hsum8(acc);
+#else
+      float acc = 0.f;
+      for (int64_t b = 0; b < nb; ++b) {
+        const uint8_t* wb = row + b * Q4_0_BLOCK_BYTES;
+        const uint8_t* xb = xr + b * Q8_0_BLOCK_BYTES;
+        uint16_t dw, dx;
+        memcpy(&dw, wb, 2);
+        memcpy(&dx, xb, 2);
+        int32_t s = 0;
+        for (int j = 0; j < QK4_0 / 2; ++j) {
+          s += ((int)(wb[2 + j] & 0x0F) - 8) * (int)((const int8_t*)(xb + 2))[j];
+          s += ((int)(wb[2 + j] >> 4) - 8) * (int)((const int8_t*)(xb + 2))[QK4_0 / 2 + j];
+        }
+        acc += f16_to_f32(dw) * f16_to_f32(dx) * (float)s;
+      }
+      Y[t * n_out + n] = acc;
+#endif
     }
   }
 }

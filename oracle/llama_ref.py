@@ -63,8 +63,10 @@ class LlamaRef:
             from .synth_native import linear_bf16
             return torch.from_numpy(linear_bf16(w.bits, x.numpy()))
         if getattr(w, "dtype", None) == "q4_0":       # CPU baseline at the reference configuration's weight width (ggml Q4_0)
-            from .synth_native import linear_q4_0
-            return torch.from_numpy(linear_q4_0(w.blocks, w.k, x.numpy()))
+            from .synth_native import linear_q4_0, linear_q4_0_q8_0
+            # llama.cpp's scheme by default: activations quantised to Q8_0, integer block dot products
+            fn = linear_q4_0_q8_0 if getattr(w, "int_dot", True) else linear_q4_0
+            return torch.from_numpy(fn(w.blocks, w.k, x.numpy()))
         if w.dtype == torch.float32:
             return x @ w.t()
         return (x.to(w.dtype) @ w.t()).to(torch.float32)

@@ -80,6 +80,10 @@ def _cpu_lib():
         _cpu.oracle_quantize_q4_0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         _cpu.oracle_linear_q4_0.restype = None
         _cpu.oracle_linear_q4_0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+        _cpu.oracle_quantize_q8_0.restype = None
+        _cpu.oracle_quantize_q8_0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        _cpu.oracle_linear_q4_0_q8_0.restype = None
+        _cpu.oracle_linear_q4_0_q8_0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
         _cpu._q4_ready = True
     return _cpu
 
@@ -101,23 +105,47 @@ def linear_q4_0(wq, k, x):
     return y
 
 
+def quantize_q8_0(x):
+    """fp32 [T, k] -> ggml Q8_0 blocks, uint8 [T, k // 32 * 34] (llama.cpp quantises the ACTIVATIONS this way)"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    t, k = x.shape
+    assert k % 32 == 0
+    out = np.empty((t, k // 32 * 34), dtype=np.uint8)
+    _cpu_lib().oracle_quantize_q8_0(x.ctypes.data, out.ctypes.data, t, k)
+    return out
+
+
+def linear_q4_0_q8_0(wq, k, x):
+    """y = W(Q4_0) . x with x quantised to Q8_0 first and integer block dot products: llama.cpp's CPU scheme"""
+    xq = quantize_q8_0(x)
+    n = wq.shape[0]
+    y = np.empty((xq.shape[0], n), dtype=np.float32)
+    _cpu_lib().oracle_linear_q4_0_q8_0(wq.ctypes.data, xq.ctypes.data, y.ctypes.data, n, k, xq.shape[0])
+    return y
+
+
 class Q4Weight:
     """ggml Q4_0 blocks of a [n, k] weight; llama_ref._mm dispatches to the C kernel for it."""
 
-    def __init__(self, blocks, k):
+    def __init__(self, blocks, k, int_dot=True):
         self.blocks, self.k = blocks, k
+        self.int_dot = int_dot          # True: Q8_0 activations + integer dot (llama.cpp's CPU scheme); False: fp32 activations
         self.dtype = "q4_0"
 
 
-def synth_state_dict_q4(cfg, seed=0):
-    """The synthetic model with every matmul weight (lm_head included) quantised to Q4_0; embedding rows and norm gains as in
-    synth_state_dict_bits.  4.5 bits per weight: 4.2 GB for Llama-3-8B."""
-    sd = synth_state_dict_bits(cfg, seed)
+def q4_from_bits(sd_bits, int_dot=True):
+    """A state dict of Bf16Weight (synth_state_dict_bits) -> the same model with every matmul weight (lm_head included) as
+    ggml Q4_0 blocks; embedding rows and norm gains unchanged.  4.5 bits per weight: 4.2 GB for Llama-3-8B, ~3 s on 8 cores."""
+    sd = dict(sd_bits)
     for name in list(sd):
         w = sd[name]
         if getattr(w, "dtype", None) == "bf16_bits" and name != "model.embed_tokens.weight":
-            sd[name] = Q4Weight(quantize_q4_0(w.bits), w.bits.shape[1])
+            sd[name] = Q4Weight(quantize_q4_0(w.bits), w.bits.shape[1], int_dot)
     return sd
+
+
+def synth_state_dict_q4(cfg, seed=0, int_dot=True):
+    return q4_from_bits(synth_state_dict_bits(cfg, seed), int_dot)
 
 
 _lib = None

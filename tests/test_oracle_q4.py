@@ -45,10 +45,27 @@ def test_linear_equals_dequantised_matmul():
         assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
 
 
+def test_q8_activation_quantiser_and_integer_dot():
+    """llama.cpp multiplies a Q4_0 weight by activations quantised to Q8_0, on integers: the activation quantiser is bit-exact
+    against gguf-py and the AVX2 dot equals a float64 evaluation of the very same integers and scales."""
+    Q8 = gguf.GGMLQuantizationType.Q8_0
+    rs = np.random.RandomState(4)
+    x = (rs.randn(6, 1024) * rs.choice([1e-4, 1.0, 40.0], size=(6, 1))).astype(np.float32)
+    x[2] = 0
+    x[3, :32] = np.linspace(-1, 1, 32) * 127 / 127.0      # ties of roundf
+    q8 = S.quantize_q8_0(x)
+    assert np.array_equal(quants.quantize(x, Q8).reshape(q8.shape), q8)
+    bits, _ = _bf16(rs.randn(200, 1024) * 0.02)
+    q4 = S.quantize_q4_0(bits)
+    ref = quants.dequantize(q8, Q8).astype(np.float64) @ quants.dequantize(q4, Q4).astype(np.float64).T
+    y = S.linear_q4_0_q8_0(q4, 1024, x)
+    assert np.abs(y - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
 def test_q4_model_forward_equals_the_dequantised_fp32_model():
     from llmlb_b200 import ffi
     cfg = ffi.LLAMA_TINY
-    sd_q = S.synth_state_dict_q4(cfg, seed=0)
+    sd_q = S.synth_state_dict_q4(cfg, seed=0, int_dot=False)
     sd_f = {}
     for name, w in sd_q.items():
         if getattr(w, "dtype", None) == "q4_0":
@@ -65,3 +82,13 @@ def test_q4_model_forward_equals_the_dequantised_fp32_model():
     n_w = sum(w.blocks.shape[0] * w.k for w in sd_q.values() if getattr(w, "dtype", None) == "q4_0")
     n_b = sum(w.blocks.nbytes for w in sd_q.values() if getattr(w, "dtype", None) == "q4_0")
     assert abs(n_b * 8 / n_w - 4.5) < 1e-9
+
+
+def test_integer_path_stays_close_to_the_fp32_activation_path():
+    """Same Q4_0 weights, activations through Q8_0 (llama.cpp's scheme) vs fp32: logits move by the activation rounding only."""
+    from llmlb_b200 import ffi
+    cfg = ffi.LLAMA_TINY
+    prompt = np.random.RandomState(1).randint(0, cfg["vocab"], 24).tolist()
+    a = LlamaRef(cfg, S.synth_state_dict_q4(cfg, seed=0, int_dot=True)).forward(prompt).numpy()
+    b = LlamaRef(cfg, S.synth_state_dict_q4(cfg, seed=0, int_dot=False)).forward(prompt).numpy()
+    assert np.abs(a - b).max() < 0.05 * b.std() + 0.01 and (a.argmax(-1) == b.argmax(-1)).mean() > 0.8
