@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from llmlb_b200 import ffi  # noqa: E402
 
-EPI = {0: "bf16", 1: "resid", 2: "silu", 3: "f32", 4: "partial", 5: "pushRS"}
+EPI = {0: "bf16", 1: "resid", 2: "silu", 3: "f32", 4: "partial", 5: "pushRS", 6: "pushRS-LL"}
 
 
 def name(tag):
