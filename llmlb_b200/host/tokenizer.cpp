@@ -124,29 +124,55 @@ const Json* find_template_processing(const Json& j) {
   return nullptr;
 }
 
-// true when [pos, size) starts a UTF-8 sequence that more bytes could still complete
-bool incomplete_tail(const std::string& s, size_t pos) {
-  const uint8_t c = uint8_t(s[pos]);
-  size_t need = 0;
-  if ((c >> 5) == 0x6) need = 2;
-  else if ((c >> 4) == 0xE) need = 3;
-  else if ((c >> 3) == 0x1E) need = 4;
-  else return false;
-  const size_t have = s.size() - pos;
-  if (have >= need) return false;
-  for (size_t i = 1; i < have; ++i)
-    if ((uint8_t(s[pos + i]) >> 6) != 0x2) return false;
-  return true;
+// Well-formed UTF-8 per Unicode Table 3-7.  Returns the length (1..4) of the well-formed sequence at s[i], or 0 when it is
+// ill-formed; then *bad_len is the length of the MAXIMAL SUBPART (the longest prefix of a well-formed sequence, at least
+// the one offending byte) that String::from_utf8_lossy / Python's errors="replace" substitute by ONE U+FFFD, and
+// *truncated says the subpart runs to the end of the string and further bytes could still complete it.
+static size_t utf8_wellformed(const std::string& s, size_t i, size_t* bad_len, bool* truncated) {
+  const size_t n = s.size();
+  const uint8_t b0 = uint8_t(s[i]);
+  *bad_len = 1; *truncated = false;
+  if (b0 < 0x80) return 1;
+  size_t need;
+  uint8_t lo = 0x80, hi = 0xBF;
+  if (b0 >= 0xC2 && b0 <= 0xDF) need = 2;
+  else if (b0 == 0xE0) { need = 3; lo = 0xA0; }
+  else if ((b0 >= 0xE1 && b0 <= 0xEC) || b0 == 0xEE || b0 == 0xEF) need = 3;
+  else if (b0 == 0xED) { need = 3; hi = 0x9F; }
+  else if (b0 == 0xF0) { need = 4; lo = 0x90; }
+  else if (b0 >= 0xF1 && b0 <= 0xF3) need = 4;
+  else if (b0 == 0xF4) { need = 4; hi = 0x8F; }
+  else return 0;                                   // 80..BF, C0, C1, F5..FF: never start a sequence
+  size_t have = 1;
+  while (have < need) {
+    if (i + have >= n) { *bad_len = have; *truncated = true; return 0; }
+    const uint8_t c = uint8_t(s[i + have]);
+    const bool ok = have == 1 ? (c >= lo && c <= hi) : (c >= 0x80 && c <= 0xBF);
+    if (!ok) { *bad_len = have; return 0; }
+    ++have;
+  }
+  return need;
 }
 
+// true when [pos, size) is the beginning of a well-formed sequence that more bytes could still complete
+bool incomplete_tail(const std::string& s, size_t pos) {
+  size_t bad = 0;
+  bool truncated = false;
+  return utf8_wellformed(s, pos, &bad, &truncated) == 0 && truncated && pos + bad == s.size();
+}
+
+// String::from_utf8_lossy: well-formed sequences are copied, every maximal ill-formed subpart becomes one U+FFFD.
+// (Round 2: the first version replaced byte by byte and let a lone 0xEF lead through raw — found with the scripted token
+// source of tests/test_server_fake_engine_cpu.py, which emits byte-level tokens in random order.)
 std::string utf8_lossy(const std::string& s) {
-  std::vector<uint32_t> cps, offs;
-  decode_utf8(s, &cps, &offs);
   std::string out;
   out.reserve(s.size());
-  for (size_t i = 0; i < cps.size(); ++i) {
-    if (cps[i] == 0xFFFD && offs[i + 1] - offs[i] == 1 && uint8_t(s[offs[i]]) != 0xEF) out += "\xEF\xBF\xBD";
-    else out.append(s, offs[i], offs[i + 1] - offs[i]);
+  for (size_t i = 0; i < s.size();) {
+    size_t bad = 0;
+    bool truncated = false;
+    const size_t len = utf8_wellformed(s, i, &bad, &truncated);
+    if (len) { out.append(s, i, len); i += len; }
+    else { out += "\xEF\xBF\xBD"; i += bad; }
   }
   return out;
 }

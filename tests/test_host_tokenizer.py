@@ -204,3 +204,30 @@ def test_random_unicode_against_the_library_at_test_time(H, tok):
                 parts.append(chr(rng.randint(0x10000, 0x10FFFF)))
         s = "".join(parts)
         assert encode(H, tok, s) == hf.encode(s, add_special_tokens=False).ids, [hex(ord(c)) for c in s]
+
+
+def test_streaming_decode_of_arbitrary_token_sequences_is_always_valid_utf8(H, tok):
+    """A model with random weights (or a sampler at high temperature) emits byte-level tokens in any order: whatever comes,
+    every streamed piece and the total must be valid UTF-8 and equal Python's errors="replace" decode of the same bytes
+    (the semantics of Rust's String::from_utf8_lossy).  Regression: a lone 0xEF lead byte used to be passed through raw."""
+    import random
+    n_vocab = H.llmlb_tok_vocab_size(tok)
+    buf = C.create_string_buffer(4096)
+    rnd = random.Random(17)
+    # the two-token case that failed: a piece ending in the lead byte 0xEF followed by an ASCII piece
+    unicorn = encode(H, tok, "�", parse_special=False)      # EF BF BD split over byte tokens in this small vocabulary
+    cases = [[unicorn[0]] + encode(H, tok, "A", parse_special=False)] if len(unicorn) > 1 else []
+    cases += [[rnd.randrange(0, min(n_vocab, 3000)) for _ in range(rnd.randint(1, 60))] for _ in range(400)]
+    for ids in cases:
+        raw = decode(H, tok, ids)
+        s = H.llmlb_tok_stream_create()
+        out = b""
+        for i in ids:
+            n = H.llmlb_tok_stream_next(tok, s, i, 0, buf, 4096)
+            buf.raw[:n].decode("utf-8")
+            out += buf.raw[:n]
+        n = H.llmlb_tok_stream_flush(s, buf, 4096)
+        out += buf.raw[:n]
+        H.llmlb_tok_stream_destroy(s)
+        text = out.decode("utf-8")
+        assert text == raw.decode("utf-8", errors="replace"), ids

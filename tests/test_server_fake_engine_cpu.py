@@ -1,0 +1,121 @@
+"""The HTTP shim (llmlb_b200/host/server.cpp) on a machine WITHOUT a GPU: the same protocol tests as tests/test_server_gpu.py
+(they check framing, accounting, routing, error conventions, translation — nothing about what the tokens mean), run against
+a server binary linked to tests/support/fake_engine.cpp, a scripted token source behind the C ABI.  Test infrastructure only:
+the product library and the product server are untouched and still refuse to run without a CUDA device
+(tests/test_bench_contract_cpu.py, tests/test_server_cli_cpu.py)."""
+import http.client
+import json
+import os
+import subprocess
+import sys
+import time
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+import test_server_gpu as T  # noqa: E402  (its own tests carry the gpu mark; the functions are reused below)
+
+BUILD = os.path.join(HERE, "support", "_build")
+FAKE_LIB = os.path.join(BUILD, "libllmlb_b200.so")
+FAKE_BIN = os.path.join(BUILD, "llmlb_b200_server_fake_engine")
+
+
+def _newer(target, deps):
+    return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+@pytest.fixture(scope="module")
+def fake_bin():
+    os.makedirs(BUILD, exist_ok=True)
+    hd = os.path.join(ROOT, "llmlb_b200", "host")
+    fake_src = os.path.join(HERE, "support", "fake_engine.cpp")
+    hdr = os.path.join(ROOT, "include", "llmlb_b200.h")
+    if _newer(FAKE_LIB, [fake_src, hdr]):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread", fake_src, "-o", FAKE_LIB])
+    srcs = [os.path.join(hd, f) for f in ("server.cpp", "gateway.cpp", "tokenizer.cpp", "anthropic.cpp", "checkpoint.cpp", "download.cpp")]
+    deps = srcs + [FAKE_LIB, hdr] + [os.path.join(hd, f) for f in os.listdir(hd) if f.endswith((".hpp", ".inc"))]
+    if _newer(FAKE_BIN, deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", *srcs, "-o", FAKE_BIN, "-L" + BUILD, "-lllmlb_b200",
+                               "-Wl,-rpath," + BUILD])
+    return FAKE_BIN
+
+
+def _start(binary, *args):
+    port = T._free_port()
+    proc = subprocess.Popen([binary, "--port", str(port), *args], stderr=subprocess.PIPE)
+    deadline = time.time() + 30
+    while time.time() < deadline:
+        try:
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=2); c.request("GET", "/v1/models"); c.getresponse().read(); c.close()
+            return port, proc
+        except OSError:
+            assert proc.poll() is None, proc.stderr.read().decode()
+            time.sleep(0.05)
+    proc.kill()
+    raise AssertionError("fake-engine server did not come up")
+
+
+@pytest.fixture(scope="module")
+def server(fake_bin):
+    port, proc = _start(fake_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "8", "--max-ctx", "512")
+    yield port
+    proc.terminate(); proc.wait(timeout=20)
+
+
+@pytest.fixture(scope="module")
+def tok_server(fake_bin):
+    port, proc = _start(fake_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "8", "--max-ctx", "512", "--vocab", "3072",
+                        "--tokenizer", os.path.join(HERE, "golden", "tokenizer_llama3_style.json"))
+    yield port
+    proc.terminate(); proc.wait(timeout=20)
+
+
+@pytest.fixture()
+def built_lib():       # the reused tests only want "something is built"; here that is the fake-engine server
+    return None
+
+
+@pytest.fixture(autouse=True)
+def _fake_binary_for_tests_that_start_their_own_server(fake_bin, monkeypatch):
+    monkeypatch.setattr(T, "BIN", fake_bin)
+    from llmlb_b200 import build
+    monkeypatch.setattr(build, "build_host", lambda: None)     # those tests call build_host(): it would need the CUDA library
+
+
+# ---- the protocol tests of tests/test_server_gpu.py, unchanged --------------------------------------------------------
+test_probe_endpoints = T.test_probe_endpoints
+test_chat_completion_non_stream = T.test_chat_completion_non_stream
+test_chat_completion_stream_accounting = T.test_chat_completion_stream_accounting
+test_responses_stream_and_body = T.test_responses_stream_and_body
+test_prompt_token_ids_and_completions = T.test_prompt_token_ids_and_completions
+test_errors = T.test_errors
+test_drain_gate = T.test_drain_gate
+test_concurrent_streams = T.test_concurrent_streams
+test_chat_through_the_native_tokenizer = T.test_chat_through_the_native_tokenizer
+test_stop_at_end_of_turn_token = T.test_stop_at_end_of_turn_token
+test_messages_route_non_stream_and_stream = T.test_messages_route_non_stream_and_stream
+test_messages_route_errors_in_anthropic_shape = T.test_messages_route_errors_in_anthropic_shape
+test_server_from_a_single_gguf = T.test_server_from_a_single_gguf
+test_stop_strings_end_the_text_before_the_match = T.test_stop_strings_end_the_text_before_the_match
+test_model_download_routes = T.test_model_download_routes
+
+
+# ---- only reachable with a scripted source: the gateway's queue conventions through the shim ---------------------------
+def test_queue_full_is_429_with_retry_after(fake_bin):
+    """openai.rs:841-861: capacity exceeded -> 429 rate_limit_exceeded, Retry-After = max(1, queue timeout in seconds)."""
+    import threading
+    port, proc = _start(fake_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "1", "--max-ctx", "4096",
+                        "--queue-max", "1", "--queue-timeout-ms", "7000")
+    try:
+        body = {"model": "tiny-llama", "prompt_token_ids": [5, 6, 7], "max_tokens": 3000, "temperature": 0, "ignore_eos": True}
+        res = []
+        th = [threading.Thread(target=lambda: res.append(T.call(port, "POST", "/v1/completions", body))) for _ in range(6)]
+        [t.start() for t in th]; [t.join() for t in th]
+        full = [r for r in res if r[0] == 429]
+        assert full and len(full) + sum(r[0] == 200 for r in res) == 6
+        st, hdr, d = full[0]
+        assert hdr.get("Retry-After") == "7" and json.loads(d) == {"error": {"message": "Request queue is full", "type": "rate_limit_exceeded", "code": 429}}
+    finally:
+        proc.terminate(); proc.wait(timeout=20)
