@@ -7,6 +7,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -30,6 +31,7 @@ struct Req {
   uint32_t produced = 0;
   bool finished = false, cancel = false;
   uint64_t h = 0;
+  bool admitted = false;
   Clock::time_point t_submit;
 };
 }  // namespace
@@ -43,6 +45,7 @@ struct llmlb_engine {
   std::atomic<bool> stop{false};
   std::thread worker;
   uint64_t tokens = 0;
+  unsigned token_us = 150;          // pace of the scripted source; FAKE_ENGINE_TOKEN_US slows it down for the timeout tests
 
   static uint64_t mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
 
@@ -68,8 +71,16 @@ struct llmlb_engine {
         for (auto& kv : reqs) {
           Req& r = *kv.second;
           if (r.finished) continue;
-          if (running++ >= cfg.max_seqs) continue;            // the rest wait, like a full batch
+          const double age_ms = std::chrono::duration<double, std::milli>(Clock::now() - r.t_submit).count();
           if (r.cancel) { finish(r, LLMLB_FINISH_CANCELLED); continue; }
+          if (cfg.request_timeout_ms && age_ms > cfg.request_timeout_ms) { finish(r, LLMLB_FINISH_DEADLINE); continue; }
+          if (running++ >= cfg.max_seqs) {                      // the rest wait, like a full batch
+            if (!r.admitted && cfg.queue_timeout_ms && age_ms > cfg.queue_timeout_ms) finish(r, LLMLB_FINISH_QUEUE_TIMEOUT);
+            continue;
+          }
+          r.admitted = true;
+          // scripted failure: a prompt that starts with 666 666 dies after three tokens (the engine's FINISH_ERROR path)
+          if (r.prompt.size() >= 2 && r.prompt[0] == 666 && r.prompt[1] == 666 && r.produced >= 3) { finish(r, LLMLB_FINISH_ERROR); continue; }
           const uint64_t salt = r.s.temperature > 0 ? mix(r.s.seed + 0x9e37) : 0;
           const int32_t tok = int32_t(mix(r.h ^ salt ^ (uint64_t(r.produced) * 0x9e3779b97f4a7c15ull)) % cfg.model.vocab);
           llmlb_token_event ev{};
@@ -85,7 +96,7 @@ struct llmlb_engine {
         }
       }
       cv.notify_all();
-      std::this_thread::sleep_for(std::chrono::microseconds(150));
+      std::this_thread::sleep_for(std::chrono::microseconds(token_us));
     }
   }
 };
@@ -100,6 +111,7 @@ int llmlb_engine_create(const llmlb_engine_config* cfg, llmlb_engine** out) {
   if (!cfg->model.vocab || !cfg->max_seqs || !cfg->max_ctx) return fail(LLMLB_E_INVALID_ARG, "bad geometry");
   auto* e = new llmlb_engine;
   e->cfg = *cfg;
+  if (const char* v = getenv("FAKE_ENGINE_TOKEN_US")) e->token_us = unsigned(atoi(v));
   e->worker = std::thread([e] { e->loop(); });
   *out = e;
   return LLMLB_OK;

@@ -42,9 +42,9 @@ def fake_bin():
     return FAKE_BIN
 
 
-def _start(binary, *args):
+def _start(binary, *args, env=None):
     port = T._free_port()
-    proc = subprocess.Popen([binary, "--port", str(port), *args], stderr=subprocess.PIPE)
+    proc = subprocess.Popen([binary, "--port", str(port), *args], stderr=subprocess.PIPE, env={**os.environ, **(env or {})})
     deadline = time.time() + 30
     while time.time() < deadline:
         try:
@@ -117,5 +117,44 @@ def test_queue_full_is_429_with_retry_after(fake_bin):
         assert full and len(full) + sum(r[0] == 200 for r in res) == 6
         st, hdr, d = full[0]
         assert hdr.get("Retry-After") == "7" and json.loads(d) == {"error": {"message": "Request queue is full", "type": "rate_limit_exceeded", "code": 429}}
+    finally:
+        proc.terminate(); proc.wait(timeout=20)
+
+
+def test_failures_of_the_engine_reach_the_client_as_the_gateway_would_report_them(fake_bin):
+    """The shim maps engine outcomes the way the gateway maps an upstream's:
+      deadline        -> 504 "timeout"  "Upstream endpoint request timed out after N seconds"   (openai_util.rs:105-115, types/endpoint.rs:389)
+      queue wait      -> 504 "timeout"  "Queue wait timeout"                                     (openai.rs:863-882)
+      engine failure  -> 502 "endpoint_request_error" "Failed to proxy request to upstream endpoint" (openai_util.rs:128-134)
+    and on a stream whose headers are already out: an in-band error event and NO finish chunk / [DONE]."""
+    import threading
+    from oracle import gateway_ref as G
+    port, proc = _start(fake_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "1", "--max-ctx", "4096",
+                        "--request-timeout-ms", "1000", "--queue-timeout-ms", "300", env={"FAKE_ENGINE_TOKEN_US": "4000"})
+    try:
+        slow = {"model": "tiny-llama", "prompt_token_ids": [5, 6, 7], "max_tokens": 2000, "temperature": 0, "ignore_eos": True}
+        # deadline, non-stream: 2000 tokens at 4 ms each cannot finish in 1 s
+        st, _, d = T.call(port, "POST", "/v1/completions", slow)
+        status, etype, msg = G.classify_upstream_request_error("timeout", 1)
+        assert (st, json.loads(d)) == (status, G.openai_error_body(msg, etype, status))
+        # deadline, streamed: chunks, then the error event, and the stream ends without [DONE]
+        st, hdr, d = T.call(port, "POST", "/v1/chat/completions", {"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}],
+                                                                     "max_tokens": 2000, "temperature": 0, "ignore_eos": True, "stream": True})
+        text = d.decode()
+        events = [json.loads(l[6:]) for l in text.split("\n") if l.startswith("data: {")]
+        assert st == 200 and "[DONE]" not in text and events[-1] == G.openai_error_body(msg, etype, status)
+        assert all("finish_reason" not in c or c["finish_reason"] is None for e in events[:-1] for c in e.get("choices", []))
+        # queue wait: one sequence runs (max_seqs 1), the second waits longer than queue_timeout_ms
+        res = {}
+        t1 = threading.Thread(target=lambda: res.setdefault("a", T.call(port, "POST", "/v1/completions", slow)))
+        t1.start(); time.sleep(0.1)
+        res["b"] = T.call(port, "POST", "/v1/completions", dict(slow, prompt_token_ids=[9, 9, 9]))
+        t1.join()
+        st, hdrs, body = G.queue_wait_timeout()
+        assert (res["b"][0], json.loads(res["b"][2])) == (st, body) and "Retry-After" not in res["b"][1]
+        # engine failure after three tokens
+        st, _, d = T.call(port, "POST", "/v1/completions", dict(slow, prompt_token_ids=[666, 666, 1], max_tokens=20))
+        status, etype, msg = G.classify_upstream_request_error("other", 0)
+        assert (st, json.loads(d)) == (status, G.openai_error_body(msg, etype, status))
     finally:
         proc.terminate(); proc.wait(timeout=20)
