@@ -173,6 +173,13 @@ struct Cur {   // bounds-checked little-endian reader over the mapped file
   std::string str() { const uint64_t n = take<uint64_t>(); if (!ok || uint64_t(end - p) < n) { ok = false; return ""; } std::string s(reinterpret_cast<const char*>(p), size_t(n)); p += n; return s; }
   void skip(uint64_t n) { if (uint64_t(end - p) < n) { ok = false; p = end; } else p += n; }
 };
+// arithmetic on numbers that come out of a file: products that wrap and doubles outside the target range are
+// errors, not values (found by tools/fuzz: a zero `general.alignment`, zero-sized dims, 2^63-element shapes)
+inline bool mul_ok(uint64_t a, uint64_t b, uint64_t* out) { return !__builtin_mul_overflow(a, b, out); }
+inline uint32_t u32_of(double v) { return (v >= 0.0 && v <= 4294967295.0) ? uint32_t(v) : 0u; }
+inline int64_t i64_of(double v, int64_t dflt) { return (v >= -9.0e18 && v <= 9.0e18) ? int64_t(v) : dflt; }
+constexpr int64_t kMaxLayers = 4096;
+
 size_t scalar_size(uint32_t t) {
   switch (t) { case 0: case 1: case 7: return 1; case 2: case 3: return 2; case 4: case 5: case 6: return 4; case 10: case 11: case 12: return 8; }
   return 0;
@@ -251,18 +258,23 @@ bool Checkpoint::open_safetensors(std::string* err) {
     if (dt->str() == "F32") t.dtype = kF32; else if (dt->str() == "F16") t.dtype = kF16; else if (dt->str() == "BF16") t.dtype = kBF16;
     else continue;  // integer buffers etc. are not model weights
     uint64_t a = 0, b = 0;
-    if (!off->items()[0].as_u64(&a) || !off->items()[1].as_u64(&b) || b < a || base + b > size_) { if (err) *err = "safetensors: offsets of " + kv.first; return false; }
+    if (!off->items()[0].as_u64(&a) || !off->items()[1].as_u64(&b) || b < a || b > size_ - base) { if (err) *err = "safetensors: offsets of " + kv.first; return false; }
     t.offset = base + a;
     t.nbytes = b - a;
     std::vector<uint64_t> dims;
     for (const Json& d : sh->items()) { uint64_t v = 0; if (!d.as_u64(&v)) { if (err) *err = "safetensors: shape of " + kv.first; return false; } dims.push_back(v); }
     if (dims.size() == 2) { t.rows = dims[0]; t.cols = dims[1]; } else if (dims.size() == 1) { t.rows = 1; t.cols = dims[0]; } else continue;
-    if (t.rows * t.cols * (t.dtype == kF32 ? 4 : 2) != t.nbytes) { if (err) *err = "safetensors: size of " + kv.first; return false; }
+    uint64_t n_el = 0, n_by = 0;
+    if (!mul_ok(t.rows, t.cols, &n_el) || !mul_ok(n_el, t.dtype == kF32 ? 4 : 2, &n_by) || n_by != t.nbytes) { if (err) *err = "safetensors: size of " + kv.first; return false; }
     // geometry from shapes (head_dim is 128 for every model the engine accepts)
     if (t.name == "model.embed_tokens.weight") { geo_.vocab = uint32_t(t.rows); geo_.hidden = uint32_t(t.cols); }
     if (t.name.compare(0, 13, "model.layers.") == 0) {
       const size_t d = t.name.find('.', 13);
-      if (d != std::string::npos) max_layer = std::max<int64_t>(max_layer, atoll(t.name.substr(13, d - 13).c_str()));
+      if (d != std::string::npos && d - 13 <= 6) {
+        const int64_t layer = atoll(t.name.substr(13, d - 13).c_str());
+        if (layer < 0 || layer >= kMaxLayers) { if (err) *err = "safetensors: layer index of " + kv.first; return false; }
+        max_layer = std::max<int64_t>(max_layer, layer);
+      }
       if (t.name.find("self_attn.q_proj.weight") != std::string::npos) geo_.n_heads = uint32_t(t.rows / 128);
       if (t.name.find("self_attn.k_proj.weight") != std::string::npos) geo_.n_kv_heads = uint32_t(t.rows / 128);
       if (t.name.find("mlp.gate_proj.weight") != std::string::npos) geo_.ffn = uint32_t(t.rows);
@@ -305,13 +317,19 @@ bool Checkpoint::open_gguf(std::string* err) {
       if (et == 8) {
         for (uint64_t k = 0; k < count && c.ok; ++k) { std::string s = c.str(); if (tokens) tok_tokens_.push_back(std::move(s)); else if (merges) tok_merges_.push_back(std::move(s)); }
       } else if (scalar_size(et)) {
-        if (types) for (uint64_t k = 0; k < count && c.ok; ++k) tok_types_.push_back(int32_t(scalar(et)));
-        else c.skip(count * scalar_size(et));
+        uint64_t nb = 0;
+        if (types) for (uint64_t k = 0; k < count && c.ok; ++k) tok_types_.push_back(int32_t(i64_of(scalar(et), 0) & 0xFF));
+        else if (mul_ok(count, scalar_size(et), &nb)) c.skip(nb);
+        else c.ok = false;
       } else { c.ok = false; }
     } else num[key] = scalar(type);
   }
   if (!c.ok) { if (err) *err = "gguf: truncated or malformed metadata"; return false; }
-  if (num.count("general.alignment")) alignment = uint64_t(num["general.alignment"]);
+  if (num.count("general.alignment")) {
+    const double a = num["general.alignment"];
+    if (!(a >= 1.0 && a <= 1048576.0)) { if (err) *err = "gguf: general.alignment out of range"; return false; }
+    alignment = uint64_t(a);
+  }
   const std::string arch = str.count("general.architecture") ? str["general.architecture"] : "llama";
   auto g = [&](const char* k, double dflt) { auto it = num.find(arch + "." + k); return it == num.end() ? dflt : it->second; };
   struct Info { std::string name; std::vector<uint64_t> dims; uint32_t type; uint64_t off; };
@@ -328,22 +346,26 @@ bool Checkpoint::open_gguf(std::string* err) {
   }
   if (!c.ok) { if (err) *err = "gguf: truncated tensor table"; return false; }
   const uint64_t base = (uint64_t(c.p - data_) + alignment - 1) / alignment * alignment;
-  const uint32_t n_head = uint32_t(g("attention.head_count", 1)), n_kv_head = uint32_t(g("attention.head_count_kv", n_head));
+  const uint32_t n_head = u32_of(g("attention.head_count", 1)), n_kv_head = u32_of(g("attention.head_count_kv", n_head));
   bool has_output = false;
   for (const Info& in : infos) has_output |= in.name == "output.weight";
   for (const Info& in : infos) {
     uint32_t per = 0, bsz = 0;
     if (!block_shape(in.type, &per, &bsz)) { if (err) *err = "gguf: tensor " + in.name + " has unsupported ggml type " + std::to_string(in.type); return false; }
     uint64_t n = 1;
-    for (uint64_t d : in.dims) n *= d;
+    bool dims_ok = true;
+    for (uint64_t d : in.dims) dims_ok = dims_ok && d != 0 && mul_ok(n, d, &n);
+    if (!dims_ok) { if (err) *err = "gguf: shape of " + in.name; return false; }
     if (!in.dims.empty() && in.dims[0] % per) { if (err) *err = "gguf: row length of " + in.name; return false; }
     CkptTensor t;
     t.src_name = in.name;
     t.name = hf_name(in.name);
     t.dtype = in.type;
+    if (!mul_ok(n / per, bsz, &t.nbytes) || base > size_ || in.off > size_ - base || t.nbytes > size_ - base - in.off) {
+      if (err) *err = "gguf: data of " + in.name + " past the end of the file";
+      return false;
+    }
     t.offset = base + in.off;
-    t.nbytes = n / per * bsz;
-    if (t.offset + t.nbytes > size_) { if (err) *err = "gguf: data of " + in.name + " past the end of the file"; return false; }
     if (in.name == "token_embd.weight" && in.dims.size() == 2) geo_.vocab = uint32_t(in.dims[1]);
     if (t.name.empty()) continue;
     if (in.dims.size() == 2) { t.rows = in.dims[1]; t.cols = in.dims[0]; } else if (in.dims.size() == 1) { t.rows = 1; t.cols = in.dims[0]; } else continue;
@@ -358,8 +380,9 @@ bool Checkpoint::open_gguf(std::string* err) {
       tied_lm_head_ = true;
     }
   }
-  geo_.hidden = uint32_t(g("embedding_length", 0));
-  geo_.n_layers = uint32_t(g("block_count", 0));
+  geo_.hidden = u32_of(g("embedding_length", 0));
+  geo_.n_layers = u32_of(g("block_count", 0));
+  if (geo_.n_layers > kMaxLayers) { if (err) *err = "gguf: block_count out of range"; return false; }
   geo_.n_heads = n_head;
   geo_.n_kv_heads = n_kv_head;
   // head width: metadata when present, else the q projection's own shape (rows / heads) — a model
@@ -367,24 +390,25 @@ bool Checkpoint::open_gguf(std::string* err) {
   uint32_t hd_from_q = 0;
   for (const CkptTensor& t : tensors_)
     if (n_head && t.name.size() > 23 && t.name.compare(t.name.size() - 23, 23, "self_attn.q_proj.weight") == 0 && t.cols == geo_.hidden) { hd_from_q = uint32_t(t.rows / n_head); break; }
-  geo_.head_dim = uint32_t(g("attention.key_length", hd_from_q ? hd_from_q : (geo_.n_heads ? geo_.hidden / geo_.n_heads : 0)));
-  geo_.ffn = uint32_t(g("feed_forward_length", 0));
-  if (!geo_.vocab) geo_.vocab = uint32_t(g("vocab_size", double(tok_tokens_.size())));
+  geo_.head_dim = u32_of(g("attention.key_length", hd_from_q ? hd_from_q : (geo_.n_heads ? geo_.hidden / geo_.n_heads : 0)));
+  geo_.ffn = u32_of(g("feed_forward_length", 0));
+  if (!geo_.vocab) geo_.vocab = u32_of(g("vocab_size", double(tok_tokens_.size())));
   geo_.rope_theta = float(g("rope.freq_base", 10000.0));
   geo_.rms_eps = float(g("attention.layer_norm_rms_epsilon", 1e-5));
   geo_.known = geo_.hidden && geo_.n_layers && geo_.n_heads && geo_.ffn && geo_.vocab;
   tok_model_ = str.count("tokenizer.ggml.model") ? str["tokenizer.ggml.model"] : "";
   tok_pre_ = str.count("tokenizer.ggml.pre") ? str["tokenizer.ggml.pre"] : "llama-bpe";
-  tok_bos_ = num.count("tokenizer.ggml.bos_token_id") ? int64_t(num["tokenizer.ggml.bos_token_id"]) : -1;
+  tok_bos_ = num.count("tokenizer.ggml.bos_token_id") ? i64_of(num["tokenizer.ggml.bos_token_id"], -1) : -1;
   return true;
 }
 
 bool Checkpoint::read_bf16(size_t i, std::vector<uint16_t>* out, std::string* err) const {
   if (i >= tensors_.size()) { if (err) *err = "tensor index"; return false; }
   const CkptTensor& t = tensors_[i];
-  const size_t n = size_t(t.rows * t.cols);
+  const size_t n = size_t(t.rows * t.cols);          // open() checked the product and that [offset, offset + nbytes) is inside the file
   const uint8_t* src = data_ + t.offset;
   out->resize(n);
+  if (n == 0) return true;
   if (t.dtype == kBF16 && !t.unpermute_heads) { memcpy(out->data(), src, n * 2); return true; }
   std::vector<float> f(n);
   if (!ggml_dequantize(t.dtype, src, size_t(t.nbytes), f.data(), n)) { if (err) *err = "cannot dequantise " + t.src_name; return false; }

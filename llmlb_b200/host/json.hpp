@@ -42,7 +42,12 @@ class Json {
   }
   bool as_bool(bool dflt = false) const { return t_ == Bool ? b_ : dflt; }
   double as_double(double dflt = 0) const { return t_ == Int ? double(i_) : t_ == Double ? d_ : dflt; }
-  int64_t as_int(int64_t dflt = 0) const { return t_ == Int ? i_ : t_ == Double ? int64_t(d_) : dflt; }
+  int64_t as_int(int64_t dflt = 0) const {   // a double outside int64 (1e300, NaN) saturates instead of being cast (which is undefined)
+    if (t_ == Int) return i_;
+    if (t_ != Double) return dflt;
+    if (!(d_ == d_)) return dflt;
+    return d_ >= 9.2e18 ? INT64_MAX : d_ <= -9.2e18 ? INT64_MIN : int64_t(d_);
+  }
   const std::string& str() const { return s_; }
 
   const Json* get(const std::string& key) const {

@@ -13,6 +13,7 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <signal.h>
+#include <strings.h>
 #include <sys/socket.h>
 #include <unistd.h>
 
@@ -54,20 +55,27 @@ struct Request {
   std::map<std::string, std::string> headers;  // lower-cased names
 };
 
-static bool read_request(int fd, std::string& buf, Request* rq) {
+static bool send_all(int fd, const std::string& s);
+
+// kReqClosed: the peer went away (or sent nothing more); the other failures are answered before the connection is
+// dropped, the way hyper/axum in front of the reference's handlers do: 400 for a request line that does not parse,
+// 431 for a header block over 1 MiB, 413 over the 20 MiB body limit (DefaultBodyLimit, api/mod.rs:58,536).
+enum ReqStatus { kReqOk, kReqClosed, kReqBad = 400, kReqTooLarge = 413, kReqHeadersTooLarge = 431 };
+
+static ReqStatus read_request(int fd, std::string& buf, Request* rq) {
   size_t hdr_end;
   while ((hdr_end = buf.find("\r\n\r\n")) == std::string::npos) {
+    if (buf.size() > (1u << 20)) return kReqHeadersTooLarge;
     char tmp[8192];
     ssize_t n = recv(fd, tmp, sizeof tmp, 0);
-    if (n <= 0) return false;
+    if (n <= 0) return kReqClosed;
     buf.append(tmp, size_t(n));
-    if (buf.size() > (1u << 20)) return false;
   }
   std::string head = buf.substr(0, hdr_end);
   size_t line_end = head.find("\r\n");
   std::string first = head.substr(0, line_end);
   size_t a = first.find(' '), b = first.rfind(' ');
-  if (a == std::string::npos || b == a) return false;
+  if (a == std::string::npos || b == a || a == 0 || first.compare(b + 1, 5, "HTTP/") != 0) return kReqBad;
   rq->method = first.substr(0, a);
   rq->path = first.substr(a + 1, b - a - 1);
   rq->headers.clear();
@@ -80,26 +88,38 @@ static bool read_request(int fd, std::string& buf, Request* rq) {
     if (c != std::string::npos) {
       std::string k = line.substr(0, c), v = line.substr(c + 1);
       for (auto& ch : k) if (ch >= 'A' && ch <= 'Z') ch = char(ch - 'A' + 'a');
-      while (!v.empty() && v[0] == ' ') v.erase(0, 1);
+      while (!v.empty() && (v[0] == ' ' || v[0] == '\t')) v.erase(0, 1);
+      while (!v.empty() && (v.back() == ' ' || v.back() == '\t')) v.pop_back();
       rq->headers[k] = v;
     }
     pos = e + 2;
   }
   size_t need = 0;
   auto it = rq->headers.find("content-length");
-  if (it != rq->headers.end()) need = size_t(strtoull(it->second.c_str(), nullptr, 10));
-  if (need > (20u << 20)) return false;  // DefaultBodyLimit 20 MiB (api/mod.rs:58)
+  if (it != rq->headers.end()) {
+    const std::string& v = it->second;
+    if (v.empty() || v.size() > 18 || v.find_first_not_of("0123456789") != std::string::npos) return kReqBad;
+    need = size_t(strtoull(v.c_str(), nullptr, 10));
+  } else if (rq->headers.count("transfer-encoding")) {
+    return kReqBad;                           // the gateway's client (reqwest .json(), openai.rs:995-1005) always sends a length
+  }
+  if (need > (20u << 20)) return kReqTooLarge;
   size_t have = buf.size() - (hdr_end + 4);
+  if (have < need) {                          // curl and friends wait up to a second for this before sending a large body
+    auto ex = rq->headers.find("expect");
+    if (ex != rq->headers.end() && strncasecmp(ex->second.c_str(), "100-continue", 12) == 0 &&
+        !send_all(fd, "HTTP/1.1 100 Continue\r\n\r\n")) return kReqClosed;
+  }
   while (have < need) {
     char tmp[65536];
     ssize_t n = recv(fd, tmp, sizeof tmp, 0);
-    if (n <= 0) return false;
+    if (n <= 0) return kReqClosed;
     buf.append(tmp, size_t(n));
     have += size_t(n);
   }
   rq->body = buf.substr(hdr_end + 4, need);
   buf.erase(0, hdr_end + 4 + need);
-  return true;
+  return kReqOk;
 }
 
 static bool send_all(int fd, const std::string& s) {
@@ -113,7 +133,8 @@ static bool send_all(int fd, const std::string& s) {
 }
 static const char* reason(int st) {
   switch (st) { case 200: return "OK"; case 400: return "Bad Request"; case 401: return "Unauthorized";
-    case 404: return "Not Found"; case 405: return "Method Not Allowed"; case 429: return "Too Many Requests"; case 502: return "Bad Gateway";
+    case 404: return "Not Found"; case 405: return "Method Not Allowed"; case 413: return "Payload Too Large";
+    case 431: return "Request Header Fields Too Large"; case 429: return "Too Many Requests"; case 502: return "Bad Gateway";
     case 503: return "Service Unavailable"; case 504: return "Gateway Timeout"; default: return "Error"; }
 }
 static bool send_json(int fd, int status, const std::string& body, const char* extra = "") {
@@ -447,10 +468,17 @@ static void serve_conn(int fd) {
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
   std::string buf;
   Request rq;
-  while (read_request(fd, buf, &rq)) {
+  for (;;) {
+    const ReqStatus st = read_request(fd, buf, &rq);
+    if (st != kReqOk) {
+      if (st != kReqClosed)
+        send_json(fd, int(st), openai_error_body(st == kReqTooLarge ? "request body exceeds the 20 MiB limit" : st == kReqBad ? "malformed HTTP request" : "request headers too large",
+                                                 "invalid_request_error", int(st)), "Connection: close\r\n");
+      break;
+    }
     handle(fd, rq);
     auto c = rq.headers.find("connection");
-    if (c != rq.headers.end() && c->second == "close") break;
+    if (c != rq.headers.end() && strcasecmp(c->second.c_str(), "close") == 0) break;
   }
   close(fd);
 }

@@ -262,6 +262,10 @@ std::vector<std::pair<uint32_t, uint32_t>> BpeTokenizer::pretokenize(const std::
   return out;
 }
 
+// ids index dense tables: a file that claims an id of 10^15 must be refused, not allocated for (the largest public
+// vocabularies are ~260 k entries)
+static constexpr uint64_t kMaxTokenId = 1u << 24;
+
 bool BpeTokenizer::load_json(const std::string& text, std::string* err) {
   Json root;
   if (!Json::parse(text, &root)) { if (err) *err = "tokenizer.json: not valid JSON"; return false; }
@@ -282,7 +286,7 @@ bool BpeTokenizer::load_json(const std::string& text, std::string* err) {
   size_t max_id = 0;
   for (const auto& kv : vocab->members()) {
     uint64_t id = 0;
-    if (!kv.second.as_u64(&id)) { if (err) *err = "tokenizer.json: non-integer vocab id"; return false; }
+    if (!kv.second.as_u64(&id) || id > kMaxTokenId) { if (err) *err = "tokenizer.json: vocab id is not an integer in [0, 2^24]"; return false; }
     vocab_[kv.first] = int32_t(id);
     max_id = std::max(max_id, size_t(id));
   }
@@ -291,7 +295,10 @@ bool BpeTokenizer::load_json(const std::string& text, std::string* err) {
     for (size_t i = 0; i < added->items().size(); ++i) {
       uint64_t id = 0;
       const Json* jid = added->items()[i].get("id");
-      if (jid && jid->as_u64(&id)) max_id = std::max(max_id, size_t(id));
+      if (jid && jid->as_u64(&id)) {
+        if (id > kMaxTokenId) { if (err) *err = "tokenizer.json: added token id out of range"; return false; }
+        max_id = std::max(max_id, size_t(id));
+      }
     }
   id_to_token_.assign(max_id + 1, std::string());
   id_to_bytes_.assign(max_id + 1, std::string());

@@ -194,3 +194,63 @@ def test_embedded_tokenizer_and_errors(K, tmp_path):
     bad.write_bytes((1 << 40).to_bytes(8, "little") + b"{}" + b"\0" * 16)
     assert not K.llmlb_ckpt_open(str(bad).encode(), err, 256)
     assert not K.llmlb_ckpt_open(str(tmp_path / "missing").encode(), err, 256)
+
+
+def _gguf_bytes(kv, tensors, data=b"\0" * 4096):
+    """A GGUF v3 image assembled by hand (the package's writer refuses to produce broken files).
+    kv: [(key, type_id, packed_value)], tensors: [(name, dims innermost-first, ggml_type, offset)]."""
+    s = lambda x: len(x).to_bytes(8, "little") + x
+    out = b"GGUF" + (3).to_bytes(4, "little") + len(tensors).to_bytes(8, "little") + len(kv).to_bytes(8, "little")
+    for k, t, v in kv:
+        out += s(k.encode()) + t.to_bytes(4, "little") + v
+    for name, dims, ty, off in tensors:
+        out += s(name.encode()) + len(dims).to_bytes(4, "little") + b"".join(d.to_bytes(8, "little") for d in dims) + ty.to_bytes(4, "little") + off.to_bytes(8, "little")
+    out += b"\0" * (-len(out) % 32)
+    return out + data
+
+
+def test_files_that_lie_about_their_sizes_are_refused(K, tmp_path):
+    """Found by tools/fuzz (ASan/UBSan over mutated files): a zero `general.alignment` divided by zero, zero-sized dims
+    handed memcpy a null pointer, 2^63-element shapes wrapped the size arithmetic, offsets near 2^64 wrapped the
+    bounds check.  Every one of them is now an error from open(), with the tensor named."""
+    import struct
+    err = C.create_string_buffer(256)
+    p = tmp_path / "m.gguf"
+    u32, F32 = 4, 0
+    ok_t = [("token_embd.weight", [32, 4], F32, 0)]
+
+    def refused(kv, tensors, what):
+        p.write_bytes(_gguf_bytes(kv, tensors))
+        h = K.llmlb_ckpt_open(str(p).encode(), err, 256)
+        assert not h and what in err.value, (what, err.value)
+
+    p.write_bytes(_gguf_bytes([], ok_t))
+    h = K.llmlb_ckpt_open(str(p).encode(), err, 256)
+    assert h
+    K.llmlb_ckpt_close(h)
+    refused([("general.alignment", u32, (0).to_bytes(4, "little"))], ok_t, b"alignment")
+    refused([("general.alignment", u32, (1 << 30).to_bytes(4, "little"))], ok_t, b"alignment")
+    refused([], [("token_embd.weight", [32, 0], F32, 0)], b"shape of token_embd.weight")
+    refused([], [("token_embd.weight", [1 << 62, 1 << 62], F32, 0)], b"shape of token_embd.weight")
+    refused([], [("token_embd.weight", [1 << 62, 2], F32, 0)], b"past the end")               # n fits, n * 4 does not
+    refused([], [("token_embd.weight", [32, 4], F32, (1 << 64) - 64)], b"past the end")        # base + off wraps
+    refused([], [("token_embd.weight", [32, 4], F32, 4096 - 256)], b"past the end")            # 512 bytes do not fit in the last 256
+    refused([("llama.block_count", u32, (1 << 31).to_bytes(4, "little"))], ok_t, b"block_count")
+    # float metadata outside any integer range must not turn into garbage geometry
+    p.write_bytes(_gguf_bytes([("llama.attention.head_count", 6, struct.pack("<f", float("inf"))), ("llama.embedding_length", 12, struct.pack("<d", -1e300))], ok_t))
+    h = K.llmlb_ckpt_open(str(p).encode(), err, 256)
+    assert h
+    u7, f2 = (C.c_uint32 * 7)(), (C.c_float * 2)()
+    assert K.llmlb_ckpt_geometry(h, u7, f2) == 0 and u7[0] == 0 and u7[2] == 0
+    K.llmlb_ckpt_close(h)
+    # safetensors: the same classes
+    q = tmp_path / "m.safetensors"
+
+    def st_refused(hdr, what):
+        hj = json.dumps(hdr).encode()
+        q.write_bytes(len(hj).to_bytes(8, "little") + hj + b"\0" * 1024)
+        assert not K.llmlb_ckpt_open(str(q).encode(), err, 256) and what in err.value, (what, err.value)
+
+    st_refused({"a.weight": {"dtype": "F32", "shape": [4, 16], "data_offsets": [0, (1 << 64) - 1]}}, b"offsets of a.weight")
+    st_refused({"a.weight": {"dtype": "BF16", "shape": [1 << 59, 32], "data_offsets": [0, 0]}}, b"size of a.weight")
+    st_refused({"model.layers.999999.mlp.up_proj.weight": {"dtype": "BF16", "shape": [2, 2], "data_offsets": [0, 8]}}, b"layer index")

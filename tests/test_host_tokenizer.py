@@ -231,3 +231,19 @@ def test_streaming_decode_of_arbitrary_token_sequences_is_always_valid_utf8(H, t
         H.llmlb_tok_stream_destroy(s)
         text = out.decode("utf-8")
         assert text == raw.decode("utf-8", errors="replace"), ids
+
+
+def test_token_ids_outside_any_vocabulary_are_refused(H):
+    """tools/fuzz (structured variants): an id of 2^31 became a negative index into the id tables, 2^40 an allocation of
+    that many strings.  Both are load errors now."""
+    base = json.load(open(os.path.join(GOLD, "tokenizer_llama3_style.json"), encoding="utf-8"))
+    err = C.create_string_buffer(256)
+    for where, bad in (("vocab", 2 ** 31), ("vocab", 2 ** 40), ("vocab", -1), ("vocab", 1.5), ("added", 2 ** 40)):
+        t = json.loads(json.dumps(base))
+        if where == "vocab":
+            t["model"]["vocab"][next(iter(t["model"]["vocab"]))] = bad
+        else:
+            t["added_tokens"][0]["id"] = bad
+        raw = json.dumps(t).encode()
+        assert not H.llmlb_tok_create(raw, len(raw), err, 256), (where, bad)
+        assert b"id" in err.value

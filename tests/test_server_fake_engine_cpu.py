@@ -158,3 +158,85 @@ def test_failures_of_the_engine_reach_the_client_as_the_gateway_would_report_the
         assert (st, json.loads(d)) == (status, G.openai_error_body(msg, etype, status))
     finally:
         proc.terminate(); proc.wait(timeout=20)
+
+
+def _raw(port, payload, read=True, timeout=5):
+    import socket
+    s = socket.create_connection(("127.0.0.1", port), timeout=timeout)
+    try:
+        s.sendall(payload)
+        if not read:
+            return b""
+        out = b""
+        while True:
+            try:
+                d = s.recv(65536)
+            except (socket.timeout, ConnectionResetError):
+                break
+            if not d:
+                break
+            out += d
+        return out
+    finally:
+        s.close()
+
+
+def test_malformed_http_is_answered_or_dropped_and_the_server_stays_up(server):
+    """What hyper/axum do in front of the reference's handlers: 400 for a request that does not parse, 413 over the
+    20 MiB body limit (DefaultBodyLimit, llmlb/src/api/mod.rs:58,536), 431 for an endless header block; random bytes
+    never take the process down."""
+    import random
+    port = server
+    st = lambda raw: raw.split(b"\r\n", 1)[0]
+    assert st(_raw(port, b"NONSENSE\r\n\r\n")) == b"HTTP/1.1 400 Bad Request"
+    assert st(_raw(port, b"GET /v1/models\r\n\r\n")) == b"HTTP/1.1 400 Bad Request"                     # no HTTP version
+    for cl in (b"-1", b"abc", b"1e3", b"99999999999999999999999", b""):
+        r = _raw(port, b"POST /v1/completions HTTP/1.1\r\nContent-Length: " + cl + b"\r\n\r\n{}")
+        assert st(r) == b"HTTP/1.1 400 Bad Request", (cl, r[:80])
+        assert json.loads(r.split(b"\r\n\r\n", 1)[1])["error"]["type"] == "invalid_request_error"
+    assert st(_raw(port, b"POST /v1/completions HTTP/1.1\r\nTransfer-Encoding: chunked\r\n\r\n2\r\n{}\r\n0\r\n\r\n")) == b"HTTP/1.1 400 Bad Request"
+    r = _raw(port, b"POST /v1/completions HTTP/1.1\r\nContent-Length: %d\r\n\r\n" % ((20 << 20) + 1))
+    assert st(r) == b"HTTP/1.1 413 Payload Too Large" and b"Connection: close" in r
+    r = _raw(port, b"GET / HTTP/1.1\r\n" + b"X-Pad: " + b"a" * 8000 + b"\r\n" * 1 + (b"X-Pad: " + b"a" * 8000 + b"\r\n") * 140, timeout=10)
+    assert st(r) == b"HTTP/1.1 431 Request Header Fields Too Large"
+    # exactly at the limit is read and handled (it is not JSON: 400 from the handler, not 413)
+    big = b"x" * (20 << 20)
+    r = _raw(port, b"POST /v1/completions HTTP/1.1\r\nConnection: close\r\nContent-Length: %d\r\n\r\n" % len(big) + big, timeout=20)
+    assert st(r) == b"HTTP/1.1 400 Bad Request"
+    # Expect: 100-continue is honoured before the body is sent
+    import socket
+    body = json.dumps({"model": "tiny-llama", "prompt_token_ids": [1, 2, 3], "max_tokens": 4, "temperature": 0}).encode()
+    s = socket.create_connection(("127.0.0.1", port), timeout=5)
+    s.sendall(b"POST /v1/completions HTTP/1.1\r\nExpect: 100-continue\r\nConnection: Close\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body))
+    assert s.recv(1024) == b"HTTP/1.1 100 Continue\r\n\r\n"
+    s.sendall(body)
+    out = b""
+    while True:
+        d = s.recv(65536)
+        if not d:
+            break                                               # "Connection: Close" (any case) ends the connection
+        out += d
+    s.close()
+    assert st(out) == b"HTTP/1.1 200 OK" and json.loads(out.split(b"\r\n\r\n", 1)[1])["usage"]["completion_tokens"] == 4
+    # random and half-valid byte soup, some connections abandoned mid-request
+    rs = random.Random(5)
+    valid = b"POST /v1/chat/completions HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: 62\r\n\r\n" \
+            b'{"model":"tiny-llama","messages":[{"role":"user","content":1}]}'
+    for i in range(300):
+        kind = rs.randrange(4)
+        if kind == 0:
+            p = bytes(rs.randrange(256) for _ in range(rs.randrange(1, 400)))
+        elif kind == 1:
+            p = bytearray(valid)
+            for _ in range(rs.randrange(1, 6)):
+                p[rs.randrange(len(p))] = rs.randrange(256)
+            p = bytes(p)
+        elif kind == 2:
+            p = valid[:rs.randrange(1, len(valid))]
+        else:
+            p = valid + valid[:rs.randrange(len(valid))] + bytes(rs.randrange(256) for _ in range(rs.randrange(64)))
+        _raw(port, p, read=kind != 2, timeout=0.05)
+    s_, _, d = T.call(port, "GET", "/v1/models")
+    assert s_ == 200 and json.loads(d)["data"][0]["id"] == "tiny-llama"
+    s_, _, d = T.call(port, "GET", "/api/health")
+    assert s_ == 200
