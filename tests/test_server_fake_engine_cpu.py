@@ -240,3 +240,79 @@ def test_malformed_http_is_answered_or_dropped_and_the_server_stays_up(server):
     assert s_ == 200 and json.loads(d)["data"][0]["id"] == "tiny-llama"
     s_, _, d = T.call(port, "GET", "/api/health")
     assert s_ == 200
+
+
+_ODD = [None, True, False, -1, 0, 1, 2 ** 31, 2 ** 40, 10 ** 30, 1e300, -1e300, 1.5, -0.0, "", " ", " ", "x" * 3000, [], {}, [[]], [None], {"type": "text"},
+        {"type": "text", "text": 5}, {"type": "image_url", "image_url": {"url": "data:x"}}, [{"role": 3}], "퟿￿", ["a", 1, None]]
+
+
+def _damage(rs, node, depth=0):
+    """Replace / delete / insert at a random place of a JSON tree."""
+    if isinstance(node, dict) and node and (depth == 0 or rs.random() < 0.7):
+        k = rs.choice(list(node))
+        r = rs.random()
+        if r < 0.35:
+            node[k] = rs.choice(_ODD)
+        elif r < 0.45:
+            del node[k]
+        elif r < 0.55:
+            node[rs.choice(["stream", "max_tokens", "stop", "n", "temperature", "top_p", "top_k", "seed", "stream_options", "tools", "input", "system",
+                            "messages", "prompt", "model", "max_output_tokens", "ignore_eos", "prompt_token_ids"])] = rs.choice(_ODD)
+        else:
+            node[k] = _damage(rs, node[k], depth + 1)
+        return node
+    if isinstance(node, list) and node and rs.random() < 0.7:
+        i = rs.randrange(len(node))
+        node[i] = _damage(rs, node[i], depth + 1) if rs.random() < 0.6 else rs.choice(_ODD)
+        return node
+    return rs.choice(_ODD)
+
+
+def test_request_bodies_with_wrong_types_never_take_the_server_down(tok_server):
+    """Every front door (chat, completions, responses, Anthropic messages) with valid-JSON bodies whose fields have the
+    wrong type, absurd values or are missing: each request gets an HTTP answer (2xx/4xx with a JSON error body), and the
+    server still serves afterwards.  The same loop runs against an ASan/UBSan build of the shim in the long fuzz pass
+    (DESIGN.md, hygiene)."""
+    import copy
+    import random
+    port = tok_server
+    rs = random.Random(int(os.environ.get("LLMLB_FUZZ_SEED", "11")))
+    seeds = [
+        ("/v1/chat/completions", {"model": "tiny-llama", "messages": [{"role": "system", "content": "s"}, {"role": "user", "content": [{"type": "text", "text": "hi"}]}],
+                                  "max_tokens": 4, "temperature": 0.5, "top_p": 0.9, "seed": 3, "stop": ["x"], "stream": False, "stream_options": {"include_usage": True}}),
+        ("/v1/completions", {"model": "tiny-llama", "prompt": "hello", "max_tokens": 4, "temperature": 0, "stream": False}),
+        ("/v1/responses", {"model": "tiny-llama", "input": [{"role": "user", "content": [{"type": "input_text", "text": "hi"}]}], "max_output_tokens": 4, "stream": False}),
+        ("/v1/messages", {"model": "tiny-llama", "max_tokens": 4, "system": [{"type": "text", "text": "s"}],
+                          "messages": [{"role": "user", "content": [{"type": "text", "text": "hi"}]}], "stop_sequences": ["x"], "stream": False}),
+    ]
+    n_ok = n_err = 0
+    for i in range(int(os.environ.get("LLMLB_FUZZ_REQUESTS", "400"))):
+        path, body = seeds[i % 4]
+        b = copy.deepcopy(body)
+        for _ in range(rs.randint(1, 3)):
+            b = _damage(rs, b)
+            if not isinstance(b, dict):
+                break
+        if isinstance(b, dict) and rs.random() < 0.3:
+            b["stream"] = True
+        hdrs = {"anthropic-version": "2023-06-01"} if path == "/v1/messages" else {}
+        try:
+            raw = json.dumps(b)
+        except (TypeError, ValueError):
+            continue
+        c = http.client.HTTPConnection("127.0.0.1", port, timeout=30)
+        c.request("POST", path, raw.encode("utf-8", "surrogatepass"), {"Content-Type": "application/json", **hdrs})
+        r = c.getresponse()
+        data = r.read()
+        c.close()
+        assert r.status in (200, 400, 401, 404, 413, 422, 429, 502, 503, 504), (path, raw[:300], r.status)
+        if r.status == 200:
+            n_ok += 1
+        else:
+            n_err += 1
+            assert "error" in json.loads(data), (path, raw[:300], data[:200])
+    assert n_ok > 20 and n_err > 20, (n_ok, n_err)
+    s_, _, d = T.call(port, "GET", "/v1/models")
+    assert s_ == 200
+    s_, _, d = T.call(port, "GET", "/api/health")
+    assert s_ == 200 and json.loads(d)["load"]["active_requests"] == 0
