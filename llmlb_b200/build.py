@@ -83,6 +83,7 @@ def build_host():
     deps = [os.path.join(hd, f) for f in ("gateway.cpp", "gateway.hpp", "json.hpp", "tokenizer.cpp", "tokenizer.hpp",
                                           "unicode_tables.inc", "anthropic.cpp", "anthropic.hpp", "checkpoint.cpp", "checkpoint.hpp",
                                           "download.cpp", "download.hpp")]
+    deps += [os.path.join(HERE, "..", "include", h) for h in ("llmlb_host.h", "llmlb_gateway.h")]
     if _newer(HOST_LIB, deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread",
                                os.path.join(hd, "gateway.cpp"), os.path.join(hd, "tokenizer.cpp"),

@@ -436,6 +436,7 @@ static int64_t a_copy(const std::string& s, char* out, uint64_t cap) {
   return int64_t(s.size());
 }
 
+#include "../../include/llmlb_host.h"   // the exported signatures are checked against the public header at compile time
 extern "C" {
 // *status = 200 and out = {"openai":{...},"request_text":"...","stream":bool}, or the HTTP status and the error body
 int64_t llmlb_anthropic_convert_request(const char* json, uint64_t len, int* status, char* out, uint64_t cap) {

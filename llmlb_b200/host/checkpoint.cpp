@@ -483,6 +483,7 @@ std::string Checkpoint::tokenizer_json() const {
 // =============================================================================================
 using llmlb_host::Checkpoint;
 
+#include "../../include/llmlb_gateway.h"   // the exported signatures are checked against the public header at compile time
 extern "C" {
 void* llmlb_ckpt_open(const char* path, char* err, uint32_t err_cap) {
   auto* c = new Checkpoint();

@@ -231,6 +231,7 @@ static size_t dl_copy(const std::string& s, char* out, size_t cap) {
   if (out && cap) { size_t n = std::min(s.size(), cap - 1); memcpy(out, s.data(), n); out[n] = 0; }
   return s.size();
 }
+#include "../../include/llmlb_gateway.h"   // the exported signatures are checked against the public header at compile time
 extern "C" {
 void* llmlb_dl_create(const char* mirror_root, const char* models_dir, size_t chunk_bytes, unsigned throttle_us) {
   return new DownloadManager(mirror_root ? mirror_root : "", models_dir ? models_dir : "", chunk_bytes, throttle_us);

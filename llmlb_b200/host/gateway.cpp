@@ -800,6 +800,7 @@ static size_t copy_out(const std::string& s, char* out, size_t cap) {
   return s.size();
 }
 
+#include "../../include/llmlb_gateway.h"   // the exported signatures are checked against the public header at compile time
 extern "C" {
 void* llmlb_lm_create() { return new LoadManager(); }
 void llmlb_lm_destroy(void* p) { delete static_cast<LoadManager*>(p); }

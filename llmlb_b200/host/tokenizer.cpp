@@ -535,6 +535,7 @@ static bool parse_messages(const char* json, uint64_t len, std::vector<ChatMessa
   return true;
 }
 
+#include "../../include/llmlb_host.h"   // the exported signatures are checked against the public header at compile time
 extern "C" {
 void* llmlb_tok_create(const char* json, uint64_t len, char* err, uint32_t err_cap) {
   auto* t = new BpeTokenizer();

@@ -79,22 +79,36 @@ def test_argument_validation_without_gpu(built_lib):
 
 
 def test_host_library_exports_every_declared_symbol():
-    """include/llmlb_host.h (tokenizer + Anthropic translation, no GPU) against libllmlb_host.so, and
-    the header compiles as plain C."""
+    """include/llmlb_host.h (tokenizer + Anthropic translation) and include/llmlb_gateway.h (gateway rows a1.x,
+    checkpoint readers, download contract) against libllmlb_host.so — in both directions: every declared function is
+    exported, and the library exports nothing the headers do not declare — and both headers compile as plain C.
+    The implementing .cpp files include the headers, so a signature that drifts fails the build itself."""
     import subprocess
     import tempfile
     from llmlb_b200 import build
-    src = open(os.path.join(ROOT, "include", "llmlb_host.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    fns = sorted(set(re.findall(r"\b(llmlb_[a-z0-9_]+)\s*\(", src)))
+    declared = {}
+    for h in ("llmlb_host.h", "llmlb_gateway.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared[h] = sorted(set(re.findall(r"\b(llmlb_[a-z0-9_]+)\s*\(", src)))
+    fns = declared["llmlb_host.h"]
     assert "llmlb_tok_encode" in fns and "llmlb_anthropic_stream_feed" in fns and len(fns) >= 20
-    lib = ctypes.CDLL(build.build_host())
-    missing = [f for f in fns if not hasattr(lib, f)]
+    gw = declared["llmlb_gateway.h"]
+    for must in ("llmlb_lm_select", "llmlb_lm_update_tps", "llmlb_lm_lease_begin", "llmlb_acc_feed", "llmlb_extract_usage", "llmlb_gate_try_begin",
+                 "llmlb_classify_upstream_error", "llmlb_lb_error", "llmlb_frame", "llmlb_ckpt_open", "llmlb_dl_start"):
+        assert must in gw
+    assert not set(fns) & set(gw)
+    path = build.build_host()
+    lib = ctypes.CDLL(path)
+    missing = [f for f in fns + gw if not hasattr(lib, f)]
     assert not missing, missing
+    exported = {l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", path], text=True).splitlines() if " T llmlb_" in l}
+    assert exported == set(fns) | set(gw), sorted(exported ^ (set(fns) | set(gw)))
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "h.c")
-        open(c, "w").write('#include "llmlb_host.h"\nvoid* (*probe)(void) = llmlb_tok_stream_create;\nint main(void){return 0;}\n')
-        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "h.o")])
+        open(c, "w").write('#include "llmlb_host.h"\n#include "llmlb_gateway.h"\n#include "llmlb_b200.h"\n'
+                           'void* (*probe)(void) = llmlb_tok_stream_create;\nvoid* (*probe2)(void) = llmlb_lm_create;\nint main(void){return 0;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-c", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "h.o")])
 
 
 def test_rust_ffi_crate_matches_the_header():
