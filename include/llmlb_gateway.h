@@ -111,6 +111,13 @@ size_t llmlb_lb_error(int kind, const char* detail, char* out, size_t cap);
  * kind 0 chat SSE stream, 1 chat body, 2 responses SSE stream, 3 responses body, 4 completion body */
 size_t llmlb_frame(int kind, const char* id, const char* model, int64_t created, const char* const* pieces, uint32_t n_pieces,
                    uint32_t prompt_tokens, const char* finish_reason, char* out, size_t cap);
+/* the same stream one step at a time, for a host that frames while token events arrive.
+ * api 0 chat.completion.chunk, 1 text_completion (legacy /v1/completions), 2 Responses events.
+ * what 0 opening (chat: role chunk; Responses: created + output_item.added + content_part.added; completions: nothing),
+ *      1 text delta, 2 finish (chat / completions: text = finish_reason; Responses: output_text.done, text = whole text),
+ *      3 usage (chat / completions: the include_usage chunk; Responses: response.done), 4 "data: [DONE]".            */
+size_t llmlb_sse_event(int api, int what, const char* id, const char* model, int64_t created, const char* text,
+                       uint32_t prompt_tokens, uint32_t completion_tokens, char* out, size_t cap);
 size_t llmlb_json_roundtrip(const char* text, char* out, size_t cap);                     /* 0 = not JSON */
 /* `stop` strings over streamed text: text that may still become a stop is held back */
 void* llmlb_stop_create(const char* stops_json);

@@ -959,6 +959,37 @@ size_t llmlb_frame(int kind, const char* id, const char* model, int64_t created,
   }
   return copy_out(s, out, cap);
 }
+// one step of a stream, for hosts that frame while token events arrive (llmlb_frame above is the same thing all at once)
+size_t llmlb_sse_event(int api, int what, const char* id, const char* model, int64_t created, const char* text,
+                       uint32_t prompt_tokens, uint32_t completion_tokens, char* out, size_t cap) {
+  if (!id || !model || api < 0 || api > 2 || what < 0 || what > 4) return 0;
+  if (what == 4) return copy_out(sse_done(), out, cap);
+  const std::string t = text ? text : "", role = "assistant";
+  std::string s;
+  if (api == 0) {
+    switch (what) {
+      case 0: s = sse_event(chat_chunk(id, model, created, &role, nullptr, nullptr)); break;
+      case 1: s = sse_event(chat_chunk(id, model, created, nullptr, &t, nullptr)); break;
+      case 2: s = sse_event(chat_chunk(id, model, created, nullptr, nullptr, t.c_str())); break;
+      case 3: s = sse_event(chat_usage_chunk(id, model, created, prompt_tokens, completion_tokens)); break;
+    }
+  } else if (api == 1) {
+    switch (what) {
+      case 0: break;                                           // a text_completion stream has no role chunk
+      case 1: s = sse_event(completion_chunk(id, model, created, &t, nullptr)); break;
+      case 2: s = sse_event(completion_chunk(id, model, created, nullptr, t.c_str())); break;
+      case 3: s = sse_event(completion_usage_chunk(id, model, created, prompt_tokens, completion_tokens)); break;
+    }
+  } else {
+    switch (what) {
+      case 0: s = sse_event(responses_event_created(id, model)) + sse_event(responses_event_item_added()) + sse_event(responses_event_part_added()); break;
+      case 1: s = sse_event(responses_event_delta(t)); break;
+      case 2: s = sse_event(responses_event_text_done(t)); break;
+      case 3: s = sse_event(responses_event_done(id, prompt_tokens, completion_tokens)); break;
+    }
+  }
+  return copy_out(s, out, cap);
+}
 size_t llmlb_json_roundtrip(const char* text, char* out, size_t cap) {
   Json j;
   if (!Json::parse(text, &j)) return 0;

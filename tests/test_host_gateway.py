@@ -905,3 +905,32 @@ def test_queue_and_upstream_errors_cpp_vs_reference_and_oracle(H):
             for model in (None, "qwen2.5:7b"):
                 r = _out_json(H.llmlb_classify_upstream_error, k, secs, b(model))
                 assert (r["status"], r["type"], r["message"]) == G.classify_upstream_request_error(kind, secs, model)
+
+
+def test_incremental_sse_framing_equals_the_stream_framed_at_once(H):
+    """llmlb_sse_event (one step at a time, what a streaming host calls as token events arrive) against llmlb_frame
+    (the whole stream, pinned above to the reference's fixtures) for chat and Responses; the legacy completions stream
+    against the accumulator-independent shape the reference's benchmark client reads (api/benchmarks.rs:501-509)."""
+    H.llmlb_sse_event.restype = C.c_size_t
+    H.llmlb_sse_event.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+    out = C.create_string_buffer(1 << 14)
+
+    def ev(api, what, text=None, pt=7, ct=0):
+        n = H.llmlb_sse_event(api, what, b"id-1", b"llama-3-8b", 1704067200, None if text is None else text.encode(), pt, ct, out, 1 << 14)
+        return out.raw[:n].decode()
+
+    pieces = ["Hello", " wor", "ld", "!\n", "é\"q\"", ""]
+    chat = ev(0, 0) + "".join(ev(0, 1, p) for p in pieces) + ev(0, 2, "length") + ev(0, 3, ct=len(pieces)) + ev(0, 4)
+    assert chat == _frame(H, 0, pieces)
+    resp = ev(2, 0) + "".join(ev(2, 1, p) for p in pieces) + ev(2, 2, "".join(pieces)) + ev(2, 3, ct=len(pieces)) + ev(2, 4)
+    assert resp == _frame(H, 2, pieces)
+    comp = ev(1, 0) + "".join(ev(1, 1, p) for p in pieces) + ev(1, 2, "stop") + ev(1, 3, ct=len(pieces)) + ev(1, 4)
+    events = [json.loads(e[6:]) for e in comp.split("\n\n") if e.startswith("data: {")]
+    assert ev(1, 0) == "" and comp.endswith("data: [DONE]\n\n")
+    assert all(e["object"] == "text_completion" for e in events)
+    assert "".join(e["choices"][0]["text"] for e in events if e["choices"] and e["choices"][0].get("text")) == "".join(pieces)
+    assert [e["choices"][0]["finish_reason"] for e in events if e["choices"]][-1] == "stop"
+    assert G.extract_usage_from_response(events[-1]) == {"input_tokens": 7, "output_tokens": len(pieces), "total_tokens": 7 + len(pieces)}
+    # bad arguments produce nothing rather than a malformed event
+    assert H.llmlb_sse_event(3, 0, b"i", b"m", 0, None, 0, 0, out, 16) == 0 and H.llmlb_sse_event(0, 9, b"i", b"m", 0, None, 0, 0, out, 16) == 0
+    assert H.llmlb_sse_event(0, 1, None, b"m", 0, b"x", 0, 0, out, 16) == 0

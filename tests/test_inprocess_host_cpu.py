@@ -1,0 +1,93 @@
+"""examples/inprocess_host.c: the gateway's hot path with the engine in the process, written in C99 over the three public
+headers only — gate, TPS-EMA router, lease, submit/poll on the engine, SSE to the client, the relay's accounting over the
+same bytes, lease completion and TPS update (the Rust crate under ffi/ does the same and cannot be compiled
+here).  Built against the scripted engine of tests/support/fake_engine.cpp and checked against the gateway oracle: the
+client-visible stream parses with the reference's accumulator to the engine's own usage, and the router state after N
+requests is the oracle's, bit for bit, for the durations the program measured."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import gateway_ref as G  # noqa: E402
+
+BUILD = os.path.join(HERE, "support", "_build")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from llmlb_b200 import build
+    host = build.build_host()
+    os.makedirs(BUILD, exist_ok=True)
+    fake = os.path.join(BUILD, "libllmlb_b200.so")
+    fake_src = os.path.join(HERE, "support", "fake_engine.cpp")
+    if not os.path.exists(fake) or os.path.getmtime(fake) < os.path.getmtime(fake_src):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread", fake_src, "-o", fake])
+    out = os.path.join(BUILD, "inprocess_host")
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "inprocess_host.c"), "-L" + BUILD, "-lllmlb_b200", "-L" + os.path.dirname(host), "-lllmlb_host",
+                           "-Wl,-rpath," + BUILD, "-Wl,-rpath," + os.path.dirname(host), "-o", out])
+    return out
+
+
+def _run(exe, *args):
+    r = subprocess.run([exe, *args], capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    streams = r.stdout.decode("utf-8").split("### request ")[1:]
+    recs = [json.loads(l) for l in r.stderr.decode().splitlines() if l.startswith("{")]
+    return streams, recs[:-1], recs[-1]
+
+
+@pytest.mark.parametrize("api", ["chat", "responses"])
+def test_in_process_path_against_the_gateway_oracle(exe, api):
+    n_req, n_out = 4, 12
+    streams, per, final = _run(exe, "--api", api, "--requests", str(n_req), "--max-tokens", str(n_out), "--prompt-len", "24")
+    assert len(streams) == n_req == len(per)
+    kind = "responses" if api == "responses" else "chat_completions"
+    state = G.ModelTpsState()
+    for i, (s, rec) in enumerate(zip(streams, per)):
+        head, sse = s.split("\n", 1)
+        assert int(head) == i == rec["request"] and rec["endpoint"] == "in-process"
+        # the reference's own accounting over the bytes the client received
+        acc = G.StreamingTokenAccumulator("llama-tiny")
+        assert G.process_sse_lines(sse, acc) == "" and acc.done
+        assert acc.finalize() == {"input_tokens": 24, "output_tokens": n_out, "total_tokens": 24 + n_out}
+        assert rec["usage"] == [24, n_out, 24 + n_out] and rec["tokens"] == n_out and rec["done"] == 1 and rec["finish"] == 2
+        assert len(acc.accumulated_content.encode()) == rec["content_bytes"] == rec["sent_bytes"]
+        events = [json.loads(e[6:]) for e in sse.split("\n\n") if e.startswith("data: {")]
+        if api == "chat":
+            assert events[0]["choices"][0]["delta"] == {"role": "assistant"} and events[-2]["choices"][0]["finish_reason"] == "length"
+            assert events[-1]["usage"]["completion_tokens"] == n_out and sse.endswith("data: [DONE]\n\n")
+        else:
+            types = [e["type"] for e in events]
+            assert types[:3] == ["response.created", "response.output_item.added", "response.content_part.added"]
+            assert types[-2:] == ["response.output_text.done", "response.done"] and types.count("response.output_text.delta") == n_out
+        state.update_tps(n_out, rec["ms"])
+    # router state == the oracle's for the same (tokens, ms) sequence: EMA alpha 0.2 (balancer/types.rs:102-118), bit for bit
+    assert final["request_count"] == n_req and final["total_output_tokens"] == n_req * n_out
+    assert final["total_duration_ms"] == sum(r["ms"] for r in per)
+    if all(r["ms"] > 0 for r in per):
+        assert final["tps_ema"] == state.tps_ema
+    active, assigned, success, errors, lat_sum, tin, tout, ttot = final["stats"]
+    assert (active, assigned, success, errors) == (0, n_req, n_req, 0) and final["in_flight"] == 0
+    assert (tin, tout, ttot) == (24 * n_req, n_out * n_req, (24 + n_out) * n_req) and lat_sum == sum(r["ms"] for r in per)
+    assert kind in ("chat_completions", "responses")
+
+
+def test_in_process_path_with_the_native_tokenizer(exe):
+    """ids -> text through the streaming detokenizer: whatever the scripted ids decode to, the client only ever receives
+    complete UTF-8 and the accumulator's content is exactly what was sent."""
+    tj = os.path.join(HERE, "golden", "tokenizer_llama3_style.json")
+    streams, per, final = _run(exe, "--api", "chat", "--requests", "2", "--max-tokens", "40", "--tokenizer", tj, "--vocab", "3072")
+    for s, rec in zip(streams, per):
+        sse = s.split("\n", 1)[1]
+        acc = G.StreamingTokenAccumulator("llama-tiny")
+        G.process_sse_lines(sse, acc)
+        assert acc.done and rec["usage"][1] == 40 and rec["usage"][0] > 5          # the chat template's tokens, counted by the engine
+        assert len(acc.accumulated_content.encode()) == rec["sent_bytes"] == rec["content_bytes"]
+    assert final["stats"][2] == 2
