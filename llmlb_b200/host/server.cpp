@@ -152,6 +152,16 @@ static int map_error(int rc) {  // LbError -> status (api/error.rs:31-110)
     case LLMLB_E_QUEUE_FULL: return 503; case LLMLB_E_TIMEOUT: return 504; default: return 502; }
 }
 
+static std::string percent_decode(const std::string& s) {
+  auto hex = [](char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
+  std::string out;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] == '%' && i + 2 < s.size() && hex(s[i + 1]) >= 0 && hex(s[i + 2]) >= 0) { out.push_back(char(hex(s[i + 1]) * 16 + hex(s[i + 2]))); i += 2; }
+    else out.push_back(s[i]);
+  }
+  return out;
+}
+
 static std::string content_text(const Json& c) {  // string or [{type:text,text}] parts
   if (c.is_string()) return c.str();
   std::string s;
@@ -436,7 +446,8 @@ static void handle(int fd, const Request& rq) {
     Json root = Json::object(); root.set("status", "ok"); root.set("gpu", gpu); root.set("load", load); root.set("kv", kv);
     send_json(fd, 200, root.dump());
   } else if (rq.method == "GET" && path.compare(0, 12, "/api/models/") == 0 && path.size() > 17 && path.compare(path.size() - 5, 5, "/info") == 0) {
-    const std::string name = path.substr(12, path.size() - 17);
+    // the gateway escapes ' ', '/' and ':' in the id (metadata/xllm.rs:54-63: "meta-llama/Llama-3-8B" arrives as meta-llama%2FLlama-3-8B)
+    const std::string name = percent_decode(path.substr(12, path.size() - 17));
     if (name != G.model_id) { send_json(fd, 404, openai_error_body("model not found", "invalid_request_error", 404)); return; }
     llmlb_model_info mi; llmlb_engine_model_info(G.eng, &mi);
     Json root = Json::object(); root.set("model", G.model_id); root.set("context_length", mi.context_length);

@@ -846,3 +846,236 @@ class InferenceLatency:
 
     def for_sort(self):                      # endpoint.rs:438-440
         return float("inf") if self.ms is None else self.ms
+
+
+# =============================================================================================
+# The gateway as CLIENT of an endpoint's probe routes: what an
+# unmodified llmlb concludes about whatever answers at base_url.  The product is the RESPONDER
+# (llmlb_b200/host/server.cpp); these restatements are the conformance checker: the shim's answers
+# are fed through them in tests/test_endpoint_conformance*.py.
+#
+# `fetch(path, auth)` -> None on a connection error, else (status, headers, json_or_None);
+# headers: lower-cased names; auth: True when the reference sends `Authorization: Bearer <key>`.
+# =============================================================================================
+def _ok(r):
+    return r is not None and 200 <= r[0] < 300
+
+
+def _lm_studio_marker(value):                # detection/lm_studio.rs:133-160 marker_tokens / has_lm_studio_marker
+    toks, cur = [], ""
+    for ch in value:
+        if ch.isascii() and ch.isalnum():
+            cur += ch.lower()
+        else:
+            if cur:
+                toks.append(cur)
+            cur = ""
+    if cur:
+        toks.append(cur)
+    return "lmstudio" in toks or any(a == "lm" and b == "studio" for a, b in zip(toks, toks[1:]))
+
+
+def _looks_like_lm_studio_model(m):          # detection/lm_studio.rs:115-131
+    if not isinstance(m, dict):
+        return False
+    s = lambda k: isinstance(m.get(k), str)
+    has_state = "state" in m or isinstance(m.get("loaded_instances"), list)
+    has_shape = s("key") or s("display_name") or "format" in m or "compatibility_type" in m
+    return s("publisher") and (s("arch") or s("architecture")) and (has_state or has_shape)
+
+
+def detect_xllm(fetch):                      # detection/xllm.rs:27-66
+    r = fetch("/api/system", True)
+    if _ok(r) and isinstance(r[2], dict):
+        v = r[2].get("xllm_version")
+        sn = r[2].get("server_name")
+        if (v is None or isinstance(v, str)) and (sn is None or isinstance(sn, str)):   # serde: Option<String> fields must be strings or null
+            if isinstance(v, str):
+                return "xLLM: /api/system xllm_version=%s" % v
+    return None
+
+
+def detect_lm_studio(fetch):                 # detection/lm_studio.rs:19-97
+    r = fetch("/api/v1/models", True)
+    if _ok(r) and isinstance(r[2], dict):
+        for key in ("data", "models"):
+            arr = r[2].get(key)
+            if isinstance(arr, list) and any(_looks_like_lm_studio_model(m) for m in arr):
+                return "LM Studio: /api/v1/models returned LM Studio format"
+    r = fetch("/v1/models", True)
+    if r is None:
+        return None
+    server = r[1].get("server")
+    if server is not None and _lm_studio_marker(server):
+        return "LM Studio: Server header contains lm-studio (%s)" % server
+    if _ok(r) and isinstance(r[2], dict) and isinstance(r[2].get("data"), list):
+        for m in r[2]["data"]:
+            ob = m.get("owned_by") if isinstance(m, dict) else None
+            if isinstance(ob, str) and _lm_studio_marker(ob):
+                return "LM Studio: owned_by field contains LM Studio marker"
+    return None
+
+
+def detect_ollama(fetch):                    # detection/ollama.rs (no Authorization header on this probe)
+    r = fetch("/api/tags", False)
+    if not _ok(r) or not isinstance(r[2], dict):
+        return None
+    j = r[2]
+    models = j.get("models")
+    if models is not None:                   # serde: Option<Vec<OllamaModel{name: String, size: Option<i64>}>>
+        if not isinstance(models, list):
+            return None
+        for m in models:
+            if not isinstance(m, dict) or not isinstance(m.get("name"), str):
+                return None
+            if m.get("size") is not None and (isinstance(m["size"], bool) or not isinstance(m["size"], int)):
+                return None
+    if j.get("error") is not None:
+        return None
+    return "Ollama: /api/tags returned models" if models is not None else None
+
+
+def detect_vllm(fetch):                      # detection/vllm.rs
+    r = fetch("/v1/models", True)
+    if r is None:
+        return None
+    server = r[1].get("server")
+    if server is not None and "vllm" in server.lower():
+        return "vLLM: Server header contains vllm (%s)" % server
+    if _ok(r) and isinstance(r[2], dict) and isinstance(r[2].get("data"), list):
+        for m in r[2]["data"]:
+            ob = m.get("owned_by") if isinstance(m, dict) else None
+            if isinstance(ob, str) and "vllm" in ob.lower():
+                return "vLLM: owned_by field contains vllm"
+    return None
+
+
+def detect_llamacpp(fetch):                  # detection/llama_cpp.rs:29-96 (no Authorization header)
+    r = fetch("/v1/models", False)
+    if r is not None:
+        server = r[1].get("server")
+        if server is not None and "llama.cpp" in server:
+            return "llama.cpp: Server header contains llama.cpp (%s)" % server
+    r = fetch("/v1/version", False)
+    if _ok(r) and isinstance(r[2], dict):
+        s, v = r[2].get("server"), r[2].get("version")
+        if (s is None or isinstance(s, str)) and (v is None or isinstance(v, str)) and isinstance(s, str) and "llama.cpp" in s:
+            return "llama.cpp: /v1/version server field is '%s'" % s
+    return None
+
+
+def detect_endpoint_type(fetch):
+    """detection/mod.rs:85-195: priority xLLM > LM Studio > Ollama > vLLM > llama.cpp > OpenAI-compatible.
+    Returns (endpoint_type, reason); raises ValueError("unreachable" | "unsupported")."""
+    for name, fn in (("xllm", detect_xllm), ("lm_studio", detect_lm_studio), ("ollama", detect_ollama), ("vllm", detect_vllm),
+                     ("llamacpp", detect_llamacpp)):
+        reason = fn(fetch)
+        if reason:
+            return name, reason
+    r = fetch("/v1/models", True)            # detect_openai_compatible :208-238
+    if r is not None:
+        if _ok(r) and isinstance(r[2], dict) and ("data" in r[2] or "object" in r[2]):
+            return "openai_compatible", "OpenAI-compatible: /v1/models responded 200"
+        raise ValueError("unsupported")
+    if fetch("/v1/models", False) is not None:
+        raise ValueError("unsupported")
+    raise ValueError("unreachable")
+
+
+def parse_models_response(j):                # sync/parser.rs:78-110
+    if isinstance(j, dict) and isinstance(j.get("data"), list):
+        return [m["id"] for m in j["data"] if isinstance(m, dict) and isinstance(m.get("id"), str)], "openai"
+    if isinstance(j, dict) and isinstance(j.get("models"), list):
+        out = []
+        for m in j["models"]:
+            if not isinstance(m, dict):
+                continue
+            i = m.get("name") if isinstance(m.get("name"), str) else (m.get("model") if isinstance(m.get("model"), str) else None)
+            if i:
+                out.append(i)
+        return out, "ollama"
+    return [], "unknown"
+
+
+def detect_capabilities(model_name):         # sync/capabilities.rs:47-57
+    leaf = model_name.lower().rsplit("/", 1)[-1]
+    return ["embeddings"] if (leaf.startswith("embed") or "-embed" in leaf or "_embed" in leaf) else ["chat"]
+
+
+def parse_v0_health(r):
+    """health/endpoint_checker.rs:515-557 try_v0_health: Err on non-2xx / non-JSON, else GpuInfo with every field optional."""
+    if not _ok(r) or r[2] is None:
+        raise ValueError("HTTP %s" % (r[0] if r is not None else "error"))
+    body = r[2]
+    gpu = body.get("gpu") if isinstance(body, dict) else None
+    load = body.get("load") if isinstance(body, dict) else None
+
+    def u64(o, k, bits=64):
+        v = o.get(k) if isinstance(o, dict) else None
+        if isinstance(v, bool) or not isinstance(v, int) or v < 0 or v >= 2 ** 64:
+            return None
+        return v & (2 ** bits - 1)                                   # `as u32` truncates
+
+    def f32(o, k):
+        v = o.get(k) if isinstance(o, dict) else None
+        return float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) else None
+
+    return {"gpu_device_count": u64(gpu, "device_count", 32), "gpu_total_memory_bytes": u64(gpu, "total_memory_bytes"),
+            "gpu_used_memory_bytes": u64(gpu, "used_memory_bytes"), "gpu_capability_score": f32(gpu, "capability_score"),
+            "active_requests": u64(load, "active_requests", 32)}
+
+
+def xllm_model_info_url(model):              # metadata/xllm.rs:54-63: three characters are escaped, nothing else
+    return "/api/models/%s/info" % model.replace(" ", "%20").replace("/", "%2F").replace(":", "%3A")
+
+
+def parse_xllm_model_info(r):
+    """metadata/xllm.rs:11-99: `model` is a required string; context_length | n_ctx (u32), size_bytes | size | file_size (u64),
+    quantization | quant | quantization_type, family, parameter_size | params | num_params are optional (null allowed)."""
+    if r is None:
+        raise ValueError("request failed")
+    if not _ok(r):
+        raise ValueError("endpoint error %d" % r[0])
+    j = r[2]
+    if not isinstance(j, dict) or not isinstance(j.get("model"), str):
+        raise ValueError("invalid response")
+
+    def pick(names, kind, hi=None):
+        present = [n for n in names if n in j]
+        if len(present) > 1:
+            raise ValueError("invalid response")                    # serde: duplicate field through aliases
+        if not present or j[present[0]] is None:
+            return None
+        v = j[present[0]]
+        if kind is str:
+            if not isinstance(v, str):
+                raise ValueError("invalid response")
+            return v
+        if isinstance(v, bool) or not isinstance(v, int) or v < 0 or v > hi:
+            raise ValueError("invalid response")
+        return v
+
+    return {"model": j["model"], "context_length": pick(("context_length", "n_ctx"), int, 2 ** 32 - 1),
+            "size_bytes": pick(("size_bytes", "size", "file_size"), int, 2 ** 64 - 1),
+            "quantization": pick(("quantization", "quant", "quantization_type"), str), "family": pick(("family",), str),
+            "parameter_size": pick(("parameter_size", "params", "num_params"), str)}
+
+
+def sync_models(fetch, endpoint_type):
+    """sync/mod.rs:104-278 reduced to what it learns from the endpoint: GET /v1/models -> ids, capabilities by name,
+    supported_apis = [chat_completions]; for xllm (also ollama / lm_studio, whose metadata clients are not restated)
+    max_tokens = context_length of GET /api/models/{id}/info when that succeeds."""
+    r = fetch("/v1/models", True)
+    if not _ok(r) or r[2] is None:
+        raise ValueError("sync failed")
+    ids, fmt = parse_models_response(r[2])
+    out = []
+    for i in ids:
+        m = {"model_id": i, "capabilities": detect_capabilities(i), "supported_apis": ["chat_completions"], "max_tokens": None}
+        if endpoint_type == "xllm":
+            try:
+                m["max_tokens"] = parse_xllm_model_info(fetch(xllm_model_info_url(i), True))["context_length"]
+            except ValueError:
+                pass
+        out.append(m)
+    return out, fmt

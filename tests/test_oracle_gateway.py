@@ -320,3 +320,74 @@ def test_queue_and_upstream_error_responses_match_the_reference():
         assert body["error"] == {"message": c["message"], "type": c["type"], "code": c["status"]}
     for c in V["upstream_errors"]:
         assert G.classify_upstream_request_error(c["kind"], c["timeout_secs"], c["ollama_loading_model"]) == (c["status"], c["type"], c["message"])
+
+
+# ---- the gateway as client of an endpoint's probe routes (detection / sync / metadata / health) -------------------
+def _mock_fetch(routes, unreachable=False):
+    """wiremock as the reference's tests use it: unmounted paths answer 404; `unreachable` = nothing listens."""
+    def fetch(path, auth):
+        if unreachable:
+            return None
+        r = routes.get(path)
+        return (r["status"], r["headers"], r["json"]) if r else (404, {}, None)
+    return fetch
+
+
+@pytest.mark.parametrize("v", V["detection"], ids=[v["cite"][:60] for v in V["detection"]])
+def test_endpoint_type_detection(v):
+    fetch = _mock_fetch(v["routes"], v.get("unreachable", False))
+    if v["type"] is None:
+        with pytest.raises(ValueError) as ei:
+            G.detect_endpoint_type(fetch)
+        assert str(ei.value) == v["error"]
+    else:
+        assert G.detect_endpoint_type(fetch) == (v["type"], v["reason"])
+
+
+def test_detection_marker_rules():
+    # detection/lm_studio.rs tests: token-boundary matching, not substring matching
+    for s, want in (("LM-Studio/0.3.5", True), ("lm studio", True), ("lm_studio", True), ("lmstudio-community", True), ("LMStudio", True),
+                    ("film studio", False), ("calm-studio", False), ("organization_owner", False), ("vllm", False)):
+        assert G._lm_studio_marker(s) is want, s
+    # a models[] entry needs publisher + architecture + (state marker | LM Studio shape)
+    assert not G._looks_like_lm_studio_model({"publisher": "x", "arch": "llama"})
+    assert G._looks_like_lm_studio_model({"publisher": "x", "arch": "llama", "state": "loaded"})
+    # xllm_version of the wrong type is a parse failure, not a detection (serde Option<String>)
+    assert G.detect_xllm(_mock_fetch({"/api/system": {"status": 200, "headers": {}, "json": {"xllm_version": 3}}})) is None
+    assert G.detect_xllm(_mock_fetch({"/api/system": {"status": 200, "headers": {}, "json": {"server_name": "other"}}})) is None
+    assert G.detect_xllm(_mock_fetch({"/api/system": {"status": 500, "headers": {}, "json": {"xllm_version": "1"}}})) is None
+
+
+@pytest.mark.parametrize("v", V["models_parse"], ids=[v["cite"][-40:] for v in V["models_parse"]])
+def test_parse_models_response(v):
+    assert G.parse_models_response(v["json"]) == (v["ids"], v["format"])
+
+
+def test_detect_capabilities():
+    for v in V["capabilities"]:
+        assert G.detect_capabilities(v["name"]) == v["caps"], v["name"]
+    assert G.detect_capabilities("org/embed-x") == ["embeddings"] and G.detect_capabilities("embed-org/chat-model") == ["chat"]    # leaf only
+
+
+@pytest.mark.parametrize("v", V["xllm_model_info"], ids=[v["cite"][-44:] for v in V["xllm_model_info"]])
+def test_xllm_model_info(v):
+    r = (200, {}, v["json"])
+    if v["want"] is None:
+        with pytest.raises(ValueError):
+            G.parse_xllm_model_info(r)
+    else:
+        assert G.parse_xllm_model_info(r) == v["want"]
+    assert G.xllm_model_info_url("meta-llama/Llama 3:8b") == "/api/models/meta-llama%2FLlama%203%3A8b/info"      # metadata/xllm.rs:54-63
+    with pytest.raises(ValueError):
+        G.parse_xllm_model_info((404, {}, {"error": "model not found"}))                                         # tests/support/xllm.rs:35-44
+
+
+def test_v0_health_fields_are_all_optional():
+    # health/endpoint_checker.rs:515-557
+    full = {"gpu": {"device_count": 8, "total_memory_bytes": 8 * 183 * 2 ** 30, "used_memory_bytes": 5, "capability_score": 99.5}, "load": {"active_requests": 3}}
+    assert G.parse_v0_health((200, {}, full)) == {"gpu_device_count": 8, "gpu_total_memory_bytes": 8 * 183 * 2 ** 30, "gpu_used_memory_bytes": 5,
+                                                 "gpu_capability_score": 99.5, "active_requests": 3}
+    assert set(G.parse_v0_health((200, {}, {})).values()) == {None}
+    assert G.parse_v0_health((200, {}, {"gpu": {"device_count": -1, "capability_score": 7}}))["gpu_device_count"] is None
+    with pytest.raises(ValueError):
+        G.parse_v0_health((503, {}, {}))

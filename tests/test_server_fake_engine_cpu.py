@@ -100,6 +100,7 @@ test_messages_route_errors_in_anthropic_shape = T.test_messages_route_errors_in_
 test_server_from_a_single_gguf = T.test_server_from_a_single_gguf
 test_stop_strings_end_the_text_before_the_match = T.test_stop_strings_end_the_text_before_the_match
 test_model_download_routes = T.test_model_download_routes
+test_an_unmodified_gateway_would_register_and_sync_this_endpoint = T.test_an_unmodified_gateway_would_register_and_sync_this_endpoint
 
 
 # ---- only reachable with a scripted source: the gateway's queue conventions through the shim ---------------------------

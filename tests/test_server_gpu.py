@@ -356,3 +356,67 @@ def test_model_download_routes(server, built_lib, tmp_path):
     finally:
         proc.terminate()
         proc.wait(timeout=20)
+
+
+def _gateway_fetch(port, api_key=None):
+    """The HTTP the reference's detection / health / sync / metadata clients send (GET, optional bearer), as the `fetch`
+    the restated clients in oracle/gateway_ref.py take."""
+    def fetch(path, auth):
+        try:
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=10)
+            c.request("GET", path, headers={"Authorization": "Bearer " + api_key} if (auth and api_key) else {})
+            r = c.getresponse()
+            data = r.read()
+            c.close()
+        except OSError:
+            return None
+        try:
+            j = json.loads(data)
+        except ValueError:
+            j = None
+        return r.status, {k.lower(): v for k, v in r.getheaders()}, j
+    return fetch
+
+
+def test_an_unmodified_gateway_would_register_and_sync_this_endpoint(server, built_lib):
+    """Registration, health and model sync as llmlb performs them, with the reference's CLIENT
+    logic restated in the oracle and pinned to its own test vectors: the shim is typed `xllm` by the priority chain
+    (detection/mod.rs:85-195), its /api/health parses into GpuInfo (health/endpoint_checker.rs:515-557), /v1/models syncs to
+    one chat-capable model whose max_tokens comes from /api/models/{id}/info (sync/mod.rs:104-278, metadata/xllm.rs:48-99)."""
+    fetch = _gateway_fetch(server)
+    assert G.detect_endpoint_type(fetch) == ("xllm", "xLLM: /api/system xllm_version=llmlb_b200-0.1")
+    hz = G.parse_v0_health(fetch("/api/health", True))
+    assert hz["gpu_device_count"] == 1 and hz["gpu_total_memory_bytes"] > 0 and hz["gpu_used_memory_bytes"] is not None
+    assert hz["gpu_capability_score"] == 100.0 and hz["active_requests"] is not None
+    models, fmt = G.sync_models(fetch, "xllm")
+    assert fmt == "openai" and models == [{"model_id": "tiny-llama", "capabilities": ["chat"], "supported_apis": ["chat_completions"], "max_tokens": 512}]
+    info = G.parse_xllm_model_info(fetch(G.xllm_model_info_url("tiny-llama"), True))
+    assert info["model"] == "tiny-llama" and info["context_length"] == 512
+    with pytest.raises(ValueError):
+        G.parse_xllm_model_info(fetch(G.xllm_model_info_url("nonexistent-model"), True))          # tests/support/xllm.rs:35-44: 404
+    # an id with the three characters the gateway escapes, behind an API key: every probe that carries the key works, the two
+    # probes the reference sends WITHOUT it (Ollama /api/tags, llama.cpp) are refused and the chain still ends at xllm
+    port = _free_port()
+    mid = "meta-llama/Tiny Llama:q8"
+    proc = subprocess.Popen([BIN, "--port", str(port), "--model", "tiny", "--model-id", mid, "--max-seqs", "2", "--max-ctx", "256", "--api-key", "sk-test"],
+                            stderr=subprocess.PIPE)
+    try:
+        deadline = time.time() + 120
+        while time.time() < deadline:
+            try:
+                c = http.client.HTTPConnection("127.0.0.1", port, timeout=2); c.request("GET", "/v1/models"); c.getresponse().read(); c.close()
+                break
+            except OSError:
+                assert proc.poll() is None, proc.stderr.read().decode()
+                time.sleep(0.2)
+        fetch = _gateway_fetch(port, "sk-test")
+        assert fetch("/api/tags", False)[0] == 401 and G.detect_endpoint_type(fetch)[0] == "xllm"
+        models, _ = G.sync_models(fetch, "xllm")
+        assert models == [{"model_id": mid, "capabilities": ["chat"], "supported_apis": ["chat_completions"], "max_tokens": 256}]
+        # without the key the gateway gets 401s everywhere: it answers, so "unsupported", not "unreachable" (registration fails loudly)
+        with pytest.raises(ValueError) as ei:
+            G.detect_endpoint_type(_gateway_fetch(port, None))
+        assert str(ei.value) == "unsupported"
+    finally:
+        proc.terminate()
+        proc.wait(timeout=20)
