@@ -5,9 +5,12 @@ vectors of the reference's own tests, transcribed in tests/golden/gateway_vector
 vector cites the reference test it comes from).  The product implementation is the C++ in
 llmlb_b200/host/, which tests/test_host_gateway.py compares against this file.
 
-Not restated: tiktoken `estimate_tokens` (llmlb/src/token/mod.rs:217-223 — third-party BPE
-tiktoken-rs 0.11.0 cl100k_base, absent here).  It is only the fallback when an endpoint omits
-`usage`; the in-process engine always reports usage, so that branch is unreachable on this path.
+tiktoken's vocabulary (llmlb/src/token/mod.rs:217-223 — tiktoken-rs 0.11.0 cl100k_base, third-party data absent
+here) is not restated: `extract_or_estimate_tokens` takes the counting function as an argument.  It is only the
+fallback when an endpoint omits `usage`; the in-process engine always reports usage.
+
+The last section restates the gateway as CLIENT of an endpoint's probe routes (type detection, /api/health,
+/v1/models sync, xLLM model info): the conformance checker for the shim's responder side.
 """
 import hashlib
 import json
