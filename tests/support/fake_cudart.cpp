@@ -1,0 +1,194 @@
+// A test double of libcudart.so.12 — TEST INFRASTRUCTURE, never linked or shipped with the product.
+//
+// Purpose: the engine (llmlb_b200/csrc/engine.cu) is half host code — request queue, iteration-level scheduler, page
+// allocator, preemption, timeouts, event delivery, the C ABI's locking — and until now none of it could run where
+// there is no GPU, so none of it had ever seen a sanitizer.  Preloading this library under the UNMODIFIED product
+// libllmlb_b200.so makes every CUDA runtime call a host-side no-op: "device" memory is zero-filled host memory
+// (anonymous shared memory, so that the IPC-handle calls work across processes like CUDA IPC does between ranks), copies
+// are memcpy, kernel launches and graph launches do nothing, events complete at once.  No arithmetic happens — every
+// sampled token id is whatever the zero-filled buffers hold (0) — so this says NOTHING about the kernels or about
+// parity; it exercises counts, ordering, resource accounting and thread safety of the host side, at a step rate no
+// GPU would reach.  The product still refuses to start without a real device: nothing here is reachable unless a test
+// sets LD_PRELOAD (tests/test_engine_host_logic_cpu.py).
+//
+// Build: g++ -shared -fPIC -I/usr/local/cuda/include fake_cudart.cpp -Wl,-soname,libcudart.so.12
+//            -Wl,--version-script=fake_cudart.map -o libcudart.so.12
+#include <cuda_runtime_api.h>
+
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+namespace {
+struct Alloc { int fd = -1; size_t size = 0; };
+std::mutex g_mu;
+std::map<void*, Alloc> g_allocs;
+std::map<void*, size_t> g_opened;
+std::atomic<unsigned long long> g_seq{0};
+std::atomic<size_t> g_allocated{0};
+std::atomic<uint64_t> g_launches{0};
+struct Ev { double t_ms; };
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+thread_local struct { dim3 grid, block; size_t smem; void* stream; } g_cfg;
+// cuTensorMapEncodeTiled stand-in: the descriptor is opaque to the host; zero it and report success
+int fake_encode_tiled(void* map, int, unsigned, void*, const void*, const void*, const void*, const void*, int, int, int, int) {
+  memset(map, 0, 128);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "fake cudart"; }
+// "Device" allocations are anonymous shared memory (memfd) so that another PROCESS can map them through the IPC-handle
+// calls, the way tensor-parallel ranks map each other's exchange regions: zero-filled like calloc, nothing named in
+// /dev/shm, gone with the process however it dies.
+cudaError_t cudaMalloc(void** p, size_t n) {
+  if (!n) n = 1;
+  const int fd = memfd_create("fakecuda", 0);
+  void* m = MAP_FAILED;
+  if (fd >= 0 && ftruncate(fd, off_t(n)) == 0) m = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (m == MAP_FAILED) { if (fd >= 0) close(fd); return cudaErrorMemoryAllocation; }
+  { std::lock_guard<std::mutex> lk(g_mu); g_allocs[m] = Alloc{fd, n}; }
+  *p = m;
+  g_allocated += n;
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+  if (!p) return cudaSuccess;
+  Alloc a;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) return cudaErrorInvalidValue;
+    a = it->second;
+    g_allocs.erase(it);
+  }
+  munmap(p, a.size);
+  close(a.fd);
+  g_allocated -= a.size;
+  return cudaSuccess;
+}
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemGetInfo(size_t* fr, size_t* total) {
+  *total = size_t(183) << 30;
+  *fr = *total - (g_allocated.load() < *total ? g_allocated.load() : 0);
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (d && s && n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (d && s && n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind) {
+  for (size_t r = 0; r < h; ++r) memmove(static_cast<char*>(d) + r * dp, static_cast<const char*>(s) + r * sp, w);
+  return cudaSuccess;
+}
+// the symbol argument is the host shadow of the __device__ / __constant__ variable: same size, harmless to write
+cudaError_t cudaMemcpyToSymbol(const void* sym, const void* s, size_t n, size_t off, cudaMemcpyKind) {
+  if (sym && s && n) memmove(static_cast<char*>(const_cast<void*>(sym)) + off, s, n);
+  return cudaSuccess;
+}
+cudaError_t cudaMemset(void* d, int v, size_t n) { if (d && n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (d && n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = static_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(new Ev{now_ms()}); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<Ev*>(e); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { reinterpret_cast<Ev*>(e)->t_ms = now_ms(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  const double d = reinterpret_cast<Ev*>(b)->t_ms - reinterpret_cast<Ev*>(a)->t_ms;
+  *ms = float(d > 0 ? d : 0.001);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaSuccess; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = static_cast<cudaGraph_t>(malloc(8)); return cudaSuccess; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* x, cudaGraph_t, unsigned long long) { *x = static_cast<cudaGraphExec_t>(malloc(8)); return cudaSuccess; }
+// One decode step = one graph launch.  FAKE_CUDART_STEP_US gives it a duration (so that deadlines and queue timeouts can
+// expire while a request is running), FAKE_CUDART_FAIL_AFTER=n makes the n-th graph launch — and every launch after it —
+// fail the way a device fault would (the engine must fail every request in flight, and say so on later submits).
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) {
+  static const long step_us = getenv("FAKE_CUDART_STEP_US") ? atol(getenv("FAKE_CUDART_STEP_US")) : 0;
+  static const long fail_after = getenv("FAKE_CUDART_FAIL_AFTER") ? atol(getenv("FAKE_CUDART_FAIL_AFTER")) : -1;
+  static std::atomic<long> graph_launches{0};
+  const long n = ++graph_launches;
+  ++g_launches;
+  if (fail_after >= 0 && n >= fail_after) return cudaErrorLaunchFailure;
+  if (step_us > 0) usleep(useconds_t(step_us));
+  return cudaSuccess;
+}
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { free(g); return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t x) { free(x); return cudaSuccess; }
+cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { ++g_launches; return cudaSuccess; }
+cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t*, const void*, void**) { ++g_launches; return cudaSuccess; }
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDriverEntryPoint(const char* sym, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* st) {
+  const bool known = sym && !strcmp(sym, "cuTensorMapEncodeTiled");
+  *fn = known ? reinterpret_cast<void*>(&fake_encode_tiled) : nullptr;
+  if (st) *st = known ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+  return known ? cudaSuccess : cudaErrorSymbolNotFound;
+}
+// the 64-byte handle carries (size, owner pid, owner fd); a peer opens the owner's descriptor through /proc
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_allocs.find(p);
+  if (it == g_allocs.end()) return cudaErrorInvalidValue;
+  memset(h, 0, sizeof *h);
+  const uint64_t v[3] = {it->second.size, uint64_t(getpid()), uint64_t(it->second.fd)};
+  memcpy(h, v, sizeof v);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  uint64_t v[3];
+  memcpy(v, &h, sizeof v);
+  char path[64];
+  snprintf(path, sizeof path, "/proc/%llu/fd/%llu", (unsigned long long)v[1], (unsigned long long)v[2]);
+  const int fd = open(path, O_RDWR);
+  if (fd < 0) return cudaErrorInvalidValue;
+  void* m = mmap(nullptr, size_t(v[0]), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+  { std::lock_guard<std::mutex> lk(g_mu); g_opened[m] = size_t(v[0]); }
+  *p = m;
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+  size_t n = 0;
+  { std::lock_guard<std::mutex> lk(g_mu); auto it = g_opened.find(p); if (it == g_opened.end()) return cudaErrorInvalidValue; n = it->second; g_opened.erase(it); }
+  munmap(p, n);
+  return cudaSuccess;
+}
+
+// what nvcc's host stubs call
+void** __cudaRegisterFatBinary(void*) { static void* dummy[4]; return dummy; }
+void __cudaRegisterFatBinaryEnd(void**) {}
+void __cudaUnregisterFatBinary(void**) {}
+void __cudaRegisterFunction(void**, const char*, char*, const char*, int, uint3*, uint3*, dim3*, dim3*, int*) {}
+void __cudaRegisterVar(void**, char*, char*, const char*, int, size_t, int, int) {}
+unsigned __cudaPushCallConfiguration(dim3 grid, dim3 block, size_t smem, struct CUstream_st* stream) {
+  g_cfg.grid = grid; g_cfg.block = block; g_cfg.smem = smem; g_cfg.stream = stream;
+  return 0;
+}
+cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, void* stream) {
+  *grid = g_cfg.grid; *block = g_cfg.block; *smem = g_cfg.smem; *static_cast<void**>(stream) = g_cfg.stream;
+  return cudaSuccess;
+}
+// for the tests: how many launches the engine issued
+unsigned long long fake_cudart_launches(void) { return g_launches.load(); }
+}  // extern "C"

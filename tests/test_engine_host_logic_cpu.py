@@ -1,0 +1,321 @@
+"""The engine's HOST side — request queue, iteration-level scheduler, page allocator, preemption, timeouts, event
+delivery, the locking of the C ABI — on a machine without a GPU: the UNMODIFIED product library runs over
+tests/support/fake_cudart.cpp, a test double of libcudart in which memory is host memory and launches do nothing.
+No arithmetic happens (every token id is 0), so nothing here says anything about kernels or parity; what is checked is
+counts, ordering, resource accounting and thread safety, at a step rate no GPU reaches.  The same scenarios run under
+ThreadSanitizer / AddressSanitizer builds of the library in the long pass recorded in DESIGN.md.
+
+Mechanics: the outer test starts pytest on this file in a child process with LD_PRELOAD = the fake runtime (it must not
+be loaded into a process that imports torch); the scenario tests skip themselves unless they run in that child."""
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+FAKE_DIR = os.path.join(HERE, "support", "_build", "fake_cudart")
+FAKE = os.path.join(FAKE_DIR, "libcudart.so.12")
+INNER = os.environ.get("LLMLB_FAKE_CUDART") == "1"
+inner = pytest.mark.skipif(not INNER, reason="runs in the child process that preloads the fake CUDA runtime")
+
+
+def build_fake():
+    os.makedirs(FAKE_DIR, exist_ok=True)
+    src = os.path.join(HERE, "support", "fake_cudart.cpp")
+    if not os.path.exists(FAKE) or os.path.getmtime(FAKE) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include", src, "-Wl,-soname,libcudart.so.12",
+                               "-Wl,--version-script=" + os.path.join(HERE, "support", "fake_cudart.map"), "-o", FAKE])
+    return FAKE
+
+
+def test_engine_host_logic_over_the_fake_cuda_runtime(built_lib):
+    if INNER:
+        pytest.skip("already inside")
+    env = dict(os.environ, LD_PRELOAD=build_fake(), LLMLB_FAKE_CUDART="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider", "-k", "scenario"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+TINY = dict(hidden=512, n_layers=2, n_heads=8, n_kv_heads=2, head_dim=128, ffn=1024, vocab=2048, rope_theta=500000.0, rms_eps=1e-5)
+NONE, STOP, LENGTH, CANCELLED, ERROR, QUEUE_TIMEOUT, DEADLINE = range(7)
+
+
+def _ffi():
+    from llmlb_b200 import ffi
+    alt = os.environ.get("LLMLB_HOST_LOGIC_LIB")      # a sanitizer build of the same sources (long pass)
+    if alt:
+        ffi.LIB_PATH = alt
+    return ffi
+
+
+def drain(eng, rid, timeout_s=30):
+    evs, t0 = [], time.time()
+    while time.time() - t0 < timeout_s:
+        got = eng.poll(rid, timeout_ms=50)
+        evs += got
+        if got and got[-1]["finish_reason"]:
+            return evs
+    raise AssertionError("request %d did not finish: %s" % (rid, evs[-3:]))
+
+
+def settle(eng, timeout_s=10):
+    """wait until the scheduler has nothing left, then return health"""
+    t0 = time.time()
+    while time.time() - t0 < timeout_s:
+        h = eng.health()
+        if h["active_requests"] == 0 and h["queued_requests"] == 0:
+            return h
+        time.sleep(0.01)
+    raise AssertionError("engine did not go idle: %s" % eng.health())
+
+
+@inner
+def test_scenario_events_are_complete_ordered_and_accounted():
+    ffi = _ffi()
+    with ffi.Engine(TINY, max_seqs=8, max_ctx=1024) as eng:
+        h0 = eng.health()
+        rids = [eng.submit(list(range(1, 1 + n)), m, ignore_eos=True) for n, m in ((5, 1), (64, 7), (65, 40), (300, 128), (1, 3))]
+        for rid, (n, m) in zip(rids, ((5, 1), (64, 7), (65, 40), (300, 128), (1, 3))):
+            evs = drain(eng, rid)
+            toks = [e for e in evs if e["token_id"] >= 0]
+            assert [e["index"] for e in toks] == list(range(m)) and len(toks) == m
+            assert all(e["prompt_tokens"] == n for e in evs) and [e["completion_tokens"] for e in toks] == list(range(1, m + 1))
+            assert [e["finish_reason"] for e in evs[:-1]] == [NONE] * (len(evs) - 1) and evs[-1]["finish_reason"] == LENGTH
+            assert all(a["t_ms"] <= b["t_ms"] for a, b in zip(evs, evs[1:]))
+            eng.release(rid)
+        h = settle(eng)
+        assert h["free_kv_pages"] == h["total_kv_pages"] == h0["total_kv_pages"]          # every page came back
+        assert h["tokens_prefill"] - h0["tokens_prefill"] == 5 + 64 + 65 + 300 + 1
+        # a prefill step samples the first token; every later token is one decode step of its sequence
+        assert h["tokens_decode"] - h0["tokens_decode"] == sum(m - 1 for m in (1, 7, 40, 128, 3))
+        with pytest.raises(ffi.LlmlbError):
+            eng.poll(rids[0])                                                              # released ids are gone
+
+
+@inner
+def test_scenario_stop_ids_cancel_release_and_argument_checks():
+    ffi = _ffi()
+    with ffi.Engine(TINY, max_seqs=4, max_ctx=512) as eng:
+        # every sampled id is 0 here: a stop id of 0 ends the request at its first token, ignore_eos overrides it
+        evs = drain(eng, eng.submit([3, 4, 5], 50, stop_ids=[0]))
+        assert [e["finish_reason"] for e in evs] == [STOP] and evs[0]["completion_tokens"] == 1
+        evs = drain(eng, eng.submit([3, 4, 5], 6, stop_ids=[0], ignore_eos=True))
+        assert len(evs) == 6 and evs[-1]["finish_reason"] == LENGTH
+        evs = drain(eng, eng.submit([3, 4, 5], 6, stop_ids=[7, 9]))
+        assert len(evs) == 6 and evs[-1]["finish_reason"] == LENGTH
+        # cancel: while paused nothing is scheduled, so the request is still waiting when the cancel lands
+        eng.pause(True)
+        rid = eng.submit([1] * 40, 100, ignore_eos=True)
+        assert eng.poll(rid, timeout_ms=20) == []
+        eng.cancel(rid)
+        eng.pause(False)
+        evs = drain(eng, rid)
+        assert evs[-1]["finish_reason"] == CANCELLED and evs[-1]["token_id"] == -1 and evs[-1]["completion_tokens"] == 0
+        # release of a request in flight cancels it and frees everything it held
+        rid = eng.submit([1] * 200, 300, ignore_eos=True)
+        eng.release(rid)
+        h = settle(eng)
+        assert h["free_kv_pages"] == h["total_kv_pages"]
+        for bad in (lambda: eng.submit([], 4), lambda: eng.submit([1, 2], 0), lambda: eng.submit([TINY["vocab"]], 4), lambda: eng.submit([-1], 4),
+                    lambda: eng.submit([1] * 500, 100), lambda: eng.submit([1], 4, temperature=-1.0), lambda: eng.cancel(10 ** 9), lambda: eng.release(10 ** 9)):
+            with pytest.raises(ffi.LlmlbError):
+                bad()
+        assert settle(eng)["free_kv_pages"] == h["total_kv_pages"]
+
+
+@inner
+def test_scenario_oversubscribed_pages_preempt_and_everything_still_completes():
+    """kv_pages far below what the running set needs: sequences take pages as they grow, the youngest is evicted when the
+    pool runs dry and recomputed later; every request still delivers exactly max_tokens events, in order, once."""
+    ffi = _ffi()
+    with ffi.Engine(TINY, max_seqs=8, max_ctx=1024, kv_pages=14) as eng:          # 14 pages x 64 tokens for 8 x (100 + 300) tokens
+        rids = [eng.submit([1 + i] * 100, 300, ignore_eos=True) for i in range(8)]
+        for rid in rids:
+            evs = drain(eng, rid, 60)
+            toks = [e for e in evs if e["token_id"] >= 0]
+            assert [e["index"] for e in toks] == list(range(300)) and evs[-1]["finish_reason"] == LENGTH
+            assert all(e["prompt_tokens"] == 100 for e in evs)                  # usage reports the client's prompt, not the recompute context
+            eng.release(rid)
+        h = settle(eng)
+        assert h["preemptions"] > 0 and h["free_kv_pages"] == h["total_kv_pages"] == 14
+        assert h["tokens_prefill"] > 800                                        # recomputed contexts were prefilled again
+        # a request the pool can never hold is refused at submit, not starved
+        with pytest.raises(ffi.LlmlbError):
+            eng.submit([1] * 600, 400)
+
+
+@inner
+def test_scenario_queue_limit_queue_timeout_and_deadline():
+    ffi = _ffi()
+    with ffi.Engine(TINY, max_seqs=1, max_ctx=512, queue_max=2, queue_timeout_ms=150, request_timeout_ms=60000) as eng:
+        eng.pause(True)                                                         # nothing is admitted: the queue only grows
+        a, b = eng.submit([1, 2, 3], 5), eng.submit([1, 2, 3], 5)
+        with pytest.raises(ffi.LlmlbError) as ei:
+            eng.submit([1, 2, 3], 5)
+        assert ei.value.code == ffi.E_QUEUE_FULL
+        time.sleep(0.4)                                                         # both waited longer than queue_timeout_ms
+        eng.pause(False)
+        for rid in (a, b):
+            evs = drain(eng, rid)
+            assert [e["finish_reason"] for e in evs] == [QUEUE_TIMEOUT] and evs[0]["completion_tokens"] == 0
+        assert settle(eng)["queued_requests"] == 0
+    with ffi.Engine(TINY, max_seqs=2, max_ctx=512, request_timeout_ms=120) as eng:
+        eng.pause(True)
+        rid = eng.submit([1, 2, 3], 5, ignore_eos=True)
+        time.sleep(0.3)
+        eng.pause(False)
+        assert drain(eng, rid)[-1]["finish_reason"] == DEADLINE
+        evs = drain(eng, eng.submit([1, 2, 3], 5, ignore_eos=True))            # a fresh request is unaffected
+        assert len(evs) == 5 and evs[-1]["finish_reason"] == LENGTH
+
+
+@inner
+def test_scenario_many_threads_submit_poll_cancel_release_concurrently():
+    """The ABI promises thread safety (tokio workers call it): 12 threads mix every entry point against one engine whose
+    steps take microseconds, so interleavings that a GPU's millisecond steps hide are hit thousands of times."""
+    import random
+    ffi = _ffi()
+    with ffi.Engine(TINY, max_seqs=8, max_ctx=512, kv_pages=24, queue_max=4096) as eng:
+        errors, done = [], [0]
+        lock = threading.Lock()
+
+        def worker(seed):
+            rs = random.Random(seed)
+            try:
+                for _ in range(60):
+                    n, m = rs.randint(1, 120), rs.randint(1, 60)
+                    rid = eng.submit([rs.randrange(TINY["vocab"]) for _ in range(n)], m, ignore_eos=True, temperature=rs.choice([0.0, 0.7]), seed=seed)
+                    action = rs.random()
+                    if action < 0.15:
+                        eng.release(rid)                                        # fire and forget
+                        continue
+                    if action < 0.35:
+                        time.sleep(rs.random() * 0.002)
+                        eng.cancel(rid)
+                    evs = drain(eng, rid, 60)
+                    toks = [e for e in evs if e["token_id"] >= 0]
+                    assert [e["index"] for e in toks] == list(range(len(toks)))
+                    fr = evs[-1]["finish_reason"]
+                    assert fr in (LENGTH, CANCELLED) and (fr != LENGTH or len(toks) == m) and len(toks) <= m
+                    eng.health()
+                    eng.release(rid)
+                    with lock:
+                        done[0] += 1
+            except Exception as e:                                              # noqa: BLE001
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(12)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errors, errors[:3]
+        h = settle(eng, 30)
+        assert done[0] > 400 and h["free_kv_pages"] == h["total_kv_pages"] == 24 and h["active_requests"] == 0
+
+
+@inner
+def test_scenario_destroy_with_requests_in_flight_and_many_engines():
+    ffi = _ffi()
+    for i in range(20):
+        eng = ffi.Engine(TINY, max_seqs=4, max_ctx=512)
+        rids = [eng.submit([1, 2, 3, 4], 200, ignore_eos=True) for _ in range(6)]
+        if i % 2:
+            eng.poll(rids[0], timeout_ms=5)
+        eng.close()                                                             # waiting + running + in-flight steps: must not hang or crash
+
+
+# ---- tensor-parallel serving through the plan channel: two PROCESSES, rank 0 owns the queue, rank 1 replays its log ----
+def _tp_rank(rank, world, handles, barrier, name, out_q):
+    try:
+        # give a decode step a duration: with zero-time steps the scheduler thread re-takes the engine mutex so fast that a
+        # cancel() can wait behind hundreds of steps (std::mutex is not fair; on a GPU the scheduler sleeps in the event wait)
+        os.environ["FAKE_CUDART_STEP_US"] = "200"
+        ffi = _ffi()
+        eng = ffi.Engine(TINY, model_id="tp-plan", device=0, tp_rank=rank, tp_size=world, max_seqs=8, max_ctx=1024, seed=0)
+        h = eng.tp_export()
+        handles[rank * 64:(rank + 1) * 64] = list(h)
+        barrier.wait(60)
+        blob = bytes(handles[:])
+        eng.tp_import([blob[r * 64:(r + 1) * 64] for r in range(world)])       # maps the peer's exchange region (shared memory under the fake runtime)
+        barrier.wait(60)
+        if rank == 0:
+            eng.tp_plan_channel(name)
+        barrier.wait(60)
+        if rank != 0:
+            eng.tp_plan_channel(name)
+        barrier.wait(60)
+        res = {}
+        if rank == 0:
+            prompts = [[(7 * i + j) % TINY["vocab"] for j in range(n)] for i, n in enumerate((64, 200, 17, 333, 90, 41))]
+            gens = [24, 40, 12, 30, 900, 20]
+            solo = drain(eng, eng.submit(prompts[0], gens[0], ignore_eos=True))
+            rids = []
+            for i, (p, g) in enumerate(zip(prompts, gens)):
+                rids.append(eng.submit(p, g, ignore_eos=True))
+                if i == 4:
+                    eng.cancel(rids[4])                                         # steps take microseconds here: cancel before it can run dry
+                time.sleep(0.001 * (i % 3))
+            outs = [drain(eng, r, 60) for r in rids]
+            for r in rids:
+                eng.release(r)
+            res = {"solo": len(solo), "lens": [sum(e["token_id"] >= 0 for e in o) for o in outs], "reasons": [o[-1]["finish_reason"] for o in outs]}
+            settle(eng, 30)
+        else:
+            try:
+                eng.submit([1, 2, 3], 4)
+                res["follower_accepted_submit"] = True
+            except ffi.LlmlbError:
+                pass
+        barrier.wait(120)                                                       # the follower keeps replaying until rank 0 is done
+        if rank != 0:                                                           # ... and has drained the log: poll its counters until they stop moving
+            last, t0 = None, time.time()
+            while time.time() - t0 < 20:
+                cur = eng.health()["kernel_launches"]
+                if cur == last:
+                    break
+                last = cur
+                time.sleep(0.2)
+        hz = eng.health()
+        res["counters"] = {k: hz[k] for k in ("steps_prefill", "steps_decode", "tokens_decode", "tokens_prefill", "kernel_launches", "preemptions")}
+        res["pages"] = (hz["free_kv_pages"], hz["total_kv_pages"])
+        out_q.put((rank, res))
+        barrier.wait(60)
+        eng.close()
+    except Exception as e:                                                      # noqa: BLE001
+        out_q.put((rank, {"error": repr(e)}))
+        try:
+            barrier.abort()
+        except Exception:                                                       # noqa: BLE001
+            pass
+
+
+@inner
+def test_scenario_two_rank_plan_channel_follower_replays_the_leader():
+    """What `tools/tp_plan_check.py` does on GPUs, on the host side only: the follower's scheduler, fed by the leader's
+    shared-memory log, takes the same steps — identical step / token / launch counters, all pages back on both ranks —
+    through staggered arrivals, chunked prefill and a mid-flight cancellation; a follower refuses submits."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world = 2
+    handles = ctx.Array("B", 64 * world)
+    barrier = ctx.Barrier(world)
+    q = ctx.Queue()
+    name = "llmlb_plan_cpu_%d" % os.getpid()
+    ps = [ctx.Process(target=_tp_rank, args=(r, world, handles, barrier, name, q)) for r in range(world)]
+    [p.start() for p in ps]
+    got = dict(q.get(timeout=180) for _ in range(world))
+    [p.join(60) for p in ps]
+    assert all("error" not in v for v in got.values()), got
+    lead, foll = got[0], got[1]
+    assert lead["solo"] == 24 and lead["reasons"][4] == CANCELLED and lead["lens"][4] < 900
+    assert all(lead["lens"][i] == g and lead["reasons"][i] == LENGTH for i, g in ((0, 24), (1, 40), (2, 12), (3, 30), (5, 20)))
+    assert "follower_accepted_submit" not in foll
+    assert lead["counters"] == foll["counters"], (lead["counters"], foll["counters"])
+    assert lead["pages"][0] == lead["pages"][1] and foll["pages"][0] == foll["pages"][1]
+    assert all(p.exitcode == 0 for p in ps)
