@@ -48,6 +48,14 @@ def _start(binary, *args, env=None):
     raise AssertionError("server did not come up")
 
 
+@pytest.fixture(autouse=True)
+def _servers_started_by_the_reused_tests_also_get_the_fake_runtime(monkeypatch, product_bin):
+    # a few reused tests start their own server from T.BIN: child processes of this test inherit the preload (this process,
+    # whose libraries are already loaded, is unaffected)
+    monkeypatch.setenv("LD_PRELOAD", ":".join(x for x in (os.environ.get("LLMLB_SERVER_PRELOAD_FIRST"), HL.build_fake()) if x))
+    monkeypatch.setattr(T, "BIN", product_bin)
+
+
 @pytest.fixture(scope="module")
 def server(product_bin):
     port, proc = _start(product_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "8", "--max-ctx", "512")
@@ -74,6 +82,12 @@ test_drain_gate = T.test_drain_gate
 test_concurrent_streams = T.test_concurrent_streams
 test_messages_route_non_stream_and_stream = T.test_messages_route_non_stream_and_stream
 test_messages_route_errors_in_anthropic_shape = T.test_messages_route_errors_in_anthropic_shape
+test_chat_through_the_native_tokenizer = T.test_chat_through_the_native_tokenizer
+test_stop_at_end_of_turn_token = T.test_stop_at_end_of_turn_token
+test_server_from_a_single_gguf = T.test_server_from_a_single_gguf
+test_stop_strings_end_the_text_before_the_match = T.test_stop_strings_end_the_text_before_the_match
+test_model_download_routes = T.test_model_download_routes
+test_an_unmodified_gateway_would_register_and_sync_this_endpoint = T.test_an_unmodified_gateway_would_register_and_sync_this_endpoint
 
 
 def test_deadline_and_queue_timeout_expire_inside_the_real_scheduler(product_bin):
