@@ -319,3 +319,50 @@ def test_scenario_two_rank_plan_channel_follower_replays_the_leader():
     assert lead["counters"] == foll["counters"], (lead["counters"], foll["counters"])
     assert lead["pages"][0] == lead["pages"][1] and foll["pages"][0] == foll["pages"][1]
     assert all(p.exitcode == 0 for p in ps)
+
+
+@inner
+def test_scenario_scheduler_invariants_over_random_workloads():
+    """Property test of the scheduler (hypothesis): random engine shapes (sequences, page pool, prefill chunk, run-ahead) and
+    random request mixes, some cancelled.  Invariants: exactly max_tokens events per surviving request with contiguous
+    indices; usage reports the client's prompt; every page and slot comes back; prefill work >= the prompts (equal without
+    preemption) in >= ceil(tokens / chunk) steps; without preemption one decode launch per token after the first."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    ffi = _ffi()
+    N = [0]
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.integers(1, 8), st.integers(6, 40), st.sampled_from([64, 128, 500, 2048]), st.sampled_from([0, 1, 3]),
+           st.lists(st.tuples(st.integers(1, 300), st.integers(1, 80), st.booleans()), min_size=1, max_size=14))
+    def run(max_seqs, kv_pages, chunk, lookahead, reqs):
+        N[0] += 1
+        reqs = [(n, m, c) for n, m, c in reqs if (n + m + 63) // 64 <= kv_pages]            # submit refuses what can never fit
+        if not reqs:
+            return
+        with ffi.Engine(TINY, max_seqs=max_seqs, max_ctx=512, kv_pages=kv_pages, max_step_tokens=chunk, lookahead=lookahead) as eng:
+            eng.pause(True)                                                                  # one well-defined arrival order
+            rids = [eng.submit([(i + j) % TINY["vocab"] for j in range(n)], m, ignore_eos=True) for i, (n, m, c) in enumerate(reqs)]
+            for rid, (n, m, c) in zip(rids, reqs):
+                if c:
+                    eng.cancel(rid)
+            eng.pause(False)
+            for rid, (n, m, c) in zip(rids, reqs):
+                evs = drain(eng, rid, 60)
+                toks = [e for e in evs if e["token_id"] >= 0]
+                assert all(e["prompt_tokens"] == n for e in evs)
+                if c:
+                    assert evs[-1]["finish_reason"] == CANCELLED and not toks                 # cancelled before it was ever scheduled
+                else:
+                    assert [e["index"] for e in toks] == list(range(m)) and evs[-1]["finish_reason"] == LENGTH
+                eng.release(rid)
+            h = settle(eng)
+            live = [(n, m) for n, m, c in reqs if not c]
+            assert h["free_kv_pages"] == h["total_kv_pages"] == kv_pages and h["active_requests"] == 0
+            assert h["tokens_prefill"] >= sum(n for n, _ in live)
+            assert h["steps_prefill"] >= -(-sum(n for n, _ in live) // chunk) or not live
+            if h["preemptions"] == 0:
+                assert h["tokens_prefill"] == sum(n for n, _ in live)
+                assert h["tokens_decode"] == sum(m - 1 for _, m in live)
+
+    run()
+    assert N[0] >= 100, N                                                                   # the property really ran
