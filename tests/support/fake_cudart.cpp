@@ -32,10 +32,11 @@
 #include <string>
 
 namespace {
-struct Alloc { int fd = -1; size_t size = 0; };
+struct Alloc { int fd = -1; size_t size = 0; bool dirty = false; };   // dirty: something was copied / set into it
 std::mutex g_mu;
 std::map<void*, Alloc> g_allocs;
 std::map<void*, size_t> g_opened;
+std::map<const void*, std::string> g_kernels;      // host stub -> mangled device name (__cudaRegisterFunction)
 std::atomic<unsigned long long> g_seq{0};
 std::atomic<size_t> g_allocated{0};
 std::atomic<uint64_t> g_launches{0};
@@ -50,6 +51,7 @@ int fake_encode_tiled(void* map, int, unsigned, void*, const void*, const void*,
 }  // namespace
 
 extern "C" {
+static void mark_dirty(void* d);
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
@@ -91,9 +93,10 @@ cudaError_t cudaMemGetInfo(size_t* fr, size_t* total) {
   *fr = *total - (g_allocated.load() < *total ? g_allocated.load() : 0);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (d && s && n) memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (d && s && n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (d && s && n) { mark_dirty(d); memmove(d, s, n); } return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (d && s && n) { mark_dirty(d); memmove(d, s, n); } return cudaSuccess; }
 cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind) {
+  mark_dirty(d);
   for (size_t r = 0; r < h; ++r) memmove(static_cast<char*>(d) + r * dp, static_cast<const char*>(s) + r * sp, w);
   return cudaSuccess;
 }
@@ -102,8 +105,27 @@ cudaError_t cudaMemcpyToSymbol(const void* sym, const void* s, size_t n, size_t 
   if (sym && s && n) memmove(static_cast<char*>(const_cast<void*>(sym)) + off, s, n);
   return cudaSuccess;
 }
-cudaError_t cudaMemset(void* d, int v, size_t n) { if (d && n) memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (d && n) memset(d, v, n); return cudaSuccess; }
+// Zeroing a whole allocation that nothing has written yet is skipped (it is zero pages already): an engine with 8B- or
+// 70B-shaped weights then costs address space, not memory — nothing ever touches the weights here.
+static bool untouched_whole_alloc(void* d, size_t n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_allocs.find(d);
+  return it != g_allocs.end() && it->second.size == n && !it->second.dirty;
+}
+static void mark_dirty(void* d) {            // d points into a device allocation (or into host memory: then nothing to do)
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_allocs.upper_bound(d);
+  if (it == g_allocs.begin()) return;
+  --it;
+  if (static_cast<char*>(d) < static_cast<char*>(it->first) + it->second.size) it->second.dirty = true;
+}
+static void fake_memset(void* d, int v, size_t n) {
+  if (!d || !n || (v == 0 && untouched_whole_alloc(d, n))) return;
+  mark_dirty(d);
+  memset(d, v, n);
+}
+cudaError_t cudaMemset(void* d, int v, size_t n) { fake_memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { fake_memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = static_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
@@ -134,8 +156,34 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) {
 }
 cudaError_t cudaGraphDestroy(cudaGraph_t g) { free(g); return cudaSuccess; }
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t x) { free(x); return cudaSuccess; }
-cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { ++g_launches; return cudaSuccess; }
-cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t*, const void*, void**) { ++g_launches; return cudaSuccess; }
+// FAKE_CUDART_LAUNCH_LOG=<file>: one line per kernel launch — mangled kernel name, grid, block, dynamic shared memory,
+// cluster dims and whether it was launched as a programmatic dependent (PDL) — the engine's LAUNCH PLAN for any geometry,
+// readable without a GPU (tests/test_launch_plan_cpu.py checks co-residency and resource limits on it).
+static void log_launch(const void* fn, dim3 g, dim3 b, size_t smem, dim3 cluster, int pdl) {
+  static FILE* f = getenv("FAKE_CUDART_LAUNCH_LOG") ? fopen(getenv("FAKE_CUDART_LAUNCH_LOG"), "a") : nullptr;
+  if (!f) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_kernels.find(fn);
+  fprintf(f, "%s %u %u %u %u %u %u %zu %u %u %u %d\n", it == g_kernels.end() ? "?" : it->second.c_str(), g.x, g.y, g.z, b.x, b.y, b.z, smem,
+          cluster.x, cluster.y, cluster.z, pdl);
+  fflush(f);
+}
+cudaError_t cudaLaunchKernel(const void* fn, dim3 g, dim3 b, void**, size_t smem, cudaStream_t) {
+  ++g_launches;
+  log_launch(fn, g, b, smem, dim3(1, 1, 1), 0);
+  return cudaSuccess;
+}
+cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* fn, void**) {
+  ++g_launches;
+  dim3 cluster(1, 1, 1);
+  int pdl = 0;
+  for (unsigned i = 0; i < c->numAttrs; ++i) {
+    if (c->attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = dim3(c->attrs[i].val.clusterDim.x, c->attrs[i].val.clusterDim.y, c->attrs[i].val.clusterDim.z);
+    if (c->attrs[i].id == cudaLaunchAttributeProgrammaticStreamSerialization) pdl = c->attrs[i].val.programmaticStreamSerializationAllowed;
+  }
+  log_launch(fn, c->gridDim, c->blockDim, c->dynamicSmemBytes, cluster, pdl);
+  return cudaSuccess;
+}
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetDriverEntryPoint(const char* sym, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* st) {
@@ -179,7 +227,10 @@ cudaError_t cudaIpcCloseMemHandle(void* p) {
 void** __cudaRegisterFatBinary(void*) { static void* dummy[4]; return dummy; }
 void __cudaRegisterFatBinaryEnd(void**) {}
 void __cudaUnregisterFatBinary(void**) {}
-void __cudaRegisterFunction(void**, const char*, char*, const char*, int, uint3*, uint3*, dim3*, dim3*, int*) {}
+void __cudaRegisterFunction(void**, const char* host_fn, char*, const char* device_name, int, uint3*, uint3*, dim3*, dim3*, int*) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_kernels[host_fn] = device_name ? device_name : "?";
+}
 void __cudaRegisterVar(void**, char*, char*, const char*, int, size_t, int, int) {}
 unsigned __cudaPushCallConfiguration(dim3 grid, dim3 block, size_t smem, struct CUstream_st* stream) {
   g_cfg.grid = grid; g_cfg.block = block; g_cfg.smem = smem; g_cfg.stream = stream;

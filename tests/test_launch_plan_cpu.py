@@ -1,0 +1,59 @@
+"""The engine's launch plan, read without a GPU: tests/support/launch_plan_sweep.py runs the product library over the fake
+CUDA runtime and logs every kernel launch for EVERY prefill width 1..2048 and decode batch width 1..128 of Llama-3-8B
+(tp 1, 2, 4, 8) and Llama-3-70B (tp 8) shapes.  Checked on each launch:
+
+  * co-residency: kernels whose CTAs wait for each other inside the grid (the in-kernel K-split of gemm_tc / gemm_tc2 parks
+    partial tiles and spins on a per-tile counter; the gemv_ks gather variant waits for owner CTAs) must fit the GPU in one
+    wave — at most 148 CTAs at one CTA per SM.  A wider grid would hang the device; GPU tests only ever try a few widths.
+  * hardware limits: <= 1024 threads per CTA, <= 227 KiB dynamic shared memory, cluster size <= 16 and grid divisible by it.
+"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import test_engine_host_logic_cpu as HL  # noqa: E402
+
+SM_COUNT, MAX_SMEM = 148, 227 * 1024
+
+
+def plan(tmp_path, model, tp):
+    log = str(tmp_path / ("launch_%s_tp%d.log" % (model, tp)))
+    env = dict(os.environ, LD_PRELOAD=HL.build_fake(), FAKE_CUDART_LAUNCH_LOG=log)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "support", "launch_plan_sweep.py"), model, str(tp)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ctx, out = "init", collections.defaultdict(list)                 # engine creation: weight generation, tables, warm-up
+    for line in open(log):
+        if line.startswith("###"):
+            ctx = line[4:].strip()
+            continue
+        p = line.split()
+        name = re.sub(r"^_ZN5llmlb\d+|^_Z\d+", "", p[0])
+        out[ctx].append((name, tuple(map(int, p[1:4])), tuple(map(int, p[4:7])), int(p[7]), tuple(map(int, p[8:11])), int(p[11])))
+    return out
+
+
+@pytest.mark.parametrize("model,tp", [("8b", 1), ("8b", 2), ("8b", 4), ("8b", 8), ("70b", 8)])
+def test_every_width_of_the_launch_plan_respects_co_residency_and_hardware_limits(built_lib, tmp_path, model, tp):
+    steps = plan(tmp_path, model, tp)
+    assert len([k for k in steps if k.startswith("prefill")]) == 2048 and len([k for k in steps if k.startswith("decode")]) == 128
+    n = 0
+    seen_ksplit_kernels = set()
+    for ctx, launches in steps.items():
+        assert launches, ctx
+        for name, grid, block, smem, cluster, pdl in launches:
+            n += 1
+            ctas, threads, csize = grid[0] * grid[1] * grid[2], block[0] * block[1] * block[2], cluster[0] * cluster[1] * cluster[2]
+            assert threads <= 1024 and smem <= MAX_SMEM, (ctx, name, block, smem)
+            assert csize <= 16 and all(g % c == 0 for g, c in zip(grid, cluster)), (ctx, name, grid, cluster)
+            if name.startswith(("gemm_tc_kernel", "gemm_tc2_kernel", "gemv_ks_kernel")):
+                seen_ksplit_kernels.add(name.split("I")[0])
+                assert ctas <= SM_COUNT, "%s: %s launches %d CTAs that wait for each other: more than one wave of %d SMs" % (ctx, name, ctas, SM_COUNT)
+                if name.startswith("gemm_tc2_kernel"):
+                    assert cluster == (2, 1, 1) and ctas % 2 == 0, (ctx, name, cluster)        # cta_group::2 pairs
+    assert {"gemm_tc_kernel", "gemm_tc2_kernel", "gemv_ks_kernel"} <= seen_ksplit_kernels and n > 50000
