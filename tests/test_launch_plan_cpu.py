@@ -20,9 +20,19 @@ sys.path.insert(0, HERE)
 import test_engine_host_logic_cpu as HL  # noqa: E402
 
 SM_COUNT, MAX_SMEM = 148, 227 * 1024
+MANGLED = {}
+
+
+_PLANS = {}
 
 
 def plan(tmp_path, model, tp):
+    if (model, tp) not in _PLANS:
+        _PLANS[(model, tp)] = _plan(tmp_path, model, tp)
+    return _PLANS[(model, tp)]
+
+
+def _plan(tmp_path, model, tp):
     log = str(tmp_path / ("launch_%s_tp%d.log" % (model, tp)))
     env = dict(os.environ, LD_PRELOAD=HL.build_fake(), FAKE_CUDART_LAUNCH_LOG=log)
     r = subprocess.run([sys.executable, os.path.join(HERE, "support", "launch_plan_sweep.py"), model, str(tp)], env=env, capture_output=True, text=True, timeout=900)
@@ -34,6 +44,7 @@ def plan(tmp_path, model, tp):
             continue
         p = line.split()
         name = re.sub(r"^_ZN5llmlb\d+|^_Z\d+", "", p[0])
+        MANGLED[name] = p[0]
         out[ctx].append((name, tuple(map(int, p[1:4])), tuple(map(int, p[4:7])), int(p[7]), tuple(map(int, p[8:11])), int(p[11])))
     return out
 
@@ -57,3 +68,32 @@ def test_every_width_of_the_launch_plan_respects_co_residency_and_hardware_limit
                 if name.startswith("gemm_tc2_kernel"):
                     assert cluster == (2, 1, 1) and ctas % 2 == 0, (ctx, name, cluster)        # cta_group::2 pairs
     assert {"gemm_tc_kernel", "gemm_tc2_kernel", "gemv_ks_kernel"} <= seen_ksplit_kernels and n > 50000
+
+
+@pytest.mark.skipif(__import__("shutil").which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_every_kernel_launched_as_a_programmatic_dependent_waits_for_its_predecessor(built_lib, tmp_path):
+    """Launch plan x SASS: a kernel that the engine launches with the programmatic-stream-serialization attribute may start
+    while its predecessor is still running, so it MUST execute griddepcontrol.wait (SASS: ACQBULK) before touching what the
+    predecessor writes.  Every kernel name that appears with the attribute anywhere in the plans (all widths, tp 1 and 8) has
+    to contain that instruction; the companion test tests/test_sass_pdl_cpu.py bounds what may be loaded ahead of it."""
+    import glob
+    pdl_kernels, plain_kernels = set(), set()
+    for model, tp in (("8b", 1), ("8b", 8)):
+        for launches in plan(tmp_path, model, tp).values():
+            for name, grid, block, smem, cluster, pdl in launches:
+                (pdl_kernels if pdl else plain_kernels).add(MANGLED[name])
+    assert len(pdl_kernels) >= 10
+    waits = set()
+    for o in sorted(glob.glob(os.path.join(os.path.dirname(HERE), "llmlb_b200", "_build", "*.o"))):
+        txt = subprocess.run(["cuobjdump", "-sass", o], capture_output=True, text=True).stdout
+        for f in re.split(r"\n\s*Function : ", txt)[1:]:
+            if "ACQBULK" in f:
+                waits.add(f.split("\n", 1)[0].strip())
+    # Reviewed exception: tp_reduce_norm_kernel has no dependency wait on purpose — it must be resident while its producer
+    # GEMM is still pushing.  It orders itself through the exchange instead: it reads the residual row only after THIS rank's
+    # own words / end-of-grid flag of the collective arrived, which proves the local GEMM finished, whose own dependency wait
+    # covers everything before it (csrc/tp_exchange.cu; DESIGN.md section 5, "what went wrong" item 3 is the bug this fixed).
+    ordered_by_exchange = {k for k in pdl_kernels if "tp_reduce_norm_kernel" in k}
+    assert len(ordered_by_exchange) == 2
+    missing = sorted(k for k in pdl_kernels - ordered_by_exchange if k not in waits)
+    assert not missing, "launched as programmatic dependents without a griddepcontrol.wait: %s" % missing
