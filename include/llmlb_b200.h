@@ -89,6 +89,10 @@ typedef struct llmlb_engine_config {
 } llmlb_engine_config;
 
 int llmlb_engine_create(const llmlb_engine_config* cfg, llmlb_engine** out);
+/* Stops the scheduler, drops whatever is still queued or running and frees the device.  The ONE call that is not safe
+ * against the others: no call on `e` may be in progress (a thread blocked in llmlb_request_poll included) or start once
+ * this one has begun.  A gateway drains first (inference_gate.rs: reject new work, wait for in-flight bodies, then abort
+ * the rest with llmlb_request_cancel) and destroys the engine last. */
 void llmlb_engine_destroy(llmlb_engine* e);
 
 /* Tensor-parallel wiring (one process per GPU).  Each rank exports a CUDA IPC handle of its
