@@ -394,3 +394,55 @@ def test_scenario_config5_workload_shape_through_the_scheduler():
         assert h["free_kv_pages"] == h["total_kv_pages"] == kv_pages
         assert h["preemptions"] > 0 and h["tokens_prefill"] > sum(lens)                      # recomputation happened
         assert h["steps_prefill"] >= -(-sum(lens) // 2048)
+
+
+@inner
+def test_scenario_load_and_read_tensor_shard_slices():
+    """llmlb_engine_load_tensor takes the FULL Hugging Face tensor on every rank and keeps that rank's Megatron slice
+    (q/k/v/gate/up/lm_head by output rows, o/down by input columns, norms and the embedding replicated);
+    llmlb_engine_read_tensor returns the slice.  Under the fake runtime "device" memory is real memory, so the product's own
+    address arithmetic (fused qkv, interleaved gate/up rows) is checked against plain numpy slicing for tp = 1, 2 and 4."""
+    import numpy as np
+    ffi = _ffi()
+    M = dict(TINY, n_kv_heads=4, n_heads=16)
+    H, F, V, hd = M["hidden"], M["ffn"], M["vocab"], M["head_dim"]
+    full = {"model.embed_tokens.weight": (V, H), "model.norm.weight": (1, H), "lm_head.weight": (V, H)}
+    for l in range(M["n_layers"]):
+        p = "model.layers.%d." % l
+        full.update({p + "self_attn.q_proj.weight": (M["n_heads"] * hd, H), p + "self_attn.k_proj.weight": (M["n_kv_heads"] * hd, H),
+                     p + "self_attn.v_proj.weight": (M["n_kv_heads"] * hd, H), p + "self_attn.o_proj.weight": (H, M["n_heads"] * hd),
+                     p + "mlp.gate_proj.weight": (F, H), p + "mlp.up_proj.weight": (F, H), p + "mlp.down_proj.weight": (H, F),
+                     p + "input_layernorm.weight": (1, H), p + "post_attention_layernorm.weight": (1, H)})
+    rs = np.random.RandomState(0)
+    data = {k: rs.randint(0, 65536, size=s).astype(np.uint16) for k, s in full.items()}
+    by_rows = ("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj", "lm_head")
+    by_cols = ("o_proj", "down_proj")
+    for tp in (1, 2, 4):
+        engs = [ffi.Engine(M, tp_rank=r, tp_size=tp, max_seqs=2, max_ctx=256) for r in range(tp)]
+        try:
+            for r, e in enumerate(engs):
+                for name, a in data.items():
+                    e.load_tensor(name, a if a.shape[0] > 1 else a.reshape(-1))
+                for name, a in data.items():           # read everything back only after everything was loaded: slices must not overlap
+                    got = e.read_tensor(name, a.size)
+                    if any(k in name for k in by_rows):
+                        n = a.shape[0] // tp
+                        want = a[r * n:(r + 1) * n]
+                    elif any(k in name for k in by_cols):
+                        n = a.shape[1] // tp
+                        want = a[:, r * n:(r + 1) * n]
+                    else:
+                        want = a
+                    assert got.shape == want.shape and np.array_equal(got, want), (tp, r, name)
+            e = engs[0]
+            with pytest.raises(ffi.LlmlbError):
+                e.load_tensor("model.layers.0.mlp.up_proj.weight", data["model.layers.0.mlp.down_proj.weight"])      # transposed shape
+            with pytest.raises(ffi.LlmlbError):
+                e.load_tensor("model.layers.9.mlp.up_proj.weight", data["model.layers.0.mlp.up_proj.weight"])        # no such layer
+            with pytest.raises(ffi.LlmlbError):
+                e.read_tensor("model.rotary.inv_freq", 16)
+            with pytest.raises(ffi.LlmlbError):
+                e.read_tensor("lm_head.weight", 8)                                                                   # buffer too small
+        finally:
+            for e in engs:
+                e.close()
