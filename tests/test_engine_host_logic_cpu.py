@@ -446,3 +446,27 @@ def test_scenario_load_and_read_tensor_shard_slices():
         finally:
             for e in engs:
                 e.close()
+
+
+@inner
+def test_scenario_allocation_footprint_of_the_baseline_configurations_fits_a_b200():
+    """What the engine allocates (every cudaMalloc, counted by the fake runtime) for the BASELINE.json configurations, against
+    180 GB per GPU and against the sizes DESIGN.md section 3 states: bf16 matmul weights per rank, 2 x layers x kv_heads/tp x
+    64 x 128 x 2 B per KV page, and a remainder (embedding table, activations, workspaces, exchange region) under 3 GB."""
+    ffi = _ffi()
+    GB = 1e9
+    for tag, model, kw, weights_gb in (
+            ("configs[1] 8B batch 1", ffi.LLAMA3_8B, dict(max_seqs=8, max_ctx=1024), 15.01),
+            ("configs[2] 8B 64 streams", ffi.LLAMA3_8B, dict(max_seqs=64, max_ctx=1024), 15.01),
+            ("8B 128 x 8192 on one GPU", ffi.LLAMA3_8B, dict(max_seqs=128, max_ctx=8192), 15.01),
+            ("configs[3] 8B tp8 128 streams", ffi.LLAMA3_8B, dict(max_seqs=128, max_ctx=1024, tp_size=8, tp_rank=3), 15.01 / 8),
+            ("configs[4] 70B tp8 8192 ctx", ffi.LLAMA3_70B, dict(max_seqs=32, max_ctx=8192, tp_size=8, tp_rank=7), 139.0 / 8)):
+        with ffi.Engine(model, **kw) as e:
+            h, mi = e.health(), e.model_info()
+            tp = kw.get("tp_size", 1)
+            assert h["total_kv_pages"] == kw["max_seqs"] * kw["max_ctx"] // 64, tag
+            kv = h["total_kv_pages"] * model["n_layers"] * 2 * (model["n_kv_heads"] // tp) * 64 * 128 * 2
+            assert abs(mi["param_bytes"] / GB - weights_gb) < 0.02 * weights_gb + 0.01, (tag, mi["param_bytes"])
+            rest = h["used_memory_bytes"] - mi["param_bytes"] - kv
+            assert 0 < rest < 3 * GB, (tag, rest)
+            assert h["used_memory_bytes"] < 180 * GB, (tag, h["used_memory_bytes"])
