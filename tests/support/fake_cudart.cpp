@@ -24,6 +24,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,12 +41,35 @@ std::map<const void*, std::string> g_kernels;      // host stub -> mangled devic
 std::atomic<unsigned long long> g_seq{0};
 std::atomic<size_t> g_allocated{0};
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_tmaps{0};
 struct Ev { double t_ms; };
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 thread_local struct { dim3 grid, block; size_t smem; void* stream; } g_cfg;
-// cuTensorMapEncodeTiled stand-in: the descriptor is opaque to the host; zero it and report success
-int fake_encode_tiled(void* map, int, unsigned, void*, const void*, const void*, const void*, const void*, int, int, int, int) {
+// cuTensorMapEncodeTiled stand-in.  The descriptor stays opaque (zeroed), but the ARGUMENTS are checked against the rules
+// the driver documents for the call, so that a geometry whose tensor map the real driver would refuse fails here too:
+// rank 1..5, 16-byte aligned base, dims in [1, 2^32], strides multiples of 16 below 2^40, box dims in [1, 256], element
+// strides in [1, 8], inner box extent a multiple of 16 bytes and within the swizzle span (32 / 64 / 128 bytes).
+int fake_encode_tiled(void* map, int data_type, unsigned rank, void* base, const unsigned long long* dims, const unsigned long long* strides,
+                      const unsigned* box, const unsigned* elem_strides, int interleave, int swizzle, int, int) {
+  static const int kElemBytes[] = {1, 2, 4, 4, 8, 8, 2, 4, 8, 2, 4, 4, 4};   // CUtensorMapDataType order: u8,u16,u32,i32,u64,i64,f16,f32,f64,bf16,...
+  const int eb = (data_type >= 0 && data_type < int(sizeof kElemBytes / sizeof *kElemBytes)) ? kElemBytes[data_type] : 0;
+  bool ok = map && eb && rank >= 1 && rank <= 5 && base && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && dims && box && elem_strides && interleave == 0;
+  for (unsigned i = 0; ok && i < rank; ++i) {
+    ok = dims[i] >= 1 && dims[i] <= (1ull << 32) && box[i] >= 1 && box[i] <= 256 && elem_strides[i] >= 1 && elem_strides[i] <= 8;
+    if (ok && i + 1 < rank) ok = strides && strides[i] % 16 == 0 && strides[i] < (1ull << 40) && strides[i] > 0;
+  }
+  if (ok) {
+    const unsigned long long inner = (unsigned long long)box[0] * unsigned(eb);
+    const unsigned long long span = swizzle == 1 ? 32 : swizzle == 2 ? 64 : swizzle >= 3 ? 128 : ~0ull;   // CU_TENSOR_MAP_SWIZZLE_{32,64,128}B(+ATOM variants)
+    ok = inner % 16 == 0 && inner <= span && swizzle >= 0 && swizzle <= 6;
+  }
+  if (!ok) {
+    fprintf(stderr, "fake cudart: cuTensorMapEncodeTiled would be refused (type %d rank %u base %p box0 %u swizzle %d)\n", data_type, rank, base,
+            box ? box[0] : 0u, swizzle);
+    return 1;   // CUDA_ERROR_INVALID_VALUE
+  }
   memset(map, 0, 128);
+  ++g_tmaps;
   return 0;
 }
 }  // namespace
@@ -242,4 +266,5 @@ cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, vo
 }
 // for the tests: how many launches the engine issued
 unsigned long long fake_cudart_launches(void) { return g_launches.load(); }
+unsigned long long fake_cudart_tensor_maps(void) { return g_tmaps.load(); }
 }  // extern "C"
