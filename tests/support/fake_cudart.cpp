@@ -37,6 +37,7 @@ struct Alloc { int fd = -1; size_t size = 0; bool dirty = false; };   // dirty: 
 std::mutex g_mu;
 std::map<void*, Alloc> g_allocs;
 std::map<void*, size_t> g_opened;
+std::map<const void*, size_t> g_smem_optin;          // cudaFuncAttributeMaxDynamicSharedMemorySize per kernel function
 std::map<const void*, std::string> g_kernels;      // host stub -> mangled device name (__cudaRegisterFunction)
 std::atomic<unsigned long long> g_seq{0};
 std::atomic<size_t> g_allocated{0};
@@ -76,6 +77,7 @@ int fake_encode_tiled(void* map, int data_type, unsigned rank, void* base, const
 
 extern "C" {
 static void mark_dirty(void* d);
+static bool smem_allowed(const void* fn, size_t smem);
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
@@ -193,11 +195,13 @@ static void log_launch(const void* fn, dim3 g, dim3 b, size_t smem, dim3 cluster
   fflush(f);
 }
 cudaError_t cudaLaunchKernel(const void* fn, dim3 g, dim3 b, void**, size_t smem, cudaStream_t) {
+  if (!smem_allowed(fn, smem)) return cudaErrorInvalidValue;
   ++g_launches;
   log_launch(fn, g, b, smem, dim3(1, 1, 1), 0);
   return cudaSuccess;
 }
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* fn, void**) {
+  if (!smem_allowed(fn, c->dynamicSmemBytes)) return cudaErrorInvalidValue;
   ++g_launches;
   dim3 cluster(1, 1, 1);
   int pdl = 0;
@@ -208,7 +212,28 @@ cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* fn, voi
   log_launch(fn, c->gridDim, c->blockDim, c->dynamicSmemBytes, cluster, pdl);
   return cudaSuccess;
 }
-cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+// More than 48 KiB of dynamic shared memory needs an opt-in per kernel FUNCTION (each template instantiation is its own):
+// the opt-in is recorded here and every launch is checked against it, like the driver does (cudaErrorInvalidValue).
+cudaError_t cudaFuncSetAttribute(const void* fn, cudaFuncAttribute attr, int value) {
+  if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+    if (value > 227 * 1024) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_smem_optin[fn] = size_t(value);
+  }
+  return cudaSuccess;
+}
+static bool smem_allowed(const void* fn, size_t smem) {
+  if (smem <= 48 * 1024) return true;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_smem_optin.find(fn);
+  const bool ok = it != g_smem_optin.end() && smem <= it->second;
+  if (!ok) {
+    auto k = g_kernels.find(fn);
+    fprintf(stderr, "fake cudart: launch of %s with %zu bytes of dynamic shared memory without a sufficient opt-in (%zu)\n",
+            k == g_kernels.end() ? "?" : k->second.c_str(), smem, it == g_smem_optin.end() ? size_t(0) : it->second);
+  }
+  return ok;
+}
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetDriverEntryPoint(const char* sym, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* st) {
   const bool known = sym && !strcmp(sym, "cuTensorMapEncodeTiled");

@@ -6,6 +6,9 @@ CUDA runtime and logs every kernel launch for EVERY prefill width 1..2048 and de
     partial tiles and spins on a per-tile counter; the gemv_ks gather variant waits for owner CTAs) must fit the GPU in one
     wave — at most 148 CTAs at one CTA per SM.  A wider grid would hang the device; GPU tests only ever try a few widths.
   * hardware limits: <= 1024 threads per CTA, <= 227 KiB dynamic shared memory, cluster size <= 16 and grid divisible by it.
+  * every launch with more than 48 KiB of dynamic shared memory was preceded by the opt-in for THAT kernel function (each
+    template instantiation needs its own cudaFuncSetAttribute; a missing one only fails at the widths that pick it) — the
+    fake runtime refuses the launch otherwise, like the driver.
   * every TMA descriptor the engine builds for these geometries passes the argument rules of cuTensorMapEncodeTiled (checked
     inside the fake runtime's stand-in: alignment, dims, strides, box dims, swizzle span); a refused descriptor fails engine
     creation here exactly as it would on the device.
