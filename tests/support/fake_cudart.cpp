@@ -46,6 +46,15 @@ std::atomic<uint64_t> g_tmaps{0};
 struct Ev { double t_ms; };
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 thread_local struct { dim3 grid, block; size_t smem; void* stream; } g_cfg;
+// Stream capture (thread-local mode, as the engine uses it): between Begin and End the capturing thread may only enqueue
+// work; synchronous calls are refused like the driver refuses them (cudaErrorStreamCaptureUnsupported) and poison the capture.
+thread_local bool g_capturing = false, g_capture_poisoned = false;
+inline bool illegal_in_capture(const char* what) {
+  if (!g_capturing) return false;
+  g_capture_poisoned = true;
+  fprintf(stderr, "fake cudart: %s during stream capture\n", what);
+  return true;
+}
 // cuTensorMapEncodeTiled stand-in.  The descriptor stays opaque (zeroed), but the ARGUMENTS are checked against the rules
 // the driver documents for the call, so that a geometry whose tensor map the real driver would refuse fails here too:
 // rank 1..5, 16-byte aligned base, dims in [1, 2^32], strides multiples of 16 below 2^40, box dims in [1, 256], element
@@ -80,13 +89,14 @@ static void mark_dirty(void* d);
 static bool smem_allowed(const void* fn, size_t smem);
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return illegal_in_capture("cudaDeviceSynchronize") ? cudaErrorStreamCaptureUnsupported : cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "fake cudart"; }
 // "Device" allocations are anonymous shared memory (memfd) so that another PROCESS can map them through the IPC-handle
 // calls, the way tensor-parallel ranks map each other's exchange regions: zero-filled like calloc, nothing named in
 // /dev/shm, gone with the process however it dies.
 cudaError_t cudaMalloc(void** p, size_t n) {
+  if (illegal_in_capture("cudaMalloc")) return cudaErrorStreamCaptureUnsupported;
   if (!n) n = 1;
   const int fd = memfd_create("fakecuda", 0);
   void* m = MAP_FAILED;
@@ -119,7 +129,7 @@ cudaError_t cudaMemGetInfo(size_t* fr, size_t* total) {
   *fr = *total - (g_allocated.load() < *total ? g_allocated.load() : 0);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (d && s && n) { mark_dirty(d); memmove(d, s, n); } return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (illegal_in_capture("cudaMemcpy")) return cudaErrorStreamCaptureUnsupported; if (d && s && n) { mark_dirty(d); memmove(d, s, n); } return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (d && s && n) { mark_dirty(d); memmove(d, s, n); } return cudaSuccess; }
 cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind) {
   mark_dirty(d);
@@ -150,22 +160,33 @@ static void fake_memset(void* d, int v, size_t n) {
   mark_dirty(d);
   memset(d, v, n);
 }
-cudaError_t cudaMemset(void* d, int v, size_t n) { fake_memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { if (illegal_in_capture("cudaMemset")) return cudaErrorStreamCaptureUnsupported; fake_memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { fake_memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = static_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return illegal_in_capture("cudaStreamSynchronize") ? cudaErrorStreamCaptureUnsupported : cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(new Ev{now_ms()}); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<Ev*>(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { reinterpret_cast<Ev*>(e)->t_ms = now_ms(); return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return illegal_in_capture("cudaEventSynchronize") ? cudaErrorStreamCaptureUnsupported : cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
   const double d = reinterpret_cast<Ev*>(b)->t_ms - reinterpret_cast<Ev*>(a)->t_ms;
   *ms = float(d > 0 ? d : 0.001);
   return cudaSuccess;
 }
-cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaSuccess; }
-cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = static_cast<cudaGraph_t>(malloc(8)); return cudaSuccess; }
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+  if (g_capturing) return cudaErrorIllegalState;
+  g_capturing = true;
+  g_capture_poisoned = false;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {
+  if (!g_capturing) return cudaErrorIllegalState;
+  g_capturing = false;
+  if (g_capture_poisoned) { *g = nullptr; return cudaErrorStreamCaptureInvalidated; }
+  *g = static_cast<cudaGraph_t>(malloc(8));
+  return cudaSuccess;
+}
 cudaError_t cudaGraphInstantiate(cudaGraphExec_t* x, cudaGraph_t, unsigned long long) { *x = static_cast<cudaGraphExec_t>(malloc(8)); return cudaSuccess; }
 // One decode step = one graph launch.  FAKE_CUDART_STEP_US gives it a duration (so that deadlines and queue timeouts can
 // expire while a request is running), FAKE_CUDART_FAIL_AFTER=n makes the n-th graph launch — and every launch after it —
