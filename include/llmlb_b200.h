@@ -224,9 +224,9 @@ enum { LLMLB_EPI_STORE_BF16 = 0,   /* out_bf16[t,n]  = acc                      
 int llmlb_op_gemv(const void* w_bf16, const void* x, const void* gain_bf16, float eps, void* out,
                   uint32_t n_tokens, uint32_t n_out, uint32_t k, uint32_t epilogue,
                   uint32_t out_stride, void* stream);
-/* prefill / batched path: out[t,n] = sum_k x[t,k]*W[n,k] on tensor cores.
- * impl 0 = tcgen05+TMEM+TMA tiles, 1 = mma.sync, 2 = tcgen05 with the stream-K work split
- * (n_tokens <= 128; opt-in experiment). x is bf16 [n_tokens,k]. */
+/* prefill / batched path: out[t,n] = sum_k x[t,k]*W[n,k] on tensor cores (tcgen05 + TMEM + TMA tiles).
+ * impl must be 0: the round-1 mma.sync (1) and stream-K (2) variants left the library (tools/experiments/) and return
+ * LLMLB_E_UNSUPPORTED.  x is bf16 [n_tokens,k]; k a multiple of 8; SILU_MUL needs an even n_out (interleaved gate/up rows). */
 int llmlb_op_gemm(const void* w_bf16, const void* x_bf16, void* out, uint32_t n_tokens,
                   uint32_t n_out, uint32_t k, uint32_t epilogue, uint32_t out_stride,
                   uint32_t impl, void* stream);

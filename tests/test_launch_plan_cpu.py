@@ -103,3 +103,24 @@ def test_every_kernel_launched_as_a_programmatic_dependent_waits_for_its_predece
     assert len(ordered_by_exchange) == 2
     missing = sorted(k for k in pdl_kernels - ordered_by_exchange if k not in waits)
     assert not missing, "launched as programmatic dependents without a griddepcontrol.wait: %s" % missing
+
+
+def test_op_gemm_accepts_arbitrary_shapes_within_the_same_limits(built_lib, tmp_path):
+    """The public kernel-level entry point takes any (tokens, n_out, k) with k % 8 == 0 — ragged last tiles, n_out that is not a
+    multiple of the 128-row tile, K shorter than one 64-wide slab: 6000 random shapes, each accepted, each launch within one
+    wave for the K-split kernels, with its shared-memory opt-in and legal TMA descriptors (checked by the fake runtime)."""
+    log = str(tmp_path / "op.log")
+    env = dict(os.environ, LD_PRELOAD=HL.build_fake(), FAKE_CUDART_LAUNCH_LOG=log)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "support", "op_gemm_sweep.py"), "6000", "1"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    calls = launches = 0
+    for line in open(log):
+        if line.startswith("###"):
+            calls += 1
+            ctx = line
+            continue
+        p = line.split()
+        launches += 1
+        ctas = int(p[1]) * int(p[2]) * int(p[3])
+        assert "gemm_tc" in p[0] and ctas <= SM_COUNT and int(p[7]) <= MAX_SMEM, (ctx, line)
+    assert calls > 5000 and launches >= calls
