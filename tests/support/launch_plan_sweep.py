@@ -46,6 +46,15 @@ def main():
             e.pause(False)
             for r in rids:
                 drain(e, r)
+    # long contexts: prompts chunked over two prefill steps (the second attends to cached pages), then decode over ~3900 tokens
+    for B in (1, 3, 5, 32):
+        mark("long B=%d" % B)
+        for e in engs:
+            e.pause(True)
+            rids = [e.submit([1] * (3800 + 7 * i), 4, ignore_eos=True) for i in range(B)]
+            e.pause(False)
+            for r in rids:
+                drain(e, r)
     for e in engs:
         e.close()
 
