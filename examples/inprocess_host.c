@@ -148,7 +148,8 @@ static int serve_one(llmlb_engine* eng, void* lm, void* gate, void* tok, const O
     emit_event(acc, sse_api, 4, id, o->model_id, NULL, 0, 0);
   }
   llmlb_request_release(eng, rid);
-  const uint64_t ms = (uint64_t)(now_ms() - t0);           /* request start -> last byte, as proxy.rs:154-160 */
+  uint64_t ms = (uint64_t)(now_ms() - t0);                 /* request start -> last byte ... */
+  if (ms < 1) ms = 1;                                      /* ... clamped like `elapsed().as_millis().max(1)`, proxy.rs:154-160 */
 
   /* end of stream: what the relay learned from the bytes it forwarded */
   int64_t u[3];

@@ -17,6 +17,7 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <fstream>
@@ -353,7 +354,7 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     TokenUsage tu; tu.has_in = tu.has_out = tu.has_total = true; tu.in = prompt_tokens; tu.out = completion_tokens; tu.total = prompt_tokens + completion_tokens;
     lease.complete_with_tokens(success ? RequestOutcome::Success : RequestOutcome::Error, ms, &tu);
   }
-  if (success && completion_tokens) G.lm.update_tps(ep, pm.base, api, completion_tokens, ms);
+  if (success && completion_tokens) G.lm.update_tps(ep, pm.base, api, completion_tokens, std::max<uint64_t>(1, ms));   // `.as_millis().max(1)`: openai.rs:1241-1245, proxy.rs:157
   const char* fr = finish == LLMLB_FINISH_STOP ? "stop" : "length";
   // failures map like the gateway maps an upstream's (openai.rs:862-882, openai_util.rs:86-134)
   const bool failed = finish != LLMLB_FINISH_STOP && finish != LLMLB_FINISH_LENGTH && !(client_gone && completion_tokens > 0);

@@ -55,8 +55,7 @@ def test_c_host_serves_in_process_and_agrees_with_the_ctypes_host(built_lib, tmp
         assert len(got_tokens[-1]) == n_out
         state.update_tps(n_out, rec["ms"])
     assert final["request_count"] == n_req and final["stats"][:4] == [0, n_req, n_req, 0] and final["in_flight"] == 0
-    if all(x["ms"] > 0 for x in per):
-        assert final["tps_ema"] == state.tps_ema
+    assert all(x["ms"] >= 1 for x in per) and final["tps_ema"] == state.tps_ema          # durations are clamped to >= 1 ms (proxy.rs:157)
     # the same requests through the Python host of the same library
     with ffi.Engine(MODEL, model_id="llama-tiny", max_seqs=8, max_ctx=1024, seed=0) as eng:
         for i in range(n_req):
