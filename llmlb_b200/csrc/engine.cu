@@ -472,9 +472,12 @@ struct llmlb_engine {
     }
   }
   void plan_log_locked(uint32_t type) { if (plan_on && plan.leader) { std::lock_guard<std::mutex> lk(mu); plan_log(type); } }
-  void finish_request(const ReqPtr& r, uint32_t reason);
-  void release_resources(const ReqPtr& r);
-  void preempt(const ReqPtr& r);
+  // by value: callers pass elements of `running` / `waiting`, and these functions erase from those containers — a reference
+  // would dangle, and for a request the client already released the container holds the LAST owner (found by ASan over the
+  // fake CUDA runtime: heap-use-after-free in finish_request on cancel of a released, running request)
+  void finish_request(ReqPtr r, uint32_t reason);
+  void release_resources(ReqPtr r);
+  void preempt(ReqPtr r);
   void expire_requests();     // leader / single rank: queue timeouts and request deadlines (time-based)
   std::atomic<uint64_t> preemptions{0};
   cudaEvent_t get_event();
@@ -1182,7 +1185,7 @@ int llmlb_engine::run_decode(const std::vector<ReqPtr>& batch) {
   return LLMLB_OK;
 }
 
-void llmlb_engine::release_resources(const ReqPtr& r) {  // mu held
+void llmlb_engine::release_resources(ReqPtr r) {  // mu held
   if (r->slot >= 0) {
     free_slots.push_back(r->slot);
     r->slot = -1;
@@ -1196,7 +1199,7 @@ void llmlb_engine::release_resources(const ReqPtr& r) {  // mu held
 // Evict a running sequence: its pages and slot go back to the pools and it returns to the HEAD of the
 // queue with its context extended by what it generated (recomputed at re-admission).  Only called
 // with nothing in flight, so every launched token has been harvested.  mu held.
-void llmlb_engine::preempt(const ReqPtr& r) {
+void llmlb_engine::preempt(ReqPtr r) {
   r->prompt.insert(r->prompt.end(), r->gen.begin() + r->gen_in_prompt, r->gen.end());
   r->gen_in_prompt = uint32_t(r->gen.size());
   r->prefilled = 0;
@@ -1207,7 +1210,7 @@ void llmlb_engine::preempt(const ReqPtr& r) {
   preemptions++;
 }
 
-void llmlb_engine::finish_request(const ReqPtr& r, uint32_t reason) {  // mu held
+void llmlb_engine::finish_request(ReqPtr r, uint32_t reason) {  // mu held
   if (r->finished) return;
   r->finished = true;
   r->finish_reason = reason;

@@ -36,10 +36,13 @@ def test_engine_host_logic_over_the_fake_cuda_runtime(built_lib):
     if INNER:
         pytest.skip("already inside")
     env = dict(os.environ, LD_PRELOAD=build_fake(), LLMLB_FAKE_CUDART="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider", "-k", "scenario"],
-                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
-    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
+    # two child sessions: steps that take no time at all, and (for the scenarios that need requests to BE running while the
+    # test acts on them) decode steps of 2 ms.  -s: a sanitizer report must reach the log, not pytest's capture file
+    for extra_env, select in (({}, "scenario and not slowstep"), ({"FAKE_CUDART_STEP_US": "2000"}, "slowstep")):
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-s", "-p", "no:cacheprovider", "-k", select],
+                           capture_output=True, text=True, timeout=900, env=dict(env, **extra_env), cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-3000:]
+        assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -470,3 +473,101 @@ def test_scenario_allocation_footprint_of_the_baseline_configurations_fits_a_b20
             rest = h["used_memory_bytes"] - mi["param_bytes"] - kv
             assert 0 < rest < 3 * GB, (tag, rest)
             assert h["used_memory_bytes"] < 180 * GB, (tag, h["used_memory_bytes"])
+
+
+@inner
+def test_scenario_random_api_call_sequences_never_break_the_engine():
+    """A stateful random walk over the whole C ABI of one engine — submit (valid and invalid), poll, cancel, release (also
+    twice, also of ids that never existed), pause toggles, health, model info, tensor load / read, the debug hooks while
+    requests are in flight (they must refuse, not interfere) — 6000 operations.  Every call returns OK or a documented
+    error code; at the end everything drains and every page is back.  (Runs under ASan/TSan in the sanitizer pass.)"""
+    import random
+    import numpy as np
+    ffi = _ffi()
+    rs = random.Random(3)
+    ok_errors = {ffi.E_INVALID_ARG, ffi.E_QUEUE_FULL, ffi.E_TIMEOUT, getattr(ffi, "E_NOT_FOUND", -4), getattr(ffi, "E_UNSUPPORTED", -6)}
+    with ffi.Engine(TINY, max_seqs=4, max_ctx=512, kv_pages=20, queue_max=16) as eng:
+        live, dead = [], []
+        paused = False
+        n_ok = n_err = 0
+        for step in range(6000):
+            op = rs.randrange(12)
+            try:
+                if op <= 2:
+                    n = rs.choice([0, 1, 5, 64, 65, 200, 511, 600])
+                    m = rs.choice([0, 1, 3, 40, 300])
+                    ids = [rs.randrange(-1 if rs.random() < 0.02 else 0, TINY["vocab"] + (1 if rs.random() < 0.02 else 0)) for _ in range(n)]
+                    live.append(eng.submit(ids, m, ignore_eos=rs.random() < 0.5, temperature=rs.choice([0.0, 0.5, -1.0]), stop_ids=rs.choice([(), (0,), (5, 6)])))
+                elif op <= 5 and live:
+                    rid = rs.choice(live)
+                    evs = eng.poll(rid, cap=rs.choice([1, 4, 256]), timeout_ms=rs.choice([0, 0, 1]))
+                    assert all(a["index"] <= b["index"] for a, b in zip(evs, evs[1:]))
+                elif op == 6 and live:
+                    eng.cancel(rs.choice(live))
+                elif op == 7 and (live or dead):
+                    rid = rs.choice(live + dead)
+                    eng.release(rid)
+                    if rid in live:
+                        live.remove(rid); dead.append(rid)
+                elif op == 8:
+                    paused = not paused
+                    eng.pause(paused)
+                elif op == 9:
+                    h = eng.health()
+                    assert h["free_kv_pages"] <= h["total_kv_pages"] == 20
+                    eng.model_info()
+                elif op == 10:
+                    name = rs.choice(["model.norm.weight", "model.layers.1.mlp.up_proj.weight", "model.layers.7.mlp.up_proj.weight", "nope"])
+                    if rs.random() < 0.5:
+                        eng.read_tensor(name, rs.choice([16, 1 << 20]))
+                    else:
+                        eng.load_tensor(name, np.zeros(rs.choice([(1, 512), (1024, 512), (3, 3)]), dtype=np.uint16))
+                elif op == 11:
+                    if rs.random() < 0.5:
+                        eng.debug_prefill_logits([1, 2, 3])
+                    else:
+                        eng.debug_reset()
+                n_ok += 1
+            except ffi.LlmlbError as e:
+                assert e.code in ok_errors, (step, op, e)
+                n_err += 1
+        eng.pause(False)
+        try:
+            eng.debug_reset()
+        except ffi.LlmlbError:
+            pass
+        for rid in live:
+            eng.release(rid)
+        h = settle(eng, 60)
+        assert h["free_kv_pages"] == h["total_kv_pages"] == 20 and n_ok > 2000 and n_err > 300, (n_ok, n_err, h)
+
+
+@inner
+def test_scenario_slowstep_release_of_a_running_request_does_not_touch_its_neighbour():
+    """Regression (found by AddressSanitizer over the fake runtime, fixed in engine.cu): finish_request took the request by
+    reference to an element of `running` and erased that element — the reference then named the NEXT running request: the
+    released request was never dropped from the id table (a leak per fire-and-forget release), the neighbour could be dropped
+    instead while still running (its client would then get "unknown request id", and the last owner died inside erase:
+    heap-use-after-free).  Needs requests that are running while the test acts, hence 2 ms decode steps."""
+    assert os.environ.get("FAKE_CUDART_STEP_US") == "2000"
+    ffi = _ffi()
+    with ffi.Engine(TINY, max_seqs=4, max_ctx=512) as eng:
+        a = eng.submit([1, 2, 3], 300, ignore_eos=True)
+        b = eng.submit([4, 5, 6], 120, ignore_eos=True)
+        c = eng.submit([7, 8, 9], 120, ignore_eos=True)
+        for rid in (a, b, c):                                     # all three are running (each has produced a token)
+            t0 = time.time()
+            while not eng.poll(rid, cap=1, timeout_ms=100):
+                assert time.time() - t0 < 10
+        eng.release(a)                                            # in flight: cancelled by the scheduler, then dropped
+        eng.release(b)                                            # its neighbour in `running`, also fire-and-forget
+        time.sleep(0.1)
+        for rid in (a, b):
+            with pytest.raises(ffi.LlmlbError) as ei:             # both are gone from the id table (a second release finds nothing)
+                eng.release(rid)
+            assert ei.value.code == ffi.E_NOT_FOUND
+        evs = drain(eng, c, 30)                                   # the third one is untouched: every token, still pollable
+        assert evs[-1]["finish_reason"] == LENGTH and evs[-1]["completion_tokens"] == 120
+        eng.release(c)
+        h = settle(eng)
+        assert h["free_kv_pages"] == h["total_kv_pages"]

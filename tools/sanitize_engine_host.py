@@ -55,10 +55,14 @@ def main():
                UBSAN_OPTIONS="print_stacktrace=1")
     log = os.path.join(out, "run.log")
     with open(log, "w") as f:
-        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_engine_host_logic_cpu.py"), "-q", "-p", "no:cacheprovider",
-                            "-k", "scenario"], stdout=f, stderr=subprocess.STDOUT, env=env, cwd=ROOT, timeout=3000)
+        # -s: sanitizer reports are written to fd 2; under pytest's capture they would go to a temp file and vanish with _exit(1)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_engine_host_logic_cpu.py"), "-q", "-s", "-p", "no:cacheprovider",
+                            "-k", "scenario and not slowstep"], stdout=f, stderr=subprocess.STDOUT, env=env, cwd=ROOT, timeout=3000)
+        r1 = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_engine_host_logic_cpu.py"), "-q", "-s", "-p", "no:cacheprovider",
+                             "-k", "slowstep"], stdout=f, stderr=subprocess.STDOUT, env=dict(env, FAKE_CUDART_STEP_US="2000"), cwd=ROOT, timeout=3000)
+        r.returncode = r.returncode or r1.returncode
     with open(log, "a") as f:        # the server is instrumented itself: only the fake runtime is preloaded (by the test module)
-        r2 = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_server_real_engine_cpu.py"), "-q", "-p", "no:cacheprovider"],
+        r2 = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_server_real_engine_cpu.py"), "-q", "-s", "-p", "no:cacheprovider"],
                             stdout=f, stderr=subprocess.STDOUT, cwd=ROOT, timeout=3000,
                             env=dict(os.environ, LLMLB_SERVER_BIN=server, LLMLB_SERVER_STDERR=os.path.join(out, "server_stderr.log"),
                                      LLMLB_SERVER_PRELOAD_FIRST=rt if kind == "address" else "",       # ASan insists on being first in the list
