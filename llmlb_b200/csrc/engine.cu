@@ -1131,13 +1131,18 @@ int llmlb_engine::run_prefill(const std::vector<ReqPtr>& reqs, const std::vector
     LLMLB_CUDA_CHECK(cudaMemcpyAsync(step.host_ids, B.out_ids, R * 4, cudaMemcpyDeviceToHost, st));
   }
   LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_end, st));
-  for (size_t i = 0; i < reqs.size(); ++i) {
-    reqs[i]->prefilled += take[i];
-    if (reqs[i]->prefilled == reqs[i]->prompt.size()) reqs[i]->launched = reqs[i]->harvested + 1;
+  {
+    // bookkeeping that API threads read (health counters; `inflight` in the debug hooks and the plan-channel attach) is
+    // written under mu — ThreadSanitizer over the fake CUDA runtime flagged the deque (step_mu alone is held here)
+    std::lock_guard<std::mutex> lk(mu);
+    for (size_t i = 0; i < reqs.size(); ++i) {
+      reqs[i]->prefilled += take[i];
+      if (reqs[i]->prefilled == reqs[i]->prompt.size()) reqs[i]->launched = reqs[i]->harvested + 1;
+    }
+    steps_prefill++;
+    tokens_prefill += T;
+    inflight.push_back(std::move(step));
   }
-  steps_prefill++;
-  tokens_prefill += T;
-  inflight.push_back(std::move(step));
   return LLMLB_OK;
 }
 
@@ -1178,10 +1183,13 @@ int llmlb_engine::run_decode(const std::vector<ReqPtr>& batch) {
   step.host_ids = h_out[(out_seq++) % kRing];
   LLMLB_CUDA_CHECK(cudaMemcpyAsync(step.host_ids, B.out_ids, nb * 4, cudaMemcpyDeviceToHost, st));
   LLMLB_CUDA_CHECK(cudaEventRecord(step.ev_end, st));
-  for (auto& r : batch) r->launched++;
-  steps_decode++;
-  tokens_decode += nb;
-  inflight.push_back(std::move(step));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& r : batch) r->launched++;
+    steps_decode++;
+    tokens_decode += nb;
+    inflight.push_back(std::move(step));
+  }
   return LLMLB_OK;
 }
 
@@ -1234,8 +1242,12 @@ void llmlb_engine::finish_request(ReqPtr r, uint32_t reason) {  // mu held
 }
 
 void llmlb_engine::harvest_one() {
-  InflightStep step = std::move(inflight.front());
-  inflight.pop_front();
+  InflightStep step;
+  {
+    std::lock_guard<std::mutex> lk(mu);      // readers of `inflight` on API threads hold mu
+    step = std::move(inflight.front());
+    inflight.pop_front();
+  }
   cudaError_t ce = cudaEventSynchronize(step.ev_end);
   float ms = 0.f;
   if (ce == cudaSuccess) cudaEventElapsedTime(&ms, step.ev_start, step.ev_end);

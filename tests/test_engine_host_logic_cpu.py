@@ -571,3 +571,62 @@ def test_scenario_slowstep_release_of_a_running_request_does_not_touch_its_neigh
         eng.release(c)
         h = settle(eng)
         assert h["free_kv_pages"] == h["total_kv_pages"]
+
+
+@inner
+def test_scenario_concurrent_random_walks_share_requests_across_threads():
+    """Six threads run the random walk of the previous scenario against ONE engine and ONE shared list of request ids, so
+    a thread polls what another cancels, releases what a third one is draining, and toggles pause under everybody: the
+    interleavings the id-table bug above needed, thousands of times.  Every call returns OK or a documented error; in the
+    end the engine drains and every page is back."""
+    import random
+    ffi = _ffi()
+    ok_errors = {ffi.E_INVALID_ARG, ffi.E_QUEUE_FULL, ffi.E_TIMEOUT, ffi.E_NOT_FOUND, ffi.E_UNSUPPORTED}
+    with ffi.Engine(TINY, max_seqs=6, max_ctx=512, kv_pages=30, queue_max=64) as eng:
+        ids, lock, errors = [], threading.Lock(), []
+
+        def walk(seed):
+            rs = random.Random(seed)
+            try:
+                for _ in range(1500):
+                    op = rs.randrange(10)
+                    with lock:
+                        rid = rs.choice(ids) if ids else None
+                    try:
+                        if op <= 2:
+                            n, m = rs.choice([1, 5, 64, 65, 200]), rs.choice([1, 3, 40, 200])
+                            new = eng.submit([rs.randrange(TINY["vocab"]) for _ in range(n)], m, ignore_eos=rs.random() < 0.7, stop_ids=rs.choice([(), (0,)]))
+                            with lock:
+                                ids.append(new)
+                        elif op <= 5 and rid is not None:
+                            evs = eng.poll(rid, cap=rs.choice([1, 8, 256]), timeout_ms=rs.choice([0, 0, 1]))
+                            assert all(a["index"] <= b["index"] for a, b in zip(evs, evs[1:]))
+                        elif op == 6 and rid is not None:
+                            eng.cancel(rid)
+                        elif op == 7 and rid is not None:
+                            eng.release(rid)
+                            with lock:
+                                if rid in ids and rs.random() < 0.8:
+                                    ids.remove(rid)                      # sometimes the id stays listed: double releases, polls of dead ids
+                        elif op == 8:
+                            eng.pause(rs.random() < 0.3)
+                        else:
+                            h = eng.health()
+                            assert h["free_kv_pages"] <= h["total_kv_pages"] == 30
+                    except ffi.LlmlbError as e:
+                        assert e.code in ok_errors, e
+            except Exception as e:                                       # noqa: BLE001
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=walk, args=(s,)) for s in range(6)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errors, errors[:3]
+        eng.pause(False)
+        for rid in list(ids):
+            try:
+                eng.release(rid)
+            except ffi.LlmlbError:
+                pass
+        h = settle(eng, 60)
+        assert h["free_kv_pages"] == h["total_kv_pages"] == 30
