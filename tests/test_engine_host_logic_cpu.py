@@ -630,3 +630,99 @@ def test_scenario_concurrent_random_walks_share_requests_across_threads():
                 pass
         h = settle(eng, 60)
         assert h["free_kv_pages"] == h["total_kv_pages"] == 30
+
+
+def _tp_rank_random(rank, world, handles, barrier, name, out_q):
+    try:
+        import random
+        os.environ["FAKE_CUDART_STEP_US"] = "100"
+        ffi = _ffi()
+        eng = ffi.Engine(TINY, model_id="tp-plan", device=0, tp_rank=rank, tp_size=world, max_seqs=4, max_ctx=512, kv_pages=10, queue_max=32,
+                         queue_timeout_ms=10, request_timeout_ms=40, seed=0)
+        handles[rank * 64:(rank + 1) * 64] = list(eng.tp_export())
+        barrier.wait(60)
+        blob = bytes(handles[:])
+        eng.tp_import([blob[r * 64:(r + 1) * 64] for r in range(world)])
+        barrier.wait(60)
+        if rank == 0:
+            eng.tp_plan_channel(name)
+        barrier.wait(60)
+        if rank != 0:
+            eng.tp_plan_channel(name)
+        barrier.wait(60)
+        res = {"finish": {}}
+        if rank == 0:
+            rs = random.Random(11)
+            live = []
+            for _ in range(700):
+                op = rs.randrange(10)
+                try:
+                    if op <= 3:
+                        live.append(eng.submit([rs.randrange(TINY["vocab"]) for _ in range(rs.choice([1, 30, 64, 65, 150]))], rs.choice([1, 5, 40, 300]),
+                                               ignore_eos=True, temperature=rs.choice([0.0, 0.8]), seed=rs.randrange(100)))
+                    elif op <= 5 and live:
+                        for e in eng.poll(rs.choice(live), timeout_ms=rs.choice([0, 1])):
+                            if e["finish_reason"]:
+                                res["finish"][e["finish_reason"]] = res["finish"].get(e["finish_reason"], 0) + 1
+                    elif op == 6 and live:
+                        eng.cancel(rs.choice(live))
+                    elif op == 7 and live:
+                        eng.release(live.pop(rs.randrange(len(live))))
+                    elif op == 8:
+                        eng.pause(rs.random() < 0.25)
+                    else:
+                        time.sleep(rs.choice([0, 0.001, 0.02]))              # lets queue timeouts and deadlines expire on the leader's clock
+                except ffi.LlmlbError as e:
+                    assert e.code in (ffi.E_QUEUE_FULL, ffi.E_INVALID_ARG, ffi.E_NOT_FOUND), e
+            eng.pause(False)
+            for r in live:
+                eng.release(r)
+            settle(eng, 60)
+        barrier.wait(180)
+        if rank != 0:
+            last, t0 = None, time.time()
+            while time.time() - t0 < 30:
+                cur = eng.health()["kernel_launches"]
+                if cur == last:
+                    break
+                last = cur
+                time.sleep(0.3)
+        hz = eng.health()
+        res["counters"] = {k: hz[k] for k in ("steps_prefill", "steps_decode", "tokens_decode", "tokens_prefill", "kernel_launches", "preemptions")}
+        res["pages"] = (hz["free_kv_pages"], hz["total_kv_pages"])
+        out_q.put((rank, res))
+        barrier.wait(60)
+        eng.close()
+    except Exception as e:                                                      # noqa: BLE001
+        import traceback
+        out_q.put((rank, {"error": repr(e) + traceback.format_exc()[-800:]}))
+        try:
+            barrier.abort()
+        except Exception:                                                       # noqa: BLE001
+            pass
+
+
+@inner
+def test_scenario_two_rank_plan_channel_replays_every_kind_of_event():
+    """The leader runs a 700-operation random walk — submits (greedy and sampled), polls, cancels, releases in flight, pause
+    toggles, sleeps that let queue timeouts (10 ms) and deadlines (40 ms) expire on ITS clock, a 10-page pool that forces
+    preemption — and the follower, which sees nothing but the shared-memory log, must end with the same step, token, launch
+    and preemption counters and every page free: each logged event type (submit, cancel, release, pause, expire, schedule,
+    harvest) is replayed in order."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world = 2
+    handles, barrier, q = ctx.Array("B", 64 * world), ctx.Barrier(world), ctx.Queue()
+    name = "llmlb_plan_rnd_%d" % os.getpid()
+    ps = [ctx.Process(target=_tp_rank_random, args=(r, world, handles, barrier, name, q)) for r in range(world)]
+    [p.start() for p in ps]
+    got = dict(q.get(timeout=300) for _ in range(world))
+    [p.join(60) for p in ps]
+    assert all("error" not in v for v in got.values()), got
+    lead, foll = got[0], got[1]
+    assert lead["counters"] == foll["counters"], (lead["counters"], foll["counters"])
+    assert lead["pages"][0] == lead["pages"][1] == 10 and foll["pages"] == lead["pages"]
+    assert lead["counters"]["steps_decode"] > 100
+    # which of cancel / queue timeout / deadline / preemption occur depends on the leader's clock; at least expiry did
+    assert set(lead["finish"]) & {5, 6}, lead["finish"]
+    assert all(p.exitcode == 0 for p in ps)
