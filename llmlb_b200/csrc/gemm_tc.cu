@@ -613,6 +613,12 @@ extern "C" int llmlb_op_gemm(const void* w, const void* x, void* out, uint32_t n
     set_error("llmlb_op_gemm: bad argument (k must be a multiple of 8)");
     return LLMLB_E_INVALID_ARG;
   }
+  // tile counts are 32-bit: a dimension near 2^32 wraps them to zero (fuzzing the entry point over the fake CUDA runtime
+  // divided by that zero); nothing the engine serves comes near these bounds
+  if (n_tokens > (1u << 20) || n_out > (1u << 24) || k > (1u << 20)) {
+    set_error("llmlb_op_gemm: dimension out of range (tokens <= 2^20, n_out <= 2^24, k <= 2^20)");
+    return LLMLB_E_INVALID_ARG;
+  }
   if (epilogue > LLMLB_EPI_STORE_F32) {
     set_error("llmlb_op_gemm: unknown epilogue");
     return LLMLB_E_INVALID_ARG;

@@ -87,10 +87,13 @@ int fake_encode_tiled(void* map, int data_type, unsigned rank, void* base, const
 extern "C" {
 static void mark_dirty(void* d);
 static bool smem_allowed(const void* fn, size_t smem);
+static bool config_allowed(dim3 g, dim3 b);
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return illegal_in_capture("cudaDeviceSynchronize") ? cudaErrorStreamCaptureUnsupported : cudaSuccess; }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+// launches made with <<<...>>> report their error through cudaGetLastError (returned once, then cleared)
+thread_local cudaError_t g_last_error = cudaSuccess;
+cudaError_t cudaGetLastError(void) { const cudaError_t e = g_last_error; g_last_error = cudaSuccess; return e; }
 const char* cudaGetErrorString(cudaError_t) { return "fake cudart"; }
 // "Device" allocations are anonymous shared memory (memfd) so that another PROCESS can map them through the IPC-handle
 // calls, the way tensor-parallel ranks map each other's exchange regions: zero-filled like calloc, nothing named in
@@ -216,13 +219,15 @@ static void log_launch(const void* fn, dim3 g, dim3 b, size_t smem, dim3 cluster
   fflush(f);
 }
 cudaError_t cudaLaunchKernel(const void* fn, dim3 g, dim3 b, void**, size_t smem, cudaStream_t) {
-  if (!smem_allowed(fn, smem)) return cudaErrorInvalidValue;
+  if (!config_allowed(g, b)) return g_last_error = cudaErrorInvalidConfiguration;
+  if (!smem_allowed(fn, smem)) return g_last_error = cudaErrorInvalidValue;
   ++g_launches;
   log_launch(fn, g, b, smem, dim3(1, 1, 1), 0);
   return cudaSuccess;
 }
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* fn, void**) {
-  if (!smem_allowed(fn, c->dynamicSmemBytes)) return cudaErrorInvalidValue;
+  if (!config_allowed(c->gridDim, c->blockDim)) return g_last_error = cudaErrorInvalidConfiguration;
+  if (!smem_allowed(fn, c->dynamicSmemBytes)) return g_last_error = cudaErrorInvalidValue;
   ++g_launches;
   dim3 cluster(1, 1, 1);
   int pdl = 0;
@@ -242,6 +247,14 @@ cudaError_t cudaFuncSetAttribute(const void* fn, cudaFuncAttribute attr, int val
     g_smem_optin[fn] = size_t(value);
   }
   return cudaSuccess;
+}
+// launch configuration limits of the device (compute capability 10.0): refused with cudaErrorInvalidConfiguration
+static bool config_allowed(dim3 g, dim3 b) {
+  const unsigned long long threads = (unsigned long long)b.x * b.y * b.z;
+  const bool ok = g.x >= 1 && g.y >= 1 && g.z >= 1 && g.x <= 2147483647u && g.y <= 65535u && g.z <= 65535u &&
+                  b.x >= 1 && b.y >= 1 && b.z >= 1 && b.x <= 1024 && b.y <= 1024 && b.z <= 64 && threads <= 1024;
+  if (!ok) fprintf(stderr, "fake cudart: invalid launch configuration grid %ux%ux%u block %ux%ux%u\n", g.x, g.y, g.z, b.x, b.y, b.z);
+  return ok;
 }
 static bool smem_allowed(const void* fn, size_t smem) {
   if (smem <= 48 * 1024) return true;

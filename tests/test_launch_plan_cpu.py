@@ -125,3 +125,16 @@ def test_op_gemm_accepts_arbitrary_shapes_within_the_same_limits(built_lib, tmp_
         ctas = int(p[1]) * int(p[2]) * int(p[3])
         assert "gemm_tc" in p[0] and ctas <= SM_COUNT and int(p[7]) <= MAX_SMEM, (ctx, line)
     assert calls > 5000 and launches >= calls
+
+
+def test_kernel_level_entry_points_survive_random_arguments(built_lib, tmp_path):
+    """Every llmlb_op_* entry point with random pointers (valid or NULL) and integers from {0, 1, odd, model-sized, 2^32 - 1}:
+    25000 calls, each returns OK or a negative error code — never a crash.  Found on the first run: a dimension near 2^32
+    wrapped llmlb_op_gemm's 32-bit tile count to zero and the launch planner divided by it (SIGFPE); dimensions are
+    bounded at the entry point now.  Launches whose configuration the device would refuse come back as errors through
+    the fake runtime's cudaGetLastError, like on the GPU."""
+    env = dict(os.environ, LD_PRELOAD=HL.build_fake(), FAKE_CUDART_LAUNCH_LOG=str(tmp_path / "opf.log"))
+    for seed in ("1", "2"):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "support", "op_fuzz.py"), "12500", seed], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, "seed %s rc %d\n%s" % (seed, r.returncode, r.stderr[-1500:])
+        assert "calls 12500" in r.stdout and "(0, " in r.stdout and "(-1, " in r.stdout, r.stdout[-300:]
