@@ -138,3 +138,14 @@ def test_kernel_level_entry_points_survive_random_arguments(built_lib, tmp_path)
         r = subprocess.run([sys.executable, os.path.join(HERE, "support", "op_fuzz.py"), "12500", seed], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, "seed %s rc %d\n%s" % (seed, r.returncode, r.stderr[-1500:])
         assert "calls 12500" in r.stdout and "(0, " in r.stdout and "(-1, " in r.stdout, r.stdout[-300:]
+
+
+def test_engine_create_with_random_configurations_refuses_or_serves(built_lib, tmp_path):
+    """llmlb_engine_create from a valid configuration with up to three fields knocked to odd values (zero, not a multiple of
+    the page, more ranks than kv heads, a 2^20-page pool, NaN rope base, a foreign ABI version ...), 3000 times: every call
+    either returns an error code and no engine, or an engine that then serves a request to completion and is destroyed."""
+    env = dict(os.environ, LD_PRELOAD=HL.build_fake())
+    r = subprocess.run([sys.executable, os.path.join(HERE, "support", "create_fuzz.py"), "3000", "1"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-2500:]
+    n_ok, n_err = [int(x) for x in re.search(r"engines (\d+) refused (\d+)", r.stdout).groups()]
+    assert n_ok > 1000 and n_err > 500
