@@ -57,6 +57,17 @@ def main():
                 drain(e, r)
     for e in engs:
         e.close()
+    # a 131072-token context: 64 prefill chunks over ever longer cached contexts, then decode over 130 k tokens
+    engs = [ffi.Engine(model, tp_rank=r, tp_size=tp, max_seqs=2, max_ctx=131072, max_step_tokens=2048) for r in range(tp)]
+    if tp > 1:
+        hs = [e.tp_export() for e in engs]
+        for e in engs:
+            e.tp_import(hs)
+    mark("ctx131072")
+    for e in engs:
+        drain(e, e.submit([i % 1000 for i in range(130000)], 8, ignore_eos=True))
+    for e in engs:
+        e.close()
 
 
 if __name__ == "__main__":

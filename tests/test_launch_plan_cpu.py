@@ -60,6 +60,7 @@ def test_every_width_of_the_launch_plan_respects_co_residency_and_hardware_limit
     steps = plan(tmp_path, model, tp)
     assert len([k for k in steps if k.startswith("prefill")]) == 2048 and len([k for k in steps if k.startswith("decode")]) == 128
     assert len([k for k in steps if k.startswith("long")]) == 4                              # 3800-token contexts, batch 1 / 3 / 5 / 32
+    assert len(steps["ctx131072"]) > 64 * 10                                                 # one 130 000-token prompt in 64 chunks + decode
     n = 0
     seen_ksplit_kernels = set()
     for ctx, launches in steps.items():
