@@ -88,6 +88,10 @@ test_server_from_a_single_gguf = T.test_server_from_a_single_gguf
 test_stop_strings_end_the_text_before_the_match = T.test_stop_strings_end_the_text_before_the_match
 test_model_download_routes = T.test_model_download_routes
 test_an_unmodified_gateway_would_register_and_sync_this_endpoint = T.test_an_unmodified_gateway_would_register_and_sync_this_endpoint
+# the structured request fuzz and the raw-HTTP abuse of tests/test_server_fake_engine_cpu.py, against the real engine
+import test_server_fake_engine_cpu as _F  # noqa: E402
+test_request_bodies_with_wrong_types_never_take_the_server_down = _F.test_request_bodies_with_wrong_types_never_take_the_server_down
+test_malformed_http_is_answered_or_dropped_and_the_server_stays_up = _F.test_malformed_http_is_answered_or_dropped_and_the_server_stays_up
 
 
 def test_deadline_and_queue_timeout_expire_inside_the_real_scheduler(product_bin):
