@@ -531,6 +531,12 @@ int llmlb_engine::init() {
     set_error("unsupported model geometry (GQA group must be a multiple of 4; dims divisible by tp)");
     return LLMLB_E_INVALID_ARG;
   }
+  // the 32-bit exchange epoch keeps the collective's index (+1) in its low 8 bits (tp_common.cuh tp_epoch32): two collectives
+  // per layer, so a deeper stack would carry into the step bits and a stale word of the NEXT step could pass for a fresh one
+  if (tp > 1 && 2ull * M.n_layers + 1 > 255) {
+    set_error("tensor parallel: at most 127 layers (two exchange collectives per layer are numbered in 8 bits)");
+    return LLMLB_E_INVALID_ARG;
+  }
   if (cfg.max_seqs == 0 || cfg.max_ctx == 0) { set_error("max_seqs/max_ctx must be > 0"); return LLMLB_E_INVALID_ARG; }
   nq_l = M.n_heads / tp; nkv_l = M.n_kv_heads / tp; ffn_l = M.ffn / tp; vocab_l = M.vocab / tp;
   qkv_w = (nq_l + 2 * nkv_l) * kHeadDim;

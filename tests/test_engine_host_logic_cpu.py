@@ -726,3 +726,16 @@ def test_scenario_two_rank_plan_channel_replays_every_kind_of_event():
     # which of cancel / queue timeout / deadline / preemption occur depends on the leader's clock; at least expiry did
     assert set(lead["finish"]) & {5, 6}, lead["finish"]
     assert all(p.exitcode == 0 for p in ps)
+
+
+@inner
+def test_scenario_tensor_parallel_depth_limit_is_refused_not_wrapped():
+    """The decode exchange numbers its collectives (two per layer) in the low 8 bits of a 32-bit epoch: 127 layers fit
+    (Llama-3.1-405B has 126), a deeper tensor-parallel stack would alias epochs of consecutive steps — create refuses it;
+    a single-GPU engine has no such limit."""
+    ffi = _ffi()
+    ffi.Engine(dict(ffi.LLAMA3_70B, n_layers=126), tp_size=8, tp_rank=0, max_seqs=2, max_ctx=256).close()
+    with pytest.raises(ffi.LlmlbError) as ei:
+        ffi.Engine(dict(ffi.LLAMA3_70B, n_layers=128), tp_size=8, tp_rank=0, max_seqs=2, max_ctx=256)
+    assert "127 layers" in str(ei.value)
+    ffi.Engine(dict(TINY, n_layers=200), max_seqs=2, max_ctx=256).close()
