@@ -247,3 +247,28 @@ def test_token_ids_outside_any_vocabulary_are_refused(H):
         raw = json.dumps(t).encode()
         assert not H.llmlb_tok_create(raw, len(raw), err, 256), (where, bad)
         assert b"id" in err.value
+
+
+def test_long_unbroken_runs_merge_like_the_library_and_in_bounded_time(H, tok):
+    """A pre-token is an unbounded run of letters (or of punctuation): the rescanning merge loop was quadratic in its length
+    (80 000 characters: 11-18 s on one thread, a 20 MiB request body would never finish).  Pieces longer than 48 symbols now
+    merge from a heap of (rank, position) candidates over a linked list — the same merge order, O(n log n).  Checked against
+    the `tokenizers` library on runs of 49 ... 20 000 characters of several alphabets, and timed on 400 000."""
+    tk = pytest.importorskip("tokenizers")
+    import random
+    import time
+    hf = tk.Tokenizer.from_file(os.path.join(GOLD, "tokenizer_llama3_style.json"))
+    rng = random.Random(7)
+    alphabets = ["ab", "abcdefghijklmnopqrstuvwxyz", "etaoinshrdlu", "!?.,;:-", "!", "éèêëàâäôöûüç", "日本語漢字かなカナ", "0123456789", "aA", "\n", " \t"]
+    for n in (49, 50, 63, 64, 65, 100, 257, 1000, 4097, 20000):
+        for alpha in alphabets:
+            s = "".join(rng.choice(alpha) for _ in range(n))
+            assert encode(H, tok, s) == hf.encode(s, add_special_tokens=False).ids, (n, alpha)
+    # mixed text around the 48-symbol switch between the two merge loops
+    for _ in range(300):
+        s = " ".join("".join(rng.choice("abcdefghij") for _ in range(rng.randint(40, 56))) for _ in range(4))
+        assert encode(H, tok, s) == hf.encode(s, add_special_tokens=False).ids
+    big = "".join(rng.choice("abcdefghij") for _ in range(400000))
+    t0 = time.time()
+    ids = encode(H, tok, big)
+    assert time.time() - t0 < 5.0 and decode(H, tok, ids) == big.encode()
