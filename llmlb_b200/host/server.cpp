@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -214,7 +215,8 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     if (raw->is_array()) for (auto& v : raw->items()) ids.push_back(int32_t(v.as_int()));
   } else if (kind == 0) {
     const Json* msgs = req.get("messages");
-    if (!msgs || !msgs->is_array()) { send_err(400, "messages is required", "invalid_request_error"); return; }
+    if (!msgs || !msgs->is_array() || msgs->items().empty()) { send_err(400, "messages is required", "invalid_request_error"); return; }
+    for (auto& m : msgs->items()) if (!m.is_object()) { send_err(400, "messages must be an array of objects", "invalid_request_error"); return; }
     std::string text;
     std::vector<ChatMessage> chat;
     for (auto& m : msgs->items()) {
@@ -230,16 +232,32 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     const Json* in = req.get("input");
     std::string text;
     std::vector<ChatMessage> chat;
-    if (in && in->is_string()) { text = in->str(); chat.push_back(ChatMessage{"user", text}); }
-    else if (in && in->is_array()) for (auto& m : in->items()) {
+    if (!in || !(in->is_string() || (in->is_array() && !in->items().empty()))) { send_err(400, "input is required (a string or an array of input items)", "invalid_request_error"); return; }
+    if (in->is_string()) { text = in->str(); chat.push_back(ChatMessage{"user", text}); }
+    else for (auto& m : in->items()) {
       const Json* role = m.get("role"); const Json* c = m.get("content");
       if (c) { text += content_text(*c) + "\n"; chat.push_back(ChatMessage{role && role->is_string() ? role->str() : "user", content_text(*c)}); }
     }
     ids = G.tok ? G.tok->encode_chat(chat) : byte_tokenize(text, G.vocab);
   } else {
+    // OpenAI's four prompt forms: "text" | ["text"] | [id, ...] | [[id, ...]].  Several prompts in one request (one choice
+    // per prompt) are not served by this shim: refused, not answered for the first one only; anything else is a 400 instead of
+    // the completion of an empty prompt that a silent "" would produce.
     const Json* p = req.get("prompt");
-    const std::string text = p && p->is_string() ? p->str() : "";
-    ids = G.tok ? G.tok->encode(text, /*add_bos=*/true, /*parse_special=*/false) : byte_tokenize(text, G.vocab);
+    auto all_ints = [](const Json& a) { for (auto& v : a.items()) if (!v.is_number() || v.as_double() != double(v.as_int())) return false; return !a.items().empty(); };
+    const Json* one = p;
+    if (p && p->is_array() && p->items().size() == 1 && (p->items()[0].is_string() || p->items()[0].is_array())) one = &p->items()[0];
+    if (one && one->is_string()) {
+      ids = G.tok ? G.tok->encode(one->str(), /*add_bos=*/true, /*parse_special=*/false) : byte_tokenize(one->str(), G.vocab);
+    } else if (one && one->is_array() && all_ints(*one)) {
+      for (auto& v : one->items()) ids.push_back(int32_t(std::max<int64_t>(-1, std::min<int64_t>(v.as_int(), INT32_MAX))));
+    } else if (p && p->is_array() && p->items().size() > 1 && (p->items()[0].is_string() || p->items()[0].is_array())) {
+      send_err(400, "several prompts in one request are not supported: send one request per prompt", "invalid_request_error");
+      return;
+    } else {
+      send_err(400, "prompt must be a string, an array with one string, or an array of token ids", "invalid_request_error");
+      return;
+    }
   }
   for (int32_t t : ids)
     if (t < 0 || uint32_t(t) >= G.vocab) { send_err(400, "prompt token id outside the model vocabulary", "invalid_request_error"); return; }

@@ -317,3 +317,35 @@ def test_request_bodies_with_wrong_types_never_take_the_server_down(tok_server):
     assert s_ == 200
     s_, _, d = T.call(port, "GET", "/api/health")
     assert s_ == 200 and json.loads(d)["load"]["active_requests"] == 0
+
+
+def test_completions_prompt_forms(server):
+    """OpenAI's `prompt` is a string, an array with one string, an array of token ids or an array with one such array.  The
+    scripted engine's tokens are a hash of the prompt ids, so equal prompts give equal text: "hello" == ["hello"], and the id
+    form equals `prompt_token_ids`.  Several prompts per request and non-prompts are refused with 400 — they used to be
+    answered, silently, with the completion of an EMPTY prompt."""
+    port = server
+    ask = lambda p, **kw: T.call(port, "POST", "/v1/completions", dict({"model": "tiny-llama", "prompt": p, "max_tokens": 4, "temperature": 0}, **kw))
+    text = lambda r: json.loads(r[2])["choices"][0]["text"]
+    a, b = ask("hello"), ask(["hello"])
+    assert a[0] == b[0] == 200 and text(a) == text(b) and json.loads(a[2])["usage"]["prompt_tokens"] == json.loads(b[2])["usage"]["prompt_tokens"]
+    c, d = ask([5, 6, 7]), ask([[5, 6, 7]])
+    e = T.call(port, "POST", "/v1/completions", {"model": "tiny-llama", "prompt_token_ids": [5, 6, 7], "max_tokens": 4, "temperature": 0})
+    assert c[0] == d[0] == e[0] == 200 and text(c) == text(d) == text(e) and json.loads(c[2])["usage"]["prompt_tokens"] == 3
+    assert text(a) != text(c)
+    for bad in (["a", "b"], [[1, 2], [3, 4]], [], None, 5, {"text": "x"}, [1.5, 2], [None], ["a", 1]):
+        st, _, body = ask(bad)
+        assert st == 400 and json.loads(body)["error"]["type"] == "invalid_request_error", (bad, st, body[:120])
+    st, _, body = ask([5, 999999999])                                            # an id outside the vocabulary
+    assert st == 400
+
+
+def test_empty_or_mistyped_conversations_are_refused(server):
+    """`messages: []`, `messages: [5]`, a missing / numeric / empty `input`: 400, not a generation from the bare template."""
+    port = server
+    for path, body in (("/v1/chat/completions", {"messages": []}), ("/v1/chat/completions", {"messages": [5]}), ("/v1/chat/completions", {"messages": "hi"}),
+                       ("/v1/responses", {}), ("/v1/responses", {"input": 5}), ("/v1/responses", {"input": []}), ("/v1/responses", {"input": None})):
+        st, _, d = T.call(port, "POST", path, dict({"model": "tiny-llama", "max_tokens": 3, "max_output_tokens": 3}, **body))
+        assert st == 400 and json.loads(d)["error"]["type"] == "invalid_request_error", (path, body, st, d[:100])
+    st, _, d = T.call(port, "POST", "/v1/responses", {"model": "tiny-llama", "input": "hi", "max_output_tokens": 3})
+    assert st == 200
