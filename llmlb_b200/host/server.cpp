@@ -209,6 +209,8 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     send_err(404, "The model '" + jm->str() + "' does not exist", "invalid_request_error");
     return;
   }
+  if (const Json* n = req.get("n"))                         // one choice per request: more would be answered with one, silently
+    if (n->is_number() && n->as_int() != 1) { send_err(400, "n must be 1: this endpoint returns one choice per request", "invalid_request_error"); return; }
   // prompt
   std::vector<int32_t> ids;
   if (const Json* raw = req.get("prompt_token_ids")) {

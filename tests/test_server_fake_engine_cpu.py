@@ -349,3 +349,6 @@ def test_empty_or_mistyped_conversations_are_refused(server):
         assert st == 400 and json.loads(d)["error"]["type"] == "invalid_request_error", (path, body, st, d[:100])
     st, _, d = T.call(port, "POST", "/v1/responses", {"model": "tiny-llama", "input": "hi", "max_output_tokens": 3})
     assert st == 200
+    chat = {"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}], "max_tokens": 2}
+    assert T.call(port, "POST", "/v1/chat/completions", dict(chat, n=1))[0] == 200
+    assert T.call(port, "POST", "/v1/chat/completions", dict(chat, n=3))[0] == 400            # not one choice passed off as three
