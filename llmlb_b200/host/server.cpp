@@ -380,13 +380,18 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   const bool failed = finish != LLMLB_FINISH_STOP && finish != LLMLB_FINISH_LENGTH && !(client_gone && completion_tokens > 0);
   ClientError fe = classify_upstream_request_error(UpstreamFailure::Other, 0);                 // the engine failed the request
   if (finish == LLMLB_FINISH_QUEUE_TIMEOUT) fe = queue_wait_timeout();
-  else if (finish == LLMLB_FINISH_DEADLINE) fe = classify_upstream_request_error(UpstreamFailure::Timeout, G.request_timeout_ms / 1000);
+  else if (finish == LLMLB_FINISH_DEADLINE) fe = classify_upstream_request_error(UpstreamFailure::Timeout, (G.request_timeout_ms + 999) / 1000);
   const int fail_status = fe.status;
   const std::string fail_msg = fe.message, fail_type = fe.type;
   if (failed && !stream) { send_err(fail_status, fail_msg, fail_type.c_str()); return; }
   if (stream) {
     if (!ok) return;
     if (failed) {   // headers are gone: say so in-band and end the stream WITHOUT a finish chunk or [DONE]
+      if (anthropic) {   // Anthropic's streaming error event: `event: error` + {"type":"error","error":{"type","message"}}
+        send_chunk(fd, "event: error\ndata: " + anthropic_error_body(fail_status, fail_msg) + "\n\n");
+        send_all(fd, "0\r\n\r\n");
+        return;
+      }
       Json err = Json::object(); err.set("message", fail_msg); err.set("type", fail_type); err.set("code", fail_status);
       Json root = Json::object(); root.set("error", err);
       send_chunk(fd, sse_event(root));

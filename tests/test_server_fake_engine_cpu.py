@@ -352,3 +352,25 @@ def test_empty_or_mistyped_conversations_are_refused(server):
     chat = {"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}], "max_tokens": 2}
     assert T.call(port, "POST", "/v1/chat/completions", dict(chat, n=1))[0] == 200
     assert T.call(port, "POST", "/v1/chat/completions", dict(chat, n=3))[0] == 400            # not one choice passed off as three
+
+
+def test_messages_route_reports_engine_failures_in_anthropic_shape(fake_bin):
+    """/v1/messages when the engine's deadline expires: 504 with the Anthropic error body when nothing was sent yet; on a
+    stream whose headers are out, Anthropic's own streaming error event (`event: error`, {"type":"error","error":{...}}) and
+    no message_stop — it used to be the OpenAI-shaped `{"error":{...}}` event in the middle of an Anthropic stream.  The
+    message counts whole seconds, rounded up (a 600 ms limit is "1 seconds", not "0 seconds")."""
+    port, proc = _start(fake_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "1", "--max-ctx", "4096", "--request-timeout-ms", "600",
+                        env={"FAKE_ENGINE_TOKEN_US": "4000"})
+    try:
+        body = {"model": "tiny-llama", "max_tokens": 2000, "messages": [{"role": "user", "content": "x"}]}
+        hdr = {"anthropic-version": "2023-06-01"}
+        st, _, d = T.call(port, "POST", "/v1/messages", body, hdr)
+        assert st == 504 and json.loads(d) == {"type": "error", "error": {"type": "api_error", "message": "Upstream endpoint request timed out after 1 seconds"}}
+        st, _, d = T.call(port, "POST", "/v1/messages", dict(body, stream=True), hdr)
+        text = d.decode()
+        blocks = [b for b in text.split("\n\n") if b.strip()]
+        assert st == 200 and blocks[0].startswith("event: message_start") and "message_stop" not in text and '"error":{"message"' not in text
+        ev, data = blocks[-1].split("\n", 1)
+        assert ev == "event: error" and json.loads(data[6:]) == {"type": "error", "error": {"type": "api_error", "message": "Upstream endpoint request timed out after 1 seconds"}}
+    finally:
+        proc.terminate(); proc.wait(timeout=20)
