@@ -15,6 +15,7 @@
 #include <signal.h>
 #include <strings.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -48,6 +49,10 @@ struct Server {
   std::unique_ptr<BpeTokenizer> tok;   // null: byte-level placeholder
   std::vector<int32_t> stop_ids;       // <|eot_id|>, <|end_of_text|>, <|eom_id|> when a tokenizer is loaded
   uint32_t queue_timeout_ms = 60000, request_timeout_ms = 120000;
+  // a client that stops reading must not pin a server thread, an engine slot and its KV pages for ever: a blocked send gives
+  // up after send_timeout_ms (the request is then cancelled like any hang-up); an idle keep-alive connection is closed after
+  // idle_timeout_ms without a request (reqwest's pool re-connects transparently)
+  uint32_t send_timeout_ms = 30000, idle_timeout_ms = 300000;
   std::unique_ptr<DownloadManager> downloads;   // POST /api/models/download, GET /api/download/progress (xllm/download.rs:97,147)
 };
 static Server G;
@@ -503,6 +508,9 @@ static void handle(int fd, const Request& rq) {
 static void serve_conn(int fd) {
   int one = 1;
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  auto tv = [](uint32_t ms) { timeval t; t.tv_sec = ms / 1000; t.tv_usec = (ms % 1000) * 1000; return t; };
+  if (G.send_timeout_ms) { const timeval t = tv(G.send_timeout_ms); setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &t, sizeof t); }
+  if (G.idle_timeout_ms) { const timeval t = tv(G.idle_timeout_ms); setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &t, sizeof t); }
   std::string buf;
   Request rq;
   for (;;) {
@@ -615,6 +623,8 @@ int main(int argc, char** argv) {
     else if (k == "--queue-max") queue_max = uint32_t(atoi(v.c_str()));
     else if (k == "--queue-timeout-ms") queue_timeout_ms = uint32_t(atoi(v.c_str()));
     else if (k == "--request-timeout-ms") request_timeout_ms = uint32_t(atoi(v.c_str()));
+    else if (k == "--send-timeout-ms") G.send_timeout_ms = uint32_t(atoi(v.c_str()));
+    else if (k == "--idle-timeout-ms") G.idle_timeout_ms = uint32_t(atoi(v.c_str()));
     else if (k == "--mirror-root") mirror_root = v;      // local mirror of the model hub (the box has no network)
     else if (k == "--models-dir") models_dir = v;        // where downloaded files land
   }

@@ -202,3 +202,33 @@ def test_clients_that_hang_up_mid_stream_leave_nothing_behind(product_bin):
         assert st == 200 and json.loads(d)["usage"]["completion_tokens"] == 3 and proc.poll() is None
     finally:
         proc.terminate(); proc.wait(timeout=20)
+
+
+def test_a_client_that_stops_reading_does_not_pin_the_request_for_ever(product_bin):
+    """A streaming client that keeps the connection open but never reads: the socket buffers fill, the server's send blocks.
+    Without a send timeout that thread, the engine slot and the KV pages stayed taken until the client went away (never, for a
+    wedged one).  With --send-timeout-ms the blocked send gives up, the request is cancelled and released like any hang-up."""
+    import socket
+    port, proc = _start(product_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "2", "--max-ctx", "131072", "--request-timeout-ms", "600000",
+                        "--send-timeout-ms", "400", env={"FAKE_CUDART_STEP_US": "20"})
+    try:
+        body = json.dumps({"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}], "max_tokens": 120000, "temperature": 0, "ignore_eos": True,
+                           "stream": True}).encode()
+        s = socket.create_connection(("127.0.0.1", port), timeout=30)
+        s.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 4096)
+        s.sendall(b"POST /v1/chat/completions HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body) + body)
+        t0 = time.time()
+        seen_active = False
+        while True:                                        # never read from `s`
+            hz = json.loads(T.call(port, "GET", "/api/health")[2])
+            seen_active = seen_active or hz["load"]["active_requests"] == 1
+            if seen_active and hz["load"]["active_requests"] == 0 and hz["load"]["in_flight_http"] == 0:
+                break
+            assert time.time() - t0 < 30, hz
+            time.sleep(0.05)
+        assert hz["kv"]["free_pages"] == hz["kv"]["total_pages"]
+        s.close()
+        st, _, d = T.call(port, "POST", "/v1/completions", {"model": "tiny-llama", "prompt": "x", "max_tokens": 3})
+        assert st == 200
+    finally:
+        proc.terminate(); proc.wait(timeout=20)
