@@ -271,7 +271,11 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
   llmlb_sampling s{};
   const Json* mt = req.get(kind == 1 ? "max_output_tokens" : "max_tokens");
   if (!mt && kind == 0) mt = req.get("max_completion_tokens");
-  s.max_tokens = mt && mt->is_number() ? uint32_t(std::max<int64_t>(1, mt->as_int())) : 128;
+  if (mt && !mt->is_null() && (!mt->is_number() || mt->as_int() < 1 || mt->as_double() != double(mt->as_int()))) {
+    send_err(400, std::string(kind == 1 ? "max_output_tokens" : "max_tokens") + " must be a positive integer", "invalid_request_error");
+    return;
+  }
+  s.max_tokens = mt && mt->is_number() ? uint32_t(std::min<int64_t>(mt->as_int(), INT32_MAX)) : 128;
   const Json* t = req.get("temperature");
   s.temperature = t && t->is_number() ? float(t->as_double()) : 1.0f;
   const Json* tp = req.get("top_p");

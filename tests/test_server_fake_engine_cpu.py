@@ -374,3 +374,15 @@ def test_messages_route_reports_engine_failures_in_anthropic_shape(fake_bin):
         assert ev == "event: error" and json.loads(data[6:]) == {"type": "error", "error": {"type": "api_error", "message": "Upstream endpoint request timed out after 1 seconds"}}
     finally:
         proc.terminate(); proc.wait(timeout=20)
+
+
+def test_token_budgets_that_are_not_positive_integers_are_refused(server):
+    port = server
+    chat = {"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}]}
+    for bad in (0, -3, 2.5, "10", [4]):
+        st, _, d = T.call(port, "POST", "/v1/chat/completions", dict(chat, max_tokens=bad))
+        assert st == 400 and "max_tokens" in json.loads(d)["error"]["message"], (bad, st)
+    assert T.call(port, "POST", "/v1/responses", {"model": "tiny-llama", "input": "x", "max_output_tokens": 0})[0] == 400
+    assert T.call(port, "POST", "/v1/chat/completions", dict(chat, max_tokens=None))[0] == 200          # null = the default budget
+    st, _, d = T.call(port, "POST", "/v1/chat/completions", dict(chat, max_completion_tokens=2))
+    assert st == 200 and json.loads(d)["usage"]["completion_tokens"] == 2
