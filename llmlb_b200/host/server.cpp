@@ -53,6 +53,8 @@ struct Server {
   // up after send_timeout_ms (the request is then cancelled like any hang-up); an idle keep-alive connection is closed after
   // idle_timeout_ms without a request (reqwest's pool re-connects transparently)
   uint32_t send_timeout_ms = 30000, idle_timeout_ms = 300000;
+  std::atomic<uint32_t> connections{0};
+  uint32_t max_connections = 1024;
   std::unique_ptr<DownloadManager> downloads;   // POST /api/models/download, GET /api/download/progress (xllm/download.rs:97,147)
 };
 static Server G;
@@ -629,6 +631,7 @@ int main(int argc, char** argv) {
     else if (k == "--request-timeout-ms") request_timeout_ms = uint32_t(atoi(v.c_str()));
     else if (k == "--send-timeout-ms") G.send_timeout_ms = uint32_t(atoi(v.c_str()));
     else if (k == "--idle-timeout-ms") G.idle_timeout_ms = uint32_t(atoi(v.c_str()));
+    else if (k == "--max-connections") G.max_connections = uint32_t(atoi(v.c_str()));
     else if (k == "--mirror-root") mirror_root = v;      // local mirror of the model hub (the box has no network)
     else if (k == "--models-dir") models_dir = v;        // where downloaded files land
   }
@@ -713,6 +716,13 @@ int main(int argc, char** argv) {
   for (;;) {
     int fd = accept(ls, nullptr, nullptr);
     if (fd < 0) continue;
-    std::thread(serve_conn, fd).detach();
+    // one thread per connection: bounded, so that a flood of connections costs file descriptors for an instant, not threads
+    if (G.connections.load() >= G.max_connections) {
+      send_json(fd, 503, openai_error_body("too many connections", "service_unavailable", 503), "Connection: close\r\nRetry-After: 1\r\n");
+      close(fd);
+      continue;
+    }
+    G.connections.fetch_add(1);
+    std::thread([fd] { serve_conn(fd); G.connections.fetch_sub(1); }).detach();
   }
 }

@@ -386,3 +386,31 @@ def test_token_budgets_that_are_not_positive_integers_are_refused(server):
     assert T.call(port, "POST", "/v1/chat/completions", dict(chat, max_tokens=None))[0] == 200          # null = the default budget
     st, _, d = T.call(port, "POST", "/v1/chat/completions", dict(chat, max_completion_tokens=2))
     assert st == 200 and json.loads(d)["usage"]["completion_tokens"] == 2
+
+
+def test_connection_cap_answers_503_and_recovers(fake_bin):
+    """--max-connections 4: four idle keep-alive connections are held open; the fifth is answered 503 service_unavailable with
+    Retry-After and closed at once (no thread is spent on it); when one of the four goes away the next connection is served."""
+    import socket
+    port, proc = _start(fake_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "2", "--max-ctx", "512", "--max-connections", "4")
+    try:
+        held = []
+        for _ in range(4):
+            s = socket.create_connection(("127.0.0.1", port), timeout=5)
+            s.sendall(b"GET /v1/models HTTP/1.1\r\nHost: x\r\n\r\n")
+            assert s.recv(4096).startswith(b"HTTP/1.1 200")
+            held.append(s)
+        r = _raw(port, b"GET /v1/models HTTP/1.1\r\nHost: x\r\n\r\n")
+        assert r.startswith(b"HTTP/1.1 503") and b"Retry-After: 1" in r and json.loads(r.split(b"\r\n\r\n", 1)[1])["error"]["type"] == "service_unavailable"
+        held.pop().close()
+        deadline = time.time() + 5
+        while True:
+            r = _raw(port, b"GET /v1/models HTTP/1.1\r\nHost: x\r\nConnection: close\r\n\r\n")
+            if r.startswith(b"HTTP/1.1 200"):
+                break
+            assert time.time() < deadline, r[:80]
+            time.sleep(0.05)
+        for s in held:
+            s.close()
+    finally:
+        proc.terminate(); proc.wait(timeout=20)
