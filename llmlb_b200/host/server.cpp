@@ -19,6 +19,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <climits>
 #include <cstring>
@@ -129,6 +130,14 @@ static ReqStatus read_request(int fd, std::string& buf, Request* rq) {
   rq->body = buf.substr(hdr_end + 4, need);
   buf.erase(0, hdr_end + 4 + need);
   return kReqOk;
+}
+
+// the peer closed its end (orderly shutdown or reset) and nothing is left to read: a non-blocking one-byte peek
+static bool peer_closed(int fd) {
+  char c;
+  const ssize_t n = recv(fd, &c, 1, MSG_PEEK | MSG_DONTWAIT);
+  if (n == 0) return true;
+  return n < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR;
 }
 
 static bool send_all(int fd, const std::string& s) {
@@ -344,6 +353,9 @@ static void handle_generate(int fd, const Request& rq, int kind, const Json* pre
     uint32_t got = 0;
     rc = llmlb_request_poll(G.eng, rid, ev, 64, &got, 100);
     if (rc != LLMLB_OK && rc != LLMLB_E_TIMEOUT) { finish = LLMLB_FINISH_ERROR; break; }
+    // a client that went away stops the generation, streamed or not — the reference's handler future is dropped with the
+    // connection and its upstream request with it; a buffered response would otherwise run to its last token for nobody
+    if (!client_gone && peer_closed(fd)) { ok = false; client_gone = true; llmlb_request_cancel(G.eng, rid); }
     std::string out;
     for (uint32_t i = 0; i < got; ++i) {
       if (ev[i].token_id >= 0) {

@@ -232,3 +232,31 @@ def test_a_client_that_stops_reading_does_not_pin_the_request_for_ever(product_b
         assert st == 200
     finally:
         proc.terminate(); proc.wait(timeout=20)
+
+
+def test_a_buffered_request_whose_client_went_away_is_cancelled(product_bin):
+    """Not streamed: nothing is sent until the end, so a send can never notice the dead client.  The shim peeks at the socket
+    between polls; a closed peer cancels the generation (the reference's handler future is dropped with the connection, and
+    its upstream request with it) instead of running 100 000 tokens for nobody."""
+    import socket
+    port, proc = _start(product_bin, "--model", "tiny", "--model-id", "tiny-llama", "--max-seqs", "2", "--max-ctx", "131072", "--request-timeout-ms", "600000",
+                        env={"FAKE_CUDART_STEP_US": "200"})
+    try:
+        body = json.dumps({"model": "tiny-llama", "messages": [{"role": "user", "content": "x"}], "max_tokens": 100000, "temperature": 0, "ignore_eos": True}).encode()
+        s = socket.create_connection(("127.0.0.1", port), timeout=30)
+        s.sendall(b"POST /v1/chat/completions HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body) + body)
+        t0 = time.time()
+        while json.loads(T.call(port, "GET", "/api/health")[2])["load"]["active_requests"] != 1:
+            assert time.time() - t0 < 10
+            time.sleep(0.02)
+        s.close()                                             # 100 000 tokens x 200 us = 20 s of generation left
+        t0 = time.time()
+        while True:
+            hz = json.loads(T.call(port, "GET", "/api/health")[2])
+            if hz["load"]["active_requests"] == 0 and hz["load"]["in_flight_http"] == 0:
+                break
+            assert time.time() - t0 < 5, hz
+            time.sleep(0.05)
+        assert hz["kv"]["free_pages"] == hz["kv"]["total_pages"]
+    finally:
+        proc.terminate(); proc.wait(timeout=20)
