@@ -90,3 +90,35 @@ def test_in_process_path_with_the_native_tokenizer(exe):
         assert acc.done and rec["usage"][1] == 40 and rec["usage"][0] > 5          # the chat template's tokens, counted by the engine
         assert len(acc.accumulated_content.encode()) == rec["sent_bytes"] == rec["content_bytes"]
     assert final["stats"][2] == 2
+
+
+def test_c_host_on_the_product_engine_library_over_the_fake_cuda_runtime(built_lib, tmp_path):
+    """The same C program linked against the PRODUCT libllmlb_b200.so, run with tests/support/fake_cudart.cpp preloaded (host
+    memory, no-op launches: every token id is 0): the engine's real submit / poll / release path under a C caller, with the
+    gateway-side bookkeeping checked as above."""
+    sys.path.insert(0, HERE)
+    import test_engine_host_logic_cpu as HL
+    from llmlb_b200 import build
+    host = build.build_host()
+    d = os.path.dirname(built_lib)
+    exe_path = str(tmp_path / "inprocess_host_real")
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "inprocess_host.c"),
+                           "-L" + d, "-lllmlb_b200", "-L" + os.path.dirname(host), "-lllmlb_host", "-Wl,-rpath," + d, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe_path])
+    r = subprocess.run([exe_path, "--api", "responses", "--requests", "3", "--max-tokens", "20", "--prompt-len", "30"], capture_output=True, timeout=120,
+                       env=dict(os.environ, LD_PRELOAD=HL.build_fake()))
+    assert r.returncode == 0, r.stderr.decode()[-1500:]
+    streams = r.stdout.decode().split("### request ")[1:]
+    recs = [json.loads(l) for l in r.stderr.decode().splitlines() if l.startswith("{")]
+    state = G.ModelTpsState()
+    for s, rec in zip(streams, recs[:-1]):
+        acc = G.StreamingTokenAccumulator("llama-tiny")
+        assert G.process_sse_lines(s.split("\n", 1)[1], acc) == "" and acc.done
+        assert acc.finalize() == {"input_tokens": 30, "output_tokens": 20, "total_tokens": 50} and acc.accumulated_content == "<0> " * 20
+        assert rec["usage"] == [30, 20, 50] and rec["finish"] == 2 and rec["ms"] >= 1
+        state.update_tps(20, rec["ms"])
+    assert recs[-1]["request_count"] == 3 and recs[-1]["tps_ema"] == state.tps_ema and recs[-1]["stats"][:4] == [0, 3, 3, 0]
+    # without the preload the same binary refuses: there is no CPU path
+    r = subprocess.run([exe_path, "--requests", "1"], capture_output=True, timeout=60)
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and b"no CUDA device" in r.stderr
